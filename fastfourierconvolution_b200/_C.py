@@ -1,0 +1,123 @@
+"""ctypes binding of libffc_b200.so (include/ffc_b200.h).
+
+There is exactly one compute backend: the hand-written sm_100a CUDA library.  If it cannot be
+loaded, or a tensor is not a CUDA tensor, the call fails loudly -- there is no CPU or library
+fallback in the product.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libffc_b200.so")
+
+c_int, c_float, c_void_p, c_size_t = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+
+# name -> (restype, argtypes); mirrors include/ffc_b200.h one to one
+_SIGNATURES = {
+    "ffc_version": (c_int, []),
+    "ffc_last_error": (ctypes.c_char_p, []),
+    "ffc_is_emulation": (c_int, []),
+    "ffc_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "ffc_rfft2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "ffc_irfft2": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "ffc_conv2d_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
+                       + [c_int] * 10 + [c_void_p]),
+    "ffc_conv2d_wgrad": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 10 + [c_void_p]),
+    "ffc_bias_grad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "ffc_bn_act_fwd": (c_int, [c_void_p] * 8 + [c_int] * 5 + [c_float, c_float, c_int, c_float, c_void_p, c_size_t, c_void_p]),
+    "ffc_bn_act_bwd": (c_int, [c_void_p] * 9 + [c_int] * 6 + [c_float, c_void_p, c_size_t, c_void_p]),
+    "ffc_se_fwd": (c_int, [c_void_p] * 7 + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
+    "ffc_se_bwd": (c_int, [c_void_p] * 10 + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
+    "ffc_fu_fwd": (c_int, [c_void_p] * 10 + [c_int] * 6 + [c_float, c_float, c_void_p, c_size_t, c_void_p]),
+    "ffc_fu_bwd": (c_int, [c_void_p] * 11 + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
+    "ffc_fu_fused_supported": (c_int, [c_int] * 5),
+}
+# symbols a given build may not have yet are optional at bind time (checked by tests against the header)
+_OPTIONAL = {"ffc_fu_fwd", "ffc_fu_bwd", "ffc_fu_fused_supported"}
+
+
+class Library:
+    """A loaded libffc_b200 with typed entry points."""
+
+    def __init__(self, path: str):
+        self.path = path
+        self.cdll = ctypes.CDLL(path)
+        for name, (res, args) in _SIGNATURES.items():
+            try:
+                fn = getattr(self.cdll, name)
+            except AttributeError:
+                if name in _OPTIONAL:
+                    continue
+                raise
+            fn.restype = res
+            fn.argtypes = args
+            setattr(self, name, fn)
+
+    def has(self, name: str) -> bool:
+        return hasattr(self, name)
+
+    def last_error(self) -> str:
+        return self.ffc_last_error().decode("utf-8", "replace")
+
+
+_lib: Optional[Library] = None
+_lock = threading.Lock()
+
+
+def lib() -> Library:
+    """The CUDA library; built in-tree with nvcc on first use when missing or stale."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    from . import build as _build
+                    try:
+                        _build.build()
+                    except Exception as e:  # no nvcc either: nothing can run
+                        raise RuntimeError(
+                            f"libffc_b200.so is missing ({LIB_PATH}) and could not be built: {e}. "
+                            "This package has no CPU or PyTorch fallback.") from e
+                _lib = Library(LIB_PATH)
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise RuntimeError(f"libffc_b200 error {rc}: {lib().last_error()}")
+
+
+def require_device(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("fastfourierconvolution_b200 runs on CUDA (sm_100a) tensors only; "
+                               "got a tensor on %s (there is no CPU fallback)" % t.device)
+        if t is not None and t.dtype != torch.float32:
+            raise RuntimeError("fastfourierconvolution_b200 computes in float32; got %s" % t.dtype)
+
+
+def current_stream(device) -> c_void_p:
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t: Optional[torch.Tensor]) -> c_void_p:
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+_workspaces = {}
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    """Scratch buffer owned by PyTorch's allocator, one per (device, stream), grown on demand."""
+    key = (str(device), current_stream(device).value)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws

@@ -1,0 +1,166 @@
+// Common definitions for the ffc_b200 CUDA library (sm_100a).
+//
+// Every kernel in this library is written as a "phase program": a struct K with
+//   using Params = ...;                        (POD, passed by value)
+//   static constexpr int kThreads = ...;       (upper bound for __launch_bounds__)
+//   static FFC_DEVICE void run(const Params&, const BlockCtx&, float* smem);
+// whose body is a sequence of FFC_PHASE { ... } FFC_SYNC; blocks.  On the device a phase is
+// executed by every thread of the CTA once and FFC_SYNC is __syncthreads().  When the same
+// source is compiled with -DFFC_EMU by a host C++ compiler, a phase is a sequential loop over
+// the thread ids and FFC_SYNC is a no-op, which yields a bit-faithful (up to libm / fma
+// contraction) host execution of the kernel logic.  The emulation build exists ONLY so that
+// tests/ can check index arithmetic on a machine without a GPU; the product never loads it.
+//
+// Rules that make a kernel emulable: no warp intrinsics, no state kept in plain locals across
+// phases (use FFC_TLS for per-thread state that must survive a barrier), atomics through
+// ffc_atomic_add, and within one phase no thread reads a location another thread writes.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#ifdef FFC_EMU
+// ------------------------------------------------------------------ host emulation
+#include <vector>
+#include <cstring>
+#include <cstdlib>
+#include <string>
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+typedef void* ffc_stream_t;
+#define FFC_HD static inline
+#define FFC_DEVICE inline
+#define FFC_CONST static const
+#define FFC_RESTRICT __restrict__
+#define FFC_UNROLL
+#define FFC_LDG(p) (*(p))
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+template <class T> static inline void ffc_atomic_add(T* p, T v) { *p += v; }
+#else
+// ------------------------------------------------------------------ device build
+#include <cuda_runtime.h>
+typedef cudaStream_t ffc_stream_t;
+#define FFC_HD __host__ __device__ __forceinline__
+#define FFC_DEVICE __device__ __forceinline__
+#define FFC_CONST static __constant__
+#define FFC_RESTRICT __restrict__
+#define FFC_UNROLL _Pragma("unroll")
+#define FFC_LDG(p) __ldg(p)
+template <class T> __device__ __forceinline__ void ffc_atomic_add(T* p, T v) { atomicAdd(p, v); }
+#endif
+
+struct BlockCtx {
+    int bx, by, bz;   // block index
+    int gx, gy, gz;   // grid size
+    int nt;           // threads per block
+};
+
+#ifdef FFC_EMU
+#define FFC_PHASE for (int tid = 0; tid < ctx.nt; ++tid)
+#define FFC_SYNC ((void)0)
+// per-thread state that survives a barrier
+#define FFC_TLS(T, name) std::vector<T> name##_tls((size_t)ctx.nt)
+#define FFC_TLS_REF(T, name) T& name = name##_tls[(size_t)tid]
+#else
+#define FFC_PHASE for (int tid = (int)threadIdx.x, _ffc_once = 1; _ffc_once; _ffc_once = 0)
+#define FFC_SYNC __syncthreads()
+#define FFC_TLS(T, name) T name
+#define FFC_TLS_REF(T, name) ((void)0)
+#endif
+
+// ------------------------------------------------------------------ error reporting
+// 0 = OK.  Non-zero codes are returned by every C-ABI entry point; ffc_last_error() gives text.
+enum {
+    FFC_OK = 0,
+    FFC_ERR_BAD_ARG = 1,       // unsupported shape / mode / null pointer
+    FFC_ERR_WORKSPACE = 2,     // caller-provided workspace too small
+    FFC_ERR_CUDA = 3           // a CUDA runtime call failed (launch error etc.)
+};
+
+void ffc_set_error(const char* fmt, ...);
+
+#ifdef FFC_EMU
+// ------------------------------------------------------------------ launch (emulated)
+template <class K>
+static int ffc_launch(int gx, int gy, int gz, int nt, size_t smem_bytes, ffc_stream_t, const typename K::Params& p) {
+    std::vector<float4> smem((smem_bytes + 15) / 16 + 1);
+    for (int bz = 0; bz < gz; ++bz)
+        for (int by = 0; by < gy; ++by)
+            for (int bx = 0; bx < gx; ++bx) {
+                BlockCtx ctx{bx, by, bz, gx, gy, gz, nt};
+                K::run(p, ctx, reinterpret_cast<float*>(smem.data()));
+            }
+    return FFC_OK;
+}
+static inline int ffc_memset_async(void* p, int v, size_t n, ffc_stream_t) { memset(p, v, n); return FFC_OK; }
+#else
+// ------------------------------------------------------------------ launch (device)
+template <class K>
+__global__ void __launch_bounds__(K::kThreads) ffc_kernel(const typename K::Params p) {
+    extern __shared__ float4 ffc_smem4[];
+    BlockCtx ctx{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z,
+                 (int)gridDim.x, (int)gridDim.y, (int)gridDim.z, (int)blockDim.x};
+    K::run(p, ctx, reinterpret_cast<float*>(ffc_smem4));
+}
+
+template <class K>
+static int ffc_launch(int gx, int gy, int gz, int nt, size_t smem_bytes, ffc_stream_t stream, const typename K::Params& p) {
+    if (gx <= 0 || gy <= 0 || gz <= 0) return FFC_OK;   // empty problem
+    if (nt > K::kThreads || gy > 65535 || gz > 65535) {
+        ffc_set_error("launch config out of range (nt=%d, grid=%d,%d,%d)", nt, gx, gy, gz);
+        return FFC_ERR_BAD_ARG;
+    }
+    if (smem_bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(ffc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e != cudaSuccess) { ffc_set_error("cudaFuncSetAttribute(%zu B smem): %s", smem_bytes, cudaGetErrorString(e)); return FFC_ERR_CUDA; }
+    }
+    ffc_kernel<K><<<dim3(gx, gy, gz), dim3(nt), smem_bytes, stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { ffc_set_error("kernel launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
+    return FFC_OK;
+}
+static inline int ffc_memset_async(void* p, int v, size_t n, ffc_stream_t s) {
+    if (n == 0) return FFC_OK;
+    cudaError_t e = cudaMemsetAsync(p, v, n, s);
+    if (e != cudaSuccess) { ffc_set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
+    return FFC_OK;
+}
+#endif
+
+#define FFC_CHECK(call) do { int _e = (call); if (_e != FFC_OK) return _e; } while (0)
+#define FFC_REQUIRE(cond, ...) do { if (!(cond)) { ffc_set_error(__VA_ARGS__); return FFC_ERR_BAD_ARG; } } while (0)
+
+// ------------------------------------------------------------------ small helpers
+FFC_HD int ffc_cdiv(int a, int b) { return (a + b - 1) / b; }
+FFC_HD int ffc_ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
+FFC_HD bool ffc_is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+
+// activation codes shared by the host API and the kernels (include/ffc_b200.h mirrors them)
+enum { FFC_ACT_IDENTITY = 0, FFC_ACT_RELU = 1, FFC_ACT_LEAKY = 2, FFC_ACT_GELU = 3, FFC_ACT_TANH = 4, FFC_ACT_SIGMOID = 5 };
+
+FFC_HD float ffc_act_fwd(float z, int act, float slope) {
+    switch (act) {
+        case FFC_ACT_RELU: return z > 0.f ? z : 0.f;
+        case FFC_ACT_LEAKY: return z > 0.f ? z : slope * z;
+        case FFC_ACT_GELU: return 0.5f * z * (1.0f + erff(z * 0.70710678118654752440f));
+        case FFC_ACT_TANH: return tanhf(z);
+        case FFC_ACT_SIGMOID: return 1.0f / (1.0f + expf(-z));
+        default: return z;
+    }
+}
+// derivative of the activation with respect to its input z
+FFC_HD float ffc_act_bwd(float z, int act, float slope) {
+    switch (act) {
+        case FFC_ACT_RELU: return z > 0.f ? 1.f : 0.f;
+        case FFC_ACT_LEAKY: return z > 0.f ? 1.f : slope;
+        case FFC_ACT_GELU: {
+            float cdf = 0.5f * (1.0f + erff(z * 0.70710678118654752440f));
+            float pdf = 0.39894228040143267794f * expf(-0.5f * z * z);
+            return cdf + z * pdf;
+        }
+        case FFC_ACT_TANH: { float t = tanhf(z); return 1.0f - t * t; }
+        case FFC_ACT_SIGMOID: { float s = 1.0f / (1.0f + expf(-z)); return s * (1.0f - s); }
+        default: return 1.f;
+    }
+}

@@ -1,0 +1,175 @@
+// Stand-alone plane kernels: rfft2 (real NCHW planes -> planar half spectrum) and irfft2.
+//
+// Replaces, for the general ("spectrum staged through L2") form of the Fourier unit, the
+// reference's  torch.fft.rfftn + stack/permute/contiguous/view   (layers/ffc/fourier_unity.py:38-42)
+// and          view/permute/contiguous/complex + torch.fft.irfftn (layers/ffc/fourier_unity.py:51-56).
+// The spectrum tensor uses the reference's channel convention directly: (B, 2C, H, Wf) float32,
+// channel 2c = Re, 2c+1 = Im, so the 1x1 channel mix and the BatchNorm see an ordinary NCHW tensor
+// and no layout copy is ever made.  Along u the order is FftSplit<H>::pos() (identity for H <= 32).
+#include "ffc_fft2.cuh"
+
+template <int H, int W>
+struct Rfft2Kernel {
+    struct Params {
+        const float* x;      // (nplanes, H, W)
+        float* spec;         // (nplanes, 2, H, Wf)
+        int nplanes, P;
+        int colscale;        // 0: plain rfft2;  1: multiply interior columns (0 < v < W/2) by 2
+        float scale;         // 1/sqrt(H*W)
+    };
+    static constexpr int kThreads = 512;
+    typedef Fft2Plan<H, W> PL;
+    static size_t smem_bytes(int P) { return (size_t)(2 * P * PL::REGION) * 4 + FFC_TW_N * 8; }
+
+    static FFC_DEVICE void run(const Params& p, const BlockCtx& ctx, float* smem) {
+        const int plane0 = ctx.bx * p.P;
+        const int np = (p.nplanes - plane0) < p.P ? (p.nplanes - plane0) : p.P;
+        float* A = smem;
+        float* B = smem + p.P * PL::REGION;
+        float2* tw = reinterpret_cast<float2*>(B + p.P * PL::REGION);
+        FFC_PHASE {
+            for (int i = tid; i < FFC_TW_N; i += ctx.nt) tw[i] = c_tw128[i];
+            const int per = H * (W / 4);
+            for (int i = tid; i < np * per; i += ctx.nt) {
+                const int pl = i / per, rem = i % per, h = rem / (W / 4), j = rem % (W / 4);
+                const float4 v = FFC_LDG(reinterpret_cast<const float4*>(p.x + (size_t)(plane0 + pl) * H * W) + rem);
+                *reinterpret_cast<float4*>(A + pl * PL::REGION + h * PL::RS + 4 * j) = v;
+            }
+        } FFC_SYNC;
+        float* S = nullptr;
+        FFC_FFT2_FORWARD(H, W, np, A, B, tw, S);
+        FFC_PHASE {
+            const int per = H * PL::Wf;
+            for (int i = tid; i < np * per; i += ctx.nt) {
+                const int pl = i / per, rem = i % per, v = rem % PL::Wf;
+                const float2 s = reinterpret_cast<const float2*>(S + pl * PL::REGION)[rem];
+                const float a = (p.colscale && v != 0 && v != W / 2) ? 2.0f * p.scale : p.scale;
+                float* o = p.spec + (size_t)(plane0 + pl) * 2 * per + rem;
+                o[0] = s.x * a;
+                o[per] = s.y * a;
+            }
+        } FFC_SYNC;
+    }
+};
+
+template <int H, int W>
+struct Irfft2Kernel {
+    struct Params {
+        const float* spec;       // (nplanes, 2, H, Wf)
+        const float* residual;   // (nplanes, H, W) or null: out = residual + irfft2(spec)
+        float* out;              // (nplanes, H, W)
+        int nplanes, P;
+        int colscale;            // 0: torch c2r semantics;  1: interior columns pre-multiplied by 1/2
+        float scale;
+    };
+    static constexpr int kThreads = 512;
+    typedef Fft2Plan<H, W> PL;
+    static size_t smem_bytes(int P) { return (size_t)(2 * P * PL::REGION) * 4 + FFC_TW_N * 8; }
+
+    static FFC_DEVICE void run(const Params& p, const BlockCtx& ctx, float* smem) {
+        const int plane0 = ctx.bx * p.P;
+        const int np = (p.nplanes - plane0) < p.P ? (p.nplanes - plane0) : p.P;
+        float* R0 = smem;
+        float* R1 = smem + p.P * PL::REGION;
+        float2* tw = reinterpret_cast<float2*>(R1 + p.P * PL::REGION);
+        float* S = R0;   // spectrum region
+        float* O = R1;   // other region
+        FFC_PHASE {
+            for (int i = tid; i < FFC_TW_N; i += ctx.nt) tw[i] = c_tw128[i];
+            const int per = H * PL::Wf;
+            for (int i = tid; i < np * per; i += ctx.nt) {
+                const int pl = i / per, rem = i % per, v = rem % PL::Wf;
+                const float* s = p.spec + (size_t)(plane0 + pl) * 2 * per + rem;
+                const float a = (p.colscale && v != 0 && v != W / 2) ? 0.5f : 1.0f;
+                reinterpret_cast<float2*>(S + pl * PL::REGION)[rem] = make_float2(FFC_LDG(s) * a, FFC_LDG(s + per) * a);
+            }
+        } FFC_SYNC;
+        float* R = nullptr;
+        FFC_FFT2_INVERSE(H, W, np, S, O, tw, p.scale, R);
+        FFC_PHASE {
+            const int per = H * (W / 4);
+            for (int i = tid; i < np * per; i += ctx.nt) {
+                const int pl = i / per, rem = i % per, h = rem / (W / 4), j = rem % (W / 4);
+                float4 v = *reinterpret_cast<const float4*>(R + pl * PL::REGION + h * PL::RS + 4 * j);
+                const size_t g = (size_t)(plane0 + pl) * H * W;
+                if (p.residual) {
+                    const float4 q = FFC_LDG(reinterpret_cast<const float4*>(p.residual + g) + rem);
+                    v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+                }
+                reinterpret_cast<float4*>(p.out + g)[rem] = v;
+            }
+        } FFC_SYNC;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+template <int H, int W>
+static void fft2_tile_config(int nplanes, int* P, int* nt) {
+    typedef Fft2Plan<H, W> PL;
+    const size_t per_plane = (size_t)2 * PL::REGION * 4;
+    int p = 256 / PL::kMaxItems;
+    if (p < 1) p = 1;
+    const int pmax_smem = (int)((160 * 1024) / per_plane);
+    if (p > pmax_smem) p = pmax_smem;
+    if (p < 1) p = 1;
+    if (p > nplanes) p = nplanes;
+    int t = p * PL::kMaxItems;
+    if (t > 512) t = 512;
+    t = (t + 31) / 32 * 32;
+    if (t < 64) t = 64;
+    *P = p; *nt = t;
+}
+
+template <int N>
+static int rfft2_launch(const float* x, float* spec, int nplanes, int colscale, ffc_stream_t st) {
+    typedef Rfft2Kernel<N, N> K;
+    int P, nt; fft2_tile_config<N, N>(nplanes, &P, &nt);
+    typename K::Params p{x, spec, nplanes, P, colscale, 1.0f / sqrtf((float)N * (float)N)};
+    return ffc_launch<K>(ffc_cdiv(nplanes, P), 1, 1, nt, K::smem_bytes(P), st, p);
+}
+template <int N>
+static int irfft2_launch(const float* spec, const float* residual, float* out, int nplanes, int colscale, ffc_stream_t st) {
+    typedef Irfft2Kernel<N, N> K;
+    int P, nt; fft2_tile_config<N, N>(nplanes, &P, &nt);
+    typename K::Params p{spec, residual, out, nplanes, P, colscale, 1.0f / sqrtf((float)N * (float)N)};
+    return ffc_launch<K>(ffc_cdiv(nplanes, P), 1, 1, nt, K::smem_bytes(P), st, p);
+}
+
+static bool fft2_supported(int H, int W) { return H == W && ffc_is_pow2(H) && H >= 4 && H <= 128; }
+
+extern "C" int ffc_rfft2(const float* x, float* spec, int nplanes, int H, int W, int colscale, void* stream) {
+    FFC_REQUIRE(x && spec, "ffc_rfft2: null pointer");
+    FFC_REQUIRE(fft2_supported(H, W), "ffc_rfft2: unsupported plane %dx%d (square powers of two 4..128 only)", H, W);
+    FFC_REQUIRE(((uintptr_t)x & 15) == 0, "ffc_rfft2: x must be 16-byte aligned");
+    FFC_REQUIRE(nplanes >= 0, "ffc_rfft2: negative plane count");
+    if (nplanes == 0) return FFC_OK;
+    ffc_stream_t st = (ffc_stream_t)stream;
+    switch (H) {
+        case 4: return rfft2_launch<4>(x, spec, nplanes, colscale, st);
+        case 8: return rfft2_launch<8>(x, spec, nplanes, colscale, st);
+        case 16: return rfft2_launch<16>(x, spec, nplanes, colscale, st);
+        case 32: return rfft2_launch<32>(x, spec, nplanes, colscale, st);
+        case 64: return rfft2_launch<64>(x, spec, nplanes, colscale, st);
+        default: return rfft2_launch<128>(x, spec, nplanes, colscale, st);
+    }
+}
+
+extern "C" int ffc_irfft2(const float* spec, const float* residual, float* out, int nplanes, int H, int W,
+                          int colscale, void* stream) {
+    FFC_REQUIRE(spec && out, "ffc_irfft2: null pointer");
+    FFC_REQUIRE(fft2_supported(H, W), "ffc_irfft2: unsupported plane %dx%d (square powers of two 4..128 only)", H, W);
+    FFC_REQUIRE(((uintptr_t)out & 15) == 0 && ((uintptr_t)residual & 15) == 0, "ffc_irfft2: out/residual must be 16-byte aligned");
+    FFC_REQUIRE(nplanes >= 0, "ffc_irfft2: negative plane count");
+    if (nplanes == 0) return FFC_OK;
+    ffc_stream_t st = (ffc_stream_t)stream;
+    switch (H) {
+        case 4: return irfft2_launch<4>(spec, residual, out, nplanes, colscale, st);
+        case 8: return irfft2_launch<8>(spec, residual, out, nplanes, colscale, st);
+        case 16: return irfft2_launch<16>(spec, residual, out, nplanes, colscale, st);
+        case 32: return irfft2_launch<32>(spec, residual, out, nplanes, colscale, st);
+        case 64: return irfft2_launch<64>(spec, residual, out, nplanes, colscale, st);
+        default: return irfft2_launch<128>(spec, residual, out, nplanes, colscale, st);
+    }
+}

@@ -1,0 +1,58 @@
+"""Helpers shared by the FFC modules: parameter-holder access and activation / norm mapping."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+
+def effective_weight(mod: nn.Module) -> torch.Tensor:
+    """The weight a holder module would use in its own forward.
+
+    ``torch.nn.utils.spectral_norm`` (layers/snffc/snffc.py:23-33) installs a forward-pre-hook that
+    recomputes ``mod.weight = weight_orig / sigma`` (one power iteration in training mode).  The
+    B200 path never calls ``mod.forward``, so the hooks are run here, exactly once per forward.
+    """
+    for hook in mod._forward_pre_hooks.values():
+        hook(mod, (None,))
+    return mod.weight
+
+
+def act_code(act: nn.Module):
+    """(code, slope) for activations the fused kernel implements, else None."""
+    if isinstance(act, nn.Identity):
+        return ops.ACT_IDENTITY, 0.0
+    if isinstance(act, nn.LeakyReLU):
+        return ops.ACT_LEAKY, float(act.negative_slope)
+    if isinstance(act, nn.ReLU):
+        return ops.ACT_RELU, 0.0
+    if isinstance(act, nn.GELU) and getattr(act, "approximate", "none") == "none":
+        return ops.ACT_GELU, 0.0
+    if isinstance(act, nn.Tanh):
+        return ops.ACT_TANH, 0.0
+    if isinstance(act, nn.Sigmoid):
+        return ops.ACT_SIGMOID, 0.0
+    return None
+
+
+def bn_act(x: torch.Tensor, bn: nn.Module, act_code_slope) -> torch.Tensor:
+    """act(bn(x)) through the fused kernel; ``bn`` is an nn.BatchNorm2d holder or nn.Identity."""
+    code, slope = act_code_slope
+    if isinstance(bn, nn.Identity):
+        if code == ops.ACT_IDENTITY:
+            return x
+        return ops.bn_act(x, norm=False, act=code, slope=slope)
+    if bn.momentum is None:
+        raise NotImplementedError("BatchNorm2d(momentum=None) (cumulative average) is not supported")
+    use_batch_stats = bn.training or bn.running_mean is None
+    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)          # torch _BatchNorm.forward bookkeeping
+    gamma, beta = bn.weight, bn.bias
+    if gamma is None:                            # affine=False
+        gamma = torch.ones(bn.num_features, device=x.device)
+        beta = torch.zeros(bn.num_features, device=x.device)
+    rm = bn.running_mean if bn.track_running_stats else None
+    rv = bn.running_var if bn.track_running_stats else None
+    return ops.bn_act(x, gamma, beta, rm, rv, norm=True, training=use_batch_stats, eps=bn.eps,
+                      momentum=bn.momentum, act=code, slope=slope)

@@ -1,0 +1,143 @@
+"""FFC and FFCTranspose -- drop-ins for layers/ffc/ffc.py:9-99 and layers/ffc/ffc_transpose.py:10-110."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from . import _util
+from .spectral_transform import SpectralTransform
+
+
+def _split(in_channels, out_channels, ratio_gin, ratio_gout):
+    in_cg = int(in_channels * ratio_gin)
+    out_cg = int(out_channels * ratio_gout)
+    return in_channels - in_cg, in_cg, out_channels - out_cg, out_cg
+
+
+class _FFCBase(nn.Module):
+    """Shared forward of FFC / FFCTranspose: both are 'three local convs + spectral transform'."""
+
+    _transposed = False
+
+    def _local_sum(self, pairs, addend_fn=None):
+        """sum_i conv_i(x_i) over (holder, input) pairs in ONE kernel launch.
+
+        nn.Identity holders pass their input through (ffc.py:46-47): an int 0 is dropped, a tensor
+        is added afterwards, exactly what ``Identity(x) + conv(...)`` does in the reference.
+        """
+        segs, passthrough = [], []
+        for conv, inp in pairs:
+            if isinstance(conv, nn.Identity):
+                passthrough.append(inp)
+            else:
+                if not torch.is_tensor(inp):
+                    raise TypeError(f"{type(conv).__name__} needs a tensor input, got {inp!r} "
+                                    "(the reference raises here as well)")
+                segs.append((inp, conv))
+        out = 0
+        if segs:
+            c0 = segs[0][1]
+            k, s, p = c0.kernel_size[0], c0.stride[0], c0.padding[0]
+            if c0.kernel_size[0] != c0.kernel_size[1] or c0.dilation != (1, 1) or c0.groups != 1:
+                raise NotImplementedError("only square kernels, dilation 1, groups 1 are supported")
+            op = c0.output_padding[0] if self._transposed else 0
+            ws = [_util.effective_weight(c) for _, c in segs]
+            biases = [c.bias for _, c in segs if c.bias is not None]
+            bias = None
+            if biases:
+                bias = biases[0] if len(biases) == 1 else biases[0] + biases[1]
+            x1, w1 = (segs[1][0], ws[1]) if len(segs) > 1 else (None, None)
+            if addend_fn is not None:
+                # the spectral transform adds itself onto this result in its last kernel
+                base = ops.conv2d(segs[0][0], ws[0], x1, w1, bias, None, s, p, self._transposed, op)
+                out = addend_fn(base)
+                addend_fn = None
+            else:
+                out = ops.conv2d(segs[0][0], ws[0], x1, w1, bias, None, s, p, self._transposed, op)
+        if addend_fn is not None:
+            out = addend_fn(None)
+        for t in passthrough:
+            if torch.is_tensor(t) or t != 0:
+                out = out + t
+        return out
+
+    def forward(self, x, y=None):
+        x_l, x_g = x if type(x) is tuple else (x, 0)
+        out_xl, out_xg = 0, 0
+        if self.ratio_gout != 1:
+            out_xl = self._local_sum([(self.convl2l, x_l), (self.convg2l, x_g)])
+        if self.ratio_gout != 0:
+            if type(self.convg2g) is not nn.Identity:
+                out_xg = self._local_sum([(self.convl2g, x_l)],
+                                         addend_fn=lambda base: self.convg2g._run(x_g, y, base))
+            else:
+                out_xg = self._local_sum([(self.convl2g, x_l)])
+        return out_xl, out_xg
+
+
+class FFC(_FFCBase):
+    _transposed = False
+
+    def __init__(self, in_channels: int, out_channels: int, kernel_size: int,
+                 ratio_gin: float, ratio_gout: float, stride: int = 1, padding: int = 0,
+                 dilation: int = 1, groups: int = 1, bias: bool = False, enable_lfu: bool = True,
+                 attention: bool = False, num_classes: int = 1):
+        super().__init__()
+        assert stride == 1 or stride == 2, "Stride should be 1 or 2."
+        if groups != 1 or dilation != 1:
+            raise NotImplementedError("FFC: groups/dilation other than 1 are not supported by the sm_100a kernels")
+        self.stride = stride
+        in_cl, in_cg, out_cl, out_cg = _split(in_channels, out_channels, ratio_gin, ratio_gout)
+        self.ratio_gin = ratio_gin
+        self.ratio_gout = ratio_gout
+
+        def local(cin, cout):
+            if cin == 0 or cout == 0:
+                return nn.Identity()
+            return nn.Conv2d(cin, cout, kernel_size, stride, padding, dilation, groups, bias)
+
+        self.convl2l = local(in_cl, out_cl)
+        self.convl2g = local(in_cl, out_cg)
+        self.convg2l = local(in_cg, out_cl)
+        if in_cg == 0 or out_cg == 0:
+            self.convg2g = nn.Identity()
+        else:
+            self.convg2g = SpectralTransform(in_cg, out_cg, stride, 1, enable_lfu, False, num_classes)
+
+
+class FFCTranspose(_FFCBase):
+    _transposed = True
+
+    def __init__(self, in_channels: int, out_channels: int, kernel_size: int,
+                 ratio_gin: float, ratio_gout: float, stride: int = 1, padding: int = 0,
+                 dilation: int = 1, groups: int = 1, bias: bool = False,
+                 enable_lfu: bool = True, out_padding: int = 0, num_classes: int = 1):
+        super().__init__()
+        assert stride == 1 or stride == 2, "Stride should be 1 or 2."
+        if groups != 1 or dilation != 1:
+            raise NotImplementedError("FFCTranspose: groups/dilation other than 1 are not supported by the sm_100a kernels")
+        self.stride = stride
+        in_cl, in_cg, out_cl, out_cg = _split(in_channels, out_channels, ratio_gin, ratio_gout)
+        self.ratio_gin = ratio_gin
+        self.ratio_gout = ratio_gout
+
+        def local(cin, cout):
+            return self.convtransp2d(cin == 0 or cout == 0, cin, cout, kernel_size, stride, padding,
+                                     output_padding=out_padding, groups=groups, bias=bias, dilation=dilation)
+
+        self.convl2l = local(in_cl, out_cl)
+        self.convl2g = local(in_cl, out_cg)
+        self.convg2l = local(in_cg, out_cl)
+        if in_cg == 0 or out_cg == 0:
+            self.convg2g = nn.Identity()
+        else:
+            self.convg2g = SpectralTransform(in_cg, out_cg, stride, 1, enable_lfu, True, num_classes)
+
+    def convtransp2d(self, condition: bool, in_ch: int, out_ch: int, kernel_size: int, stride: int,
+                     padding: int, output_padding: int, groups: int, bias: int, dilation: int):
+        """Same helper name/signature as ffc_transpose.py:80-86 (subclasses may call it)."""
+        if condition:
+            return nn.Identity()
+        return nn.ConvTranspose2d(in_ch, out_ch, kernel_size, stride, padding, output_padding=output_padding,
+                                  groups=groups, bias=bias, dilation=dilation)

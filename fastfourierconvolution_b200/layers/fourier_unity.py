@@ -1,0 +1,48 @@
+"""FourierUnitSN -- drop-in for the reference's layers/ffc/fourier_unity.py:17-58.
+
+Same constructor, same submodules (``conv_layer``, ``bn``, ``relu``; they only hold parameters and
+buffers so ``state_dict`` / ``apply(weights_init)`` / optimizers see the reference layout), same
+``forward(x, y=None)``.  The forward runs hand-written sm_100a kernels: a fused shared-memory
+rfft2 -> channel mix -> BatchNorm + ReLU -> irfft2 kernel where one image's spectrum fits in a
+CTA's shared memory, otherwise the general form rfft2 | 1x1 mix | BN+ReLU | irfft2 with the
+spectrum staged through L2 in the reference's (B, 2C, H, W/2+1) channel layout (no layout copies).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from . import _util
+
+
+class FourierUnitSN(nn.Module):
+    def __init__(self, in_channels, out_channels, groups: int = 1, num_classes: int = 1):
+        super().__init__()
+        if groups != 1:
+            raise NotImplementedError("FourierUnitSN: groups != 1 is not supported by the sm_100a kernels")
+        self.groups = groups
+        # parameter holders, reference layout: conv_layer.weight (2*Cout, 2*Cin, 1, 1), bn.* over 2*Cout
+        self.conv_layer = nn.Conv2d(in_channels * 2, out_channels * 2, kernel_size=1, stride=1, padding=0,
+                                    groups=groups, bias=False)
+        self.bn = nn.BatchNorm2d(out_channels * 2)
+        self.relu = nn.ReLU(inplace=True)
+
+    def forward(self, x, y=None):
+        return self._run(x, y, None)
+
+    def _run(self, x, y, residual):
+        """fu(x) [+ residual]; the residual add of spectral_transform.py:108 rides in the irfft2 epilogue."""
+        if y is not None:
+            raise NotImplementedError("class-conditional FourierUnitSN (y is not None) crashes in the reference "
+                                      "(fourier_unity.py:46-47) and is not implemented")
+        if x.dim() != 4:
+            raise ValueError("FourierUnitSN expects (B, C, H, W)")
+        h, w = x.shape[-2:]
+        if h != w or h & (h - 1) or not 4 <= h <= 128:
+            raise NotImplementedError(f"FourierUnitSN: only square power-of-two planes 4..128 are supported, got {h}x{w}")
+        weight = _util.effective_weight(self.conv_layer)
+        spec = ops.rfft2(x)                                            # fourier_unity.py:38-42
+        mixed = ops.conv2d(spec, weight)                               # :45
+        act = _util.bn_act(mixed, self.bn, (ops.ACT_RELU, 0.0))        # :49
+        return ops.irfft2(act, residual)                               # :51-56

@@ -1,0 +1,260 @@
+"""torch.autograd.Function wrappers around the C ABI of libffc_b200.so.
+
+Each Function is one primitive of the FFC hot path with a hand-written forward and backward; the
+nn.Modules in ``fastfourierconvolution_b200.layers`` compose them exactly where the reference
+composes ATen ops.  PyTorch is used for memory, streams and the autograd tape only.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _C
+
+ACT_IDENTITY, ACT_RELU, ACT_LEAKY, ACT_GELU, ACT_TANH, ACT_SIGMOID = range(6)
+RESAMPLE_NONE, RESAMPLE_UP2, RESAMPLE_AVGPOOL2 = range(3)
+
+
+def _c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    return None if t is None else t.contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# convolution (Conv2d / ConvTranspose2d, up to two summed segments, fused bias and addend)
+# ---------------------------------------------------------------------------------------------
+def conv_out_size(hi: int, k: int, stride: int, pad: int, transposed: bool, out_pad: int = 0) -> int:
+    if transposed:
+        return (hi - 1) * stride - 2 * pad + k + out_pad
+    return (hi + 2 * pad - k) // stride + 1
+
+
+class Conv2dFn(torch.autograd.Function):
+    """y = conv(x0, w0) [+ conv(x1, w1)] [+ bias] [+ addend]   (ffc.py:91-96, ffc_transpose.py:98-106)."""
+
+    @staticmethod
+    def forward(ctx, x0, w0, x1, w1, bias, addend, stride, pad, transposed, out_pad):
+        _C.require_device(x0, w0, x1, w1, bias, addend)
+        x0, w0, x1, w1, bias, addend = _c(x0), _c(w0), _c(x1), _c(w1), _c(bias), _c(addend)
+        B, cin0, Hi, Wi = x0.shape
+        k = w0.shape[-1]
+        cout = w0.shape[1] if transposed else w0.shape[0]
+        if (w0.shape[0] if transposed else w0.shape[1]) != cin0 or w0.shape[-2] != k:
+            raise ValueError(f"weight {tuple(w0.shape)} does not match input channels {cin0} (groups=1, square kernels only)")
+        cin1 = 0
+        if x1 is not None:
+            cin1 = x1.shape[1]
+            if x1.shape[0] != B or x1.shape[2:] != x0.shape[2:] or w1.shape[-1] != k \
+                    or (w1.shape[1] if transposed else w1.shape[0]) != cout:
+                raise ValueError("second conv segment is inconsistent with the first")
+        Ho = conv_out_size(Hi, k, stride, pad, transposed, out_pad)
+        Wo = conv_out_size(Wi, k, stride, pad, transposed, out_pad)
+        y = torch.empty((B, cout, Ho, Wo), device=x0.device, dtype=torch.float32)
+        if addend is not None and addend.shape != y.shape:
+            raise ValueError(f"addend {tuple(addend.shape)} != output {tuple(y.shape)}")
+        L = _C.lib()
+        _C.check(L.ffc_conv2d_fwd(_C.ptr(x0), _C.ptr(w0), cin0, _C.ptr(x1), _C.ptr(w1), cin1,
+                                  _C.ptr(bias), _C.ptr(addend), _C.ptr(y),
+                                  B, cout, Hi, Wi, Ho, Wo, k, stride, pad, int(transposed),
+                                  _C.current_stream(x0.device)))
+        ctx.save_for_backward(x0, w0, x1, w1)
+        ctx.cfg = (stride, pad, bool(transposed), k, cout, bias is not None, addend is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x0, w0, x1, w1 = ctx.saved_tensors
+        stride, pad, transposed, k, cout, has_bias, has_addend = ctx.cfg
+        dy = dy.contiguous()
+        B, _, Ho, Wo = dy.shape
+        L = _C.lib()
+        st = _C.current_stream(dy.device)
+        grads = [None] * 10
+        for slot, (x, w) in enumerate(((x0, w0), (x1, w1))):
+            if x is None:
+                continue
+            cin, Hi, Wi = x.shape[1], x.shape[2], x.shape[3]
+            if ctx.needs_input_grad[2 * slot]:
+                dx = torch.empty_like(x)
+                # data gradient = the opposite gather form over dy with the same weight tensor
+                _C.check(L.ffc_conv2d_fwd(_C.ptr(dy), _C.ptr(w), cout, None, None, 0, None, None, _C.ptr(dx),
+                                          B, cin, Ho, Wo, Hi, Wi, k, stride, pad, int(not transposed), st))
+                grads[2 * slot] = dx
+            if ctx.needs_input_grad[2 * slot + 1]:
+                dw = torch.empty_like(w)
+                if transposed:   # S = x (cin, Hi), L = dy (cout, Ho) -> [cin][cout][k][k]
+                    _C.check(L.ffc_conv2d_wgrad(_C.ptr(x), _C.ptr(dy), _C.ptr(dw), B, cin, cout, Hi, Wi, Ho, Wo, k, stride, pad, st))
+                else:            # S = dy, L = x -> [cout][cin][k][k]
+                    _C.check(L.ffc_conv2d_wgrad(_C.ptr(dy), _C.ptr(x), _C.ptr(dw), B, cout, cin, Ho, Wo, Hi, Wi, k, stride, pad, st))
+                grads[2 * slot + 1] = dw
+        if has_bias and ctx.needs_input_grad[4]:
+            db = torch.empty(cout, device=dy.device, dtype=torch.float32)
+            ws = _C.workspace(2 * cout * 8, dy.device)
+            _C.check(L.ffc_bias_grad(_C.ptr(dy), _C.ptr(db), B, cout, Ho * Wo, _C.ptr(ws), ws.numel(), st))
+            grads[4] = db
+        if has_addend and ctx.needs_input_grad[5]:
+            grads[5] = dy
+        return tuple(grads)
+
+
+def conv2d(x0, w0, x1=None, w1=None, bias=None, addend=None, stride=1, pad=0, transposed=False, out_pad=0):
+    return Conv2dFn.apply(x0, w0, x1, w1, bias, addend, stride, pad, transposed, out_pad)
+
+
+# ---------------------------------------------------------------------------------------------
+# BatchNorm2d + activation
+# ---------------------------------------------------------------------------------------------
+class BnActFn(torch.autograd.Function):
+    """y = act(BatchNorm2d(x)) or act(x)   (ffc_bn_act.py:73-81, spectral_transform.py:89, fourier_unity.py:49)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, norm, training, eps, momentum, act, slope):
+        _C.require_device(x, gamma, beta, running_mean, running_var)
+        x = x.contiguous()
+        B, C = x.shape[0], x.shape[1]
+        HW = x.numel() // max(B * C, 1)
+        y = torch.empty_like(x)
+        L = _C.lib()
+        save_mean = save_invstd = None
+        if norm:
+            save_mean = torch.empty(C, device=x.device, dtype=torch.float32)
+            save_invstd = torch.empty(C, device=x.device, dtype=torch.float32)
+            if not training and (running_mean is None or running_var is None):
+                raise ValueError("BatchNorm in eval mode needs running statistics")
+        ws = _C.workspace(2 * C * 8, x.device)
+        _C.check(L.ffc_bn_act_fwd(_C.ptr(x), _C.ptr(y), _C.ptr(gamma), _C.ptr(beta),
+                                  _C.ptr(running_mean), _C.ptr(running_var), _C.ptr(save_mean), _C.ptr(save_invstd),
+                                  B, C, HW, int(norm), int(training), float(eps), float(momentum), int(act), float(slope),
+                                  _C.ptr(ws), ws.numel(), _C.current_stream(x.device)))
+        # running_mean / running_var are updated in place by the kernel (buffers, never saved for
+        # backward, so no version bump is needed)
+        ctx.save_for_backward(x, gamma, beta, save_mean, save_invstd)
+        ctx.cfg = (bool(norm), bool(training), int(act), float(slope))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, beta, save_mean, save_invstd = ctx.saved_tensors
+        norm, training, act, slope = ctx.cfg
+        dy = dy.contiguous()
+        B, C = x.shape[0], x.shape[1]
+        HW = x.numel() // max(B * C, 1)
+        dx = torch.empty_like(x)
+        dgamma = dbeta = None
+        if norm:
+            dgamma = torch.empty_like(gamma)
+            dbeta = torch.empty_like(beta)
+        ws = _C.workspace(2 * C * 8, x.device)
+        L = _C.lib()
+        _C.check(L.ffc_bn_act_bwd(_C.ptr(x), _C.ptr(dy), _C.ptr(dx), _C.ptr(gamma), _C.ptr(beta),
+                                  _C.ptr(save_mean), _C.ptr(save_invstd), _C.ptr(dgamma), _C.ptr(dbeta),
+                                  B, C, HW, int(norm), int(training), act, slope,
+                                  _C.ptr(ws), ws.numel(), _C.current_stream(x.device)))
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None, None
+
+
+def bn_act(x, gamma=None, beta=None, running_mean=None, running_var=None, norm=False, training=True,
+           eps=1e-5, momentum=0.1, act=ACT_IDENTITY, slope=0.1):
+    return BnActFn.apply(x, gamma, beta, running_mean, running_var, norm, training, eps, momentum, act, slope)
+
+
+# ---------------------------------------------------------------------------------------------
+# rfft2 / irfft2 on planar (B, 2C, H, Wf) spectra
+# ---------------------------------------------------------------------------------------------
+def _rfft2(x, colscale):
+    B, C, H, W = x.shape
+    spec = torch.empty((B, 2 * C, H, W // 2 + 1), device=x.device, dtype=torch.float32)
+    _C.check(_C.lib().ffc_rfft2(_C.ptr(x), _C.ptr(spec), B * C, H, W, colscale, _C.current_stream(x.device)))
+    return spec
+
+
+def _irfft2(spec, residual, colscale):
+    B, C2, H, Wf = spec.shape
+    W = 2 * (Wf - 1)
+    out = torch.empty((B, C2 // 2, H, W), device=spec.device, dtype=torch.float32)
+    _C.check(_C.lib().ffc_irfft2(_C.ptr(spec), _C.ptr(residual), _C.ptr(out), B * (C2 // 2), H, W, colscale,
+                                 _C.current_stream(spec.device)))
+    return out
+
+
+class Rfft2Fn(torch.autograd.Function):
+    """rfftn(norm='ortho') + re/im interleave into channels (fourier_unity.py:38-42)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _C.require_device(x)
+        return _rfft2(x.contiguous(), 0)
+
+    @staticmethod
+    def backward(ctx, dspec):
+        return _irfft2(dspec.contiguous(), None, 1)
+
+
+class Irfft2Fn(torch.autograd.Function):
+    """channels -> complex + irfftn(s=(H,W), norm='ortho') [+ residual] (fourier_unity.py:51-56)."""
+
+    @staticmethod
+    def forward(ctx, spec, residual):
+        _C.require_device(spec, residual)
+        ctx.has_res = residual is not None
+        return _irfft2(spec.contiguous(), _c(residual), 0)
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = dout.contiguous()
+        dspec = _rfft2(dout, 1) if ctx.needs_input_grad[0] else None
+        return dspec, (dout if ctx.has_res and ctx.needs_input_grad[1] else None)
+
+
+def rfft2(x):
+    return Rfft2Fn.apply(x)
+
+
+def irfft2(spec, residual=None):
+    return Irfft2Fn.apply(spec, residual)
+
+
+# ---------------------------------------------------------------------------------------------
+# resample + SE gate (SpectralTransform prologue)
+# ---------------------------------------------------------------------------------------------
+class SeFn(torch.autograd.Function):
+    """y = r(x) * sigmoid(W2 relu(W1 mean(r(x))))   (spectral_transform.py:79, 87, 12-28)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, w2, mode):
+        _C.require_device(x, w1, w2)
+        x, w1, w2 = x.contiguous(), w1.contiguous(), w2.contiguous()
+        B, C, Hi, Wi = x.shape
+        hid = w1.shape[0]
+        Ho, Wo = (Hi * 2, Wi * 2) if mode == RESAMPLE_UP2 else ((Hi // 2, Wi // 2) if mode == RESAMPLE_AVGPOOL2 else (Hi, Wi))
+        y = torch.empty((B, C, Ho, Wo), device=x.device, dtype=torch.float32)
+        mean = torch.empty((B, C), device=x.device, dtype=torch.float32)
+        hidden = torch.empty((B, max(hid, 1)), device=x.device, dtype=torch.float32)
+        gate = torch.empty((B, C), device=x.device, dtype=torch.float32)
+        ws = _C.workspace(B * C * 8, x.device)
+        _C.check(_C.lib().ffc_se_fwd(_C.ptr(x), _C.ptr(w1) if hid else None, _C.ptr(w2) if hid else None, _C.ptr(y),
+                                     _C.ptr(mean), _C.ptr(hidden), _C.ptr(gate), B, C, hid, Hi, Wi, int(mode),
+                                     _C.ptr(ws), ws.numel(), _C.current_stream(x.device)))
+        ctx.save_for_backward(x, w1, w2, mean, hidden, gate)
+        ctx.mode = int(mode)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w1, w2, mean, hidden, gate = ctx.saved_tensors
+        dy = dy.contiguous()
+        B, C, Hi, Wi = x.shape
+        hid = w1.shape[0]
+        dx = torch.empty_like(x)
+        dw1 = torch.empty_like(w1)
+        dw2 = torch.empty_like(w2)
+        ws = _C.workspace((3 * B * C + B * hid) * 4, x.device)
+        _C.check(_C.lib().ffc_se_bwd(_C.ptr(x), _C.ptr(dy), _C.ptr(w1) if hid else None, _C.ptr(w2) if hid else None,
+                                     _C.ptr(mean), _C.ptr(hidden), _C.ptr(gate), _C.ptr(dx),
+                                     _C.ptr(dw1) if hid else None, _C.ptr(dw2) if hid else None,
+                                     B, C, hid, Hi, Wi, ctx.mode, _C.ptr(ws), ws.numel(), _C.current_stream(x.device)))
+        return dx, dw1, dw2, None
+
+
+def se_resample(x, w1, w2, mode=RESAMPLE_NONE):
+    return SeFn.apply(x, w1, w2, mode)

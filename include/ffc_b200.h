@@ -1,0 +1,132 @@
+/* ffc_b200.h -- C ABI of libffc_b200.so (hand-written sm_100a CUDA for the FFC hot path).
+ *
+ * This is the drop-in boundary for the Fast-Fourier-Convolution layer stack of
+ * phbgomes22/FastFourierConvolution (layers/ffc/*.py, layers/snffc/*.py).  The reference is pure
+ * PyTorch, so "the reference's FFI for this path" is the set of ATen library calls its modules make;
+ * every entry point below names the reference call site(s) it replaces (paths relative to the
+ * reference checkout).  The host side (fastfourierconvolution_b200/layers/*) mirrors the reference's
+ * nn.Module API on top of these functions through ctypes; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - All tensors are contiguous FP32 NCHW device buffers owned by the caller (PyTorch's caching
+ *    allocator); the library never allocates, frees or retains pointers.
+ *  - `stream` is a cudaStream_t; work is only enqueued, never synchronised.
+ *  - `workspace` is caller-provided scratch; the required size is documented per function and
+ *    ffc_workspace_bytes() returns a bound that is sufficient for every function.
+ *  - Return value: 0 on success, non-zero on error (1 bad argument / unsupported configuration,
+ *    2 workspace too small, 3 CUDA error); ffc_last_error() returns the message (thread local).
+ *  - Re-entrant, no global mutable state besides the thread-local error string.
+ */
+#ifndef FFC_B200_H_
+#define FFC_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* activation codes (ffc_bn_act.py:63-67: nn.Identity, nn.ReLU, nn.LeakyReLU(0.1), nn.GELU (erf), nn.Tanh, nn.Sigmoid) */
+#define FFC_B200_ACT_IDENTITY 0
+#define FFC_B200_ACT_RELU     1
+#define FFC_B200_ACT_LEAKY    2
+#define FFC_B200_ACT_GELU     3
+#define FFC_B200_ACT_TANH     4
+#define FFC_B200_ACT_SIGMOID  5
+
+/* resampling modes of SpectralTransform.downsample (spectral_transform.py:42-47) */
+#define FFC_B200_RESAMPLE_NONE     0
+#define FFC_B200_RESAMPLE_UP2      1   /* nn.Upsample(scale_factor=2, mode='nearest') */
+#define FFC_B200_RESAMPLE_AVGPOOL2 2   /* nn.AvgPool2d(kernel_size=(2,2), stride=2)   */
+
+int ffc_version(void);                 /* major*1000 + minor*10 + patch */
+const char* ffc_last_error(void);
+int ffc_is_emulation(void);            /* 1 only for the host emulation build used by tests/ */
+
+/* Upper bound of the scratch needed by any entry point for a problem with `batch` images and
+ * `max_channels` channels (bytes). */
+size_t ffc_workspace_bytes(int batch, int max_channels);
+
+/* ---- Fourier unit, general form (spectrum staged through L2) ------------------------------------
+ * ffc_rfft2: replaces torch.fft.rfftn(x, dim=(-2,-1), norm="ortho") + stack/permute/contiguous/view
+ *            (layers/ffc/fourier_unity.py:38-42).
+ *   x    (nplanes, H, W)          nplanes = B*C
+ *   spec (nplanes, 2, H, W/2+1)   == (B, 2C, H, Wf) with channel 2c = Re, 2c+1 = Im.
+ *   Along u the bins of H in {64,128} are stored in the library's internal permuted order; the
+ *   consumers between ffc_rfft2 and ffc_irfft2 (1x1 conv, BatchNorm, ReLU) are pointwise in (u,v).
+ *   colscale = 1 multiplies columns 0 < v < W/2 by 2: this is the adjoint of ffc_irfft2
+ *   (autograd of torch.fft.irfftn, fourier_unity.py:56).
+ * ffc_irfft2: replaces view/permute/contiguous/torch.complex + torch.fft.irfftn(s=(H,W), norm="ortho")
+ *            (fourier_unity.py:51-56); imaginary parts of columns 0 and W/2 are ignored exactly as
+ *            cuFFT/pocketfft C2R do.  out = residual + irfft2(spec) when residual != NULL
+ *            (the x + fu(x) of spectral_transform.py:108).
+ *   colscale = 1 pre-multiplies columns 0 < v < W/2 by 1/2: the adjoint of ffc_rfft2.
+ * Supported planes: H == W in {4,8,16,32,64,128}. */
+int ffc_rfft2(const float* x, float* spec, int nplanes, int H, int W, int colscale, void* stream);
+int ffc_irfft2(const float* spec, const float* residual, float* out, int nplanes, int H, int W,
+               int colscale, void* stream);
+
+/* ---- Convolutions -----------------------------------------------------------------------------
+ * ffc_conv2d_fwd, transposed = 0: nn.Conv2d forward (layers/ffc/ffc.py:45-68 convl2l/convl2g/convg2l,
+ *   spectral_transform.py:52-53,70-71 conv1/conv2, fourier_unity.py:23-24 conv_layer) and the
+ *   data-gradient of nn.ConvTranspose2d.  Weight layout [cout][cin][k][k].
+ * transposed = 1: nn.ConvTranspose2d forward (layers/ffc/ffc_transpose.py:84-86) and the
+ *   data-gradient of nn.Conv2d.  Weight layout [cin][cout][k][k].
+ * y = conv(x0, w0) [+ conv(x1, w1)] [+ bias] [+ addend]; the second segment fuses
+ *   convl2l(x_l) + convg2l(x_g) (ffc.py:91, ffc_transpose.py:98-100); `addend` fuses the sum with the
+ *   global branch (ffc.py:94-96).  groups = 1, dilation = 1, square kernel, stride in {1,2}. */
+int ffc_conv2d_fwd(const float* x0, const float* w0, int cin0,
+                   const float* x1, const float* w1, int cin1,
+                   const float* bias, const float* addend, float* y,
+                   int B, int cout, int Hi, int Wi, int Ho, int Wo,
+                   int k, int stride, int pad, int transposed, void* stream);
+
+/* dW[sc][lc][ky][kx] = sum_{b,y,x} S[b,sc,y,x] * L[b,lc,y*stride-pad+ky,x*stride-pad+kx]
+ * nn.Conv2d:          S = dy (cout, Ho x Wo), L = x  (cin,  Hi x Wi)  -> dW [cout][cin][k][k]
+ * nn.ConvTranspose2d: S = x  (cin,  Hi x Wi), L = dy (cout, Ho x Wo)  -> dW [cin][cout][k][k]
+ * dW is overwritten. */
+int ffc_conv2d_wgrad(const float* S, const float* L, float* dW,
+                     int B, int SC, int LC, int Hs, int Ws, int Hl, int Wl,
+                     int k, int stride, int pad, void* stream);
+
+/* db[c] = sum_{b,hw} dy[b,c,hw].  workspace >= 2*C*8 bytes. */
+int ffc_bias_grad(const float* dy, float* db, int B, int C, int HW,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- BatchNorm2d + activation -----------------------------------------------------------------
+ * Replaces nn.BatchNorm2d followed by the activation at layers/ffc/ffc_bn_act.py:73-81,
+ * spectral_transform.py:89 and fourier_unity.py:49.
+ *   norm = 0: y = act(x) (norm_layer = nn.Identity);  norm = 1: BatchNorm2d(eps, momentum, affine).
+ *   training = 1: batch statistics (biased variance for normalisation, unbiased for running_var,
+ *   running stats updated in place); training = 0: running statistics.
+ *   save_mean / save_invstd [C] are written (norm = 1) and must be handed to ffc_bn_act_bwd.
+ *   workspace >= 2*C*8 bytes. */
+int ffc_bn_act_fwd(const float* x, float* y, const float* gamma, const float* beta,
+                   float* running_mean, float* running_var, float* save_mean, float* save_invstd,
+                   int B, int C, int HW, int norm, int training, float eps, float momentum,
+                   int act, float slope, void* workspace, size_t workspace_bytes, void* stream);
+int ffc_bn_act_bwd(const float* x, const float* dy, float* dx, const float* gamma, const float* beta,
+                   const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta,
+                   int B, int C, int HW, int norm, int training, int act, float slope,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- SE gate + resampling ---------------------------------------------------------------------
+ * y = r(x) * sigmoid(W2 relu(W1 mean_hw(r(x)))): SpectralTransform.downsample followed by SELayer
+ * (spectral_transform.py:79, 87 -> :12-28).  w1 [hid][C], w2 [C][hid] (hid = C // 16, may be 0).
+ * x (B,C,Hi,Wi); y (B,C,Ho,Wo) with Ho = Hi, 2*Hi or Hi/2 for mode 0/1/2.
+ * save_mean [B*C], save_hidden [B*hid], save_gate [B*C] are written by fwd and read by bwd.
+ * workspace: fwd >= B*C*8 bytes; bwd >= (3*B*C + B*hid)*4 bytes.  dw1/dw2 are overwritten. */
+int ffc_se_fwd(const float* x, const float* w1, const float* w2, float* y,
+               float* save_mean, float* save_hidden, float* save_gate,
+               int B, int C, int hid, int Hi, int Wi, int mode,
+               void* workspace, size_t workspace_bytes, void* stream);
+int ffc_se_bwd(const float* x, const float* dy, const float* w1, const float* w2,
+               const float* save_mean, const float* save_hidden, const float* save_gate,
+               float* dx, float* dw1, float* dw2,
+               int B, int C, int hid, int Hi, int Wi, int mode,
+               void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFC_B200_H_ */
