@@ -1,0 +1,176 @@
+"""Model classes that call the hot path (SURVEY.md section 8(b) "who calls it").
+
+The reference defines these inline in its training scripts, which run ``main()`` and download
+datasets at import time, and its ``models/*`` classes do not construct (FFCModel.__init__ rejects
+``inplanes=``); neither can be imported on the GPU box.  They are therefore restated here,
+table-driven, on top of ``fastfourierconvolution_b200.layers`` with the reference's attribute names so
+that a reference ``state_dict`` loads with ``strict=True`` (tests/test_golden_models.py checks the
+key lists and the outputs against fixtures generated from the reference classes themselves).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..layers import FFC_BN_ACT, NoiseInjection, Resizer, Print
+
+
+def weights_init(m):
+    """fgan_complete.py:22-31: N(0, 0.02) on *Conv* weights, N(1, 0.02) / 0 on *BatchNorm*."""
+    name = m.__class__.__name__
+    if name.find("Conv") != -1:
+        nn.init.normal_(m.weight.data, 0.0, 0.02)
+    elif name.find("BatchNorm") != -1:
+        nn.init.normal_(m.weight.data, 1.0, 0.02)
+        nn.init.constant_(m.bias.data, 0)
+
+
+def hinge_loss_dis(fake, real):
+    """fgan_complete.py:216-222."""
+    return F.relu(1.0 - real).mean() + F.relu(1.0 + fake).mean()
+
+
+def hinge_loss_gen(fake):
+    """fgan_complete.py:231-235."""
+    return -fake.mean()
+
+
+# (ngf, ratio_g, number of upsampling stages, eval-mode clamp) per script
+_FGEN = {
+    "fgan32": (64, 0.25, 3, "unit"),     # fgan_complete.py:81-140, sngan_complete.py:23-80
+    "fgan64": (64, 0.25, 4, "minmax"),   # fgan64_complete.py:85-156
+    "fgan128": (128, 0.5, 5, "minmax"),  # fgan128_complete.py:442-522
+}
+
+
+class FGenerator(nn.Module):
+    """FFC generator of the *_complete.py scripts: Linear stem -> n x FFC_BN_ACT(upsampling, BN, GELU)
+    with NoiseInjection on both branches in training mode -> FFC_BN_ACT(k3, Tanh) -> Resizer."""
+
+    def __init__(self, z_size=128, mg: int = 4, variant: str = "fgan32"):
+        super().__init__()
+        ngf, r, n_up, self._clamp = _FGEN[variant]
+        self.z_size, self.ngf, self.mg, self.variant = z_size, ngf, mg, variant
+        self.print_size = Print(False)
+        self.resizer = Resizer()
+        self.noise_to_feature = nn.Sequential(nn.Linear(z_size, mg * mg * ngf * 8))
+        chans = [ngf * 8, ngf * 4, ngf * 2, ngf] + [ngf] * (n_up - 3)
+        self._stages = []
+        for i in range(n_up):
+            n = i + 2
+            cout = chans[i + 1]
+            setattr(self, f"conv{n}", FFC_BN_ACT(chans[i], cout, 4, 0.0 if i == 0 else r, r, stride=2, padding=1,
+                                                 activation_layer=nn.GELU, norm_layer=nn.BatchNorm2d, upsampling=True,
+                                                 uses_noise=True, uses_sn=(variant != "fgan32")))
+            setattr(self, f"lcl_noise{n}", NoiseInjection(int(cout * (1 - r))))
+            setattr(self, f"glb_noise{n}", NoiseInjection(int(cout * r)))
+            self._stages.append(n)
+        self._last = n_up + 2
+        setattr(self, f"conv{self._last}", FFC_BN_ACT(ngf, 3, 3, r, 0.0, stride=1, padding=1, activation_layer=nn.Tanh,
+                                                      norm_layer=nn.Identity, upsampling=False, uses_noise=True,
+                                                      uses_sn=(variant != "fgan32")))
+
+    def forward(self, z):
+        fake = self.noise_to_feature(z)
+        fake = fake.reshape(fake.size(0), -1, self.mg, self.mg)
+        for n in self._stages:
+            fake = getattr(self, f"conv{n}")(fake)
+            if self.training:
+                fake = getattr(self, f"lcl_noise{n}")(fake[0]), getattr(self, f"glb_noise{n}")(fake[1])
+        fake = self.resizer(getattr(self, f"conv{self._last}")(fake))
+        if not self.training:                    # uint8 images for the metric code (fgan_complete.py:136-138)
+            if self._clamp == "unit":
+                fake = 255 * (fake.clamp(-1, 1) * 0.5 + 0.5)
+            else:                                # fgan64_complete.py:150-153: clamp to own min/max
+                fake = 255 * (fake.clamp(float(fake.min()), float(fake.max())) * 0.5 + 0.5)
+            fake = fake.to(torch.uint8)
+        return fake
+
+
+class SNConvDiscriminator(nn.Module):
+    """The plain spectral-norm conv discriminator the fgan scripts train against
+    (fgan_complete.py:142-171 n_convs=7, fgan64_complete.py:159-191 n_convs=8,
+    fgan128_complete.py:525-562 n_convs=9).  It contains no FFC layer and is outside the hot path
+    (SURVEY.md section 8(f) rank 1): it stays on PyTorch's own kernels."""
+
+    def __init__(self, sn=True, mg: int = 4, n_convs: int = 7):
+        super().__init__()
+        self.mg, self.n_convs = mg, n_convs
+        sn_fn = torch.nn.utils.spectral_norm if sn else (lambda m: m)
+        spec = [(3, 64, 3, 1), (64, 64, 4, 2), (64, 128, 3, 1), (128, 128, 4, 2), (128, 256, 3, 1),
+                (256, 256, 4, 2), (256, 512, 3, 1), (512, 512, 4, 2), (512, 512, 4, 2)][:n_convs]
+        for i, (ci, co, k, s) in enumerate(spec, 1):
+            setattr(self, f"conv{i}", sn_fn(nn.Conv2d(ci, co, k, stride=s, padding=(1, 1))))
+        self.fc = sn_fn(nn.Linear(mg * mg * 512, 1))
+        self.act = nn.LeakyReLU(0.1)
+
+    def forward(self, x):
+        m = x
+        for i in range(1, self.n_convs + 1):
+            m = self.act(getattr(self, f"conv{i}")(m))
+        return self.fc(m.view(-1, self.mg * self.mg * 512))
+
+
+class FDiscriminator(nn.Module):
+    """sngan_complete.py:116-157: the only FFC discriminator the reference trains."""
+
+    def __init__(self, sn=True, mg: int = 4):
+        super().__init__()
+        self.mg = mg
+        sn_fn = torch.nn.utils.spectral_norm if sn else (lambda m: m)
+        common = dict(bias=True, uses_noise=False, uses_sn=True, activation_layer=nn.LeakyReLU)
+        self.print_size = Print(False)
+        self.resizer = Resizer()
+        self.main = nn.Sequential(
+            FFC_BN_ACT(3, 64, 3, 0.0, 0.25, stride=1, padding=1, norm_layer=nn.Identity, **common),
+            FFC_BN_ACT(64, 128, 4, 0.25, 0.25, stride=2, padding=1, norm_layer=nn.BatchNorm2d, **common),
+            FFC_BN_ACT(128, 256, 4, 0.25, 0.25, stride=2, padding=1, norm_layer=nn.BatchNorm2d, **common),
+            FFC_BN_ACT(256, 512, 4, 0.25, 0.0, stride=2, padding=1, norm_layer=nn.BatchNorm2d, **common),
+        )
+        self.fc = sn_fn(nn.Linear(mg * mg * 512, 1))
+
+    def forward(self, x):
+        m = self.resizer(self.main(x))
+        return self.fc(m.view(-1, self.mg * self.mg * 512))
+
+
+class FFCGenerator(nn.Module):
+    """models/ffc_generator.py:14-45 (config 1: nz=100, nc=1, ngf=32, g_factor=0.5)."""
+
+    def __init__(self, nz: int, nc: int, ngf: int, g_factor: float = 0.5, debug: bool = False):
+        super().__init__()
+        self.print_size = Print(False)
+        self.resizer = Resizer()
+        a = dict(activation_layer=nn.LeakyReLU, upsampling=True)
+        self.ffc0 = FFC_BN_ACT(nz, ngf * 8, 4, 0, g_factor, 1, 0, **a)
+        self.ffc1 = FFC_BN_ACT(ngf * 8, ngf * 4, 4, g_factor, g_factor, 2, 1, **a)
+        self.ffc2 = FFC_BN_ACT(ngf * 4, ngf * 2, 4, g_factor, g_factor, 2, 1, **a)
+        self.ffc3 = FFC_BN_ACT(ngf * 2, ngf * 1, 4, g_factor, g_factor, 2, 1, **a)
+        self.ffc4 = FFC_BN_ACT(ngf * 1, nc, 4, g_factor, 0, 2, 1, norm_layer=nn.Identity,
+                               activation_layer=nn.Tanh, upsampling=True)
+
+    def forward(self, x):
+        for i in range(5):
+            x = getattr(self, f"ffc{i}")(x)
+        return self.resizer(x)
+
+
+class FFCDiscriminator(nn.Module):
+    """models/ffc_discriminator.py:14-60 (needs 64x64 inputs)."""
+
+    def __init__(self, nc: int, ndf: int, debug: bool = False):
+        super().__init__()
+        self.print_size = Print(False)
+        self.resizer = Resizer()
+        a = dict(activation_layer=nn.LeakyReLU)
+        self.ffc0 = FFC_BN_ACT(nc, ndf * 2, 4, 0, 0.5, 2, 1, **a)
+        self.ffc1 = FFC_BN_ACT(ndf * 2, ndf * 4, 4, 0.5, 0.5, 2, 1, **a)
+        self.ffc2 = FFC_BN_ACT(ndf * 4, ndf * 8, 4, 0.5, 0.5, 2, 1, **a)
+        self.ffc3 = FFC_BN_ACT(ndf * 8, ndf * 16, 4, 0.5, 0.5, 2, 1, **a)
+        self.ffc4 = FFC_BN_ACT(ndf * 16, 1, 4, 0.5, 0, 1, 0, norm_layer=nn.Identity, activation_layer=nn.Sigmoid)
+
+    def forward(self, x):
+        for i in range(5):
+            x = getattr(self, f"ffc{i}")(x)
+        return self.resizer(x)

@@ -378,11 +378,11 @@ def deterministic_fill(P: Params, seed: int = 0) -> None:
             val = 0.05 * base
         elif k.endswith(("weight_u", "weight_v")):
             val = base / base.norm()
-        elif t.dim() <= 1 and k.endswith("weight") and "noise" not in k:   # BN gamma
+        elif t.dim() <= 1 and k.endswith("weight") and "_noise" not in k:   # BN gamma
             val = 1.0 + 0.1 * base
         elif t.dim() <= 1 or k.endswith("bias"):
             val = 0.05 * base
-        elif "noise" in k:
+        elif "_noise" in k:                                            # NoiseInjection.weight
             val = 0.05 * base
         else:
             fan_in = max(1, n // t.shape[0])

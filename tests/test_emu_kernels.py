@@ -1,0 +1,185 @@
+"""C-ABI level checks of every kernel family on the host emulation build (index arithmetic, edge
+cases, all supported plane sizes) against numpy / torch CPU math."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import emu_backend
+import parity
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from fastfourierconvolution_b200 import _C
+    return _C.Library(emu_backend.build())
+
+
+def P(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def ok(lib, rc):
+    assert rc == 0, lib.last_error()
+
+
+def upos(k, n):
+    n1 = n if n <= 32 else n // 8
+    n2 = n // n1
+    return n2 * (k % n1) + k // n1
+
+
+@pytest.mark.parametrize("n", [4, 8, 16, 32, 64, 128])
+def test_rfft2_irfft2_all_sizes(lib, n):
+    rng = np.random.default_rng(n)
+    npl, wf = 5, n // 2 + 1
+    perm = [upos(k, n) for k in range(n)]
+    x = torch.from_numpy(rng.standard_normal((npl, n, n)).astype(np.float32))
+    spec = torch.zeros(npl, 2, n, wf)
+    ok(lib, lib.ffc_rfft2(P(x), P(spec), npl, n, n, 0, None))
+    ref = torch.fft.rfftn(x.double(), dim=(-2, -1), norm="ortho")
+    got = torch.complex(spec[:, 0].double(), spec[:, 1].double())[:, perm, :]
+    assert parity.relerr(torch.view_as_real(got), torch.view_as_real(ref)) < 1e-6
+    # non-Hermitian spectrum through the inverse (torch c2r semantics), with residual
+    z = torch.from_numpy(rng.standard_normal((npl, 2, n, wf)).astype(np.float32))
+    refo = torch.fft.irfftn(torch.complex(z[:, 0].double(), z[:, 1].double()), s=(n, n), dim=(-2, -1), norm="ortho")
+    zp = torch.empty_like(z)
+    zp[:, :, perm, :] = z
+    res = torch.from_numpy(rng.standard_normal((npl, n, n)).astype(np.float32))
+    out = torch.zeros(npl, n, n)
+    ok(lib, lib.ffc_irfft2(P(zp), P(res), P(out), npl, n, n, 0, None))
+    assert parity.relerr(out.double() - res.double(), refo) < 1e-6
+
+
+@pytest.mark.parametrize("n", [8, 64])
+def test_fft_adjoint_pairs(lib, n):
+    """colscale=1 variants are the exact adjoints: <rfft2(x), s> == <x, irfft2_adj(s)> and vice versa."""
+    rng = np.random.default_rng(1)
+    npl, wf = 3, n // 2 + 1
+    x = torch.from_numpy(rng.standard_normal((npl, n, n)).astype(np.float32))
+    s = torch.from_numpy(rng.standard_normal((npl, 2, n, wf)).astype(np.float32))
+    fx, ats = torch.zeros_like(s), torch.zeros_like(x)
+    ok(lib, lib.ffc_rfft2(P(x), P(fx), npl, n, n, 0, None))
+    ok(lib, lib.ffc_irfft2(P(s), None, P(ats), npl, n, n, 1, None))
+    assert abs((fx.double() * s.double()).sum() - (x.double() * ats.double()).sum()) < 1e-3 * n
+    ix, atx = torch.zeros_like(x), torch.zeros_like(s)
+    ok(lib, lib.ffc_irfft2(P(s), None, P(ix), npl, n, n, 0, None))
+    ok(lib, lib.ffc_rfft2(P(x), P(atx), npl, n, n, 1, None))
+    assert abs((ix.double() * x.double()).sum() - (s.double() * atx.double()).sum()) < 1e-3 * n
+
+
+CONV_CASES = [
+    # B, cins, cout, Hi, k, s, p, transposed, bias, addend, out_pad
+    (2, [5], 7, 8, 3, 1, 1, False, True, False, 0),
+    (3, [6, 3], 70, 8, 4, 2, 1, False, True, True, 0),
+    (2, [4], 3, 8, 1, 1, 0, False, False, True, 0),
+    (2, [9, 5], 33, 4, 4, 2, 1, True, False, False, 0),
+    (2, [10], 6, 1, 4, 1, 0, True, True, False, 0),
+    (1, [3], 5, 5, 3, 2, 1, True, False, True, 1),
+    (2, [3], 5, 7, 3, 2, 1, False, False, False, 0),
+    (2, [20], 130, 6, 3, 1, 1, True, True, False, 0),
+    (1, [17], 1, 4, 4, 1, 0, False, False, False, 0),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_forward_dgrad_wgrad(lib, case):
+    B, cins, cout, Hi, k, s, p, tr, bias, addend, op = case
+    torch.manual_seed(0)
+    xs = [torch.randn(B, c, Hi, Hi) for c in cins]
+    ws = [torch.randn(*((c, cout) if tr else (cout, c)), k, k) * 0.1 for c in cins]
+    b = torch.randn(cout) if bias else None
+
+    def op_ref(x, w):
+        return F.conv_transpose2d(x, w, None, s, p, op) if tr else F.conv2d(x, w, None, s, p)
+
+    ref = sum(op_ref(x.double(), w.double()) for x, w in zip(xs, ws))
+    Ho = ref.shape[-1]
+    ad = torch.randn(B, cout, Ho, Ho) if addend else None
+    if b is not None:
+        ref = ref + b.double().view(1, -1, 1, 1)
+    if ad is not None:
+        ref = ref + ad.double()
+    y = torch.empty(B, cout, Ho, Ho)
+    x1, w1 = (xs[1], ws[1]) if len(xs) > 1 else (None, None)
+    ok(lib, lib.ffc_conv2d_fwd(P(xs[0]), P(ws[0]), cins[0], P(x1), P(w1), cins[1] if x1 is not None else 0, P(b), P(ad), P(y),
+                               B, cout, Hi, Hi, Ho, Ho, k, s, p, int(tr), None))
+    assert parity.relerr(y, ref) < 2e-6
+    dy = torch.randn(B, cout, Ho, Ho)
+    for x, w in zip(xs, ws):
+        xd, wd = x.double().requires_grad_(True), w.double().requires_grad_(True)
+        op_ref(xd, wd).backward(dy.double())
+        dW, dx = torch.empty_like(w), torch.empty_like(x)
+        if tr:
+            ok(lib, lib.ffc_conv2d_wgrad(P(x), P(dy), P(dW), B, x.shape[1], cout, Hi, Hi, Ho, Ho, k, s, p, None))
+        else:
+            ok(lib, lib.ffc_conv2d_wgrad(P(dy), P(x), P(dW), B, cout, x.shape[1], Ho, Ho, Hi, Hi, k, s, p, None))
+        assert parity.relerr(dW, wd.grad) < 3e-6
+        ok(lib, lib.ffc_conv2d_fwd(P(dy), P(w), cout, None, None, 0, None, None, P(dx), B, x.shape[1], Ho, Ho, Hi, Hi, k, s, p, int(not tr), None))
+        assert parity.relerr(dx, xd.grad) < 3e-6
+
+
+ACTS = {0: lambda z: z, 1: F.relu, 2: lambda z: F.leaky_relu(z, 0.1), 3: F.gelu, 4: torch.tanh, 5: torch.sigmoid}
+
+
+@pytest.mark.parametrize("case", [(4, 5, 4, 4, 1, 1, 3), (3, 7, 3, 5, 1, 1, 2), (2, 3, 8, 8, 0, 1, 4), (5, 6, 4, 4, 1, 0, 1),
+                                  (2, 4, 2, 2, 0, 1, 5), (3, 300, 2, 2, 1, 1, 0), (2, 2, 1, 3, 1, 1, 1)])
+def test_bn_act_forward_backward(lib, case):
+    B, C, H, W, norm, training, act = case
+    cf = ctypes.c_float
+    torch.manual_seed(1)
+    x = torch.randn(B, C, H, W) * 2 + 0.5
+    g, b = torch.rand(C) + 0.5, torch.randn(C) * 0.1
+    rm, rv = torch.randn(C) * 0.1, torch.rand(C) + 0.5
+    xd, gd, bd = x.double().requires_grad_(True), g.double().requires_grad_(True), b.double().requires_grad_(True)
+    rmd, rvd = rm.double().clone(), rv.double().clone()
+    z = F.batch_norm(xd, rmd, rvd, gd, bd, bool(training), 0.1, 1e-5) if norm else xd
+    yref = ACTS[act](z)
+    dy = torch.randn(B, C, H, W)
+    yref.backward(dy.double())
+    y, sm, si = torch.empty_like(x), torch.empty(C), torch.empty(C)
+    ws = torch.empty(2 * C, dtype=torch.float64)
+    nb = ctypes.c_size_t(ws.numel() * 8)
+    ok(lib, lib.ffc_bn_act_fwd(P(x), P(y), P(g), P(b), P(rm), P(rv), P(sm), P(si), B, C, H * W, norm, training,
+                               cf(1e-5), cf(0.1), act, cf(0.1), P(ws), nb, None))
+    dx, dg, db = torch.empty_like(x), torch.zeros(C), torch.zeros(C)
+    ok(lib, lib.ffc_bn_act_bwd(P(x), P(dy), P(dx), P(g), P(b), P(sm), P(si), P(dg), P(db), B, C, H * W, norm, training,
+                               act, cf(0.1), P(ws), nb, None))
+    assert parity.relerr(y, yref.detach()) < 5e-6
+    if B * H * W > 1:
+        assert parity.relerr(dx, xd.grad) < 5e-6
+    if norm:
+        assert parity.relerr(dg, gd.grad, 1e-3) < 5e-6 and parity.relerr(db, bd.grad) < 5e-6
+        assert parity.relerr(rm, rmd) < 5e-6 and parity.relerr(rv, rvd) < 5e-6
+
+
+@pytest.mark.parametrize("case", [(3, 32, 2, 4, 0), (2, 16, 1, 4, 1), (2, 48, 3, 8, 2), (2, 8, 0, 4, 1)])
+def test_se_forward_backward(lib, case):
+    B, C, hid, H, mode = case
+    torch.manual_seed(2)
+    x, w1, w2 = torch.randn(B, C, H, H), torch.randn(hid, C) * 0.3, torch.randn(C, hid) * 0.3
+    xd, w1d, w2d = x.double().requires_grad_(True), w1.double().requires_grad_(True), w2.double().requires_grad_(True)
+    r = xd if mode == 0 else (F.interpolate(xd, scale_factor=2, mode="nearest") if mode == 1 else F.avg_pool2d(xd, 2, 2))
+    gate = torch.sigmoid(F.linear(F.relu(F.linear(r.mean((2, 3)), w1d)), w2d))
+    yref = r * gate.view(B, C, 1, 1)
+    dy = torch.randn_like(yref).float()
+    yref.backward(dy.double())
+    y, sm, sh, sg = torch.empty(yref.shape), torch.empty(B, C), torch.empty(B, max(hid, 1)), torch.empty(B, C)
+    ws = torch.empty(B * C * 4 + B * (C + hid) + 16, dtype=torch.float64)
+    nb = ctypes.c_size_t(ws.numel() * 8)
+    ok(lib, lib.ffc_se_fwd(P(x), P(w1), P(w2), P(y), P(sm), P(sh), P(sg), B, C, hid, H, H, mode, P(ws), nb, None))
+    dx, dw1, dw2 = torch.empty_like(x), torch.empty_like(w1), torch.empty_like(w2)
+    ok(lib, lib.ffc_se_bwd(P(x), P(dy), P(w1), P(w2), P(sm), P(sh), P(sg), P(dx), P(dw1), P(dw2), B, C, hid, H, H, mode, P(ws), nb, None))
+    assert parity.relerr(y, yref.detach()) < 5e-6 and parity.relerr(dx, xd.grad) < 5e-6
+    if hid:
+        assert parity.relerr(dw1, w1d.grad) < 5e-6 and parity.relerr(dw2, w2d.grad) < 5e-6
+
+
+def test_empty_batch_is_a_noop(lib):
+    x = torch.zeros(0, 4, 8, 8)
+    ok(lib, lib.ffc_rfft2(P(torch.zeros(4)), P(torch.zeros(4)), 0, 8, 8, 0, None))
+    y = torch.zeros(0, 3, 8, 8)
+    w = torch.randn(3, 4, 3, 3)
+    ok(lib, lib.ffc_conv2d_fwd(P(torch.zeros(4)), P(w), 4, None, None, 0, None, None, P(torch.zeros(4)), 0, 3, 8, 8, 8, 8, 3, 1, 1, 0, None))

@@ -1,0 +1,95 @@
+"""Host-logic tests: the product's nn.Modules and autograd Functions, executed on the host
+*emulation* build of the CUDA sources (tests/emu_backend.py), against the reference's golden
+outputs.  This checks the Python wiring and every kernel's index arithmetic without a GPU; the
+GPU parity tests proper are tests/test_gpu_parity.py."""
+import pytest
+import torch
+
+import cases
+import parity
+import fastfourierconvolution_b200 as ffc
+from fastfourierconvolution_b200 import harness as H
+from oracle import ffc_ref as R
+
+
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+def test_module_matches_reference_golden(name, emu):
+    fx = parity.load_fixture(name)
+    mod = cases.CASES[name][0](ffc.layers)
+    got = parity.run_module(mod, fx, "cpu")
+    parity.compare(got, fx, tol=parity.TOL, what=name)
+
+
+def _model_case(fn):
+    return {"fgan32": lambda: H.FGenerator(128, 4, "fgan32"), "fd": lambda: H.FDiscriminator(True, 4),
+            "cfg1": lambda: H.FFCGenerator(100, 1, 32)}[fn]()
+
+
+def run_model_fixture(name, fn, device):
+    fx = parity.load_fixture(name)
+    mod = _model_case(fn)
+    sd = mod.state_dict()
+    R.deterministic_fill(sd, int(fx["seed"]))
+    for k in sd:
+        if "_noise" in k:
+            sd[k].zero_()
+    mod.load_state_dict(sd)
+    mod.to(device).train(True)
+    x = torch.from_numpy(fx["in0"]).to(device).requires_grad_(True)
+    out = mod(x)
+    (out * torch.from_numpy(fx["cot0"]).to(device)).sum().backward()
+    got = {"out0": out.detach(), "din0": x.grad}
+    params, bufs = dict(mod.named_parameters()), dict(mod.named_buffers())
+    for k in fx:
+        if k.startswith("grad/"):
+            got[k] = params[k[5:]].grad
+        if k.startswith("post/"):
+            got[k] = bufs[k[5:]]
+    return {k: parity.relerr(got[k], fx[k]) for k in got}
+
+
+@pytest.mark.parametrize("name,fn", [("model_fgan32_G", "fgan32"), ("model_sngan_FD", "fd"), ("model_ffcgen_cfg1", "cfg1")])
+def test_model_matches_reference_golden(name, fn, emu):
+    errs = run_model_fixture(name, fn, "cpu")
+    # whole networks at batch 2: the reference's own FP32-vs-FP64 spread is ~6e-5 here
+    assert max(errs.values()) < 2e-4, errs
+
+
+def test_cpu_tensor_is_rejected_without_emulation():
+    """No CPU fallback: the product path refuses CPU tensors."""
+    m = ffc.FourierUnitSN(2, 2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.randn(1, 2, 8, 8))
+
+
+def test_unsupported_configs_raise():
+    with pytest.raises(NotImplementedError):
+        ffc.FFC(8, 8, 3, .5, .5, groups=2)
+    with pytest.raises(NotImplementedError):
+        ffc.FourierUnitSN(4, 4, groups=2)
+    with pytest.raises(AssertionError):
+        ffc.FFC(8, 8, 3, .5, .5, stride=3)
+
+
+def test_eval_generator_emits_uint8(emu):
+    g = H.FGenerator(128, 4, "fgan32").eval()
+    with torch.no_grad():
+        out = g(torch.randn(2, 128))
+    assert out.dtype == torch.uint8 and out.shape == (2, 3, 32, 32)
+
+
+def test_requires_grad_toggling_like_the_training_loop(emu):
+    """fgan_complete.py:368-381 flips requires_grad on G and D every half step."""
+    torch.manual_seed(0)
+    m = ffc.FFC_BN_ACT(16, 8, 4, .25, .25, 2, 1, upsampling=True, norm_layer=torch.nn.BatchNorm2d,
+                       activation_layer=torch.nn.GELU)
+    x = (torch.randn(2, 12, 4, 4), torch.randn(2, 4, 4, 4))
+    m.requires_grad_(False)
+    out = m(x)
+    assert not out[0].requires_grad and not out[1].requires_grad
+    m.requires_grad_(True)
+    out = m(x)
+    (out[0].sum() + out[1].sum()).backward()
+    grads = {k: p.grad is not None for k, p in m.named_parameters()}
+    assert not any(v for k, v in grads.items() if ".lfu." in k)          # unused branch: no gradient
+    assert all(v for k, v in grads.items() if ".lfu." not in k)
