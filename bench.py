@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""Benchmark of the FFC hot path on B200 (contract: see the task statement / DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload fgan32]
+
+Workload (BASELINE.json configs[1]): fgan_complete FFC generator + spectral-norm discriminator GAN
+training step on synthetic CIFAR-shaped data (3x32x32), global batch 256, AdamW, hinge losses --
+G fwd x2, G bwd, D fwd x3, D bwd x2, two optimiser steps (fgan_complete.py:357-393).
+metric = images/s (global batch / step time, max over ranks).
+
+One JSON line on stdout (rank 0).  `value`: inputs resident in HBM.  `e2e`: the same step through the
+public module API with pinned HOST buffers, host->device copies of z / real images and the device->host
+read of both losses inside the timed region.  `roofline`: the FourierUnit kernels of this workload against
+the measured HBM peak.  `cpu_baseline`: the CPU restatement of the reference step (oracle/train_ref.py),
+timed on this host's cores on a bounded sample.  `--impl reference` times that CPU step alone.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch
+
+WORKLOADS = {
+    # name: (generator variant, discriminator convs, image size, default global batch, weak scaling?)
+    "fgan32": ("fgan32", 7, 32, 256, False),     # configs[1]: global batch 256 on 1/2/4/8 GPUs (strong)
+    "fgan64": ("fgan64", 8, 64, 128, True),      # configs[2]: 128 per GPU (weak)
+    "fgan128": ("fgan128", 9, 128, 64, True),    # configs[3]: 64 per GPU (weak)
+}
+# FourierUnit instances inside each generator: (channels, plane size) -- SURVEY.md appendix A.2/A.3
+FU_SHAPES = {"fgan32": [(16, 16), (8, 32)], "fgan64": [(16, 16), (8, 32), (8, 64)],
+             "fgan128": [(64, 16), (32, 32), (32, 64), (32, 128)]}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        return False
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the CPU restatement of the reference training step
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_step_rate(workload, batch, steps, warmup, seed=1234):
+    from fastfourierconvolution_b200 import harness as H
+    from oracle.train_ref import RefTrainer
+    variant, n_convs, size, _, _ = WORKLOADS[workload]
+    torch.manual_seed(seed)
+    torch.set_num_threads(os.cpu_count() or 1)
+    G = H.FGenerator(128, 4, variant); G.apply(H.weights_init)
+    D = H.SNDiscriminator(True, 4, n_convs); D.apply(H.weights_init)
+    tr = RefTrainer(G.state_dict(), D.state_dict(), variant, n_convs)
+    def data():
+        return torch.randn(batch, 128), torch.randn(batch, 128), torch.rand(batch, 3, size, size) * 2 - 1
+    for _ in range(warmup):
+        tr.step(*data())
+    times = []
+    for _ in range(steps):
+        d = data()
+        t0 = time.perf_counter()
+        tr.step(*d)
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return batch * steps / total, 1000.0 * total / steps, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    workload = args.workload
+    gb = args.batch or WORKLOADS[workload][3] * (args.gpus if WORKLOADS[workload][4] else 1)
+    # bounded sample: the CPU step is run at a capped batch so K+W steps end within minutes
+    sample = min(gb, args.cpu_batch)
+    rate, ms, cores = cpu_reference_step_rate(workload, sample, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "FFC-GAN training images/s", "value": rate, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak" if WORKLOADS[workload][4] else "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{workload}: fgan_complete FGenerator + SN Discriminator GAN step, 3x{WORKLOADS[workload][2]}x{WORKLOADS[workload][2]}, global batch {gb}",
+                   "cpu_step_batch": sample},
+        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps at batch {sample} (of global batch {gb}) of the same G+D step, oracle/train_ref.py on PyTorch CPU kernels"},
+        "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def time_fourier_unit(workload, per_rank_batch, dev, iters=20):
+    """FourierUnit forward+backward of the workload's largest unit, timed alone with CUDA events on
+    rotating inputs whose total footprint exceeds L2.  Returns the roofline dict pieces."""
+    import fastfourierconvolution_b200 as ffc
+    from fastfourierconvolution_b200 import _C
+    C, N = max(FU_SHAPES[workload], key=lambda s: s[0] * s[1] * s[1])
+    B = per_rank_batch
+    torch.manual_seed(0)
+    fu = ffc.FourierUnitSN(C, C).to(dev).train()
+    bytes_in = 4 * B * C * N * N
+    nbuf = max(2, int(160e6 // bytes_in) + 1)             # > 126 MB L2 across the rotation
+    xs = [torch.randn(B, C, N, N, device=dev, requires_grad=True) for _ in range(nbuf)]
+    gs = [torch.randn(B, C, N, N, device=dev) for _ in range(min(nbuf, 4))]
+    for i in range(3):
+        fu(xs[i % nbuf]).backward(gs[i % len(gs)])
+    torch.cuda.synchronize(dev)
+    L = _C.lib()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    n0 = L.ffc_launch_count()
+    t_f = t_b = 0.0
+    for i in range(iters):
+        x = xs[i % nbuf]
+        x.grad = None
+        ev[0].record()
+        y = fu(x)
+        ev[1].record()
+        y.backward(gs[i % len(gs)])
+        ev[2].record()
+        torch.cuda.synchronize(dev)
+        t_f += ev[0].elapsed_time(ev[1]); t_b += ev[1].elapsed_time(ev[2])
+    launches = (L.ffc_launch_count() - n0) / iters
+    ms_f, ms_b = t_f / iters, t_b / iters
+    alg_f = 4.0 * B * N * N * (C + C)                      # fwd 4BHW(Cin+Cout)
+    alg_b = 4.0 * B * N * N * (C + 2 * C)                  # bwd 4BHW(Cout + 2Cin)
+    return {"C": C, "N": N, "B": B, "ms_fwd": ms_f, "ms_bwd": ms_b, "launches": launches,
+            "gbs_fwd": alg_f / ms_f / 1e6, "gbs_bwd": alg_b / ms_b / 1e6, "gbs": (alg_f + alg_b) / (ms_f + ms_b) / 1e6,
+            "alg_bytes": alg_f + alg_b, "rotating_buffers": nbuf}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: libffc_b200 has no CPU fallback")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, f"WORLD_SIZE={world} but --gpus {args.gpus}"
+    from fastfourierconvolution_b200 import _C, harness as H
+    L = _C.lib()
+    workload = args.workload
+    variant, n_convs, size, base_batch, weak = WORKLOADS[workload]
+    gb = args.batch or (base_batch * world if weak else base_batch)
+    assert gb % world == 0
+    pb = gb // world
+    torch.manual_seed(1234 + rank)
+    # the reference's convolutions run in TF32 on GPUs by default (cudnn.allow_tf32); the FFC path here is
+    # true FP32, and the (out-of-scope, PyTorch) discriminator is kept at PyTorch's defaults
+    G = H.FGenerator(128, 4, variant).to(dev).train(); G.apply(H.weights_init)
+    D = H.SNDiscriminator(True, 4, n_convs).to(dev).train(); D.apply(H.weights_init)
+    if world > 1:                                    # identical replicas
+        for p in list(G.parameters()) + list(D.parameters()) + list(G.buffers()) + list(D.buffers()):
+            dist.broadcast(p.data, 0)
+    tr = H.GanTrainer(G, D)
+
+    h_zg = torch.randn(pb, 128).pin_memory(); h_zd = torch.randn(pb, 128).pin_memory()
+    h_real = (torch.rand(pb, 3, size, size) * 2 - 1).pin_memory()
+    d_zg, d_zd, d_real = h_zg.to(dev), h_zd.to(dev), h_real.to(dev)
+    h_loss = torch.zeros(2).pin_memory()
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def step_resident():
+        return tr.step(d_zg, d_zd, d_real)
+
+    def step_e2e():
+        zg = h_zg.to(dev, non_blocking=True); zd = h_zd.to(dev, non_blocking=True); re = h_real.to(dev, non_blocking=True)
+        lg, ld = tr.step(zg, zd, re)
+        h_loss.copy_(torch.stack((lg, ld)), non_blocking=False)       # device -> host read of the step's result
+        return h_loss
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sync_all()
+
+    def timed(fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        n0 = L.ffc_launch_count()
+        e0.record()
+        for _ in range(args.steps):
+            fn()
+        e1.record()
+        sync_all()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms / args.steps, (L.ffc_launch_count() - n0) / args.steps
+
+    with ClockSampler(local_rank) as clk:
+        ms_res, launches = timed(step_resident)
+        ms_e2e, _ = timed(step_e2e)
+    clocks = clk.summary()
+
+    fu = time_fourier_unit(workload, pb, dev) if rank == 0 else None
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, ms, cores = cpu_reference_step_rate(workload, min(gb, args.cpu_batch), args.cpu_steps, 1)
+        cpu = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_steps} steps at batch {min(gb, args.cpu_batch)} of the same G+D training step "
+                         f"(oracle/train_ref.py, PyTorch CPU kernels, {ms:.0f} ms/step)"}
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        act_mb = sum(p.numel() for p in G.parameters()) * 4 / 1e6
+        line = {
+            "metric": "FFC-GAN training images/s", "value": gb / ms_res * 1000.0, "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_res,
+            "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{workload}: fgan_complete FGenerator + SN Discriminator GAN step, 3x{size}x{size}, global batch {gb}",
+                       "global_batch": gb, "per_gpu_batch": pb, "parallelism": f"dp{world} (batch shards, per-rank BatchNorm, flat-grad NCCL all-reduce)",
+                       "l2": "per-step working set (activations of batch %d, > 400 MB) exceeds the 126 MB L2; FourierUnit timing rotates %d input buffers"
+                             % (pb, fu["rotating_buffers"]),
+                       "discriminator": "plain SN conv net (no FFC layer; PyTorch kernels, out of the hot-path scope)",
+                       "generator_params_MB": round(act_mb, 1)},
+            "e2e": {"value": gb / ms_e2e * 1000.0, "unit": "images/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": world * (h_zg.numel() + h_zd.numel() + h_real.numel()) * 4,
+                    "d2h_bytes_per_step": world * 8},
+            "gpu_launches": int(round(launches * args.steps)),
+            "gpu_launches_per_step": launches,
+            "roofline": {"bound": "hbm", "achieved": fu["gbs"], "peak": peak, "unit": "GB/s", "frac": fu["gbs"] / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "kernel": f"FourierUnitSN({fu['C']},{fu['C']}) fwd+bwd @ {fu['N']}x{fu['N']}, batch {fu['B']}: "
+                                   f"{fu['launches']:.0f} launches, fwd {fu['ms_fwd']*1000:.1f} us ({fu['gbs_fwd']:.0f} GB/s), "
+                                   f"bwd {fu['ms_bwd']*1000:.1f} us ({fu['gbs_bwd']:.0f} GB/s)",
+                         "algorithmic_bytes": fu["alg_bytes"]},
+            "clocks": clocks,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
+    ap.add_argument("--workload", default="fgan32", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="global batch (default: the workload's)")
+    ap.add_argument("--cpu-batch", type=int, default=64, help="batch of the bounded CPU sample")
+    ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

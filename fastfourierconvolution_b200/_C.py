@@ -23,6 +23,7 @@ _SIGNATURES = {
     "ffc_version": (c_int, []),
     "ffc_last_error": (ctypes.c_char_p, []),
     "ffc_is_emulation": (c_int, []),
+    "ffc_launch_count": (ctypes.c_ulonglong, []),
     "ffc_workspace_bytes": (c_size_t, [c_int, c_int]),
     "ffc_rfft2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "ffc_irfft2": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

@@ -31,3 +31,16 @@ extern "C" size_t ffc_workspace_bytes(int batch, int max_channels) {
     // max over: 2*C doubles (BN, bias grad), B*C doubles (SE fwd), (3*B*C + B*hid) floats (SE bwd)
     return ((size_t)batch + 2) * (size_t)max_channels * 16 + 1024;
 }
+
+// Number of kernel launches issued by this library since load (monotonic; bench.py reports the
+// difference over its timed region as "gpu_launches").
+#ifdef FFC_EMU
+static unsigned long long g_ffc_launches = 0;
+void ffc_count_launch() { ++g_ffc_launches; }
+extern "C" unsigned long long ffc_launch_count(void) { return g_ffc_launches; }
+#else
+#include <atomic>
+static std::atomic<unsigned long long> g_ffc_launches{0};
+void ffc_count_launch() { g_ffc_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" unsigned long long ffc_launch_count(void) { return g_ffc_launches.load(std::memory_order_relaxed); }
+#endif

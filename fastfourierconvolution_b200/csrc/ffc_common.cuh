@@ -79,6 +79,7 @@ enum {
 };
 
 void ffc_set_error(const char* fmt, ...);
+void ffc_count_launch();
 
 #ifdef FFC_EMU
 // ------------------------------------------------------------------ launch (emulated)
@@ -91,6 +92,7 @@ static int ffc_launch(int gx, int gy, int gz, int nt, size_t smem_bytes, ffc_str
                 BlockCtx ctx{bx, by, bz, gx, gy, gz, nt};
                 K::run(p, ctx, reinterpret_cast<float*>(smem.data()));
             }
+    ffc_count_launch();
     return FFC_OK;
 }
 static inline int ffc_memset_async(void* p, int v, size_t n, ffc_stream_t) { memset(p, v, n); return FFC_OK; }
@@ -118,6 +120,7 @@ static int ffc_launch(int gx, int gy, int gz, int nt, size_t smem_bytes, ffc_str
     ffc_kernel<K><<<dim3(gx, gy, gz), dim3(nt), smem_bytes, stream>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { ffc_set_error("kernel launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
+    ffc_count_launch();
     return FFC_OK;
 }
 static inline int ffc_memset_async(void* p, int v, size_t n, ffc_stream_t s) {

@@ -88,7 +88,7 @@ class FGenerator(nn.Module):
         return fake
 
 
-class SNConvDiscriminator(nn.Module):
+class SNDiscriminator(nn.Module):
     """The plain spectral-norm conv discriminator the fgan scripts train against
     (fgan_complete.py:142-171 n_convs=7, fgan64_complete.py:159-191 n_convs=8,
     fgan128_complete.py:525-562 n_convs=9).  It contains no FFC layer and is outside the hot path

@@ -42,6 +42,7 @@ extern "C" {
 int ffc_version(void);                 /* major*1000 + minor*10 + patch */
 const char* ffc_last_error(void);
 int ffc_is_emulation(void);            /* 1 only for the host emulation build used by tests/ */
+unsigned long long ffc_launch_count(void);   /* kernels launched by this library since load */
 
 /* Upper bound of the scratch needed by any entry point for a problem with `batch` images and
  * `max_channels` channels (bytes). */

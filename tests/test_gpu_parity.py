@@ -1,0 +1,207 @@
+"""GPU parity tests proper: the product's modules on cuda:0 (libffc_b200.so, sm_100a) against
+  (1) the reference's own outputs (tests/golden/*.npz),
+  (2) the float64 CPU oracle (oracle/ffc_ref.py) on seeded inputs at the sizes of the BASELINE configs,
+  (3) size-independent properties at full BASELINE sizes (round trips, adjointness, normalisation).
+Tolerance: 1e-4 max|d|/max|ref| on outputs and gradients (BASELINE.json north_star, FP32 path)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+import cases
+import parity
+import fastfourierconvolution_b200 as ffc
+from fastfourierconvolution_b200 import _C, harness as H, ops
+from oracle import ffc_ref as R
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_library_is_the_cuda_build_and_launches_kernels():
+    L = _C.lib()
+    assert L.ffc_is_emulation() == 0
+    n0 = L.ffc_launch_count()
+    m = ffc.FourierUnitSN(4, 4).to(DEV)
+    m(torch.randn(2, 4, 16, 16, device=DEV))
+    torch.cuda.synchronize()
+    assert L.ffc_launch_count() - n0 >= 4
+
+
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+def test_module_matches_reference_golden(name):
+    fx = parity.load_fixture(name)
+    mod = cases.CASES[name][0](ffc.layers)
+    got = parity.run_module(mod, fx, DEV)
+    parity.compare(got, fx, tol=parity.TOL, what=name)
+
+
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+def test_module_matches_float64_oracle(name):
+    fx = parity.load_fixture(name)
+    mod = cases.CASES[name][0](ffc.layers)
+    got = parity.run_module(mod, fx, DEV)
+    ref = parity.run_oracle(name, fx, torch.float64)
+    parity.compare(got, ref, tol=parity.TOL, what=name)
+
+
+@pytest.mark.parametrize("name,fn", [("model_fgan32_G", "fgan32"), ("model_sngan_FD", "fd"), ("model_ffcgen_cfg1", "cfg1")])
+def test_model_matches_reference_golden(name, fn):
+    from test_layers_emu import run_model_fixture
+    errs = run_model_fixture(name, fn, DEV)
+    assert max(errs.values()) < 2e-4, errs       # reference's own FP32-vs-FP64 spread is ~6e-5 here
+
+
+def _oracle_vs_module(mod, cfg_fn, xs, train=True, tol=parity.TOL, seed=0):
+    """Random-init module on the GPU vs the float64 oracle on the same weights and inputs."""
+    torch.manual_seed(seed)
+    mod.train(train)
+    sd = {k: v.detach().clone() for k, v in mod.state_dict().items()}
+    P = {}
+    for k, v in sd.items():
+        leaf = v.is_floating_point() and not k.endswith(("running_mean", "running_var", "weight_u", "weight_v"))
+        P[k] = v.double().requires_grad_(True) if leaf else (v.double() if v.is_floating_point() else v.clone())
+    xd = [x.double().requires_grad_(True) for x in xs]
+    ref = cfg_fn(P, xd, train)
+    refs = [o for o in (ref if isinstance(ref, tuple) else (ref,)) if torch.is_tensor(o)]
+    cots = [torch.randn(o.shape) for o in refs]
+    sum((o * c.double()).sum() for o, c in zip(refs, cots)).backward()
+    mod.to(DEV)
+    xg = [x.to(DEV).requires_grad_(True) for x in xs]
+    out = mod(xg[0] if len(xg) == 1 else tuple(xg))
+    outs = [o for o in (out if isinstance(out, tuple) else (out,)) if torch.is_tensor(o)]
+    sum((o * c.to(DEV)).sum() for o, c in zip(outs, cots)).backward()
+    errs = {}
+    for i, (a, b) in enumerate(zip(outs, refs)):
+        errs[f"out{i}"] = parity.relerr(a.detach(), b.detach())
+    for i, (a, b) in enumerate(zip(xg, xd)):
+        errs[f"din{i}"] = parity.relerr(a.grad, b.grad)
+    for k, p in mod.named_parameters():
+        if p.grad is None:
+            assert P[k].grad is None, k
+            continue
+        floor = 0.0
+        if k.endswith("bias"):
+            sib = k[:-4] + "weight"
+            sib = sib if sib in P and P[sib].grad is not None else k[:-4] + "weight_orig"
+            if sib in P and P[sib].grad is not None:
+                floor = P[sib].grad.abs().max().item()
+        errs["grad/" + k] = parity.relerr(p.grad, P[k].grad, floor)
+    for k, b in mod.named_buffers():
+        if b.is_floating_point():
+            errs["post/" + k] = parity.relerr(b, P[k])
+    bad = {k: v for k, v in errs.items() if not v <= tol}
+    assert not bad, bad
+    return errs
+
+
+# FourierUnit shapes of the BASELINE configs and of the isolated sweep
+FU_SHAPES = [(8, 8, 32), (8, 16, 16), (8, 32, 8), (8, 8, 64), (4, 64, 16), (4, 32, 32), (2, 32, 64), (2, 32, 128),
+             (8, 128, 4), (4, 24, 16), (2, 96, 32), (2, 192, 16)]
+
+
+@pytest.mark.parametrize("B,C,N", FU_SHAPES)
+@pytest.mark.parametrize("train", [True, False])
+def test_fourier_unit_config_shapes(B, C, N, train):
+    torch.manual_seed(C * 1000 + N)
+    mod = ffc.FourierUnitSN(C, C)
+    with torch.no_grad():
+        mod.bn.running_mean.normal_(0, 0.1)
+        mod.bn.running_var.uniform_(0.5, 1.5)
+        mod.bn.weight.uniform_(0.5, 1.5)
+        mod.bn.bias.normal_(0, 0.1)
+    x = torch.randn(B, C, N, N)
+    _oracle_vs_module(mod, lambda P, xs, tr: R.fourier_unit(xs[0], P, "", tr), [x], train)
+
+
+@pytest.mark.parametrize("cin,cout,N,stride,up", [(64, 32, 16, 1, False), (32, 16, 16, 2, True), (16, 32, 32, 2, False),
+                                                  (64, 64, 32, 2, True), (256, 128, 8, 2, True)])
+def test_spectral_transform_config_shapes(cin, cout, N, stride, up):
+    mod = ffc.SpectralTransform(cin, cout, stride, 1, True, up)
+    x = torch.randn(4, cin, N, N)
+    _oracle_vs_module(mod, lambda P, xs, tr: R.spectral_transform(xs[0], P, "", stride, up, tr), [x])
+
+
+def test_ffc_bn_act_fgan128_stage():
+    """conv4 of fgan128_complete.py:468-471 (256 -> 128, ratio .5, 16x16 -> 32x32) at batch 4."""
+    mod = ffc.FFC_BN_ACT(256, 128, 4, .5, .5, stride=2, padding=1, activation_layer=nn.GELU, norm_layer=nn.BatchNorm2d,
+                         upsampling=True)
+    cfg = R.FFCConfig(256, 128, 4, .5, .5, 2, 1, norm="bn", act="gelu", upsampling=True)
+    xs = [torch.randn(4, 128, 16, 16), torch.randn(4, 128, 16, 16)]
+    _oracle_vs_module(mod, lambda P, x, tr: R.ffc_bn_act(tuple(x), P, "", cfg, tr), xs)
+
+
+def test_generator_fgan32_random_init_vs_oracle():
+    """Config 2's generator (fgan_complete.py FGenerator + weights_init) forward/backward, batch 16."""
+    torch.manual_seed(1)
+    g = H.FGenerator(128, 4, "fgan32")
+    g.apply(H.weights_init)
+    z = torch.randn(16, 128)
+    errs = _oracle_vs_module(g, lambda P, xs, tr: R.fgenerator(xs[0], P, tr, "fgan32"), [z], tol=2e-4)
+    assert errs["out0"] < parity.TOL
+
+
+# ---- size-independent properties at full BASELINE sizes ---------------------------------------
+def test_fft_round_trip_full_size_fgan128():
+    """irfft2(rfft2(x)) == x for the largest spectrum of config 4: B64 x C32 @ 128x128 (268 MB in+out)."""
+    x = torch.randn(64, 32, 128, 128, device=DEV)
+    y = ops.irfft2(ops.rfft2(x))
+    assert (y - x).abs().max().item() < 2e-5
+    spec = ops.rfft2(x)
+    # Parseval for the one-sided spectrum: interior columns count twice
+    w = torch.full((65,), 2.0, device=DEV); w[0] = 1; w[64] = 1
+    e_spec = (spec.double().square().view(64, 32, 2, 128, 65).sum(2) * w).sum()
+    e_x = x.double().square().sum()
+    assert abs(e_spec / e_x - 1) < 1e-5
+
+
+def test_fourier_unit_linearity_before_relu_full_size():
+    """With BN in eval mode and a positive-only operating point the unit is linear in x up to FP32 rounding;
+    here: fu(a*x) == a*fu(x) for a > 0 when beta = 0 and running_mean = 0 (ReLU is positively homogeneous)."""
+    torch.manual_seed(0)
+    m = ffc.FourierUnitSN(16, 16).to(DEV).eval()
+    with torch.no_grad():
+        m.bn.bias.zero_(); m.bn.running_mean.zero_()
+    x = torch.randn(256, 16, 16, 16, device=DEV)          # config 2, conv3's Fourier unit at global batch 256
+    with torch.no_grad():
+        y1, y2 = m(x), m(3.0 * x)
+    assert (y2 - 3.0 * y1).abs().max().item() < 1e-4 * y2.abs().max().item()
+
+
+def test_batchnorm_output_statistics_full_size():
+    x = torch.randn(256, 48, 32, 32, device=DEV) * 3 + 2
+    bn = nn.BatchNorm2d(48).to(DEV)
+    from fastfourierconvolution_b200.layers import _util
+    y = _util.bn_act(x, bn, (ops.ACT_IDENTITY, 0.0))
+    assert y.mean((0, 2, 3)).abs().max().item() < 1e-4
+    assert (y.var((0, 2, 3), unbiased=False) - 1).abs().max().item() < 1e-3
+    ref = nn.BatchNorm2d(48).to(DEV)
+    yr = ref(x)
+    assert (y - yr).abs().max().item() < 1e-4
+    assert torch.allclose(bn.running_var, ref.running_var, rtol=1e-5) and torch.allclose(bn.running_mean, ref.running_mean, rtol=1e-5, atol=1e-6)
+
+
+def test_conv_transpose_is_adjoint_of_conv_full_size():
+    """<convT(x, w), y> == <x, conv(y, w)> for the 64->64 k4 s2 p1 stage of fgan128 (conv6) at batch 8, 64x64."""
+    torch.manual_seed(0)
+    x = torch.randn(8, 64, 64, 64, device=DEV)
+    w = torch.randn(64, 64, 4, 4, device=DEV) * 0.05
+    y = torch.randn(8, 64, 128, 128, device=DEV)
+    up = ops.conv2d(x, w, stride=2, pad=1, transposed=True)
+    down = ops.conv2d(y, w, stride=2, pad=1, transposed=False)    # weight [cout=64][cin=64]: same tensor read as conv layout
+    lhs = (up.double() * y.double()).sum()
+    rhs = (x.double() * down.double()).sum()
+    assert abs(lhs - rhs) / abs(lhs) < 1e-5
+
+
+def test_training_step_runs_and_updates_both_networks():
+    torch.manual_seed(0)
+    G = H.FGenerator(128, 4, "fgan32").to(DEV).train(); G.apply(H.weights_init)
+    D = H.SNDiscriminator(True, 4, 7).to(DEV).train(); D.apply(H.weights_init)
+    tr = H.GanTrainer(G, D)
+    g0 = G.conv3.ffc.convg2g.fu.conv_layer.weight.detach().clone()
+    d0 = D.conv1.weight_orig.detach().clone()
+    lg, ld = tr.step(torch.randn(8, 128, device=DEV), torch.randn(8, 128, device=DEV), torch.rand(8, 3, 32, 32, device=DEV) * 2 - 1)
+    assert torch.isfinite(lg) and torch.isfinite(ld)
+    assert not torch.equal(g0, G.conv3.ffc.convg2g.fu.conv_layer.weight) and not torch.equal(d0, D.conv1.weight_orig)
+    assert all(p.grad is None for k, p in G.named_parameters() if ".lfu." in k)

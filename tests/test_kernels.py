@@ -1,5 +1,6 @@
-"""C-ABI level checks of every kernel family on the host emulation build (index arithmetic, edge
-cases, all supported plane sizes) against numpy / torch CPU math."""
+"""C-ABI level checks of every kernel family against numpy / torch CPU math, on two backends:
+  emu  -- the host emulation build of the CUDA sources (index arithmetic, edge cases; runs anywhere)
+  cuda -- libffc_b200.so on the GPU (marked gpu): the same calls with device buffers."""
 import ctypes
 
 import numpy as np
@@ -11,18 +12,27 @@ import emu_backend
 import parity
 
 
-@pytest.fixture(scope="module")
-def lib():
+@pytest.fixture(scope="module", params=["emu", pytest.param("cuda", marks=pytest.mark.gpu)])
+def lib(request):
     from fastfourierconvolution_b200 import _C
-    return _C.Library(emu_backend.build())
+    if request.param == "emu":
+        return _C.Library(emu_backend.build()), "cpu"
+    return _C.lib(), "cuda"
 
 
-def P(t):
-    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
-
-
-def ok(lib, rc):
-    assert rc == 0, lib.last_error()
+def call(backend, name, *args):
+    """Calls a C-ABI entry point with the tensors moved to the backend's device and copies every
+    tensor back afterwards (outputs are written in place), so test bodies are backend agnostic."""
+    library, device = backend
+    moved = [a.to(device) if torch.is_tensor(a) else a for a in args]
+    raw = [ctypes.c_void_p(a.data_ptr()) if torch.is_tensor(a) else a for a in moved]
+    rc = getattr(library, name)(*raw)
+    assert rc == 0, library.last_error()
+    if device != "cpu":
+        torch.cuda.synchronize()
+        for a, m in zip(args, moved):
+            if torch.is_tensor(a):
+                a.copy_(m)
 
 
 def upos(k, n):
@@ -38,7 +48,7 @@ def test_rfft2_irfft2_all_sizes(lib, n):
     perm = [upos(k, n) for k in range(n)]
     x = torch.from_numpy(rng.standard_normal((npl, n, n)).astype(np.float32))
     spec = torch.zeros(npl, 2, n, wf)
-    ok(lib, lib.ffc_rfft2(P(x), P(spec), npl, n, n, 0, None))
+    call(lib, "ffc_rfft2", x, spec, npl, n, n, 0, None)
     ref = torch.fft.rfftn(x.double(), dim=(-2, -1), norm="ortho")
     got = torch.complex(spec[:, 0].double(), spec[:, 1].double())[:, perm, :]
     assert parity.relerr(torch.view_as_real(got), torch.view_as_real(ref)) < 1e-6
@@ -49,7 +59,7 @@ def test_rfft2_irfft2_all_sizes(lib, n):
     zp[:, :, perm, :] = z
     res = torch.from_numpy(rng.standard_normal((npl, n, n)).astype(np.float32))
     out = torch.zeros(npl, n, n)
-    ok(lib, lib.ffc_irfft2(P(zp), P(res), P(out), npl, n, n, 0, None))
+    call(lib, "ffc_irfft2", zp, res, out, npl, n, n, 0, None)
     assert parity.relerr(out.double() - res.double(), refo) < 1e-6
 
 
@@ -61,12 +71,12 @@ def test_fft_adjoint_pairs(lib, n):
     x = torch.from_numpy(rng.standard_normal((npl, n, n)).astype(np.float32))
     s = torch.from_numpy(rng.standard_normal((npl, 2, n, wf)).astype(np.float32))
     fx, ats = torch.zeros_like(s), torch.zeros_like(x)
-    ok(lib, lib.ffc_rfft2(P(x), P(fx), npl, n, n, 0, None))
-    ok(lib, lib.ffc_irfft2(P(s), None, P(ats), npl, n, n, 1, None))
+    call(lib, "ffc_rfft2", x, fx, npl, n, n, 0, None)
+    call(lib, "ffc_irfft2", s, None, ats, npl, n, n, 1, None)
     assert abs((fx.double() * s.double()).sum() - (x.double() * ats.double()).sum()) < 1e-3 * n
     ix, atx = torch.zeros_like(x), torch.zeros_like(s)
-    ok(lib, lib.ffc_irfft2(P(s), None, P(ix), npl, n, n, 0, None))
-    ok(lib, lib.ffc_rfft2(P(x), P(atx), npl, n, n, 1, None))
+    call(lib, "ffc_irfft2", s, None, ix, npl, n, n, 0, None)
+    call(lib, "ffc_rfft2", x, atx, npl, n, n, 1, None)
     assert abs((ix.double() * x.double()).sum() - (s.double() * atx.double()).sum()) < 1e-3 * n
 
 
@@ -104,8 +114,8 @@ def test_conv_forward_dgrad_wgrad(lib, case):
         ref = ref + ad.double()
     y = torch.empty(B, cout, Ho, Ho)
     x1, w1 = (xs[1], ws[1]) if len(xs) > 1 else (None, None)
-    ok(lib, lib.ffc_conv2d_fwd(P(xs[0]), P(ws[0]), cins[0], P(x1), P(w1), cins[1] if x1 is not None else 0, P(b), P(ad), P(y),
-                               B, cout, Hi, Hi, Ho, Ho, k, s, p, int(tr), None))
+    call(lib, "ffc_conv2d_fwd", xs[0], ws[0], cins[0], x1, w1, cins[1] if x1 is not None else 0, b, ad, y,
+                               B, cout, Hi, Hi, Ho, Ho, k, s, p, int(tr), None)
     assert parity.relerr(y, ref) < 2e-6
     dy = torch.randn(B, cout, Ho, Ho)
     for x, w in zip(xs, ws):
@@ -113,11 +123,11 @@ def test_conv_forward_dgrad_wgrad(lib, case):
         op_ref(xd, wd).backward(dy.double())
         dW, dx = torch.empty_like(w), torch.empty_like(x)
         if tr:
-            ok(lib, lib.ffc_conv2d_wgrad(P(x), P(dy), P(dW), B, x.shape[1], cout, Hi, Hi, Ho, Ho, k, s, p, None))
+            call(lib, "ffc_conv2d_wgrad", x, dy, dW, B, x.shape[1], cout, Hi, Hi, Ho, Ho, k, s, p, None)
         else:
-            ok(lib, lib.ffc_conv2d_wgrad(P(dy), P(x), P(dW), B, cout, x.shape[1], Ho, Ho, Hi, Hi, k, s, p, None))
+            call(lib, "ffc_conv2d_wgrad", dy, x, dW, B, cout, x.shape[1], Ho, Ho, Hi, Hi, k, s, p, None)
         assert parity.relerr(dW, wd.grad) < 3e-6
-        ok(lib, lib.ffc_conv2d_fwd(P(dy), P(w), cout, None, None, 0, None, None, P(dx), B, x.shape[1], Ho, Ho, Hi, Hi, k, s, p, int(not tr), None))
+        call(lib, "ffc_conv2d_fwd", dy, w, cout, None, None, 0, None, None, dx, B, x.shape[1], Ho, Ho, Hi, Hi, k, s, p, int(not tr), None)
         assert parity.relerr(dx, xd.grad) < 3e-6
 
 
@@ -142,11 +152,11 @@ def test_bn_act_forward_backward(lib, case):
     y, sm, si = torch.empty_like(x), torch.empty(C), torch.empty(C)
     ws = torch.empty(2 * C, dtype=torch.float64)
     nb = ctypes.c_size_t(ws.numel() * 8)
-    ok(lib, lib.ffc_bn_act_fwd(P(x), P(y), P(g), P(b), P(rm), P(rv), P(sm), P(si), B, C, H * W, norm, training,
-                               cf(1e-5), cf(0.1), act, cf(0.1), P(ws), nb, None))
+    call(lib, "ffc_bn_act_fwd", x, y, g, b, rm, rv, sm, si, B, C, H * W, norm, training,
+                               cf(1e-5), cf(0.1), act, cf(0.1), ws, nb, None)
     dx, dg, db = torch.empty_like(x), torch.zeros(C), torch.zeros(C)
-    ok(lib, lib.ffc_bn_act_bwd(P(x), P(dy), P(dx), P(g), P(b), P(sm), P(si), P(dg), P(db), B, C, H * W, norm, training,
-                               act, cf(0.1), P(ws), nb, None))
+    call(lib, "ffc_bn_act_bwd", x, dy, dx, g, b, sm, si, dg, db, B, C, H * W, norm, training,
+                               act, cf(0.1), ws, nb, None)
     assert parity.relerr(y, yref.detach()) < 5e-6
     if B * H * W > 1:
         assert parity.relerr(dx, xd.grad) < 5e-6
@@ -169,9 +179,9 @@ def test_se_forward_backward(lib, case):
     y, sm, sh, sg = torch.empty(yref.shape), torch.empty(B, C), torch.empty(B, max(hid, 1)), torch.empty(B, C)
     ws = torch.empty(B * C * 4 + B * (C + hid) + 16, dtype=torch.float64)
     nb = ctypes.c_size_t(ws.numel() * 8)
-    ok(lib, lib.ffc_se_fwd(P(x), P(w1), P(w2), P(y), P(sm), P(sh), P(sg), B, C, hid, H, H, mode, P(ws), nb, None))
+    call(lib, "ffc_se_fwd", x, w1, w2, y, sm, sh, sg, B, C, hid, H, H, mode, ws, nb, None)
     dx, dw1, dw2 = torch.empty_like(x), torch.empty_like(w1), torch.empty_like(w2)
-    ok(lib, lib.ffc_se_bwd(P(x), P(dy), P(w1), P(w2), P(sm), P(sh), P(sg), P(dx), P(dw1), P(dw2), B, C, hid, H, H, mode, P(ws), nb, None))
+    call(lib, "ffc_se_bwd", x, dy, w1, w2, sm, sh, sg, dx, dw1, dw2, B, C, hid, H, H, mode, ws, nb, None)
     assert parity.relerr(y, yref.detach()) < 5e-6 and parity.relerr(dx, xd.grad) < 5e-6
     if hid:
         assert parity.relerr(dw1, w1d.grad) < 5e-6 and parity.relerr(dw2, w2d.grad) < 5e-6
@@ -179,7 +189,7 @@ def test_se_forward_backward(lib, case):
 
 def test_empty_batch_is_a_noop(lib):
     x = torch.zeros(0, 4, 8, 8)
-    ok(lib, lib.ffc_rfft2(P(torch.zeros(4)), P(torch.zeros(4)), 0, 8, 8, 0, None))
+    call(lib, "ffc_rfft2", torch.zeros(4), torch.zeros(4), 0, 8, 8, 0, None)
     y = torch.zeros(0, 3, 8, 8)
     w = torch.randn(3, 4, 3, 3)
-    ok(lib, lib.ffc_conv2d_fwd(P(torch.zeros(4)), P(w), 4, None, None, 0, None, None, P(torch.zeros(4)), 0, 3, 8, 8, 8, 8, 3, 1, 1, 0, None))
+    call(lib, "ffc_conv2d_fwd", torch.zeros(4), w, 4, None, None, 0, None, None, torch.zeros(4), 0, 3, 8, 8, 8, 8, 3, 1, 1, 0, None)
