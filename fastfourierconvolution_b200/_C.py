@@ -36,11 +36,9 @@ _SIGNATURES = {
     "ffc_se_fwd": (c_int, [c_void_p] * 7 + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
     "ffc_se_bwd": (c_int, [c_void_p] * 10 + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
     "ffc_fu_fwd": (c_int, [c_void_p] * 10 + [c_int] * 6 + [c_float, c_float, c_void_p, c_size_t, c_void_p]),
-    "ffc_fu_bwd": (c_int, [c_void_p] * 11 + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
     "ffc_fu_fused_supported": (c_int, [c_int] * 5),
 }
-# symbols a given build may not have yet are optional at bind time (checked by tests against the header)
-_OPTIONAL = {"ffc_fu_fwd", "ffc_fu_bwd", "ffc_fu_fused_supported"}
+_OPTIONAL = set()
 
 
 class Library:

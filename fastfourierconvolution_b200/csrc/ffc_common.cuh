@@ -30,6 +30,7 @@ static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y;
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 typedef void* ffc_stream_t;
 #define FFC_HD static inline
+#define FFC_HDM inline
 #define FFC_DEVICE inline
 #define FFC_CONST static const
 #define FFC_RESTRICT __restrict__
@@ -42,6 +43,7 @@ template <class T> static inline void ffc_atomic_add(T* p, T v) { *p += v; }
 #include <cuda_runtime.h>
 typedef cudaStream_t ffc_stream_t;
 #define FFC_HD __host__ __device__ __forceinline__
+#define FFC_HDM __host__ __device__ __forceinline__
 #define FFC_DEVICE __device__ __forceinline__
 #define FFC_CONST static __constant__
 #define FFC_RESTRICT __restrict__
@@ -98,8 +100,13 @@ static int ffc_launch(int gx, int gy, int gz, int nt, size_t smem_bytes, ffc_str
 static inline int ffc_memset_async(void* p, int v, size_t n, ffc_stream_t) { memset(p, v, n); return FFC_OK; }
 #else
 // ------------------------------------------------------------------ launch (device)
+#include <type_traits>
+// optional K::kMinBlocks (resident CTAs per SM the register allocation must allow); default 1
+template <class K, class = void> struct FfcMinBlocks { static constexpr int v = 1; };
+template <class K> struct FfcMinBlocks<K, std::void_t<decltype(K::kMinBlocks)>> { static constexpr int v = K::kMinBlocks; };
+
 template <class K>
-__global__ void __launch_bounds__(K::kThreads) ffc_kernel(const typename K::Params p) {
+__global__ void __launch_bounds__(K::kThreads, FfcMinBlocks<K>::v) ffc_kernel(const typename K::Params p) {
     extern __shared__ float4 ffc_smem4[];
     BlockCtx ctx{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z,
                  (int)gridDim.x, (int)gridDim.y, (int)gridDim.z, (int)blockDim.x};
@@ -113,9 +120,18 @@ static int ffc_launch(int gx, int gy, int gz, int nt, size_t smem_bytes, ffc_str
         ffc_set_error("launch config out of range (nt=%d, grid=%d,%d,%d)", nt, gx, gy, gz);
         return FFC_ERR_BAD_ARG;
     }
-    if (smem_bytes > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(ffc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    // Kernels that stage tiles in shared memory: raise the dynamic limit and ask for the largest shared
+    // carve-out so that occupancy is not capped by the default L1/shared split (set once per high-water mark;
+    // a benign race if two host threads launch the same kernel for the first time).
+    static size_t configured_smem = 0;
+    if (smem_bytes > 16 * 1024 && smem_bytes > configured_smem) {
+        cudaError_t e = cudaSuccess;
+        if (smem_bytes > 48 * 1024)
+            e = cudaFuncSetAttribute(ffc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(ffc_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) { ffc_set_error("cudaFuncSetAttribute(%zu B smem): %s", smem_bytes, cudaGetErrorString(e)); return FFC_ERR_CUDA; }
+        configured_smem = smem_bytes;
     }
     ffc_kernel<K><<<dim3(gx, gy, gz), dim3(nt), smem_bytes, stream>>>(p);
     cudaError_t e = cudaGetLastError();

@@ -8,11 +8,25 @@
 #include "ffc_common.cuh"
 #include "ffc_twiddles.h"
 
-FFC_HD float2 ffc_cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-FFC_HD float2 ffc_csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Packed FP32x2 arithmetic: sm_100 issues add/mul/fma on a register pair as ONE instruction
+// (FADD2 / FMUL2 / FFMA2), which halves the instruction count of the complex butterflies and of the
+// channel mix.  The emulation build uses plain scalar math (same rounding: each half is an IEEE op).
+#if !defined(FFC_EMU)
+FFC_DEVICE float2 ffc_add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+FFC_DEVICE float2 ffc_sub2(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); }
+FFC_DEVICE float2 ffc_mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+FFC_DEVICE float2 ffc_fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+#else
+FFC_DEVICE float2 ffc_add2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+FFC_DEVICE float2 ffc_sub2(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+FFC_DEVICE float2 ffc_mul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+FFC_DEVICE float2 ffc_fma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+#endif
+FFC_DEVICE float2 ffc_cadd(float2 a, float2 b) { return ffc_add2(a, b); }
+FFC_DEVICE float2 ffc_csub(float2 a, float2 b) { return ffc_sub2(a, b); }
 // a * (c + i*s*sign)
 template <int SIGN>
-FFC_HD float2 ffc_cmul_tw(float2 a, float2 w) {
+FFC_DEVICE float2 ffc_cmul_tw(float2 a, float2 w) {
     return SIGN > 0 ? make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x)
                     : make_float2(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y);
 }

@@ -15,6 +15,14 @@
 #pragma once
 #include "ffc_fft.cuh"
 
+// Where plane `pl` of a work list lives inside a spectrum region: identity by default; for the fused
+// Fourier unit the region holds images of `cb` planes each of which only the first `cn` are transformed.
+struct PlaneMap {
+    int cn, cb;
+    FFC_HDM int operator()(int pl) const { return cn == 0 ? pl : (pl / cn) * cb + (pl % cn); }
+};
+FFC_HD PlaneMap ffc_identity_map() { PlaneMap m; m.cn = 0; m.cb = 0; return m; }
+
 template <int H, int W>
 struct Fft2Plan {
     static constexpr int Wf = W / 2 + 1;
@@ -37,12 +45,15 @@ struct Fft2Plan {
 // Returns (via the plan) where the spectrum lives: dst if one-level, src if two-level.
 // The functions below are single phases; callers put FFC_SYNC between them.
 // ---------------------------------------------------------------------------------------------
-template <int H, int W>
-FFC_DEVICE void fft2_rows_fwd_L1(int tid, int nt, int np, const float* src, float* dst) {
+// SPS = float2 per spectrum row: Wf (dense spec layout) or RS/2 (spectrum row u overlays real row u, which
+// lets the row transforms run IN PLACE: a thread overwrites exactly the two rows it has read).
+template <int H, int W, int SPS = W / 2 + 1>
+FFC_DEVICE void fft2_rows_fwd_L1(int tid, int nt, int np, const float* src, float* dst, PlaneMap dmap = ffc_identity_map(),
+                                 PlaneMap smap = ffc_identity_map()) {
     typedef Fft2Plan<H, W> PL;
     for (int it = tid; it < np * (H / 2); it += nt) {
         const int pl = it / (H / 2), r = it % (H / 2);
-        const float* ra = src + pl * PL::REGION + r * PL::RS;
+        const float* ra = src + smap(pl) * PL::REGION + r * PL::RS;
         const float* rb = ra + (H / 2) * PL::RS;
         float2 z[W];
         FFC_UNROLL
@@ -55,8 +66,8 @@ FFC_DEVICE void fft2_rows_fwd_L1(int tid, int nt, int np, const float* src, floa
             z[4 * j + 3] = make_float2(a.w, b.w);
         }
         ffc_fft_regs<W, -1>(z);
-        float2* sa = reinterpret_cast<float2*>(dst + pl * PL::REGION) + r * PL::Wf;
-        float2* sb = sa + (H / 2) * PL::Wf;
+        float2* sa = reinterpret_cast<float2*>(dst + dmap(pl) * PL::REGION) + r * SPS;
+        float2* sb = sa + (H / 2) * SPS;
         FFC_UNROLL
         for (int v = 0; v < PL::Wf; ++v) {
             const float2 zv = z[v], zc = z[(W - v) % W];
@@ -124,18 +135,18 @@ FFC_DEVICE void fft2_rows_fwd_L2sep(int tid, int nt, int np, const float* scr, f
 // ---------------------------------------------------------------------------------------------
 // columns (complex, in place in a spec-layout region), element stride Wf
 // ---------------------------------------------------------------------------------------------
-template <int H, int W, int SIGN>
-FFC_DEVICE void fft2_cols_L1(int tid, int nt, int np, float* spec) {
+template <int H, int W, int SIGN, int SPS = W / 2 + 1>
+FFC_DEVICE void fft2_cols_L1(int tid, int nt, int np, float* spec, PlaneMap map = ffc_identity_map()) {
     typedef Fft2Plan<H, W> PL;
     for (int it = tid; it < np * PL::Wf; it += nt) {
         const int v = it % PL::Wf, pl = it / PL::Wf;
-        float2* col = reinterpret_cast<float2*>(spec + pl * PL::REGION) + v;
+        float2* col = reinterpret_cast<float2*>(spec + map(pl) * PL::REGION) + v;
         float2 c[H];
         FFC_UNROLL
-        for (int u = 0; u < H; ++u) c[u] = col[u * PL::Wf];
+        for (int u = 0; u < H; ++u) c[u] = col[u * SPS];
         ffc_fft_regs<H, SIGN>(c);
         FFC_UNROLL
-        for (int u = 0; u < H; ++u) col[u * PL::Wf] = c[u];
+        for (int u = 0; u < H; ++u) col[u * SPS] = c[u];
     }
 }
 // strided level: gathers positions H2*i + n2 (i < H1).  Forward: first level (twiddle after).
@@ -183,13 +194,14 @@ FFC_DEVICE void fft2_cols_L2_contig(int tid, int nt, int np, float* spec, const 
 // inverse rows: spec layout -> real layout, c2r semantics of torch.fft.irfftn's last dimension
 // (imaginary parts of bins 0 and W/2 are ignored, interior bins count twice).
 // ---------------------------------------------------------------------------------------------
-template <int H, int W>
-FFC_DEVICE void fft2_rows_inv_L1(int tid, int nt, int np, const float* spec, float* dst, float scale) {
+template <int H, int W, int SPS = W / 2 + 1>
+FFC_DEVICE void fft2_rows_inv_L1(int tid, int nt, int np, const float* spec, float* dst, const float scale, PlaneMap smap = ffc_identity_map(),
+                                 PlaneMap dmap = ffc_identity_map()) {
     typedef Fft2Plan<H, W> PL;
     for (int it = tid; it < np * (H / 2); it += nt) {
         const int pl = it / (H / 2), r = it % (H / 2);
-        const float2* sa = reinterpret_cast<const float2*>(spec + pl * PL::REGION) + r * PL::Wf;
-        const float2* sb = sa + (H / 2) * PL::Wf;
+        const float2* sa = reinterpret_cast<const float2*>(spec + smap(pl) * PL::REGION) + r * SPS;
+        const float2* sb = sa + (H / 2) * SPS;
         float2 z[W];
         FFC_UNROLL
         for (int v = 0; v <= W / 2; ++v) {
@@ -202,7 +214,7 @@ FFC_DEVICE void fft2_rows_inv_L1(int tid, int nt, int np, const float* spec, flo
             }
         }
         ffc_fft_regs<W, +1>(z);
-        float* ra = dst + pl * PL::REGION + r * PL::RS;
+        float* ra = dst + dmap(pl) * PL::REGION + r * PL::RS;
         float* rb = ra + (H / 2) * PL::RS;
         FFC_UNROLL
         for (int j = 0; j < W / 4; ++j) {

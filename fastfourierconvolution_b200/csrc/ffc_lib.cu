@@ -4,3 +4,4 @@
 #include "ffc_fft2.cu"
 #include "ffc_conv.cu"
 #include "ffc_bnact.cu"
+#include "ffc_fu_fused.cu"

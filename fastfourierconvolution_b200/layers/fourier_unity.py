@@ -27,6 +27,7 @@ class FourierUnitSN(nn.Module):
                                     groups=groups, bias=False)
         self.bn = nn.BatchNorm2d(out_channels * 2)
         self.relu = nn.ReLU(inplace=True)
+        self.fused = True     # False forces the general (spectrum-through-L2) form; used by tests and benchmarks
 
     def forward(self, x, y=None):
         return self._run(x, y, None)
@@ -42,6 +43,14 @@ class FourierUnitSN(nn.Module):
         if h != w or h & (h - 1) or not 4 <= h <= 128:
             raise NotImplementedError(f"FourierUnitSN: only square power-of-two planes 4..128 are supported, got {h}x{w}")
         weight = _util.effective_weight(self.conv_layer)
+        bn = self.bn
+        cin, cout = x.shape[1], weight.shape[0] // 2
+        plain_bn = bn.affine and bn.track_running_stats and bn.momentum is not None
+        if plain_bn and self.fused and ops.fu_fused_supported(x.shape[0], cin, cout, h, w):
+            if bn.training:
+                bn.num_batches_tracked.add_(1)
+            return ops.fourier_unit_fused(x, weight.view(2 * cout, 2 * cin), bn.weight, bn.bias, bn.running_mean,
+                                          bn.running_var, residual, bn.training, bn.eps, bn.momentum)
         spec = ops.rfft2(x)                                            # fourier_unity.py:38-42
         mixed = ops.conv2d(spec, weight)                               # :45
         act = _util.bn_act(mixed, self.bn, (ops.ACT_RELU, 0.0))        # :49

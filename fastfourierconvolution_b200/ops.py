@@ -215,6 +215,77 @@ def irfft2(spec, residual=None):
 
 
 # ---------------------------------------------------------------------------------------------
+# fused Fourier unit (forward in one / two kernels; backward recomputes through the general form)
+# ---------------------------------------------------------------------------------------------
+def fu_fused_supported(B, Cin, Cout, H, W) -> bool:
+    return bool(_C.lib().ffc_fu_fused_supported(int(B), int(Cin), int(Cout), int(H), int(W)))
+
+
+class FusedFuFn(torch.autograd.Function):
+    """out = [residual +] irfft2(relu(bn(conv1x1(rfft2(x)))))   (fourier_unity.py:32-58 in one op).
+
+    Forward: ffc_fu_fwd (spectrum stays in shared memory).  Backward: the spectrum is recomputed from
+    x with the general-form kernels (rfft2, 1x1 mix, BN+ReLU backward, wgrad/dgrad, irfft2); nothing
+    spectral is saved between forward and backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, running_mean, running_var, residual, training, eps, momentum):
+        _C.require_device(x, weight, gamma, beta, running_mean, running_var, residual)
+        x, weight, residual = x.contiguous(), weight.contiguous(), _c(residual)
+        B, Cin, H, W = x.shape
+        Cout = weight.shape[0] // 2
+        out = torch.empty((B, Cout, H, W), device=x.device, dtype=torch.float32)
+        save_mean = torch.empty(2 * Cout, device=x.device, dtype=torch.float32)
+        save_invstd = torch.empty(2 * Cout, device=x.device, dtype=torch.float32)
+        ws = _C.workspace(4 * Cout * 8, x.device)
+        _C.check(_C.lib().ffc_fu_fwd(_C.ptr(x), _C.ptr(weight), _C.ptr(gamma), _C.ptr(beta),
+                                     _C.ptr(running_mean), _C.ptr(running_var), _C.ptr(save_mean), _C.ptr(save_invstd),
+                                     _C.ptr(residual), _C.ptr(out), B, Cin, Cout, H, W, int(training), float(eps),
+                                     float(momentum), _C.ptr(ws), ws.numel(), _C.current_stream(x.device)))
+        ctx.save_for_backward(x, weight, gamma, beta, save_mean, save_invstd)
+        ctx.cfg = (bool(training), residual is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, weight, gamma, beta, save_mean, save_invstd = ctx.saved_tensors
+        training, has_res = ctx.cfg
+        dout = dout.contiguous()
+        B, Cin, H, W = x.shape
+        C2o, C2i = weight.shape[0], weight.shape[1]
+        Wf = W // 2 + 1
+        L = _C.lib()
+        st = _C.current_stream(x.device)
+        w4 = weight.view(C2o, C2i, 1, 1)
+        spec = _rfft2(x, 0)                                            # recompute S
+        y = torch.empty((B, C2o, H, Wf), device=x.device, dtype=torch.float32)
+        _C.check(L.ffc_conv2d_fwd(_C.ptr(spec), _C.ptr(w4), C2i, None, None, 0, None, None, _C.ptr(y),
+                                  B, C2o, H, Wf, H, Wf, 1, 1, 0, 0, st))         # recompute Y = W S
+        g = _rfft2(dout, 1)                                            # adjoint of irfft2
+        dy = torch.empty_like(y)
+        dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(beta)
+        ws = _C.workspace(2 * C2o * 8, x.device)
+        _C.check(L.ffc_bn_act_bwd(_C.ptr(y), _C.ptr(g), _C.ptr(dy), _C.ptr(gamma), _C.ptr(beta),
+                                  _C.ptr(save_mean), _C.ptr(save_invstd), _C.ptr(dgamma), _C.ptr(dbeta),
+                                  B, C2o, H * Wf, 1, int(training), ACT_RELU, 0.0, _C.ptr(ws), ws.numel(), st))
+        dx = dw = None
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(weight)
+            _C.check(L.ffc_conv2d_wgrad(_C.ptr(dy), _C.ptr(spec), _C.ptr(dw), B, C2o, C2i, H, Wf, H, Wf, 1, 1, 0, st))
+        if ctx.needs_input_grad[0]:
+            dspec = torch.empty_like(spec)
+            _C.check(L.ffc_conv2d_fwd(_C.ptr(dy), _C.ptr(w4), C2o, None, None, 0, None, None, _C.ptr(dspec),
+                                      B, C2i, H, Wf, H, Wf, 1, 1, 0, 1, st))     # dS = W^T dY
+            dx = _irfft2(dspec, None, 1)                               # adjoint of rfft2
+        dres = dout if (has_res and ctx.needs_input_grad[6]) else None
+        return dx, dw, dgamma, dbeta, None, None, dres, None, None, None
+
+
+def fourier_unit_fused(x, weight2d, gamma, beta, running_mean, running_var, residual, training, eps, momentum):
+    return FusedFuFn.apply(x, weight2d, gamma, beta, running_mean, running_var, residual, training, eps, momentum)
+
+
+# ---------------------------------------------------------------------------------------------
 # resample + SE gate (SpectralTransform prologue)
 # ---------------------------------------------------------------------------------------------
 class SeFn(torch.autograd.Function):

