@@ -220,7 +220,8 @@ def run_ours(args):
     if world > 1:                                    # identical replicas
         for p in list(G.parameters()) + list(D.parameters()) + list(G.buffers()) + list(D.buffers()):
             dist.broadcast(p.data, 0)
-    tr = H.GanTrainer(G, D)
+    use_graph = not args.no_graph
+    tr = H.GanTrainer(G, D, capturable=use_graph)
 
     h_zg = torch.randn(pb, 128).pin_memory(); h_zd = torch.randn(pb, 128).pin_memory()
     h_real = (torch.rand(pb, 3, size, size) * 2 - 1).pin_memory()
@@ -233,14 +234,28 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    def step_resident():
-        return tr.step(d_zg, d_zd, d_real)
+    import warnings
+    warnings.filterwarnings("ignore", message=".*lr_scheduler.step.*")
+    if use_graph:
+        # the whole G+D step (our kernels, the PyTorch discriminator, both optimisers and, for N > 1, the NCCL
+        # all-reduces) is captured once into a CUDA graph and replayed: same kernels, no host launch cost
+        tr.capture(d_zg, d_zd, d_real)
 
-    def step_e2e():
-        zg = h_zg.to(dev, non_blocking=True); zd = h_zd.to(dev, non_blocking=True); re = h_real.to(dev, non_blocking=True)
-        lg, ld = tr.step(zg, zd, re)
-        h_loss.copy_(torch.stack((lg, ld)), non_blocking=False)       # device -> host read of the step's result
-        return h_loss
+        def step_resident():
+            return tr.step_graphed(d_zg, d_zd, d_real)
+
+        def step_e2e():
+            h_loss.copy_(tr.step_graphed(h_zg, h_zd, h_real), non_blocking=False)   # H2D of inputs, D2H of both losses
+            return h_loss
+    else:
+        def step_resident():
+            return tr.step(d_zg, d_zd, d_real)
+
+        def step_e2e():
+            zg = h_zg.to(dev, non_blocking=True); zd = h_zd.to(dev, non_blocking=True); re = h_real.to(dev, non_blocking=True)
+            lg, ld = tr.step(zg, zd, re)
+            h_loss.copy_(torch.stack((lg, ld)), non_blocking=False)       # device -> host read of the step's result
+            return h_loss
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
@@ -260,7 +275,8 @@ def run_ours(args):
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = t.item()
-        return ms / args.steps, (L.ffc_launch_count() - n0) / args.steps
+        per_step = tr.launches_per_step if use_graph else (L.ffc_launch_count() - n0) / args.steps
+        return ms / args.steps, per_step
 
     with ClockSampler(local_rank) as clk:
         ms_res, launches = timed(step_resident)
@@ -286,6 +302,7 @@ def run_ours(args):
                        "global_batch": gb, "per_gpu_batch": pb, "parallelism": f"dp{world} (batch shards, per-rank BatchNorm, flat-grad NCCL all-reduce)",
                        "l2": "per-step working set (activations of batch %d, > 400 MB) exceeds the 126 MB L2; FourierUnit timing rotates %d input buffers"
                              % (pb, fu["rotating_buffers"]),
+                       "launch": "whole step replayed as one CUDA graph" if use_graph else "eager launches",
                        "discriminator": "plain SN conv net (no FFC layer; PyTorch kernels, out of the hot-path scope)",
                        "generator_params_MB": round(act_mb, 1)},
             "e2e": {"value": gb / ms_e2e * 1000.0, "unit": "images/s", "ms_per_step": ms_e2e,
@@ -320,6 +337,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=64, help="batch of the bounded CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

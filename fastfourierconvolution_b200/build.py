@@ -16,12 +16,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libffc_b200.so")
-UNIT = os.path.join(CSRC, "ffc_lib.cu")
+UNITS = [os.path.join(CSRC, "ffc_unit_core.cu"), os.path.join(CSRC, "ffc_unit_fu.cu")]
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
     "-Xptxas=-v",
 ]
 
@@ -47,13 +47,26 @@ def find_nvcc() -> str:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
-    cmd = [find_nvcc()] + NVCC_FLAGS + ["-o", LIB + ".tmp", UNIT]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    nvcc = find_nvcc()
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    procs = []
+    for unit in UNITS:                                   # translation units compile in parallel
+        obj = os.path.join(objdir, os.path.basename(unit)[:-3] + ".o")
+        procs.append((obj, subprocess.Popen([nvcc] + NVCC_FLAGS + ["-c", "-o", obj, unit],
+                                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    log = ""
+    for obj, pr in procs:
+        out, err = pr.communicate()
+        log += err
+        if pr.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + out + err)
+    r = subprocess.run([nvcc, "-shared", "-o", LIB + ".tmp"] + [o for o, _ in procs], capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        raise RuntimeError("nvcc link failed:\n" + r.stdout + r.stderr)
     os.replace(LIB + ".tmp", LIB)
     if verbose:
-        sys.stderr.write(r.stderr)
+        sys.stderr.write(log)
     return LIB
 
 
@@ -65,7 +78,7 @@ def build_emulation(out_path: str) -> str:
         return out_path
     os.makedirs(os.path.dirname(out_path), exist_ok=True)
     cmd = ["g++", "-std=c++17", "-O2", "-DFFC_EMU", "-x", "c++", "-shared", "-fPIC",
-           "-ffp-contract=off", "-o", out_path + ".tmp", UNIT]
+           "-ffp-contract=off", "-o", out_path + ".tmp"] + UNITS
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("g++ (emulation build) failed:\n" + r.stdout + r.stderr)

@@ -56,11 +56,18 @@ class GanTrainer:
     generator update (G fwd, D fwd, backward through both, optimiser step), then discriminator
     update (G fwd without graph, D fwd x2, hinge loss, backward, optimiser step), then LR decay."""
 
-    def __init__(self, G, D, lr=2e-4, betas=(0.5, 0.999), num_total_steps=100000, optimizer="adamw"):
+    def __init__(self, G, D, lr=2e-4, betas=(0.5, 0.999), num_total_steps=100000, optimizer="adamw", capturable=False):
         self.G, self.D = G, D
         opt = torch.optim.AdamW if optimizer == "adamw" else torch.optim.Adam   # sngan_complete.py:247-248 uses Adam
-        self.optim_G = opt(G.parameters(), lr=lr, betas=betas)
-        self.optim_D = opt(D.parameters(), lr=lr, betas=betas)
+        kw = {}
+        if capturable:
+            # whole-step CUDA-graph capture: the optimiser keeps step counters and the learning rate on the device
+            dev = next(G.parameters()).device
+            kw = dict(capturable=True)
+            lr = torch.tensor(float(lr), device=dev)
+        self.optim_G = opt(G.parameters(), lr=lr.clone() if capturable else lr, betas=betas, **kw)
+        self.optim_D = opt(D.parameters(), lr=lr.clone() if capturable else lr, betas=betas, **kw)
+        self._graph = None
         decay = lambda step: 1.0 - step / num_total_steps                        # fgan_complete.py:318-319
         self.sched_G = torch.optim.lr_scheduler.LambdaLR(self.optim_G, decay)
         self.sched_D = torch.optim.lr_scheduler.LambdaLR(self.optim_D, decay)
@@ -89,6 +96,44 @@ class GanTrainer:
         loss_D.backward()
         self.allreduce_bytes += self.reduce_D()
         self.optim_D.step()
+        if self._capturing:
+            return loss_G.detach(), loss_D.detach()      # LR decay is applied outside the graph
         self.sched_G.step()
         self.sched_D.step()
         return loss_G.detach(), loss_D.detach()
+
+    # ---- whole-step CUDA graph (launch-bound at these layer sizes: ~500 kernels of a few microseconds each)
+    _capturing = False
+
+    def capture(self, z_g, z_d, real, warmup=3):
+        """Captures one training step into a CUDA graph on static input buffers shaped like the arguments.
+        The step is the same sequence of kernels as ``step``; only the host-side launch cost is removed."""
+        assert z_g.is_cuda, "graph capture needs CUDA tensors"
+        self._static = (z_g.clone(), z_d.clone(), real.clone())
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step(*self._static)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        from .. import _C
+        n0 = _C.lib().ffc_launch_count()
+        self._graph = torch.cuda.CUDAGraph()
+        self._capturing = True
+        try:
+            with torch.cuda.graph(self._graph):
+                self._static_losses = torch.stack(self.step(*self._static))
+        finally:
+            self._capturing = False
+        self.launches_per_step = _C.lib().ffc_launch_count() - n0
+        return self
+
+    def step_graphed(self, z_g, z_d, real):
+        """Copies the inputs (device or pinned host tensors) into the static buffers and replays the graph."""
+        for dst, src in zip(self._static, (z_g, z_d, real)):
+            dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        self.sched_G.step()
+        self.sched_D.step()
+        return self._static_losses

@@ -145,6 +145,11 @@ int ffc_se_bwd(const float* x, const float* dy, const float* w1, const float* w2
                int B, int C, int hid, int Hi, int Wi, int mode,
                void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- test hook ---------------------------------------------------------------------------------
+ * ffc_conv2d_fwd / ffc_conv2d_wgrad dispatch to the tuned kernels (register prefetch, double-buffered
+ * shared memory); on = 1 selects the simple single-buffered forms of the same math so tests can compare. */
+void ffc_debug_conv_reference(int on);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,11 +91,23 @@ CONV_CASES = [
     (2, [3], 5, 7, 3, 2, 1, False, False, False, 0),
     (2, [20], 130, 6, 3, 1, 1, True, True, False, 0),
     (1, [17], 1, 4, 4, 1, 0, False, False, False, 0),
+    (3, [40, 24], 100, 6, 4, 2, 1, True, True, True, 0),
+    (2, [33], 20, 9, 3, 1, 1, False, True, False, 0),
 ]
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
-def test_conv_forward_dgrad_wgrad(lib, case):
+@pytest.mark.parametrize("reference_form", [0, 1])
+def test_conv_forward_dgrad_wgrad(lib, case, reference_form):
+    """reference_form=0: the tuned double-buffered kernels; 1: the simple single-buffered forms."""
+    lib[0].ffc_debug_conv_reference(reference_form)
+    try:
+        _conv_case(lib, case)
+    finally:
+        lib[0].ffc_debug_conv_reference(0)
+
+
+def _conv_case(lib, case):
     B, cins, cout, Hi, k, s, p, tr, bias, addend, op = case
     torch.manual_seed(0)
     xs = [torch.randn(B, c, Hi, Hi) for c in cins]
