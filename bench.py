@@ -156,43 +156,66 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
-def time_fourier_unit(workload, per_rank_batch, dev, iters=20):
-    """FourierUnit forward+backward of the workload's largest unit, timed alone with CUDA events on
-    rotating inputs whose total footprint exceeds L2.  Returns the roofline dict pieces."""
+def _graph_time(fn, xs, replays=10):
+    """Device time per call of fn(x): one pass over the rotating inputs xs (total footprint > L2) is captured
+    into a CUDA graph and replayed; CUDA events bracket the replays on the replay stream."""
+    for x in xs[:2]:
+        fn(x)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            for x in xs:
+                fn(x)
+    torch.cuda.synchronize()
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(replays):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / (replays * len(xs))
+
+
+def time_fourier_unit(workload, per_rank_batch, dev):
+    """The fused FourierUnit kernels on the workload's largest unit, timed alone on the device."""
     import fastfourierconvolution_b200 as ffc
     from fastfourierconvolution_b200 import _C
     C, N = max(FU_SHAPES[workload], key=lambda s: s[0] * s[1] * s[1])
     B = per_rank_batch
     torch.manual_seed(0)
-    fu = ffc.FourierUnitSN(C, C).to(dev).train()
+    fu = ffc.FourierUnitSN(C, C).to(dev)
     bytes_in = 4 * B * C * N * N
-    nbuf = max(2, int(160e6 // bytes_in) + 1)             # > 126 MB L2 across the rotation
-    xs = [torch.randn(B, C, N, N, device=dev, requires_grad=True) for _ in range(nbuf)]
-    gs = [torch.randn(B, C, N, N, device=dev) for _ in range(min(nbuf, 4))]
-    for i in range(3):
-        fu(xs[i % nbuf]).backward(gs[i % len(gs)])
-    torch.cuda.synchronize(dev)
+    nbuf = min(max(2, int(160e6 // bytes_in) + 1), 24)          # rotation larger than the 126 MB L2
+    xs = [torch.randn(B, C, N, N, device=dev) for _ in range(nbuf)]
     L = _C.lib()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    n0 = L.ffc_launch_count()
-    t_f = t_b = 0.0
-    for i in range(iters):
-        x = xs[i % nbuf]
-        x.grad = None
-        ev[0].record()
-        y = fu(x)
-        ev[1].record()
-        y.backward(gs[i % len(gs)])
-        ev[2].record()
-        torch.cuda.synchronize(dev)
-        t_f += ev[0].elapsed_time(ev[1]); t_b += ev[1].elapsed_time(ev[2])
-    launches = (L.ffc_launch_count() - n0) / iters
-    ms_f, ms_b = t_f / iters, t_b / iters
+    out = {"C": C, "N": N, "B": B, "rotating_buffers": nbuf, "fused": bool(L.ffc_fu_fused_supported(B, C, C, N, N))}
+    with torch.no_grad():
+        fu.train()
+        n0 = L.ffc_launch_count()
+        fu(xs[0])
+        out["launches_fwd_train"] = L.ffc_launch_count() - n0
+        out["ms_fwd_train"] = _graph_time(lambda x: fu(x), xs)
+        fu.eval()
+        out["ms_fwd_eval"] = _graph_time(lambda x: fu(x), xs)
+    fu.train()
+    xg = [x.clone().requires_grad_(True) for x in xs[:max(2, nbuf // 3)]]
+    gy = torch.randn(B, C, N, N, device=dev)
+
+    def fwd_bwd(x):
+        return torch.autograd.grad(fu(x), (x, fu.conv_layer.weight, fu.bn.weight, fu.bn.bias), gy)
+    out["ms_fwd_bwd_train"] = _graph_time(fwd_bwd, xg)
     alg_f = 4.0 * B * N * N * (C + C)                      # SURVEY.md 8(d): fwd 4BHW(Cin+Cout)
-    alg_b = 4.0 * B * N * N * (C + 2 * C)                  # bwd 4BHW(Cout + 2Cin)
-    return {"C": C, "N": N, "B": B, "ms_fwd": ms_f, "ms_bwd": ms_b, "launches": launches,
-            "gbs_fwd": alg_f / ms_f / 1e6, "gbs_bwd": alg_b / ms_b / 1e6, "gbs": (alg_f + alg_b) / (ms_f + ms_b) / 1e6,
-            "alg_bytes": alg_f + alg_b, "rotating_buffers": nbuf}
+    alg_fb = 20.0 * B * C * N * N                          # fwd + bwd
+    out["alg_bytes_fwd"] = alg_f
+    out["gbs_fwd_train"] = alg_f / out["ms_fwd_train"] / 1e6
+    out["gbs_fwd_eval"] = alg_f / out["ms_fwd_eval"] / 1e6
+    out["gbs_fwd_bwd_train"] = alg_fb / out["ms_fwd_bwd_train"] / 1e6
+    return out
 
 
 def run_ours(args):
@@ -310,12 +333,17 @@ def run_ours(args):
                     "d2h_bytes_per_step": world * 8},
             "gpu_launches": int(round(launches * args.steps)),
             "gpu_launches_per_step": launches,
-            "roofline": {"bound": "hbm", "achieved": fu["gbs"], "peak": peak, "unit": "GB/s", "frac": fu["gbs"] / peak,
-                         "traffic": None, "peak_source": peak_src,
-                         "kernel": f"FourierUnitSN({fu['C']},{fu['C']}) fwd+bwd @ {fu['N']}x{fu['N']}, batch {fu['B']}: "
-                                   f"{fu['launches']:.0f} launches, fwd {fu['ms_fwd']*1000:.1f} us ({fu['gbs_fwd']:.0f} GB/s), "
-                                   f"bwd {fu['ms_bwd']*1000:.1f} us ({fu['gbs_bwd']:.0f} GB/s)",
-                         "algorithmic_bytes": fu["alg_bytes"]},
+            "roofline": {"bound": "hbm", "achieved": fu["gbs_fwd_train"], "peak": peak, "unit": "GB/s",
+                         "frac": fu["gbs_fwd_train"] / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": f"fused FourierUnit forward (FuFwdKernel stats pass + apply pass, {fu['launches_fwd_train']} launches) "
+                                   f"FourierUnitSN({fu['C']},{fu['C']}) @ {fu['N']}x{fu['N']}, batch {fu['B']}, training mode"
+                                   if fu["fused"] else "general-form FourierUnit forward (rfft2 | mix | BN+ReLU | irfft2)",
+                         "algorithmic_bytes_per_launch": fu["alg_bytes_fwd"],
+                         "us_per_launch": 1000 * fu["ms_fwd_train"],
+                         "eval_mode_single_pass": {"us": 1000 * fu["ms_fwd_eval"], "achieved": fu["gbs_fwd_eval"], "frac": fu["gbs_fwd_eval"] / peak},
+                         "fwd_plus_bwd": {"us": 1000 * fu["ms_fwd_bwd_train"], "achieved": fu["gbs_fwd_bwd_train"], "frac": fu["gbs_fwd_bwd_train"] / peak,
+                                          "algorithmic_bytes": 20.0 * fu["B"] * fu["C"] * fu["N"] * fu["N"]},
+                         "timing": "CUDA events around CUDA-graph replays of the op over %d rotating inputs (> L2)" % fu["rotating_buffers"]},
             "clocks": clocks,
         }
         if cpu:

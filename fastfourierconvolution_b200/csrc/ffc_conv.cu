@@ -179,53 +179,7 @@ struct ConvFwdKernel {
     }
 };
 
-// ---------------------------------------------------------------------------------------------
-// ConvFwdV2: the production forward / data-gradient kernel.  Same math as ConvFwdKernel (kept as the
-// simple reference form), restructured for FMA throughput:
-//   * K is ordered tap-major (tap, ci): a BK chunk shares one tap, so the gather address of a thread's pixel
-//     is computed once per chunk and advances by a constant channel stride;
-//   * register prefetch + two shared-memory buffers: the global loads of chunk c+1 are issued before the
-//     FMAs of chunk c and stored afterwards, one barrier per chunk;
-//   * 128 x BN CTA tile, 8 x TN register tile (TN = BN/16), float4 shared-memory reads that are conflict free.
-// ---------------------------------------------------------------------------------------------
-template <int BN>
-struct ConvFwdV2 {
-    typedef ConvParams Params;
-    static constexpr int BM = 128, BK = FFC_CONV_BK, TM = 8, TN = BN / 16;
-    static constexpr int kThreads = 256;
-    static constexpr int kMinBlocks = 2;
-    static constexpr int AS = BM + 4, BS = BN + 4;
-    static constexpr int A_PER = BK * BM / kThreads;          // 8 gathered inputs per thread per chunk
-    static constexpr int B_PER = BK * BN / kThreads;          // 4 / 2 / 1 weights per thread per chunk
-    static_assert(BN == 64 || BN == 32 || BN == 16, "BN");
-    static size_t smem_bytes() { return (size_t)2 * (BK * AS + BK * BS) * 4; }
-    struct Acc { float v[TM * TN]; };
-    struct Pix { int b, yq, xq; bool ok; };
-
-    static FFC_DEVICE void run(const Params& p, const BlockCtx& ctx, float* smem) {
-        float* As = smem;                       // [2][BK][AS]
-        float* Bs = smem + 2 * BK * AS;         // [2][BK][BS]
-        const int s = p.transposed ? p.stride : 1;
-        const int py = ctx.bz / s, px = ctx.bz % s;
-        const int Hc = (p.Ho - py + s - 1) / s, Wc = (p.Wo - px + s - 1) / s;
-        const int Mc = p.B * Hc * Wc;
-        const int m0 = ctx.bx * BM, n0 = ctx.by * BN;
-        int ky0 = 0, kx0 = 0, qy = 0, qx = 0, Ta = p.k, Tb = p.k;
-        if (p.transposed) {
-            ky0 = (py + p.pad) % s; kx0 = (px + p.pad) % s;
-            qy = (py + p.pad - ky0) / s; qx = (px + p.pad - kx0) / s;
-            Ta = ky0 < p.k ? (p.k - ky0 + s - 1) / s : 0;
-            Tb = kx0 < p.k ? (p.k - kx0 + s - 1) / s : 0;
-        }
-        const int T = Ta * Tb;
-        const int KK = p.k * p.k;
-        const int HWi = p.Hi * p.Wi;
-        const int cpk0 = (p.seg[0].cin + BK - 1) / BK;
-        const int cpk1 = p.nseg > 1 ? (p.seg[1].cin + BK - 1) / BK : 0;
-        const int nch0 = T * cpk0, nchunks = (m0 < Mc) ? T * (cpk0 + cpk1) : 0;
-
-        FFC_TLS(Acc, acc);
-        FFC_TLS(Pix, pix);
+// Chunk gather / scatter shared by ConvFwdV2 and ConvFwdV3 (expanded inside run(); they use its locals).
         // gathers chunk `c` into registers: ra[] (inputs of this thread's pixel) and rb[] (weights of its channel)
 #define FFC_CONV_LOAD_CHUNK(c, ra, rb)                                                                      \
         {                                                                                                   \
@@ -269,6 +223,54 @@ struct ConvFwdV2 {
             for (int i = 0; i < B_PER; ++i) bs_[(tid / BN + i * (kThreads / BN)) * BS + tid % BN] = rb[i];  \
         }
 
+
+// ---------------------------------------------------------------------------------------------
+// ConvFwdV2: the production forward / data-gradient kernel.  Same math as ConvFwdKernel (kept as the
+// simple reference form), restructured for FMA throughput:
+//   * K is ordered tap-major (tap, ci): a BK chunk shares one tap, so the gather address of a thread's pixel
+//     is computed once per chunk and advances by a constant channel stride;
+//   * register prefetch + two shared-memory buffers: the global loads of chunk c+1 are issued before the
+//     FMAs of chunk c and stored afterwards, one barrier per chunk;
+//   * 128 x BN CTA tile, 8 x TN register tile (TN = BN/16), float4 shared-memory reads that are conflict free.
+// ---------------------------------------------------------------------------------------------
+template <int BN>
+struct ConvFwdV2 {
+    typedef ConvParams Params;
+    static constexpr int BM = 128, BK = FFC_CONV_BK, TM = 8, TN = BN / 16, kBN = BN;
+    static constexpr int kThreads = 256;
+    static constexpr int kMinBlocks = 2;
+    static constexpr int AS = BM + 4, BS = BN + 4;
+    static constexpr int A_PER = BK * BM / kThreads;          // 8 gathered inputs per thread per chunk
+    static constexpr int B_PER = BK * BN / kThreads;          // 4 / 2 / 1 weights per thread per chunk
+    static_assert(BN == 64 || BN == 32 || BN == 16, "BN");
+    static size_t smem_bytes() { return (size_t)2 * (BK * AS + BK * BS) * 4; }
+    struct Acc { float v[TM * TN]; };
+    struct Pix { int b, yq, xq; bool ok; };
+
+    static FFC_DEVICE void run(const Params& p, const BlockCtx& ctx, float* smem) {
+        float* As = smem;                       // [2][BK][AS]
+        float* Bs = smem + 2 * BK * AS;         // [2][BK][BS]
+        const int s = p.transposed ? p.stride : 1;
+        const int py = ctx.bz / s, px = ctx.bz % s;
+        const int Hc = (p.Ho - py + s - 1) / s, Wc = (p.Wo - px + s - 1) / s;
+        const int Mc = p.B * Hc * Wc;
+        const int m0 = ctx.bx * BM, n0 = ctx.by * BN;
+        int ky0 = 0, kx0 = 0, qy = 0, qx = 0, Ta = p.k, Tb = p.k;
+        if (p.transposed) {
+            ky0 = (py + p.pad) % s; kx0 = (px + p.pad) % s;
+            qy = (py + p.pad - ky0) / s; qx = (px + p.pad - kx0) / s;
+            Ta = ky0 < p.k ? (p.k - ky0 + s - 1) / s : 0;
+            Tb = kx0 < p.k ? (p.k - kx0 + s - 1) / s : 0;
+        }
+        const int T = Ta * Tb;
+        const int KK = p.k * p.k;
+        const int HWi = p.Hi * p.Wi;
+        const int cpk0 = (p.seg[0].cin + BK - 1) / BK;
+        const int cpk1 = p.nseg > 1 ? (p.seg[1].cin + BK - 1) / BK : 0;
+        const int nch0 = T * cpk0, nchunks = (m0 < Mc) ? T * (cpk0 + cpk1) : 0;
+
+        FFC_TLS(Acc, acc);
+        FFC_TLS(Pix, pix);
         FFC_PHASE {
             FFC_TLS_REF(Acc, acc);
             FFC_TLS_REF(Pix, pix);
@@ -307,8 +309,6 @@ struct ConvFwdV2 {
                 if (more) FFC_CONV_STORE_CHUNK((c + 1) & 1, ra, rb);
             } FFC_SYNC;
         }
-#undef FFC_CONV_LOAD_CHUNK
-#undef FFC_CONV_STORE_CHUNK
         FFC_PHASE {
             FFC_TLS_REF(Acc, acc);
             const int tm = tid % 16, tn = tid / 16;
@@ -420,6 +420,235 @@ struct ConvWgradKernel {
                     const int n = n0 + tn * TN + j;
                     if (n >= Ntot) continue;
                     ffc_atomic_add(p.dW + (size_t)sc * Ntot + n, acc.v[i * TN + j]);
+                }
+            }
+        } FFC_SYNC;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// ConvFwdV3: ConvFwdV2's pipeline with the FMAs moved to the tensor cores at FP32 accuracy ("3xTF32"):
+// every FP32 operand x is split into hi = tf32(x), lo = tf32(x - hi) and a.b is accumulated as
+// a_lo.b_hi + a_hi.b_lo + a_hi.b_hi with mma.sync.m16n8k8 (FP32 accumulate); the dropped a_lo.b_lo term is
+// ~2^-22 relative.  8 warps = 4 (M) x 2 (N), warp tile 32 x (BN/2), fragments read straight from the FP32
+// shared-memory tiles (row strides = 8 mod 32 floats make the fragment loads bank-conflict free).
+// The emulation build computes each lane's accumulators directly from shared memory (same C-fragment
+// ownership, so the epilogue indexing is exercised; the A/B fragment layout is device-only).
+// ---------------------------------------------------------------------------------------------
+#ifndef FFC_EMU
+FFC_DEVICE unsigned ffc_tf32(float x) { unsigned r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+FFC_DEVICE void ffc_mma_tf32(float* c, const unsigned* a, const unsigned* b) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+#endif
+
+template <int BN>
+struct ConvFwdV3 {
+    typedef ConvParams Params;
+    static constexpr int BM = 128, BK = FFC_CONV_BK, kBN = BN;
+    static constexpr int kThreads = 256;
+    static constexpr int kMinBlocks = 2;
+    // shared tiles hold (hi, lo) TF32 pairs as float2; row strides = 4 mod 16 float2 keep the 64-bit fragment
+    // loads conflict free (lanes g = 0..7 are consecutive, the four t groups land 8 banks apart)
+    static constexpr int AS = BM + 4, BS = BN + 4;
+    static constexpr int A_PER = BK * BM / kThreads;
+    static constexpr int B_PER = BK * BN / kThreads;
+    static constexpr int MT = 2, NT = BN / 16;               // m16 / n8 tiles per warp
+    static_assert(BN == 64 || BN == 32 || BN == 16, "BN");
+    static size_t smem_bytes() { return (size_t)2 * (BK * AS + BK * BS) * 8; }
+    struct Acc { float v[MT * NT * 4]; };
+    struct State { int b, yq, xq, ok; int seg, tap, ta, tb, c0; };   // pixel of the A loader + chunk cursor
+
+    static FFC_DEVICE float2 split(float x) {
+#ifdef FFC_EMU
+        return make_float2(x, 0.f);
+#else
+        const unsigned hi = ffc_tf32(x);
+        return make_float2(__uint_as_float(hi), __uint_as_float(ffc_tf32(x - __uint_as_float(hi))));
+#endif
+    }
+
+    static FFC_DEVICE void run(const Params& p, const BlockCtx& ctx, float* smem) {
+        float2* As = reinterpret_cast<float2*>(smem);          // [2][BK][AS]
+        float2* Bs = As + 2 * BK * AS;                         // [2][BK][BS]
+        const int s = p.transposed ? p.stride : 1;
+        const int py = ctx.bz / s, px = ctx.bz % s;
+        const int Hc = (p.Ho - py + s - 1) / s, Wc = (p.Wo - px + s - 1) / s;
+        const int Mc = p.B * Hc * Wc;
+        const int m0 = ctx.bx * BM, n0 = ctx.by * BN;
+        int ky0 = 0, kx0 = 0, qy = 0, qx = 0, Ta = p.k, Tb = p.k;
+        if (p.transposed) {
+            ky0 = (py + p.pad) % s; kx0 = (px + p.pad) % s;
+            qy = (py + p.pad - ky0) / s; qx = (px + p.pad - kx0) / s;
+            Ta = ky0 < p.k ? (p.k - ky0 + s - 1) / s : 0;
+            Tb = kx0 < p.k ? (p.k - kx0 + s - 1) / s : 0;
+        }
+        const int T = Ta * Tb;
+        const int KK = p.k * p.k;
+        const int HWi = p.Hi * p.Wi;
+        const int cpk0 = (p.seg[0].cin + BK - 1) / BK;
+        const int cpk1 = p.nseg > 1 ? (p.seg[1].cin + BK - 1) / BK : 0;
+        const int nchunks = (m0 < Mc) ? T * (cpk0 + cpk1) : 0;
+
+        FFC_TLS(Acc, acc);
+        FFC_TLS(State, st);
+        // gather of the chunk under the cursor into registers, then the cursor advances (no integer division)
+#define FFC_V3_LOAD(ra, rb)                                                                                 \
+        {                                                                                                   \
+            const float* FFC_RESTRICT xs_ = st.seg ? p.seg[1].x : p.seg[0].x;                               \
+            const float* FFC_RESTRICT ws_ = st.seg ? p.seg[1].w : p.seg[0].w;                               \
+            const int cin_ = st.seg ? p.seg[1].cin : p.seg[0].cin;                                          \
+            int iy_, ix_;                                                                                   \
+            if (p.transposed) { iy_ = st.yq + qy - st.ta; ix_ = st.xq + qx - st.tb; }                       \
+            else { iy_ = st.yq * p.stride - p.pad + st.ta; ix_ = st.xq * p.stride - p.pad + st.tb; }        \
+            const bool okp_ = st.ok && iy_ >= 0 && iy_ < p.Hi && ix_ >= 0 && ix_ < p.Wi;                    \
+            /* 32-bit element offsets (tensor sizes < 2^31 are checked on the host): one IMAD.WIDE per load */ \
+            const int ca_ = st.c0 + tid / BM;                                                               \
+            const float* xp_ = xs_ + ((st.b * cin_ + ca_) * HWi + iy_ * p.Wi + ix_);                        \
+            const int xstep_ = (kThreads / BM) * HWi;                                                       \
+            const bool full_ = st.c0 + BK <= cin_;                                                          \
+            if (okp_ && full_) {                                                                            \
+                FFC_UNROLL                                                                                  \
+                for (int i = 0; i < A_PER; ++i) ra[i] = FFC_LDG(xp_ + i * xstep_);                          \
+            } else {                                                                                        \
+                FFC_UNROLL                                                                                  \
+                for (int i = 0; i < A_PER; ++i)                                                             \
+                    ra[i] = (okp_ && ca_ + i * (kThreads / BM) < cin_) ? FFC_LDG(xp_ + i * xstep_) : 0.f;   \
+            }                                                                                               \
+            const int co_ = n0 + tid % BN;                                                                  \
+            const int cb_ = st.c0 + tid / BN;                                                               \
+            const int woff_ = p.transposed ? (ky0 + s * st.ta) * p.k + (kx0 + s * st.tb) : st.ta * p.k + st.tb; \
+            const float* wp_ = ws_ + (p.transposed ? (cb_ * p.cout + co_) * KK + woff_ : (co_ * cin_ + cb_) * KK + woff_); \
+            const int wstep_ = (kThreads / BN) * (p.transposed ? p.cout * KK : KK);                         \
+            if (co_ < p.cout && full_) {                                                                    \
+                FFC_UNROLL                                                                                  \
+                for (int i = 0; i < B_PER; ++i) rb[i] = FFC_LDG(wp_ + i * wstep_);                          \
+            } else {                                                                                        \
+                FFC_UNROLL                                                                                  \
+                for (int i = 0; i < B_PER; ++i)                                                             \
+                    rb[i] = (co_ < p.cout && cb_ + i * (kThreads / BN) < cin_) ? FFC_LDG(wp_ + i * wstep_) : 0.f; \
+            }                                                                                               \
+            st.c0 += BK;                                                                                    \
+            if (st.c0 >= cin_) {                                                                            \
+                st.c0 = 0;                                                                                  \
+                if (++st.tb == Tb) { st.tb = 0; ++st.ta; }                                                  \
+                if (++st.tap == T) { st.tap = 0; st.ta = 0; st.tb = 0; ++st.seg; }                          \
+            }                                                                                               \
+        }
+#define FFC_V3_STORE(buf, ra, rb)                                                                           \
+        {                                                                                                   \
+            float2* as_ = As + (buf) * BK * AS;                                                             \
+            float2* bs_ = Bs + (buf) * BK * BS;                                                             \
+            FFC_UNROLL                                                                                      \
+            for (int i = 0; i < A_PER; ++i) as_[(tid / BM + i * (kThreads / BM)) * AS + tid % BM] = split(ra[i]); \
+            FFC_UNROLL                                                                                      \
+            for (int i = 0; i < B_PER; ++i) bs_[(tid / BN + i * (kThreads / BN)) * BS + tid % BN] = split(rb[i]); \
+        }
+
+        FFC_PHASE {
+            FFC_TLS_REF(Acc, acc);
+            FFC_TLS_REF(State, st);
+            FFC_UNROLL
+            for (int i = 0; i < MT * NT * 4; ++i) acc.v[i] = 0.f;
+            const int m = m0 + tid % BM;
+            st.ok = m < Mc;
+            st.xq = m % Wc; st.yq = (m / Wc) % Hc; st.b = m / (Wc * Hc);
+            st.seg = 0; st.tap = 0; st.ta = 0; st.tb = 0; st.c0 = 0;
+            if (nchunks > 0) {
+                float ra[A_PER], rb[B_PER];
+                FFC_V3_LOAD(ra, rb);
+                FFC_V3_STORE(0, ra, rb);
+            }
+        } FFC_SYNC;
+        for (int c = 0; c < nchunks; ++c) {
+            FFC_PHASE {
+                FFC_TLS_REF(Acc, acc);
+                FFC_TLS_REF(State, st);
+                float ra[A_PER], rb[B_PER];
+                const bool more = c + 1 < nchunks;
+                if (more) FFC_V3_LOAD(ra, rb);
+                const float2* as = As + (c & 1) * BK * AS;
+                const float2* bs = Bs + (c & 1) * BK * BS;
+                const int lane = tid & 31, warp = tid >> 5;
+                const int g = lane >> 2, t = lane & 3;
+                const int mw = (warp & 3) * 32, nw = (warp >> 2) * (BN / 2);
+#ifdef FFC_EMU
+                for (int mt = 0; mt < MT; ++mt)
+                    for (int nt_ = 0; nt_ < NT; ++nt_)
+                        for (int r = 0; r < 4; ++r) {
+                            const int row = mw + 16 * mt + g + (r >> 1) * 8, col = nw + 8 * nt_ + 2 * t + (r & 1);
+                            float sum = acc.v[(mt * NT + nt_) * 4 + r];
+                            for (int kl = 0; kl < BK; ++kl) {
+                                const float2 a = as[kl * AS + row], b = bs[kl * BS + col];
+                                sum = fmaf(a.x + a.y, b.x + b.y, sum);
+                            }
+                            acc.v[(mt * NT + nt_) * 4 + r] = sum;
+                        }
+#else
+                FFC_UNROLL
+                for (int k8 = 0; k8 < BK; k8 += 8) {
+                    unsigned ah[MT][4], al[MT][4], bh[NT][2], bl[NT][2];
+                    FFC_UNROLL
+                    for (int mt = 0; mt < MT; ++mt) {
+                        FFC_UNROLL
+                        for (int r = 0; r < 4; ++r) {
+                            const float2 x = as[(k8 + t + (r >> 1) * 4) * AS + mw + 16 * mt + g + (r & 1) * 8];
+                            ah[mt][r] = __float_as_uint(x.x);
+                            al[mt][r] = __float_as_uint(x.y);
+                        }
+                    }
+                    FFC_UNROLL
+                    for (int nt_ = 0; nt_ < NT; ++nt_) {
+                        FFC_UNROLL
+                        for (int r = 0; r < 2; ++r) {
+                            const float2 x = bs[(k8 + t + r * 4) * BS + nw + 8 * nt_ + g];
+                            bh[nt_][r] = __float_as_uint(x.x);
+                            bl[nt_][r] = __float_as_uint(x.y);
+                        }
+                    }
+                    FFC_UNROLL
+                    for (int mt = 0; mt < MT; ++mt)
+                        FFC_UNROLL
+                        for (int nt_ = 0; nt_ < NT; ++nt_) {
+                            float* cc = acc.v + (mt * NT + nt_) * 4;
+                            ffc_mma_tf32(cc, al[mt], bh[nt_]);
+                            ffc_mma_tf32(cc, ah[mt], bl[nt_]);
+                            ffc_mma_tf32(cc, ah[mt], bh[nt_]);
+                        }
+                }
+#endif
+                if (more) FFC_V3_STORE((c + 1) & 1, ra, rb);
+            } FFC_SYNC;
+        }
+#undef FFC_V3_LOAD
+#undef FFC_V3_STORE
+        FFC_PHASE {
+            FFC_TLS_REF(Acc, acc);
+            const int lane = tid & 31, warp = tid >> 5;
+            const int g = lane >> 2, t = lane & 3;
+            const int mw = (warp & 3) * 32, nw = (warp >> 2) * (BN / 2);
+            FFC_UNROLL
+            for (int mt = 0; mt < MT; ++mt) {
+                FFC_UNROLL
+                for (int h = 0; h < 2; ++h) {
+                    const int m = m0 + mw + 16 * mt + g + 8 * h;
+                    if (m >= Mc) continue;
+                    const int xq = m % Wc, yq = (m / Wc) % Hc, b = m / (Wc * Hc);
+                    const int oy = yq * s + py, ox = xq * s + px;
+                    FFC_UNROLL
+                    for (int nt_ = 0; nt_ < NT; ++nt_) {
+                        FFC_UNROLL
+                        for (int e = 0; e < 2; ++e) {
+                            const int co = n0 + nw + 8 * nt_ + 2 * t + e;
+                            if (co >= p.cout) continue;
+                            const size_t o = ((size_t)(b * p.cout + co) * p.Ho + oy) * p.Wo + ox;
+                            float v = acc.v[(mt * NT + nt_) * 4 + 2 * h + e];
+                            if (p.bias) v += FFC_LDG(p.bias + co);
+                            if (p.addend) v += FFC_LDG(p.addend + o);
+                            p.y[o] = v;
+                        }
+                    }
                 }
             }
         } FFC_SYNC;
@@ -569,13 +798,12 @@ static int conv_fwd_launch(const ConvParams& p, ffc_stream_t st) {
     return ffc_launch<K>(ffc_cdiv(Mc, BM), ffc_cdiv(p.cout, BN), s * s, K::kThreads, K::smem_bytes(), st, p);
 }
 
-template <int BN>
+template <class K>
 static int conv_fwd_v2_launch(const ConvParams& p, ffc_stream_t st) {
-    typedef ConvFwdV2<BN> K;
     const int s = p.transposed ? p.stride : 1;
     const int Hc = ffc_cdiv(p.Ho, s), Wc = ffc_cdiv(p.Wo, s);
     const int Mc = p.B * Hc * Wc;
-    return ffc_launch<K>(ffc_cdiv(Mc, K::BM), ffc_cdiv(p.cout, BN), s * s, K::kThreads, K::smem_bytes(), st, p);
+    return ffc_launch<K>(ffc_cdiv(Mc, K::BM), ffc_cdiv(p.cout, K::kBN), s * s, K::kThreads, K::smem_bytes(), st, p);
 }
 
 static int ffc_conv_use_reference_kernel = 0;
@@ -599,7 +827,9 @@ extern "C" int ffc_conv2d_fwd(const float* x0, const float* w0, int cin0,
                     "ffc_conv2d_fwd: transposed output size %dx%d inconsistent with input %dx%d k=%d s=%d p=%d", Ho, Wo, Hi, Wi, k, stride, pad);
     }
     if (B == 0) return FFC_OK;
-    FFC_REQUIRE((long long)B * Ho * Wo < (1LL << 31) && (long long)B * (cin0 + cin1) * Hi * Wi < (1LL << 31), "ffc_conv2d_fwd: tensor too large for 32-bit pixel indices");
+    FFC_REQUIRE((long long)B * cout * Ho * Wo < (1LL << 31) && (long long)B * (cin0 > cin1 ? cin0 : cin1) * Hi * Wi < (1LL << 31)
+                && (long long)cout * (cin0 > cin1 ? cin0 : cin1) * k * k < (1LL << 31),
+                "ffc_conv2d_fwd: tensor too large for 32-bit element offsets");
     ConvParams p;
     p.seg[0] = ConvSeg{x0, w0, cin0};
     p.seg[1] = ConvSeg{x1, w1, cin1};
@@ -608,17 +838,19 @@ extern "C" int ffc_conv2d_fwd(const float* x0, const float* w0, int cin0,
     p.B = B; p.cout = cout; p.Hi = Hi; p.Wi = Wi; p.Ho = Ho; p.Wo = Wo;
     p.k = k; p.stride = stride; p.pad = pad; p.transposed = transposed;
     ffc_stream_t st = (ffc_stream_t)stream;
-    if (ffc_conv_use_reference_kernel) {          // the simple single-buffered form (tests compare both)
+    if (ffc_conv_use_reference_kernel == 1) {     // the simple single-buffered form (tests compare all three)
         if (cout <= 8) return conv_fwd_launch<256, 8, 4, 2>(p, st);
         if (cout <= 32) return conv_fwd_launch<128, 32, 4, 4>(p, st);
         return conv_fwd_launch<64, 64, 4, 4>(p, st);
     }
-    if (cout <= 16) return conv_fwd_v2_launch<16>(p, st);
-    if (cout <= 32 || (cout > 64 && cout % 64 != 0 && cout % 64 <= 32 && cout < 128)) return conv_fwd_v2_launch<32>(p, st);
-    return conv_fwd_v2_launch<64>(p, st);
+    const bool simt = ffc_conv_use_reference_kernel == 2;
+    if (cout <= 16) return simt ? conv_fwd_v2_launch<ConvFwdV2<16>>(p, st) : conv_fwd_v2_launch<ConvFwdV3<16>>(p, st);
+    if (cout <= 32 || (cout > 64 && cout % 64 != 0 && cout % 64 <= 32 && cout < 128))
+        return simt ? conv_fwd_v2_launch<ConvFwdV2<32>>(p, st) : conv_fwd_v2_launch<ConvFwdV3<32>>(p, st);
+    return simt ? conv_fwd_v2_launch<ConvFwdV2<64>>(p, st) : conv_fwd_v2_launch<ConvFwdV3<64>>(p, st);
 }
 
-// test hook: 1 selects the simple reference-form kernels for ffc_conv2d_fwd
+// test hook: 0 tensor-core 3xTF32 kernels (default), 1 simple reference-form kernels, 2 tuned FP32 SIMT kernels
 extern "C" void ffc_debug_conv_reference(int on) { ffc_conv_use_reference_kernel = on; }
 
 extern "C" int ffc_conv2d_wgrad(const float* S, const float* L, float* dW,
@@ -634,7 +866,7 @@ extern "C" int ffc_conv2d_wgrad(const float* S, const float* L, float* dW,
     if (B == 0) return FFC_OK;
     WgradParams p{S, L, dW, B, SC, LC, Hs, Ws, Hl, Wl, k, stride, pad, 0};
     const int Ktot = B * Hs * Ws;
-    const bool ref = ffc_conv_use_reference_kernel != 0;
+    const bool ref = ffc_conv_use_reference_kernel == 1;
     const int BMt = 64, BNt = ref ? 64 : 128;
     const int gx = ffc_cdiv(SC, BMt), gy = ffc_cdiv(LC * k * k, BNt);
     // split K so that the grid has ~3 CTAs per SM (148 SMs), at least 8 K-steps per CTA

@@ -146,9 +146,10 @@ int ffc_se_bwd(const float* x, const float* dy, const float* w1, const float* w2
                void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- test hook ---------------------------------------------------------------------------------
- * ffc_conv2d_fwd / ffc_conv2d_wgrad dispatch to the tuned kernels (register prefetch, double-buffered
- * shared memory); on = 1 selects the simple single-buffered forms of the same math so tests can compare. */
-void ffc_debug_conv_reference(int on);
+ * Kernel family used by ffc_conv2d_fwd / ffc_conv2d_wgrad: 0 (default) tensor-core kernels at FP32 accuracy
+ * (3xTF32 mma, register prefetch, double-buffered shared memory); 1 the simple single-buffered FP32 forms of
+ * the same math; 2 the tuned FP32 SIMT kernels.  Tests compare all three. */
+void ffc_debug_conv_reference(int mode);
 
 #ifdef __cplusplus
 }

@@ -97,14 +97,21 @@ CONV_CASES = [
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
-@pytest.mark.parametrize("reference_form", [0, 1])
+@pytest.mark.parametrize("reference_form", [0, 1, 2])
 def test_conv_forward_dgrad_wgrad(lib, case, reference_form):
-    """reference_form=0: the tuned double-buffered kernels; 1: the simple single-buffered forms."""
+    """0: tensor-core 3xTF32 kernels (production); 1: the simple single-buffered forms; 2: tuned FP32 SIMT kernels."""
     lib[0].ffc_debug_conv_reference(reference_form)
+    _conv_mode[0] = reference_form if lib[1] != "cpu" else 1      # the emulation build computes every family in FP32
     try:
         _conv_case(lib, case)
     finally:
         lib[0].ffc_debug_conv_reference(0)
+
+
+# 3xTF32 on the tensor cores: the dropped lo*lo term and the MMA's internal accumulation leave ~1e-5
+# (still an order of magnitude inside the 1e-4 FP32 parity bound); the FP32 FMA families reach ~1e-7.
+CONV_TOL = {0: 4e-5, 1: 3e-6, 2: 3e-6}
+_conv_mode = [0]
 
 
 def _conv_case(lib, case):
@@ -128,7 +135,7 @@ def _conv_case(lib, case):
     x1, w1 = (xs[1], ws[1]) if len(xs) > 1 else (None, None)
     call(lib, "ffc_conv2d_fwd", xs[0], ws[0], cins[0], x1, w1, cins[1] if x1 is not None else 0, b, ad, y,
                                B, cout, Hi, Hi, Ho, Ho, k, s, p, int(tr), None)
-    assert parity.relerr(y, ref) < 2e-6
+    assert parity.relerr(y, ref) < CONV_TOL[_conv_mode[0]]
     dy = torch.randn(B, cout, Ho, Ho)
     for x, w in zip(xs, ws):
         xd, wd = x.double().requires_grad_(True), w.double().requires_grad_(True)
@@ -138,9 +145,9 @@ def _conv_case(lib, case):
             call(lib, "ffc_conv2d_wgrad", x, dy, dW, B, x.shape[1], cout, Hi, Hi, Ho, Ho, k, s, p, None)
         else:
             call(lib, "ffc_conv2d_wgrad", dy, x, dW, B, cout, x.shape[1], Ho, Ho, Hi, Hi, k, s, p, None)
-        assert parity.relerr(dW, wd.grad) < 3e-6
+        assert parity.relerr(dW, wd.grad) < 3e-6          # wgrad is FP32 FMA in every family
         call(lib, "ffc_conv2d_fwd", dy, w, cout, None, None, 0, None, None, dx, B, x.shape[1], Ho, Ho, Hi, Hi, k, s, p, int(not tr), None)
-        assert parity.relerr(dx, xd.grad) < 3e-6
+        assert parity.relerr(dx, xd.grad) < CONV_TOL[_conv_mode[0]]
 
 
 ACTS = {0: lambda z: z, 1: F.relu, 2: lambda z: F.leaky_relu(z, 0.1), 3: F.gelu, 4: torch.tanh, 5: torch.sigmoid}
