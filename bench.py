@@ -351,7 +351,10 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush()
+        # NCCL communicator teardown can block while captured graphs still hold its kernels: leave without it
+        os._exit(0)
 
 
 def main():
