@@ -97,6 +97,21 @@ static int ffc_launch(int gx, int gy, int gz, int nt, size_t smem_bytes, ffc_str
     ffc_count_launch();
     return FFC_OK;
 }
+// cooperative two-part kernels (a grid-wide barrier between K::part0 and K::part1): every block keeps its own
+// shared memory alive across the barrier, exactly like co-resident CTAs do on the device
+template <class K>
+static int ffc_launch_coop(int gx, int nt, size_t smem_bytes, ffc_stream_t, const typename K::Params& p) {
+    std::vector<std::vector<float4>> smem((size_t)gx, std::vector<float4>((smem_bytes + 15) / 16 + 1));
+    for (int part = 0; part < 2; ++part)
+        for (int bx = 0; bx < gx; ++bx) {
+            BlockCtx ctx{bx, 0, 0, gx, 1, 1, nt};
+            if (part == 0) K::part0(p, ctx, reinterpret_cast<float*>(smem[bx].data()));
+            else K::part1(p, ctx, reinterpret_cast<float*>(smem[bx].data()));
+        }
+    ffc_count_launch();
+    return FFC_OK;
+}
+template <class K> static int ffc_coop_capacity_blocks(int, size_t) { return 1 << 30; }
 static inline int ffc_memset_async(void* p, int v, size_t n, ffc_stream_t) { memset(p, v, n); return FFC_OK; }
 #else
 // ------------------------------------------------------------------ launch (device)
@@ -136,6 +151,41 @@ static int ffc_launch(int gx, int gy, int gz, int nt, size_t smem_bytes, ffc_str
     ffc_kernel<K><<<dim3(gx, gy, gz), dim3(nt), smem_bytes, stream>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { ffc_set_error("kernel launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
+    ffc_count_launch();
+    return FFC_OK;
+}
+// ---- cooperative two-part kernels: part0, grid-wide barrier, part1 (all CTAs co-resident)
+#include <cooperative_groups.h>
+template <class K>
+__global__ void __launch_bounds__(K::kThreads, FfcMinBlocks<K>::v) ffc_kernel_coop(const typename K::Params p) {
+    extern __shared__ float4 ffc_smem4[];
+    BlockCtx ctx{(int)blockIdx.x, 0, 0, (int)gridDim.x, 1, 1, (int)blockDim.x};
+    K::part0(p, ctx, reinterpret_cast<float*>(ffc_smem4));
+    cooperative_groups::this_grid().sync();
+    K::part1(p, ctx, reinterpret_cast<float*>(ffc_smem4));
+}
+// how many CTAs of this kernel can be resident at once on the current device (0 on error)
+template <class K>
+static int ffc_coop_capacity_blocks(int nt, size_t smem_bytes) {
+    static size_t configured_smem = 0;
+    if (smem_bytes > configured_smem) {
+        if (smem_bytes > 48 * 1024 &&
+            cudaFuncSetAttribute(ffc_kernel_coop<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) return 0;
+        if (cudaFuncSetAttribute(ffc_kernel_coop<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) return 0;
+        configured_smem = smem_bytes;
+    }
+    int dev = 0, sms = 0, per_sm = 0, coop = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (!coop || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ffc_kernel_coop<K>, nt, smem_bytes) != cudaSuccess) return 0;
+    return per_sm * sms;
+}
+template <class K>
+static int ffc_launch_coop(int gx, int nt, size_t smem_bytes, ffc_stream_t stream, const typename K::Params& p) {
+    void* args[] = {(void*)&p};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)ffc_kernel_coop<K>, dim3(gx), dim3(nt), args, smem_bytes, stream);
+    if (e != cudaSuccess) { ffc_set_error("cooperative launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
     ffc_count_launch();
     return FFC_OK;
 }

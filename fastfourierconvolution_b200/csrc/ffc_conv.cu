@@ -611,10 +611,15 @@ struct ConvFwdV3 {
                     for (int mt = 0; mt < MT; ++mt)
                         FFC_UNROLL
                         for (int nt_ = 0; nt_ < NT; ++nt_) {
+                            // The three products of one k8 step are summed in a fresh accumulator and folded into the
+                            // running FP32 sum with a round-to-nearest FADD: the tensor core aligns (truncates) its
+                            // addend, which over a long K would cost ~1e-5; per-step folding keeps the error ~1e-6.
+                            float tmp[4] = {0.f, 0.f, 0.f, 0.f};
+                            ffc_mma_tf32(tmp, al[mt], bh[nt_]);
+                            ffc_mma_tf32(tmp, ah[mt], bl[nt_]);
+                            ffc_mma_tf32(tmp, ah[mt], bh[nt_]);
                             float* cc = acc.v + (mt * NT + nt_) * 4;
-                            ffc_mma_tf32(cc, al[mt], bh[nt_]);
-                            ffc_mma_tf32(cc, ah[mt], bl[nt_]);
-                            ffc_mma_tf32(cc, ah[mt], bh[nt_]);
+                            cc[0] += tmp[0]; cc[1] += tmp[1]; cc[2] += tmp[2]; cc[3] += tmp[3];
                         }
                 }
 #endif

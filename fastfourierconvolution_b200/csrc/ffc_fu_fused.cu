@@ -49,6 +49,47 @@ struct FuFwdKernel {
     }
 
     static FFC_DEVICE void run(const Params& p, const BlockCtx& ctx, float* smem) {
+        const int ntiles = (p.B + p.imgs - 1) / p.imgs;
+        run_tiles(p, ctx, smem, ctx.bx, ntiles);
+    }
+
+    // inverse columns + rows of the tile's Cout planes (in place) and the coalesced, batched store
+    static FFC_DEVICE void inverse_and_store(const Params& p, const BlockCtx& ctx, float* spec, int img0, int ni, PlaneMap map_out) {
+        const int nt = ctx.nt, Cout = p.Cout;
+        FFC_PHASE { fft2_cols_L1<N, N, +1, SPS>(tid, nt, ni * Cout, spec, map_out); } FFC_SYNC;
+        FFC_PHASE { fft2_rows_inv_L1<N, N, SPS>(tid, nt, ni * Cout, spec, spec, 1.0f, map_out, map_out); } FFC_SYNC;
+        FFC_PHASE {
+            constexpr int per = N * (N / 4);
+            constexpr int LDU = 8;
+            const int total = ni * Cout * per;
+            const size_t g0 = (size_t)img0 * Cout * N * N;
+            float4* dst = reinterpret_cast<float4*>(p.out + g0);
+            const float4* res = p.residual ? reinterpret_cast<const float4*>(p.residual + g0) : nullptr;
+            for (int i0 = tid; i0 < total; i0 += nt * LDU) {
+                float4 q[LDU];
+                if (res) {
+                    FFC_UNROLL
+                    for (int u = 0; u < LDU; ++u) {
+                        const int i = i0 + u * nt;
+                        if (i < total) q[u] = FFC_LDG(res + i);
+                    }
+                }
+                FFC_UNROLL
+                for (int u = 0; u < LDU; ++u) {
+                    const int i = i0 + u * nt;
+                    if (i < total) {
+                        const int pl = i / per, rem = i % per, h = rem / (N / 4), j = rem % (N / 4);
+                        float4 v = *reinterpret_cast<const float4*>(spec + (size_t)map_out(pl) * PL::REGION + h * PL::RS + 4 * j);
+                        if (res) { v.x += q[u].x; v.y += q[u].y; v.z += q[u].z; v.w += q[u].w; }
+                        dst[i] = v;
+                    }
+                }
+            }
+        } FFC_SYNC;
+    }
+
+    // tiles [t_begin, t_end) with stride gridDim.x starting at t_begin (t_end = t_begin + 1: exactly one tile)
+    static FFC_DEVICE void run_tiles(const Params& p, const BlockCtx& ctx, float* smem, int t_begin, int t_end) {
         const int Cin = p.Cin, Cout = p.Cout;
         const int CB = Cin > Cout ? Cin : Cout;
         const int nt = ctx.nt;
@@ -60,7 +101,6 @@ struct FuFwdKernel {
         float* bn_b = bn_a + 2 * Cout;
         const float scale = 1.0f / (float)N;                    // ortho: 1/sqrt(N*N), applied once per direction
         const double count = (double)p.B * BINS;
-        const int ntiles = (p.B + p.imgs - 1) / p.imgs;
         const int S = nt / Cout;                                // stats: slices per complex channel
         // identity maps (no runtime integer division) in the usual Cin == Cout case
         PlaneMap map_in; map_in.cn = (Cin == CB) ? 0 : Cin; map_in.cb = CB;
@@ -108,7 +148,7 @@ struct FuFwdKernel {
             }
         }   // no barrier: the first tile's load phase writes a different shared region and ends with one
 
-        for (int tile = ctx.bx; tile < ntiles; tile += ctx.gx) {
+        for (int tile = t_begin; tile < t_end; tile += ctx.gx) {
             const int img0 = tile * p.imgs;
             const int ni = (p.B - img0) < p.imgs ? (p.B - img0) : p.imgs;
             // ---- coalesced load of the tile's planes into the real layout.  LDU float4 loads are issued
@@ -204,36 +244,7 @@ struct FuFwdKernel {
                     }
                 } FFC_SYNC;
             } else {
-                FFC_PHASE { fft2_cols_L1<N, N, +1, SPS>(tid, nt, ni * Cout, spec, map_out); } FFC_SYNC;
-                FFC_PHASE { fft2_rows_inv_L1<N, N, SPS>(tid, nt, ni * Cout, spec, spec, 1.0f, map_out, map_out); } FFC_SYNC;
-                FFC_PHASE {
-                    constexpr int per = N * (N / 4);
-                    constexpr int LDU = 8;
-                    const int total = ni * Cout * per;
-                    const size_t g0 = (size_t)img0 * Cout * N * N;
-                    float4* dst = reinterpret_cast<float4*>(p.out + g0);
-                    const float4* res = p.residual ? reinterpret_cast<const float4*>(p.residual + g0) : nullptr;
-                    for (int i0 = tid; i0 < total; i0 += nt * LDU) {
-                        float4 q[LDU];
-                        if (res) {
-                            FFC_UNROLL
-                            for (int u = 0; u < LDU; ++u) {
-                                const int i = i0 + u * nt;
-                                if (i < total) q[u] = FFC_LDG(res + i);
-                            }
-                        }
-                        FFC_UNROLL
-                        for (int u = 0; u < LDU; ++u) {
-                            const int i = i0 + u * nt;
-                            if (i < total) {
-                                const int pl = i / per, rem = i % per, h = rem / (N / 4), j = rem % (N / 4);
-                                float4 v = *reinterpret_cast<const float4*>(spec + (size_t)map_out(pl) * PL::REGION + h * PL::RS + 4 * j);
-                                if (res) { v.x += q[u].x; v.y += q[u].y; v.z += q[u].z; v.w += q[u].w; }
-                                dst[i] = v;
-                            }
-                        }
-                    }
-                } FFC_SYNC;
+                inverse_and_store(p, ctx, spec, img0, ni, map_out);
             }
         }
         if (PASS == 0) {
@@ -259,9 +270,93 @@ struct FuFwdKernel {
 };
 
 // ---------------------------------------------------------------------------------------------
+// Training-mode forward in ONE pass: when every image tile of the batch fits on the chip at once (B200: 148 SMs x
+// up to 227 KB of shared memory), the mixed spectrum simply stays in shared memory across a grid-wide barrier while
+// the BatchNorm statistics are finished, instead of being recomputed from x by a second pass.
+//   part0: load -> rfft2 -> mix -> per-channel sum / sum^2 -> atomics          (spectrum kept in smem)
+//   ---- cooperative grid barrier ----
+//   part1: BN constants -> normalise + ReLU in place -> irfft2 -> (+residual) store
+// One tile per CTA (grid == number of tiles); the host falls back to the two-pass form when the grid does not fit.
+// ---------------------------------------------------------------------------------------------
+template <int N, int CP>
+struct FuFwdCoop {
+    typedef FuFwdParams Params;
+    typedef FuFwdKernel<N, CP, 0> Base;
+    typedef Fft2Plan<N, N> PL;
+    static constexpr int kThreads = Base::kThreads;
+    static constexpr int kMinBlocks = Base::kMinBlocks;
+    static constexpr int Wf = PL::Wf, SPS = Base::SPS, BINS = Base::BINS;
+
+    struct Lay { float* spec; double* red; float* wq; float* bn_mu; float* bn_a; float* bn_b; int CB; };
+    static FFC_DEVICE Lay layout(const Params& p, int nt, float* smem) {
+        Lay l;
+        l.CB = p.Cin > p.Cout ? p.Cin : p.Cout;
+        l.spec = smem;
+        l.red = reinterpret_cast<double*>(smem + (size_t)p.imgs * l.CB * PL::REGION);
+        l.wq = reinterpret_cast<float*>(l.red) + (size_t)nt * 8;
+        l.bn_mu = l.wq + (size_t)p.Cout * CP * 4;
+        l.bn_a = l.bn_mu + 2 * p.Cout;
+        l.bn_b = l.bn_a + 2 * p.Cout;
+        return l;
+    }
+
+    static FFC_DEVICE void part0(const Params& p, const BlockCtx& ctx, float* smem) {
+        // identical to the stats pass over the single tile ctx.bx; the spectrum (mixed, not normalised) stays in smem
+        Params q = p;
+        FuFwdKernel<N, CP, 0>::run_tiles(q, ctx, smem, ctx.bx, ctx.bx + 1);
+    }
+
+    static FFC_DEVICE void part1(const Params& p, const BlockCtx& ctx, float* smem) {
+        const int Cin = p.Cin, Cout = p.Cout, nt = ctx.nt;
+        const Lay l = layout(p, nt, smem);
+        const int CB = l.CB;
+        const float scale = 1.0f / (float)N;
+        const double count = (double)p.B * BINS;
+        const int img0 = ctx.bx * p.imgs;
+        const int ni = (p.B - img0) < p.imgs ? (p.B - img0) : p.imgs;
+        PlaneMap map_out; map_out.cn = (Cout == CB) ? 0 : Cout; map_out.cb = CB;
+        (void)Cin;
+        FFC_PHASE {
+            for (int o = tid; o < 2 * Cout; o += nt) {
+                const double m = p.sums[o] / count;
+                double var = p.sums[2 * Cout + o] / count - m * m;
+                if (var < 0.0) var = 0.0;
+                const float mean = (float)m;
+                const float invstd = 1.0f / sqrtf((float)var + p.eps);
+                if (ctx.bx == 0) {
+                    p.save_mean[o] = mean; p.save_invstd[o] = invstd;
+                    if (p.running_mean) {
+                        const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+                        p.running_mean[o] = (1.f - p.momentum) * p.running_mean[o] + p.momentum * mean;
+                        p.running_var[o] = (1.f - p.momentum) * p.running_var[o] + p.momentum * (float)unb;
+                    }
+                }
+                l.bn_mu[o] = mean;
+                l.bn_a[o] = invstd * FFC_LDG(p.gamma + o) * scale;
+                l.bn_b[o] = FFC_LDG(p.beta + o) * scale;
+            }
+        } FFC_SYNC;
+        FFC_PHASE {      // normalise + ReLU in place over the Cout spectrum planes of the tile
+            for (int it = tid; it < ni * Cout * BINS; it += nt) {
+                const int bin = it % BINS, c2 = (it / BINS) % Cout, im = it / (BINS * Cout);
+                float2* q = reinterpret_cast<float2*>(l.spec + (size_t)(im * CB + c2) * PL::REGION) + (bin / Wf) * SPS + (bin % Wf);
+                float2 y = *q;
+                y.x = (y.x - l.bn_mu[2 * c2]) * l.bn_a[2 * c2] + l.bn_b[2 * c2];
+                y.y = (y.y - l.bn_mu[2 * c2 + 1]) * l.bn_a[2 * c2 + 1] + l.bn_b[2 * c2 + 1];
+                *q = make_float2(y.x > 0.f ? y.x : 0.f, y.y > 0.f ? y.y : 0.f);
+            }
+        } FFC_SYNC;
+        FuFwdKernel<N, CP, 1>::inverse_and_store(p, ctx, l.spec, img0, ni, map_out);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 struct FuPlan { int imgs, nt, grid; size_t smem; bool ok; };
+static int ffc_fu_force_two_pass = 0;
+// test hook: 1 disables the cooperative single-pass training forward (the two-pass form is then used for every batch)
+extern "C" void ffc_debug_fu_two_pass(int on) { ffc_fu_force_two_pass = on; }
 
 template <int N, int CP>
 static FuPlan fu_plan(int B, int Cin, int Cout) {
@@ -307,6 +402,9 @@ static int fu_fwd_launch(const FuFwdParams& p0, ffc_stream_t st) {
     p.imgs = pl.imgs;
     if (p.training) {
         FFC_CHECK(ffc_memset_async(p.sums, 0, (size_t)4 * p.Cout * sizeof(double), st));
+        const int ntiles = (p.B + pl.imgs - 1) / pl.imgs;
+        if (!ffc_fu_force_two_pass && ntiles <= ffc_coop_capacity_blocks<FuFwdCoop<N, CP>>(pl.nt, pl.smem))
+            return ffc_launch_coop<FuFwdCoop<N, CP>>(ntiles, pl.nt, pl.smem, st, p);      // single pass, spectrum held on chip
         FFC_CHECK((ffc_launch<FuFwdKernel<N, CP, 0>>(pl.grid, 1, 1, pl.nt, pl.smem, st, p)));
     }
     return ffc_launch<FuFwdKernel<N, CP, 1>>(pl.grid, 1, 1, pl.nt, pl.smem, st, p);

@@ -150,6 +150,9 @@ int ffc_se_bwd(const float* x, const float* dy, const float* w1, const float* w2
  * (3xTF32 mma, register prefetch, double-buffered shared memory); 1 the simple single-buffered FP32 forms of
  * the same math; 2 the tuned FP32 SIMT kernels.  Tests compare all three. */
 void ffc_debug_conv_reference(int mode);
+/* Training-mode ffc_fu_fwd runs as ONE cooperative kernel (spectrum held in shared memory across a grid barrier)
+ * when all image tiles are co-resident, else as two passes over x; on = 1 forces the two-pass form. */
+void ffc_debug_fu_two_pass(int on);
 
 #ifdef __cplusplus
 }

@@ -52,8 +52,19 @@ def test_model_matches_reference_golden(name, fn):
     assert max(errs.values()) < 2e-4, errs       # reference's own FP32-vs-FP64 spread is ~6e-5 here
 
 
-def _oracle_vs_module(mod, cfg_fn, xs, train=True, tol=parity.TOL, seed=0):
-    """Random-init module on the GPU vs the float64 oracle on the same weights and inputs."""
+def _rel_l2(got, ref):
+    got, ref = got.double().cpu(), ref.double().cpu()
+    return ((got - ref).norm() / ref.norm().clamp_min(1e-30)).item()
+
+
+def _oracle_vs_module(mod, cfg_fn, xs, train=True, tol=parity.TOL, seed=0, whole_model=False):
+    """Random-init module on the GPU vs the float64 oracle on the same weights and inputs.
+
+    whole_model=True (deep networks at tiny batch): outputs are still held to ``parity.TOL`` in the max norm, but
+    gradients are measured in the relative L2 norm (< 1e-3).  One ReLU / BatchNorm mask element that flips between two
+    FP32-accurate implementations moves individual whole-model gradient entries by ~1e-2 of the max (SURVEY.md section 8(c)
+    caveat 1) while leaving the L2 norm untouched; the strict 1e-4 max-norm bound on gradients is enforced per module by
+    the golden and config-shape tests above."""
     torch.manual_seed(seed)
     mod.train(train)
     sd = {k: v.detach().clone() for k, v in mod.state_dict().items()}
@@ -88,7 +99,10 @@ def _oracle_vs_module(mod, cfg_fn, xs, train=True, tol=parity.TOL, seed=0):
             sib = sib if sib in P and P[sib].grad is not None else k[:-4] + "weight_orig"
             if sib in P and P[sib].grad is not None:
                 floor = P[sib].grad.abs().max().item()
-        errs["grad/" + k] = parity.relerr(p.grad, P[k].grad, floor)
+        errs["grad/" + k] = _rel_l2(p.grad, P[k].grad) if (whole_model and floor == 0.0) else parity.relerr(p.grad, P[k].grad, floor)
+    if whole_model:
+        for i, (a, b) in enumerate(zip(xg, xd)):
+            errs[f"din{i}"] = _rel_l2(a.grad, b.grad)
     for k, b in mod.named_buffers():
         if b.is_floating_point():
             errs["post/" + k] = parity.relerr(b, P[k])
@@ -104,22 +118,28 @@ FU_SHAPES = [(8, 8, 32), (8, 16, 16), (8, 32, 8), (8, 8, 64), (4, 64, 16), (4, 3
 
 @pytest.mark.parametrize("B,C,N", FU_SHAPES)
 @pytest.mark.parametrize("train", [True, False])
-@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("fused", [True, False, "two_pass"])
 def test_fourier_unit_config_shapes(B, C, N, train, fused):
     """fused=True: ffc_fu_fwd where the shape is supported (general form otherwise); fused=False forces
     the general rfft2 | mix | BN+ReLU | irfft2 form, so both code paths are checked on every shape."""
     torch.manual_seed(C * 1000 + N)
     if fused and not ops.fu_fused_supported(B, C, C, N, N):
         pytest.skip("shape not covered by the fused kernel (general form is tested by fused=False)")
+    if fused == "two_pass" and not train:
+        pytest.skip("eval mode is always a single pass")
     mod = ffc.FourierUnitSN(C, C)
-    mod.fused = fused
+    mod.fused = bool(fused)
     with torch.no_grad():
         mod.bn.running_mean.normal_(0, 0.1)
         mod.bn.running_var.uniform_(0.5, 1.5)
         mod.bn.weight.uniform_(0.5, 1.5)
         mod.bn.bias.normal_(0, 0.1)
     x = torch.randn(B, C, N, N)
-    _oracle_vs_module(mod, lambda P, xs, tr: R.fourier_unit(xs[0], P, "", tr), [x], train)
+    _C.lib().ffc_debug_fu_two_pass(1 if fused == "two_pass" else 0)      # default: cooperative single pass when it fits
+    try:
+        _oracle_vs_module(mod, lambda P, xs, tr: R.fourier_unit(xs[0], P, "", tr), [x], train)
+    finally:
+        _C.lib().ffc_debug_fu_two_pass(0)
 
 
 @pytest.mark.parametrize("cin,cout,N,stride,up", [(64, 32, 16, 1, False), (32, 16, 16, 2, True), (16, 32, 32, 2, False),
@@ -145,11 +165,50 @@ def test_generator_fgan32_random_init_vs_oracle():
     g = H.FGenerator(128, 4, "fgan32")
     g.apply(H.weights_init)          # NoiseInjection weights stay 0 (as at the start of the reference's training)
     z = torch.randn(16, 128)
-    # Whole network, N(0, 0.02) weights: pre-activations sit close to 0, and one flipped ReLU mask element
-    # (FP32 vs FP64 rounding) moves a whole-model gradient by ~1e-3 (SURVEY.md section 8(c) caveat 1); the 1e-4
-    # bound on gradients is pinned per module above, here it is asserted on the output only.
-    errs = _oracle_vs_module(g, lambda P, xs, tr: R.fgenerator(xs[0], P, tr, "fgan32"), [z], tol=3e-3)
+    errs = _oracle_vs_module(g, lambda P, xs, tr: R.fgenerator(xs[0], P, tr, "fgan32"), [z], tol=1e-3, whole_model=True)
     assert errs["out0"] < parity.TOL
+
+
+@pytest.mark.parametrize("variant,B", [("fgan64", 4), ("fgan128", 2)])
+def test_generator_fgan64_fgan128_vs_oracle(variant, B):
+    """Configs 3 and 4: fgan64_complete.py / fgan128_complete.py generators (multi-tile 64x64 and 128x128 spectra
+    go through the general-form Fourier unit), forward + backward at a small batch."""
+    torch.manual_seed(2)
+    g = H.FGenerator(128, 4, variant)
+    g.apply(H.weights_init)
+    z = torch.randn(B, 128)
+    errs = _oracle_vs_module(g, lambda P, xs, tr: R.fgenerator(xs[0], P, tr, variant), [z], tol=1e-3, whole_model=True)
+    assert errs["out0"] < parity.TOL
+
+
+def test_sngan_ffc_discriminator_vs_oracle():
+    """sngan_complete.py FDiscriminator (FFC downsampling direction, bias=True, BN, LeakyReLU, SN Linear head)."""
+    torch.manual_seed(3)
+    d = H.FDiscriminator(True, 4)
+    x = torch.rand(8, 3, 32, 32) * 2 - 1
+    errs = _oracle_vs_module(d, lambda P, xs, tr: R.sngan_fdiscriminator(xs[0], P, tr), [x], tol=1e-3, whole_model=True)
+    assert errs["out0"] < parity.TOL
+
+
+def test_config1_ffc_generator_and_discriminator_vs_oracle():
+    """Config 1: models/ffc_generator.py FFCGenerator(100, 1, 32) forward + backward, batch 8 (reference batch 128)."""
+    torch.manual_seed(4)
+    g = H.FFCGenerator(100, 1, 32)
+    z = torch.randn(8, 100, 1, 1)
+    errs = _oracle_vs_module(g, lambda P, xs, tr: R.ffc_generator(xs[0], P, tr), [z], tol=1e-3, whole_model=True)
+    assert errs["out0"] < parity.TOL
+
+
+def test_snffc_transpose_matches_ffc_transpose_with_spectral_norm():
+    """SNFFCTranspose cannot be constructed in the reference (snffc_transpose.py:28); its evident intent is checked
+    against the oracle's FFCTranspose with spectral norm on the three transposed convs and on ST conv1/conv2."""
+    torch.manual_seed(5)
+    m = ffc.SNFFCTranspose(32, 16, 4, .25, .25, 2, 1)
+    keys = set(m.state_dict())
+    assert {"convl2l.weight_orig", "convl2l.weight_u", "convg2g.conv1.weight_orig", "convg2g.fu.conv_layer.weight"} <= keys
+    cfg = R.FFCConfig(32, 16, 4, .25, .25, 2, 1, upsampling=True, spectral_norm=True)
+    xs = [torch.randn(4, 24, 8, 8), torch.randn(4, 8, 8, 8)]
+    _oracle_vs_module(m, lambda P, x, tr: R.ffc(tuple(x), P, "", cfg, tr), xs)
 
 
 # ---- size-independent properties at full BASELINE sizes ---------------------------------------
