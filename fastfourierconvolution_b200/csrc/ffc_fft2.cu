@@ -29,11 +29,26 @@ struct Rfft2Kernel {
         float2* tw = reinterpret_cast<float2*>(B + p.P * PL::REGION);
         FFC_PHASE {
             for (int i = tid; i < FFC_TW_N; i += ctx.nt) tw[i] = c_tw128[i];
-            const int per = H * (W / 4);
-            for (int i = tid; i < np * per; i += ctx.nt) {
-                const int pl = i / per, rem = i % per, h = rem / (W / 4), j = rem % (W / 4);
-                const float4 v = FFC_LDG(reinterpret_cast<const float4*>(p.x + (size_t)(plane0 + pl) * H * W) + rem);
-                *reinterpret_cast<float4*>(A + pl * PL::REGION + h * PL::RS + 4 * j) = v;
+            // batched loads: LDU independent float4 loads are in flight before the first shared-memory store
+            constexpr int per = H * (W / 4);
+            constexpr int LDU = 8;
+            const int total = np * per;
+            const float4* src = reinterpret_cast<const float4*>(p.x + (size_t)plane0 * H * W);
+            for (int i0 = tid; i0 < total; i0 += ctx.nt * LDU) {
+                float4 v[LDU];
+                FFC_UNROLL
+                for (int u = 0; u < LDU; ++u) {
+                    const int i = i0 + u * ctx.nt;
+                    if (i < total) v[u] = FFC_LDG(src + i);
+                }
+                FFC_UNROLL
+                for (int u = 0; u < LDU; ++u) {
+                    const int i = i0 + u * ctx.nt;
+                    if (i < total) {
+                        const int pl = i / per, rem = i % per, h = rem / (W / 4), j = rem % (W / 4);
+                        *reinterpret_cast<float4*>(A + pl * PL::REGION + h * PL::RS + 4 * j) = v[u];
+                    }
+                }
             }
         } FFC_SYNC;
         float* S = nullptr;
@@ -76,27 +91,58 @@ struct Irfft2Kernel {
         float* O = R1;   // other region
         FFC_PHASE {
             for (int i = tid; i < FFC_TW_N; i += ctx.nt) tw[i] = c_tw128[i];
-            const int per = H * PL::Wf;
-            for (int i = tid; i < np * per; i += ctx.nt) {
-                const int pl = i / per, rem = i % per, v = rem % PL::Wf;
-                const float* s = p.spec + (size_t)(plane0 + pl) * 2 * per + rem;
-                const float a = (p.colscale && v != 0 && v != W / 2) ? 0.5f : 1.0f;
-                reinterpret_cast<float2*>(S + pl * PL::REGION)[rem] = make_float2(FFC_LDG(s) * a, FFC_LDG(s + per) * a);
+            constexpr int per = H * PL::Wf;
+            constexpr int LDU = 4;
+            const int total = np * per;
+            for (int i0 = tid; i0 < total; i0 += ctx.nt * LDU) {
+                float re[LDU], im[LDU];
+                FFC_UNROLL
+                for (int u = 0; u < LDU; ++u) {
+                    const int i = i0 + u * ctx.nt;
+                    if (i < total) {
+                        const float* s = p.spec + (size_t)(plane0 + i / per) * 2 * per + i % per;
+                        re[u] = FFC_LDG(s); im[u] = FFC_LDG(s + per);
+                    }
+                }
+                FFC_UNROLL
+                for (int u = 0; u < LDU; ++u) {
+                    const int i = i0 + u * ctx.nt;
+                    if (i < total) {
+                        const int pl = i / per, rem = i % per, v = rem % PL::Wf;
+                        const float a = (p.colscale && v != 0 && v != W / 2) ? 0.5f : 1.0f;
+                        reinterpret_cast<float2*>(S + pl * PL::REGION)[rem] = make_float2(re[u] * a, im[u] * a);
+                    }
+                }
             }
         } FFC_SYNC;
         float* R = nullptr;
         FFC_FFT2_INVERSE(H, W, np, S, O, tw, p.scale, R);
         FFC_PHASE {
-            const int per = H * (W / 4);
-            for (int i = tid; i < np * per; i += ctx.nt) {
-                const int pl = i / per, rem = i % per, h = rem / (W / 4), j = rem % (W / 4);
-                float4 v = *reinterpret_cast<const float4*>(R + pl * PL::REGION + h * PL::RS + 4 * j);
-                const size_t g = (size_t)(plane0 + pl) * H * W;
-                if (p.residual) {
-                    const float4 q = FFC_LDG(reinterpret_cast<const float4*>(p.residual + g) + rem);
-                    v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+            constexpr int per = H * (W / 4);
+            constexpr int LDU = 8;
+            const int total = np * per;
+            const size_t g0 = (size_t)plane0 * H * W;
+            float4* dst = reinterpret_cast<float4*>(p.out + g0);
+            const float4* res = p.residual ? reinterpret_cast<const float4*>(p.residual + g0) : nullptr;
+            for (int i0 = tid; i0 < total; i0 += ctx.nt * LDU) {
+                float4 q[LDU];
+                if (res) {
+                    FFC_UNROLL
+                    for (int u = 0; u < LDU; ++u) {
+                        const int i = i0 + u * ctx.nt;
+                        if (i < total) q[u] = FFC_LDG(res + i);
+                    }
                 }
-                reinterpret_cast<float4*>(p.out + g)[rem] = v;
+                FFC_UNROLL
+                for (int u = 0; u < LDU; ++u) {
+                    const int i = i0 + u * ctx.nt;
+                    if (i < total) {
+                        const int pl = i / per, rem = i % per, h = rem / (W / 4), j = rem % (W / 4);
+                        float4 v = *reinterpret_cast<const float4*>(R + pl * PL::REGION + h * PL::RS + 4 * j);
+                        if (res) { v.x += q[u].x; v.y += q[u].y; v.z += q[u].z; v.w += q[u].w; }
+                        dst[i] = v;
+                    }
+                }
             }
         } FFC_SYNC;
     }

@@ -52,9 +52,10 @@ def test_model_matches_reference_golden(name, fn):
     assert max(errs.values()) < 2e-4, errs       # reference's own FP32-vs-FP64 spread is ~6e-5 here
 
 
-def _rel_l2(got, ref):
+def _rel_l2(got, ref, floor=0.0):
     got, ref = got.double().cpu(), ref.double().cpu()
-    return ((got - ref).norm() / ref.norm().clamp_min(1e-30)).item()
+    den = max(ref.norm().item(), floor * ref.numel() ** 0.5, 1e-30)
+    return (got - ref).norm().item() / den
 
 
 def _oracle_vs_module(mod, cfg_fn, xs, train=True, tol=parity.TOL, seed=0, whole_model=False):
@@ -99,7 +100,7 @@ def _oracle_vs_module(mod, cfg_fn, xs, train=True, tol=parity.TOL, seed=0, whole
             sib = sib if sib in P and P[sib].grad is not None else k[:-4] + "weight_orig"
             if sib in P and P[sib].grad is not None:
                 floor = P[sib].grad.abs().max().item()
-        errs["grad/" + k] = _rel_l2(p.grad, P[k].grad) if (whole_model and floor == 0.0) else parity.relerr(p.grad, P[k].grad, floor)
+        errs["grad/" + k] = _rel_l2(p.grad, P[k].grad, floor) if whole_model else parity.relerr(p.grad, P[k].grad, floor)
     if whole_model:
         for i, (a, b) in enumerate(zip(xg, xd)):
             errs[f"din{i}"] = _rel_l2(a.grad, b.grad)
