@@ -315,6 +315,12 @@ def run_ours(args):
                          f"(oracle/train_ref.py, PyTorch CPU kernels, {ms:.0f} ms/step)"}
     if rank == 0:
         peak, peak_src = measured_peaks()
+        traffic = None                                    # DRAM bytes per launch from the committed ncu capture (same shape only)
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic_fu.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("shape") == {"B": fu["B"], "C": fu["C"], "N": fu["N"]}:
+                traffic = tj["traffic"]
         act_mb = sum(p.numel() for p in G.parameters()) * 4 / 1e6
         line = {
             "metric": "FFC-GAN training images/s", "value": gb / ms_res * 1000.0, "unit": "images/s",
@@ -334,8 +340,8 @@ def run_ours(args):
             "gpu_launches": int(round(launches * args.steps)),
             "gpu_launches_per_step": launches,
             "roofline": {"bound": "hbm", "achieved": fu["gbs_fwd_train"], "peak": peak, "unit": "GB/s",
-                         "frac": fu["gbs_fwd_train"] / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": f"fused FourierUnit forward (FuFwdKernel stats pass + apply pass, {fu['launches_fwd_train']} launches) "
+                         "frac": fu["gbs_fwd_train"] / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": f"fused FourierUnit forward ({'cooperative single-pass FuFwdCoop' if fu['launches_fwd_train'] == 1 else 'FuFwdKernel stats pass + apply pass'}, {fu['launches_fwd_train']} launch(es)) "
                                    f"FourierUnitSN({fu['C']},{fu['C']}) @ {fu['N']}x{fu['N']}, batch {fu['B']}, training mode"
                                    if fu["fused"] else "general-form FourierUnit forward (rfft2 | mix | BN+ReLU | irfft2)",
                          "algorithmic_bytes_per_launch": fu["alg_bytes_fwd"],

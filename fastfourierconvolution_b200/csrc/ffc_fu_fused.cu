@@ -59,29 +59,29 @@ struct FuFwdKernel {
         FFC_PHASE { fft2_cols_L1<N, N, +1, SPS>(tid, nt, ni * Cout, spec, map_out); } FFC_SYNC;
         FFC_PHASE { fft2_rows_inv_L1<N, N, SPS>(tid, nt, ni * Cout, spec, spec, 1.0f, map_out, map_out); } FFC_SYNC;
         FFC_PHASE {
-            constexpr int per = N * (N / 4);
+            constexpr int Q = N / 4;
             constexpr int LDU = 8;
-            const int total = ni * Cout * per;
+            const int rows = ni * Cout * N;
+            const int j = tid % Q, rstep = nt / Q;
             const size_t g0 = (size_t)img0 * Cout * N * N;
-            float4* dst = reinterpret_cast<float4*>(p.out + g0);
-            const float4* res = p.residual ? reinterpret_cast<const float4*>(p.residual + g0) : nullptr;
-            for (int i0 = tid; i0 < total; i0 += nt * LDU) {
+            float4* dst = reinterpret_cast<float4*>(p.out + g0) + j;
+            const float4* res = p.residual ? reinterpret_cast<const float4*>(p.residual + g0) + j : nullptr;
+            for (int r0 = tid / Q; r0 < rows; r0 += rstep * LDU) {
                 float4 q[LDU];
                 if (res) {
                     FFC_UNROLL
                     for (int u = 0; u < LDU; ++u) {
-                        const int i = i0 + u * nt;
-                        if (i < total) q[u] = FFC_LDG(res + i);
+                        const int r = r0 + u * rstep;
+                        if (r < rows) q[u] = FFC_LDG(res + r * Q);
                     }
                 }
                 FFC_UNROLL
                 for (int u = 0; u < LDU; ++u) {
-                    const int i = i0 + u * nt;
-                    if (i < total) {
-                        const int pl = i / per, rem = i % per, h = rem / (N / 4), j = rem % (N / 4);
-                        float4 v = *reinterpret_cast<const float4*>(spec + (size_t)map_out(pl) * PL::REGION + h * PL::RS + 4 * j);
+                    const int r = r0 + u * rstep;
+                    if (r < rows) {
+                        float4 v = *reinterpret_cast<const float4*>(spec + (size_t)map_out(r / N) * PL::REGION + (r % N) * PL::RS + 4 * j);
                         if (res) { v.x += q[u].x; v.y += q[u].y; v.z += q[u].z; v.w += q[u].w; }
-                        dst[i] = v;
+                        dst[r * Q] = v;
                     }
                 }
             }
@@ -154,24 +154,26 @@ struct FuFwdKernel {
             // ---- coalesced load of the tile's planes into the real layout.  LDU float4 loads are issued
             // back to back before the first shared-memory store so one DRAM latency covers the batch.
             FFC_PHASE {
-                constexpr int per = N * (N / 4);
+                // The tile's planes form one tall (rows x N) matrix that is contiguous in global memory.  A thread
+                // owns one float4 column j and walks rows with a fixed stride, so addresses advance by constants;
+                // LDU loads are in flight before the first shared-memory store.
+                constexpr int Q = N / 4;                        // float4 per row
                 constexpr int LDU = 8;
-                const int total = ni * Cin * per;
-                const float4* src = reinterpret_cast<const float4*>(p.x + (size_t)img0 * Cin * N * N);
-                for (int i0 = tid; i0 < total; i0 += nt * LDU) {
+                const int rows = ni * Cin * N;
+                const int j = tid % Q, rstep = nt / Q;          // nt is a multiple of 32, Q divides 32
+                const float4* src = reinterpret_cast<const float4*>(p.x + (size_t)img0 * Cin * N * N) + j;
+                for (int r0 = tid / Q; r0 < rows; r0 += rstep * LDU) {
                     float4 v[LDU];
                     FFC_UNROLL
                     for (int u = 0; u < LDU; ++u) {
-                        const int i = i0 + u * nt;
-                        if (i < total) v[u] = FFC_LDG(src + i);
+                        const int r = r0 + u * rstep;
+                        if (r < rows) v[u] = FFC_LDG(src + r * Q);
                     }
                     FFC_UNROLL
                     for (int u = 0; u < LDU; ++u) {
-                        const int i = i0 + u * nt;
-                        if (i < total) {
-                            const int pl = i / per, rem = i % per, h = rem / (N / 4), j = rem % (N / 4);
-                            *reinterpret_cast<float4*>(spec + (size_t)map_in(pl) * PL::REGION + h * PL::RS + 4 * j) = v[u];
-                        }
+                        const int r = r0 + u * rstep;
+                        if (r < rows)
+                            *reinterpret_cast<float4*>(spec + (size_t)map_in(r / N) * PL::REGION + (r % N) * PL::RS + 4 * j) = v[u];
                     }
                 }
             } FFC_SYNC;
@@ -200,7 +202,10 @@ struct FuFwdKernel {
                             if (c < Cin) s[b][c] = base[b][(size_t)c * (PL::REGION / 2)];
                         }
                     }
-                    for (int o2 = 0; o2 < Cout; ++o2) {
+                    constexpr int OU = CP <= 16 ? CP : 4;      // full unroll for small tiles: immediate offsets everywhere
+#pragma unroll OU
+                    for (int o2 = 0; o2 < CP; ++o2) {
+                        if (o2 >= Cout) break;
                         const float4* wrow = reinterpret_cast<const float4*>(wq) + (size_t)o2 * CP;
                         float2 pa[BPT], pb[BPT];
                         FFC_UNROLL

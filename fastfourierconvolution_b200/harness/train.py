@@ -109,6 +109,7 @@ class GanTrainer:
         """Captures one training step into a CUDA graph on static input buffers shaped like the arguments.
         The step is the same sequence of kernels as ``step``; only the host-side launch cost is removed."""
         assert z_g.is_cuda, "graph capture needs CUDA tensors"
+        assert warmup >= 1, "at least one eager step must run first: optimiser state has to exist before the capture"
         self._static = (z_g.clone(), z_d.clone(), real.clone())
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())

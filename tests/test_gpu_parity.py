@@ -276,3 +276,29 @@ def test_training_step_runs_and_updates_both_networks():
     assert torch.isfinite(lg) and torch.isfinite(ld)
     assert not torch.equal(g0, G.conv3.ffc.convg2g.fu.conv_layer.weight) and not torch.equal(d0, D.conv1.weight_orig)
     assert all(p.grad is None for k, p in G.named_parameters() if ".lfu." in k)
+
+
+def test_graph_captured_step_matches_eager_step():
+    """The CUDA-graph replay of the training step (bench.py's launch mode) is the same computation as the eager step."""
+    def make():
+        torch.manual_seed(0)
+        G = H.FGenerator(128, 4, "fgan32").to(DEV).train(); G.apply(H.weights_init)
+        D = H.SNDiscriminator(True, 4, 7).to(DEV).train(); D.apply(H.weights_init)
+        return G, D
+    z1, z2 = torch.randn(8, 128, device=DEV), torch.randn(8, 128, device=DEV)
+    real = torch.rand(8, 3, 32, 32, device=DEV) * 2 - 1
+    G1, D1 = make()
+    t1 = H.GanTrainer(G1, D1, capturable=True)
+    G2, D2 = make()
+    t2 = H.GanTrainer(G2, D2, capturable=True)
+    t2.capture(z1, z2, real, warmup=1)                    # one eager step (initialises optimiser state), then capture
+    t1.step(z1, z2, real)
+    l1 = torch.stack(t1.step(z1, z2, real))               # second eager step ...
+    l2 = t2.step_graphed(z1, z2, real).clone()            # ... equals the first replay
+    torch.cuda.synchronize()
+    # not bit-identical: FP32 atomics order and cuDNN's (TF32) algorithm choice for the PyTorch discriminator differ
+    # between the two runs; Adam's normalised update then moves a weight by at most ~lr = 2e-4 per step
+    assert torch.allclose(l1, l2, rtol=2e-3, atol=1e-4), (l1, l2)
+    w1 = G1.conv3.ffc.convg2g.fu.conv_layer.weight
+    w2 = G2.conv3.ffc.convg2g.fu.conv_layer.weight
+    assert (w1 - w2).abs().max().item() < 1e-3 and t2.launches_per_step > 100
