@@ -16,7 +16,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libffc_b200.so")
-UNITS = [os.path.join(CSRC, "ffc_unit_core.cu"), os.path.join(CSRC, "ffc_unit_fu.cu")]
+# one translation unit per source file, compiled in parallel
+UNITS = [os.path.join(CSRC, f) for f in ("ffc_api.cu", "ffc_fft2.cu", "ffc_conv.cu", "ffc_conv_v4.cu", "ffc_bnact.cu",
+                                         "ffc_fu_fused.cu")]
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
@@ -50,9 +52,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = find_nvcc()
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
-    procs = []
+    headers = [s for s in sources() if not s.endswith(".cu")] + [os.path.abspath(__file__)]
+    hdr_t = max(os.path.getmtime(h) for h in headers)
+    procs, objs = [], []
     for unit in UNITS:                                   # translation units compile in parallel
         obj = os.path.join(objdir, os.path.basename(unit)[:-3] + ".o")
+        objs.append(obj)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(hdr_t, os.path.getmtime(unit)):
+            continue                                     # object is newer than its source and every header
         procs.append((obj, subprocess.Popen([nvcc] + NVCC_FLAGS + ["-c", "-o", obj, unit],
                                             stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
     log = ""
@@ -60,8 +67,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         out, err = pr.communicate()
         log += err
         if pr.returncode != 0:
+            if os.path.exists(obj):
+                os.remove(obj)
             raise RuntimeError("nvcc failed:\n" + out + err)
-    r = subprocess.run([nvcc, "-shared", "-o", LIB + ".tmp"] + [o for o, _ in procs], capture_output=True, text=True)
+    r = subprocess.run([nvcc, "-shared", "-o", LIB + ".tmp"] + objs, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc link failed:\n" + r.stdout + r.stderr)
     os.replace(LIB + ".tmp", LIB)

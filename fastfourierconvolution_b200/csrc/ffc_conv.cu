@@ -464,8 +464,12 @@ struct ConvFwdV3 {
 #ifdef FFC_EMU
         return make_float2(x, 0.f);
 #else
-        const unsigned hi = ffc_tf32(x);
-        return make_float2(__uint_as_float(hi), __uint_as_float(ffc_tf32(x - __uint_as_float(hi))));
+        // hi = x truncated to TF32 (one LOP3), lo = x - hi (exact in FP32, one FADD).  The tensor core reads only the
+        // top 19 bits of lo, so a.b keeps ~21 significant bits per product.  (cvt.rna.tf32.f32 expands to a ~7
+        // instruction sequence on sm_100 -- ncu showed it dominating the issue slots -- and round-to-nearest of hi
+        // buys nothing once lo carries the remainder.)
+        const float hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+        return make_float2(hi, x - hi);
 #endif
     }
 
@@ -811,7 +815,7 @@ static int conv_fwd_v2_launch(const ConvParams& p, ffc_stream_t st) {
     return ffc_launch<K>(ffc_cdiv(Mc, K::BM), ffc_cdiv(p.cout, K::kBN), s * s, K::kThreads, K::smem_bytes(), st, p);
 }
 
-static int ffc_conv_use_reference_kernel = 0;
+int ffc_conv_use_reference_kernel = 3;      // shared with ffc_conv_v4.cu; 3 = ConvFwdV4 (default, via ffc_conv2d_fwd_ws)
 
 // See include/ffc_b200.h for the contract.
 extern "C" int ffc_conv2d_fwd(const float* x0, const float* w0, int cin0,
@@ -855,7 +859,8 @@ extern "C" int ffc_conv2d_fwd(const float* x0, const float* w0, int cin0,
     return simt ? conv_fwd_v2_launch<ConvFwdV2<64>>(p, st) : conv_fwd_v2_launch<ConvFwdV3<64>>(p, st);
 }
 
-// test hook: 0 tensor-core 3xTF32 kernels (default), 1 simple reference-form kernels, 2 tuned FP32 SIMT kernels
+// test hook: 3 ConvFwdV4 (default when called through ffc_conv2d_fwd_ws), 0 ConvFwdV3 tensor-core 3xTF32 kernels
+// (what plain ffc_conv2d_fwd runs by default), 1 simple reference-form kernels, 2 tuned FP32 SIMT kernels
 extern "C" void ffc_debug_conv_reference(int on) { ffc_conv_use_reference_kernel = on; }
 
 extern "C" int ffc_conv2d_wgrad(const float* S, const float* L, float* dW,

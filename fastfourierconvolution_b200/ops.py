@@ -29,6 +29,17 @@ def conv_out_size(hi: int, k: int, stride: int, pad: int, transposed: bool, out_
     return (hi + 2 * pad - k) // stride + 1
 
 
+def _conv_launch(x0, w0, cin0, x1, w1, cin1, bias, addend, y, B, cout, Hi, Wi, Ho, Wo, k, stride, pad, transposed):
+    """ffc_conv2d_fwd_ws with the packed-weight scratch it needs (stream-ordered, reused by the next call)."""
+    L = _C.lib()
+    nbytes = L.ffc_conv2d_workspace_bytes(cin0, cin1, cout, k, stride, pad, int(transposed))
+    ws = _C.workspace(nbytes, y.device)
+    _C.check(L.ffc_conv2d_fwd_ws(_C.ptr(x0), _C.ptr(w0), cin0, _C.ptr(x1), _C.ptr(w1), cin1,
+                                 _C.ptr(bias), _C.ptr(addend), _C.ptr(y),
+                                 B, cout, Hi, Wi, Ho, Wo, k, stride, pad, int(transposed),
+                                 _C.ptr(ws), ws.numel(), _C.current_stream(y.device)))
+
+
 class Conv2dFn(torch.autograd.Function):
     """y = conv(x0, w0) [+ conv(x1, w1)] [+ bias] [+ addend]   (ffc.py:91-96, ffc_transpose.py:98-106)."""
 
@@ -52,11 +63,7 @@ class Conv2dFn(torch.autograd.Function):
         y = torch.empty((B, cout, Ho, Wo), device=x0.device, dtype=torch.float32)
         if addend is not None and addend.shape != y.shape:
             raise ValueError(f"addend {tuple(addend.shape)} != output {tuple(y.shape)}")
-        L = _C.lib()
-        _C.check(L.ffc_conv2d_fwd(_C.ptr(x0), _C.ptr(w0), cin0, _C.ptr(x1), _C.ptr(w1), cin1,
-                                  _C.ptr(bias), _C.ptr(addend), _C.ptr(y),
-                                  B, cout, Hi, Wi, Ho, Wo, k, stride, pad, int(transposed),
-                                  _C.current_stream(x0.device)))
+        _conv_launch(x0, w0, cin0, x1, w1, cin1, bias, addend, y, B, cout, Hi, Wi, Ho, Wo, k, stride, pad, transposed)
         ctx.save_for_backward(x0, w0, x1, w1)
         ctx.cfg = (stride, pad, bool(transposed), k, cout, bias is not None, addend is not None)
         return y
@@ -77,8 +84,7 @@ class Conv2dFn(torch.autograd.Function):
             if ctx.needs_input_grad[2 * slot]:
                 dx = torch.empty_like(x)
                 # data gradient = the opposite gather form over dy with the same weight tensor
-                _C.check(L.ffc_conv2d_fwd(_C.ptr(dy), _C.ptr(w), cout, None, None, 0, None, None, _C.ptr(dx),
-                                          B, cin, Ho, Wo, Hi, Wi, k, stride, pad, int(not transposed), st))
+                _conv_launch(dy, w, cout, None, None, 0, None, None, dx, B, cin, Ho, Wo, Hi, Wi, k, stride, pad, not transposed)
                 grads[2 * slot] = dx
             if ctx.needs_input_grad[2 * slot + 1]:
                 dw = torch.empty_like(w)

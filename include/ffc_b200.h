@@ -100,6 +100,18 @@ int ffc_conv2d_fwd(const float* x0, const float* w0, int cin0,
                    int B, int cout, int Hi, int Wi, int Ho, int Wo,
                    int k, int stride, int pad, int transposed, void* stream);
 
+/* ffc_conv2d_fwd_ws: same contract as ffc_conv2d_fwd plus caller-provided scratch of
+ * ffc_conv2d_workspace_bytes(cin0, cin1, cout, k, stride, pad, transposed) bytes.  The scratch receives the
+ * weights re-packed for this call (GEMM tile order, split into TF32 hi/lo halves) and lets the kernel stream both
+ * operands with asynchronous copies; the host modules call this form. */
+size_t ffc_conv2d_workspace_bytes(int cin0, int cin1, int cout, int k, int stride, int pad, int transposed);
+int ffc_conv2d_fwd_ws(const float* x0, const float* w0, int cin0,
+                      const float* x1, const float* w1, int cin1,
+                      const float* bias, const float* addend, float* y,
+                      int B, int cout, int Hi, int Wi, int Ho, int Wo,
+                      int k, int stride, int pad, int transposed,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* dW[sc][lc][ky][kx] = sum_{b,y,x} S[b,sc,y,x] * L[b,lc,y*stride-pad+ky,x*stride-pad+kx]
  * nn.Conv2d:          S = dy (cout, Ho x Wo), L = x  (cin,  Hi x Wi)  -> dW [cout][cin][k][k]
  * nn.ConvTranspose2d: S = x  (cin,  Hi x Wi), L = dy (cout, Ho x Wo)  -> dW [cin][cout][k][k]
@@ -146,9 +158,10 @@ int ffc_se_bwd(const float* x, const float* dy, const float* w1, const float* w2
                void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- test hook ---------------------------------------------------------------------------------
- * Kernel family used by ffc_conv2d_fwd / ffc_conv2d_wgrad: 0 (default) tensor-core kernels at FP32 accuracy
- * (3xTF32 mma, register prefetch, double-buffered shared memory); 1 the simple single-buffered FP32 forms of
- * the same math; 2 the tuned FP32 SIMT kernels.  Tests compare all three. */
+ * Kernel family used by the convolution entry points: 3 (default) ffc_conv2d_fwd_ws runs the packed-weight
+ * cp.async-pipelined tensor-core kernel (3xTF32 mma at FP32 accuracy) and ffc_conv2d_fwd the register-prefetch
+ * tensor-core kernel; 0 both run the register-prefetch tensor-core kernel; 1 the simple single-buffered FP32 forms
+ * of the same math; 2 the tuned FP32 SIMT kernels.  Tests compare all four. */
 void ffc_debug_conv_reference(int mode);
 /* Training-mode ffc_fu_fwd runs as ONE cooperative kernel (spectrum held in shared memory across a grid barrier)
  * when all image tiles are co-resident, else as two passes over x; on = 1 forces the two-pass form. */

@@ -16,7 +16,7 @@ def header_symbols():
 
 def test_header_declares_the_expected_surface():
     syms = header_symbols()
-    for s in ("ffc_rfft2", "ffc_irfft2", "ffc_conv2d_fwd", "ffc_conv2d_wgrad", "ffc_bn_act_fwd", "ffc_bn_act_bwd",
+    for s in ("ffc_rfft2", "ffc_irfft2", "ffc_conv2d_fwd", "ffc_conv2d_fwd_ws", "ffc_conv2d_workspace_bytes", "ffc_conv2d_wgrad", "ffc_bn_act_fwd", "ffc_bn_act_bwd",
               "ffc_se_fwd", "ffc_se_bwd", "ffc_bias_grad", "ffc_version", "ffc_last_error", "ffc_workspace_bytes"):
         assert s in syms
 

@@ -97,21 +97,28 @@ CONV_CASES = [
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
-@pytest.mark.parametrize("reference_form", [0, 1, 2])
+@pytest.mark.parametrize("reference_form", [0, 1, 2, 3])
 def test_conv_forward_dgrad_wgrad(lib, case, reference_form):
-    """0: tensor-core 3xTF32 kernels (production); 1: the simple single-buffered forms; 2: tuned FP32 SIMT kernels."""
+    """0: tensor-core 3xTF32 kernels; 1: the simple single-buffered forms; 2: tuned FP32 SIMT kernels;
+    3: tensor-core 3xTF32 with packed weights and a cp.async ring (ffc_conv2d_fwd_ws)."""
     lib[0].ffc_debug_conv_reference(reference_form)
     _conv_mode[0] = reference_form if lib[1] != "cpu" else 1      # the emulation build computes every family in FP32
     try:
         _conv_case(lib, case)
     finally:
-        lib[0].ffc_debug_conv_reference(0)
+        lib[0].ffc_debug_conv_reference(3)
 
 
 # 3xTF32 on the tensor cores: the dropped lo*lo term and the MMA's internal accumulation leave ~1e-5
 # (still an order of magnitude inside the 1e-4 FP32 parity bound); the FP32 FMA families reach ~1e-7.
-CONV_TOL = {0: 4e-5, 1: 3e-6, 2: 3e-6}
+CONV_TOL = {0: 4e-5, 1: 3e-6, 2: 3e-6, 3: 4e-5}
 _conv_mode = [0]
+
+
+def _conv_fwd(lib, x0, w0, cin0, x1, w1, cin1, b, ad, y, B, cout, Hi, Wi, Ho, Wo, k, s, p, tr):
+    nbytes = lib[0].ffc_conv2d_workspace_bytes(cin0, cin1, cout, k, s, p, tr)
+    ws = torch.zeros(nbytes + 64, dtype=torch.uint8)
+    call(lib, "ffc_conv2d_fwd_ws", x0, w0, cin0, x1, w1, cin1, b, ad, y, B, cout, Hi, Wi, Ho, Wo, k, s, p, tr, ws, ws.numel(), None)
 
 
 def _conv_case(lib, case):
@@ -133,8 +140,8 @@ def _conv_case(lib, case):
         ref = ref + ad.double()
     y = torch.empty(B, cout, Ho, Ho)
     x1, w1 = (xs[1], ws[1]) if len(xs) > 1 else (None, None)
-    call(lib, "ffc_conv2d_fwd", xs[0], ws[0], cins[0], x1, w1, cins[1] if x1 is not None else 0, b, ad, y,
-                               B, cout, Hi, Hi, Ho, Ho, k, s, p, int(tr), None)
+    _conv_fwd(lib, xs[0], ws[0], cins[0], x1, w1, cins[1] if x1 is not None else 0, b, ad, y,
+              B, cout, Hi, Hi, Ho, Ho, k, s, p, int(tr))
     assert parity.relerr(y, ref) < CONV_TOL[_conv_mode[0]]
     dy = torch.randn(B, cout, Ho, Ho)
     for x, w in zip(xs, ws):
@@ -146,7 +153,7 @@ def _conv_case(lib, case):
         else:
             call(lib, "ffc_conv2d_wgrad", dy, x, dW, B, cout, x.shape[1], Ho, Ho, Hi, Hi, k, s, p, None)
         assert parity.relerr(dW, wd.grad) < 3e-6          # wgrad is FP32 FMA in every family
-        call(lib, "ffc_conv2d_fwd", dy, w, cout, None, None, 0, None, None, dx, B, x.shape[1], Ho, Ho, Hi, Hi, k, s, p, int(not tr), None)
+        _conv_fwd(lib, dy, w, cout, None, None, 0, None, None, dx, B, x.shape[1], Ho, Ho, Hi, Hi, k, s, p, int(not tr))
         assert parity.relerr(dx, xd.grad) < CONV_TOL[_conv_mode[0]]
 
 
