@@ -40,6 +40,8 @@ _SIGNATURES = {
     "ffc_se_bwd": (c_int, [c_void_p] * 10 + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
     "ffc_fu_fwd": (c_int, [c_void_p] * 10 + [c_int] * 6 + [c_float, c_float, c_void_p, c_size_t, c_void_p]),
     "ffc_fu_fused_supported": (c_int, [c_int] * 5),
+    "ffc_fu_bwd": (c_int, [c_void_p] * 11 + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
+    "ffc_fu_bwd_supported": (c_int, [c_int] * 5),
     "ffc_debug_conv_reference": (None, [c_int]),
     "ffc_debug_fu_two_pass": (None, [c_int]),
 }

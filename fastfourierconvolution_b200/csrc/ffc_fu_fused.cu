@@ -359,9 +359,9 @@ struct FuFwdCoop {
 // host side
 // ---------------------------------------------------------------------------------------------
 struct FuPlan { int imgs, nt, grid; size_t smem; bool ok; };
-static int ffc_fu_force_two_pass = 0;
-// test hook: 1 disables the cooperative single-pass training forward (the two-pass form is then used for every batch)
-extern "C" void ffc_debug_fu_two_pass(int on) { ffc_fu_force_two_pass = on; }
+// test hook (ffc_fu2.cu): 1 disables the cooperative single-pass training forward
+extern int ffc_fu2_force_two_pass;
+#define ffc_fu_force_two_pass ffc_fu2_force_two_pass
 
 template <int N, int CP>
 static FuPlan fu_plan(int B, int Cin, int Cout) {
@@ -432,21 +432,16 @@ static bool fu_fits(int B, int Cin, int Cout) {
 }
 
 // 1 when ffc_fu_fwd supports the shape (otherwise callers use ffc_rfft2 | ffc_conv2d_fwd | ffc_bn_act_fwd | ffc_irfft2)
-extern "C" int ffc_fu_fused_supported(int B, int Cin, int Cout, int H, int W) {
-    if (H != W || B < 1 || Cin < 1 || Cout < 1 || Cin > 32 || Cout > 32) return 0;
-    switch (H) {
-        case 4: return fu_fits<4>(B, Cin, Cout);
-        case 8: return fu_fits<8>(B, Cin, Cout);
-        case 16: return fu_fits<16>(B, Cin, Cout);
-        case 32: return fu_fits<32>(B, Cin, Cout);
-        default: return 0;
-    }
+// First-generation kernel: since ffc_fu2.cu it only serves the 4x4 planes (several images per CTA).
+extern "C" int ffc_fu1_supported(int B, int Cin, int Cout, int H, int W) {
+    if (H != 4 || W != 4 || B < 1 || Cin < 1 || Cout < 1 || Cin > 32 || Cout > 32) return 0;
+    return fu_fits<4>(B, Cin, Cout);
 }
 
 // Fused FourierUnitSN forward.  w: conv_layer.weight viewed [2*Cout][2*Cin]; gamma/beta/running_*: bn.* [2*Cout];
 // save_mean/save_invstd [2*Cout] are written; out = [residual +] irfft2(relu(bn(mix(rfft2(x))))).
 // workspace >= 4*Cout doubles.
-extern "C" int ffc_fu_fwd(const float* x, const float* w, const float* gamma, const float* beta,
+extern "C" int ffc_fu1_fwd(const float* x, const float* w, const float* gamma, const float* beta,
                           float* running_mean, float* running_var, float* save_mean, float* save_invstd,
                           const float* residual, float* out,
                           int B, int Cin, int Cout, int H, int W, int training, float eps, float momentum,
@@ -455,7 +450,7 @@ extern "C" int ffc_fu_fwd(const float* x, const float* w, const float* gamma, co
     FFC_REQUIRE(training || (running_mean && running_var), "ffc_fu_fwd: eval mode needs running statistics");
     FFC_REQUIRE(B >= 0, "ffc_fu_fwd: negative batch");
     if (B == 0) return FFC_OK;
-    FFC_REQUIRE(ffc_fu_fused_supported(B, Cin, Cout, H, W), "ffc_fu_fwd: unsupported shape B=%d Cin=%d Cout=%d %dx%d", B, Cin, Cout, H, W);
+    FFC_REQUIRE(ffc_fu1_supported(B, Cin, Cout, H, W), "ffc_fu_fwd: unsupported shape B=%d Cin=%d Cout=%d %dx%d", B, Cin, Cout, H, W);
     FFC_REQUIRE((((uintptr_t)x | (uintptr_t)out | (uintptr_t)residual) & 15) == 0, "ffc_fu_fwd: x/out/residual must be 16-byte aligned");
     if (!(workspace && workspace_bytes >= (size_t)4 * Cout * sizeof(double))) { ffc_set_error("ffc_fu_fwd: workspace too small"); return FFC_ERR_WORKSPACE; }
     FuFwdParams p;
@@ -464,10 +459,5 @@ extern "C" int ffc_fu_fwd(const float* x, const float* w, const float* gamma, co
     p.sums = (double*)workspace; p.B = B; p.Cin = Cin; p.Cout = Cout; p.imgs = 1; p.training = training;
     p.eps = eps; p.momentum = momentum;
     ffc_stream_t st = (ffc_stream_t)stream;
-    switch (H) {
-        case 4: return fu_fwd_dispatch_cp<4>(p, st);
-        case 8: return fu_fwd_dispatch_cp<8>(p, st);
-        case 16: return fu_fwd_dispatch_cp<16>(p, st);
-        default: return fu_fwd_dispatch_cp<32>(p, st);
-    }
+    return fu_fwd_dispatch_cp<4>(p, st);
 }

@@ -223,6 +223,9 @@ def irfft2(spec, residual=None):
 # ---------------------------------------------------------------------------------------------
 # fused Fourier unit (forward in one / two kernels; backward recomputes through the general form)
 # ---------------------------------------------------------------------------------------------
+FUSED_FU_BACKWARD = True      # tests switch this off to exercise the general-form backward of FusedFuFn
+
+
 def fu_fused_supported(B, Cin, Cout, H, W) -> bool:
     return bool(_C.lib().ffc_fu_fused_supported(int(B), int(Cin), int(Cout), int(H), int(W)))
 
@@ -230,9 +233,10 @@ def fu_fused_supported(B, Cin, Cout, H, W) -> bool:
 class FusedFuFn(torch.autograd.Function):
     """out = [residual +] irfft2(relu(bn(conv1x1(rfft2(x)))))   (fourier_unity.py:32-58 in one op).
 
-    Forward: ffc_fu_fwd (spectrum stays in shared memory).  Backward: the spectrum is recomputed from
-    x with the general-form kernels (rfft2, 1x1 mix, BN+ReLU backward, wgrad/dgrad, irfft2); nothing
-    spectral is saved between forward and backward."""
+    Forward: ffc_fu_fwd (spectrum stays in shared memory).  Backward: ffc_fu_bwd, one cooperative kernel that
+    recomputes the spectrum of x, transforms dout and keeps both in shared memory; when the batch is too large for
+    one resident CTA per image the general-form kernels are used (rfft2, 1x1 mix, BN+ReLU backward, wgrad/dgrad,
+    irfft2).  Nothing spectral is saved between forward and backward."""
 
     @staticmethod
     def forward(ctx, x, weight, gamma, beta, running_mean, running_var, residual, training, eps, momentum):
@@ -262,6 +266,16 @@ class FusedFuFn(torch.autograd.Function):
         Wf = W // 2 + 1
         L = _C.lib()
         st = _C.current_stream(x.device)
+        if FUSED_FU_BACKWARD and L.ffc_fu_bwd_supported(B, Cin, C2o // 2, H, W):
+            # one cooperative kernel: both spectra stay in shared memory (csrc/ffc_fu2_bwd.cu)
+            dx, dw = torch.empty_like(x), torch.empty_like(weight)
+            dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(beta)
+            ws = _C.workspace(2 * C2o * 8, x.device)
+            _C.check(L.ffc_fu_bwd(_C.ptr(x), _C.ptr(dout), _C.ptr(weight), _C.ptr(gamma), _C.ptr(beta),
+                                  _C.ptr(save_mean), _C.ptr(save_invstd), _C.ptr(dx), _C.ptr(dw), _C.ptr(dgamma), _C.ptr(dbeta),
+                                  B, Cin, C2o // 2, H, W, int(training), _C.ptr(ws), ws.numel(), st))
+            dres = dout if (has_res and ctx.needs_input_grad[6]) else None
+            return dx, dw, dgamma, dbeta, None, None, dres, None, None, None
         w4 = weight.view(C2o, C2i, 1, 1)
         spec = _rfft2(x, 0)                                            # recompute S
         y = torch.empty((B, C2o, H, Wf), device=x.device, dtype=torch.float32)

@@ -85,6 +85,22 @@ int ffc_fu_fwd(const float* x, const float* w, const float* gamma, const float* 
                int B, int Cin, int Cout, int H, int W, int training, float eps, float momentum,
                void* workspace, size_t workspace_bytes, void* stream);
 
+/* ffc_fu_bwd: the autograd backward of FourierUnitSN.forward (fourier_unity.py:32-58; derived from ATen's
+ * fft_r2c / fft_c2r / batch_norm / relu / conv backward formulas) as ONE cooperative kernel, one image per CTA:
+ * rfft2(x) and the adjoint-c2r transform of dout stay in shared memory, Y = W S is recomputed, ReLU mask and the two
+ * BatchNorm-backward sums cross a grid barrier, then dW (atomics), dS = W^T dY and the adjoint-r2c inverse give dx.
+ *   x, dout as in the forward; save_mean / save_invstd = what ffc_fu_fwd wrote; training selects batch-statistics
+ *   BatchNorm backward; outputs dx (B,Cin,H,W), dw [2*Cout][2*Cin], dgamma, dbeta [2*Cout] (all overwritten).
+ *   The residual's gradient is dout itself.  workspace >= 4*Cout*8 bytes.
+ * ffc_fu_bwd_supported: 1 when the shape is handled on the current device (H == W in {8,16,32}, Cin, Cout <= 32,
+ * all B images co-resident); otherwise callers compose the general-form entry points. */
+int ffc_fu_bwd_supported(int B, int Cin, int Cout, int H, int W);
+int ffc_fu_bwd(const float* x, const float* dout, const float* w, const float* gamma, const float* beta,
+               const float* save_mean, const float* save_invstd,
+               float* dx, float* dw, float* dgamma, float* dbeta,
+               int B, int Cin, int Cout, int H, int W, int training,
+               void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- Convolutions -----------------------------------------------------------------------------
  * ffc_conv2d_fwd, transposed = 0: nn.Conv2d forward (layers/ffc/ffc.py:45-68 convl2l/convl2g/convg2l,
  *   spectral_transform.py:52-53,70-71 conv1/conv2, fourier_unity.py:23-24 conv_layer) and the

@@ -219,3 +219,114 @@ def test_empty_batch_is_a_noop(lib):
     y = torch.zeros(0, 3, 8, 8)
     w = torch.randn(3, 4, 3, 3)
     call(lib, "ffc_conv2d_fwd", torch.zeros(4), w, 4, None, None, 0, None, None, torch.zeros(4), 0, 3, 8, 8, 8, 8, 3, 1, 1, 0, None)
+
+
+def _fu_reference(x, w, gamma, beta, rmean, rvar, training, eps=1e-5):
+    """FourierUnitSN.forward (fourier_unity.py:32-58) in float64 torch; returns out, batch mean, batch invstd."""
+    B, Cin, H, W = x.shape
+    X = torch.fft.rfftn(x.double(), dim=(-2, -1), norm="ortho")
+    S = torch.stack((X.real, X.imag), dim=2).reshape(B, 2 * Cin, H, W // 2 + 1)
+    Y = torch.einsum("oc,bchw->bohw", w.double(), S)
+    if training:
+        mean, var = Y.mean(dim=(0, 2, 3)), Y.var(dim=(0, 2, 3), unbiased=False)
+    else:
+        mean, var = rmean.double(), rvar.double()
+    invstd = 1.0 / torch.sqrt(var + eps)
+    Z = F.relu((Y - mean.view(1, -1, 1, 1)) * (invstd * gamma.double()).view(1, -1, 1, 1) + beta.double().view(1, -1, 1, 1))
+    Cout = w.shape[0] // 2
+    Zc = torch.complex(Z.view(B, Cout, 2, H, -1)[:, :, 0], Z.view(B, Cout, 2, H, -1)[:, :, 1])
+    return torch.fft.irfftn(Zc, s=(H, W), dim=(-2, -1), norm="ortho"), mean, invstd, Y.var(dim=(0, 2, 3), unbiased=True)
+
+
+FU_CASES = [
+    # B, Cin, Cout, N, training, residual, two_pass
+    (3, 8, 8, 32, 1, True, 0), (3, 8, 8, 32, 1, False, 1), (2, 8, 8, 32, 0, True, 0),
+    (5, 16, 16, 16, 1, True, 0), (5, 16, 16, 16, 1, True, 1), (2, 16, 16, 16, 0, False, 0),
+    (3, 32, 32, 8, 1, True, 0), (3, 32, 32, 8, 1, False, 1),
+    (2, 5, 7, 16, 1, False, 0), (2, 7, 3, 8, 1, False, 1), (2, 12, 20, 8, 0, False, 0), (2, 3, 2, 32, 1, True, 0),
+    (2, 16, 16, 32, 1, True, 0), (1, 32, 32, 32, 1, True, 1), (2, 24, 9, 16, 1, False, 0), (2, 4, 4, 4, 1, True, 0),
+]
+
+
+@pytest.mark.parametrize("case", FU_CASES)
+def test_fused_fourier_unit_forward(lib, case):
+    """ffc_fu_fwd (cooperative single pass / two-pass / eval) against FourierUnitSN.forward in float64."""
+    B, Cin, Cout, N, training, has_res, two_pass = case
+    torch.manual_seed(B * 1000 + Cin * 10 + N)
+    x = torch.randn(B, Cin, N, N)
+    w = torch.randn(2 * Cout, 2 * Cin) / (2 * Cin) ** 0.5
+    gamma, beta = torch.rand(2 * Cout) + 0.5, torch.randn(2 * Cout) * 0.3
+    rmean, rvar = torch.randn(2 * Cout) * 0.1, torch.rand(2 * Cout) + 0.5
+    res = torch.randn(B, Cout, N, N) if has_res else None
+    ref, mean, invstd, var_unb = _fu_reference(x, w, gamma, beta, rmean, rvar, training)
+    if has_res:
+        ref = ref + res.double()
+    assert lib[0].ffc_fu_fused_supported(B, Cin, Cout, N, N) == 1
+    out = torch.zeros(B, Cout, N, N)
+    sm, si = torch.zeros(2 * Cout), torch.zeros(2 * Cout)
+    rm, rv = rmean.clone(), rvar.clone()
+    ws = torch.zeros(4 * Cout * 8 + 64, dtype=torch.uint8)
+    cf = ctypes.c_float
+    lib[0].ffc_debug_fu_two_pass(two_pass)
+    try:
+        call(lib, "ffc_fu_fwd", x, w, gamma, beta, rm, rv, sm, si, res, out, B, Cin, Cout, N, N, training,
+             cf(1e-5), cf(0.1), ws, ws.numel(), None)
+    finally:
+        lib[0].ffc_debug_fu_two_pass(0)
+    assert parity.relerr(out, ref) < 2e-6
+    assert parity.relerr(sm, mean) < 1e-5 and parity.relerr(si, invstd) < 1e-5
+    if training:
+        assert parity.relerr(rm, 0.9 * rmean.double() + 0.1 * mean) < 1e-5
+        assert parity.relerr(rv, 0.9 * rvar.double() + 0.1 * var_unb) < 1e-5
+    else:
+        assert torch.equal(rm, rmean) and torch.equal(rv, rvar)
+
+
+def _fu_reference_bwd(x, w, gamma, beta, rmean, rvar, training, dout, eps=1e-5):
+    """Gradients of FourierUnitSN.forward by float64 autograd of the same op sequence."""
+    xd = x.double().requires_grad_(True)
+    wd, gd, bd = (t.double().requires_grad_(True) for t in (w, gamma, beta))
+    B, Cin, H, W = x.shape
+    X = torch.fft.rfftn(xd, dim=(-2, -1), norm="ortho")
+    S = torch.stack((X.real, X.imag), dim=2).reshape(B, 2 * Cin, H, W // 2 + 1)
+    Y = torch.einsum("oc,bchw->bohw", wd, S)
+    if training:
+        mean, var = Y.mean(dim=(0, 2, 3)), Y.var(dim=(0, 2, 3), unbiased=False)
+    else:
+        mean, var = rmean.double(), rvar.double()
+    invstd = 1.0 / torch.sqrt(var + eps)
+    Z = F.relu((Y - mean.view(1, -1, 1, 1)) * (invstd * gd).view(1, -1, 1, 1) + bd.view(1, -1, 1, 1))
+    Cout = w.shape[0] // 2
+    Zc = torch.complex(Z.view(B, Cout, 2, H, -1)[:, :, 0], Z.view(B, Cout, 2, H, -1)[:, :, 1])
+    out = torch.fft.irfftn(Zc, s=(H, W), dim=(-2, -1), norm="ortho")
+    out.backward(dout.double())
+    return xd.grad, wd.grad, gd.grad, bd.grad, mean.detach(), invstd.detach()
+
+
+FU_BWD_CASES = [
+    # B, Cin, Cout, N, training
+    (3, 8, 8, 32, 1), (2, 8, 8, 32, 0), (5, 16, 16, 16, 1), (3, 32, 32, 8, 1), (2, 5, 7, 16, 1), (2, 7, 3, 8, 1),
+    (2, 12, 20, 8, 0), (2, 3, 2, 32, 1), (2, 16, 16, 32, 1), (2, 24, 9, 16, 1), (1, 32, 32, 16, 1),
+]
+
+
+@pytest.mark.parametrize("case", FU_BWD_CASES)
+def test_fused_fourier_unit_backward(lib, case):
+    """ffc_fu_bwd against float64 autograd of FourierUnitSN.forward."""
+    B, Cin, Cout, N, training = case
+    torch.manual_seed(B * 1000 + Cin * 10 + N + 1)
+    x = torch.randn(B, Cin, N, N)
+    w = torch.randn(2 * Cout, 2 * Cin) / (2 * Cin) ** 0.5
+    gamma, beta = torch.rand(2 * Cout) + 0.5, torch.randn(2 * Cout) * 0.3
+    rmean, rvar = torch.randn(2 * Cout) * 0.1, torch.rand(2 * Cout) + 0.5
+    dout = torch.randn(B, Cout, N, N)
+    dx_r, dw_r, dg_r, db_r, mean, invstd = _fu_reference_bwd(x, w, gamma, beta, rmean, rvar, training, dout)
+    assert lib[0].ffc_fu_bwd_supported(B, Cin, Cout, N, N) == 1
+    dx, dw = torch.zeros_like(x), torch.full_like(w, 7.0)
+    dg, db = torch.zeros(2 * Cout), torch.zeros(2 * Cout)
+    ws = torch.zeros(4 * Cout * 8 + 64, dtype=torch.uint8)
+    call(lib, "ffc_fu_bwd", x, dout, w, gamma, beta, mean.float(), invstd.float(), dx, dw, dg, db,
+         B, Cin, Cout, N, N, training, ws, ws.numel(), None)
+    assert parity.relerr(dx, dx_r) < 5e-6
+    assert parity.relerr(dw, dw_r) < 5e-6
+    assert parity.relerr(dg, dg_r) < 5e-6 and parity.relerr(db, db_r) < 5e-6
