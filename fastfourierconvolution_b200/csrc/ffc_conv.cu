@@ -815,7 +815,7 @@ static int conv_fwd_v2_launch(const ConvParams& p, ffc_stream_t st) {
     return ffc_launch<K>(ffc_cdiv(Mc, K::BM), ffc_cdiv(p.cout, K::kBN), s * s, K::kThreads, K::smem_bytes(), st, p);
 }
 
-int ffc_conv_use_reference_kernel = 3;      // shared with ffc_conv_v4.cu; 3 = ConvFwdV4 (default, via ffc_conv2d_fwd_ws)
+int ffc_conv_use_reference_kernel = 5;      // shared with ffc_conv_v4.cu; 5 = automatic choice (default) in ffc_conv2d_fwd_ws
 
 // See include/ffc_b200.h for the contract.
 extern "C" int ffc_conv2d_fwd(const float* x0, const float* w0, int cin0,
@@ -859,8 +859,9 @@ extern "C" int ffc_conv2d_fwd(const float* x0, const float* w0, int cin0,
     return simt ? conv_fwd_v2_launch<ConvFwdV2<64>>(p, st) : conv_fwd_v2_launch<ConvFwdV3<64>>(p, st);
 }
 
-// test hook: 3 ConvFwdV4 (default when called through ffc_conv2d_fwd_ws), 0 ConvFwdV3 tensor-core 3xTF32 kernels
-// (what plain ffc_conv2d_fwd runs by default), 1 simple reference-form kernels, 2 tuned FP32 SIMT kernels
+// test hook: 5 (default) ffc_conv2d_fwd_ws picks ConvFwdV5 (tcgen05) or ConvFwdV4 (mma.sync) by output width and plain
+// ffc_conv2d_fwd runs ConvFwdV3; 4 forces ConvFwdV5, 3 forces ConvFwdV4, 0 ConvFwdV3 everywhere, 1 simple reference-form
+// kernels, 2 tuned FP32 SIMT kernels
 extern "C" void ffc_debug_conv_reference(int on) { ffc_conv_use_reference_kernel = on; }
 
 extern "C" int ffc_conv2d_wgrad(const float* S, const float* L, float* dW,

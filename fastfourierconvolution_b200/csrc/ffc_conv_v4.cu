@@ -54,20 +54,7 @@ struct ConvV4Params {
     int B, cout, Hi, Wi, Ho, Wo, k, stride, pad, transposed;
 };
 
-// tap geometry of an output parity class (shared by the pack kernel, the main kernel and the host)
-struct ConvClassGeom { int ky0, kx0, qy, qx, Ta, Tb; };
-FFC_HD ConvClassGeom ffc_conv_class_geom(int cls, int k, int stride, int pad, int transposed) {
-    ConvClassGeom g;
-    g.ky0 = 0; g.kx0 = 0; g.qy = 0; g.qx = 0; g.Ta = k; g.Tb = k;
-    if (transposed) {
-        const int s = stride, py = cls / s, px = cls % s;
-        g.ky0 = (py + pad) % s; g.kx0 = (px + pad) % s;
-        g.qy = (py + pad - g.ky0) / s; g.qx = (px + pad - g.kx0) / s;
-        g.Ta = g.ky0 < k ? (k - g.ky0 + s - 1) / s : 0;
-        g.Tb = g.kx0 < k ? (k - g.kx0 + s - 1) / s : 0;
-    }
-    return g;
-}
+#include "ffc_conv_geom.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // weight packing: Wp[cls][(seg, tap, ci)][n] = split(W(seg)[..]) with zero padding
@@ -299,6 +286,14 @@ struct ConvFwdV4 {
 // ---------------------------------------------------------------------------------------------
 static const int kV4BK = 16;
 static const int ffc_conv_v4_mode = 3;      // value of ffc_debug_conv_reference() that selects ConvFwdV4
+static const int ffc_conv_auto_mode = 5;    // default: V5 or V4 by output width
+static const int ffc_conv_v5_mode = 4;      // ... ConvFwdV5 (tcgen05; device build only -- the emulation build runs V4 instead)
+#ifndef FFC_EMU
+size_t conv_v5_workspace_bytes(int cin0, int cin1, int cout, int k, int stride, int pad, int transposed);
+int conv_v5_run(const float* x0, const float* w0, int cin0, const float* x1, const float* w1, int cin1,
+                const float* bias, const float* addend, float* y, int B, int cout, int Hi, int Wi, int Ho, int Wo,
+                int k, int stride, int pad, int transposed, void* workspace, size_t workspace_bytes, ffc_stream_t st);
+#endif
 
 static int conv_v4_bn(int cout) { return (cout <= 32 || (cout > 64 && cout % 64 != 0 && cout % 64 <= 32 && cout < 128)) ? 32 : 64; }
 
@@ -324,7 +319,12 @@ static ConvV4Plan conv_v4_plan(int cin0, int cin1, int cout, int k, int stride, 
 
 extern "C" size_t ffc_conv2d_workspace_bytes(int cin0, int cin1, int cout, int k, int stride, int pad, int transposed) {
     if (cin0 <= 0 || cout <= 0 || k < 1 || stride < 1) return 0;
-    return conv_v4_plan(cin0, cin1, cout, k, stride, pad, transposed).wp_float2 * sizeof(float2) + 256;
+    size_t n = conv_v4_plan(cin0, cin1, cout, k, stride, pad, transposed).wp_float2 * sizeof(float2) + 256;
+#ifndef FFC_EMU
+    const size_t n5 = conv_v5_workspace_bytes(cin0, cin1, cout, k, stride, pad, transposed);
+    if (n5 > n) n = n5;
+#endif
+    return n;
 }
 
 template <int BN>
@@ -343,8 +343,17 @@ extern "C" int ffc_conv2d_fwd_ws(const float* x0, const float* w0, int cin0,
                                  int B, int cout, int Hi, int Wi, int Ho, int Wo,
                                  int k, int stride, int pad, int transposed,
                                  void* workspace, size_t workspace_bytes, void* stream) {
-    if (ffc_conv_use_reference_kernel != ffc_conv_v4_mode)       // the other kernel families need no workspace
-        return ffc_conv2d_fwd(x0, w0, cin0, x1, w1, cin1, bias, addend, y, B, cout, Hi, Wi, Ho, Wo, k, stride, pad, transposed, stream);
+    int mode = ffc_conv_use_reference_kernel;
+    if (mode == ffc_conv_auto_mode) {
+        // tcgen05 kernel wherever its 128 x N tile is reasonably filled; the mma.sync kernel for narrow outputs
+#ifndef FFC_EMU
+        mode = cout >= 24 ? ffc_conv_v5_mode : ffc_conv_v4_mode;
+#else
+        mode = ffc_conv_v4_mode;
+#endif
+    }
+    if (mode != ffc_conv_v4_mode && mode != ffc_conv_v5_mode)
+        return ffc_conv2d_fwd(x0, w0, cin0, x1, w1, cin1, bias, addend, y, B, cout, Hi, Wi, Ho, Wo, k, stride, pad, transposed, stream);   // no workspace needed
     FFC_REQUIRE(x0 && w0 && y && cin0 > 0, "ffc_conv2d_fwd_ws: null pointer / empty first segment");
     FFC_REQUIRE((x1 == nullptr) == (cin1 == 0) && (x1 == nullptr) == (w1 == nullptr), "ffc_conv2d_fwd_ws: inconsistent second segment");
     FFC_REQUIRE(k >= 1 && k <= 7 && (stride == 1 || stride == 2) && pad >= 0 && pad < 8, "ffc_conv2d_fwd_ws: unsupported k=%d stride=%d pad=%d", k, stride, pad);
@@ -358,6 +367,11 @@ extern "C" int ffc_conv2d_fwd_ws(const float* x0, const float* w0, int cin0,
     if (B == 0) return FFC_OK;
     const int cmax = cin0 > cin1 ? cin0 : cin1;
     FFC_REQUIRE((long long)B * cout * Ho * Wo < (1LL << 31) && (long long)B * cmax * Hi * Wi < (1LL << 31), "ffc_conv2d_fwd_ws: tensor too large for 32-bit element offsets");
+#ifndef FFC_EMU
+    if (mode == ffc_conv_v5_mode)
+        return conv_v5_run(x0, w0, cin0, x1, w1, cin1, bias, addend, y, B, cout, Hi, Wi, Ho, Wo, k, stride, pad, transposed,
+                           workspace, workspace_bytes, (ffc_stream_t)stream);
+#endif
     const ConvV4Plan pl = conv_v4_plan(cin0, cin1, cout, k, stride, pad, transposed);
     FFC_REQUIRE(pl.wp_float2 < (1ULL << 31), "ffc_conv2d_fwd_ws: packed weights too large");
     const uintptr_t wsa = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;

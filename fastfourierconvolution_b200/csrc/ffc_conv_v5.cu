@@ -1,0 +1,343 @@
+// ConvFwdV5: implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05 / UMMA) at FP32 accuracy.
+// Same contract as ffc_conv2d_fwd_ws (nn.Conv2d / nn.ConvTranspose2d forward and each other's data-gradient, two
+// summed input segments, fused bias / addend).  Device build only: the host emulation build keeps ConvFwdV4.
+//
+//   GEMM per output parity class:  D[M = 128 pixels][N = cout tile <= 256] += A[M][K] * B[N][K]^T,  K = (segment, tap, ci)
+//   3xTF32: D_hi += A_hi*B_hi, D_lo += A_lo*B_hi + A_hi*B_lo with hi = x truncated to TF32, lo = x - hi (exact), FP32
+//   accumulation in tensor memory (TMEM) over the whole K.  The tensor core truncates when it folds a product group
+//   into its accumulator; keeping the 2^-11 times smaller cross terms in their own accumulator means the main sum sees one
+//   truncation per K-step instead of three (measured 3x smaller error), and the two are added in the epilogue.
+//
+//   * A (im2col of the NCHW activations) is never staged in shared memory: each of 128 gather threads owns one output
+//     pixel (= one TMEM lane), loads the 32 channels of the current K chunk with coalesced 4-byte loads (consecutive lanes
+//     = consecutive pixels), splits hi/lo in registers and writes both straight into TMEM (tcgen05.st); the MMA reads A
+//     from TMEM (the .ts form).  Two gather warpgroups alternate over two TMEM stages.
+//   * B (weights) is re-packed once per call by PackV5 into the exact shared-memory image of a K-major no-swizzle UMMA
+//     operand tile, hi and lo halves adjacent, zero padded; one 1-D bulk copy (cp.async.bulk) per K chunk and stage,
+//     completion counted on an mbarrier.
+//   * One thread issues the MMAs (12 per chunk: 4 K-steps x 3 products); tcgen05.commit releases the A stage and the B
+//     stage to their producers and finally hands the accumulator to the epilogue.
+//   * Epilogue: both warpgroups read their lanes of D from TMEM (tcgen05.ld), add bias / addend and store; for a fixed
+//     output channel consecutive lanes are consecutive pixels.
+//
+// Warp roles (320 threads): warps 0-3 gather even chunks, warps 4-7 gather odd chunks, warp 8 issues MMAs and owns the
+// TMEM allocation, warp 9 streams B.
+#include "ffc_conv_geom.cuh"
+
+#ifndef FFC_EMU
+#include "ffc_umma.cuh"
+
+#define FFC_V5_MAXCLS 4
+static constexpr int V5_BK = 32;          // K per chunk (= 4 MMA K-steps of 8)
+static constexpr int V5_SB = 3;           // B stages
+static constexpr int V5_THREADS = 320;
+
+struct ConvV5Params {
+    const float* x[2]; int cin[2]; int cps[2];     // segments: input, channels, 32-channel chunks per tap
+    int nseg;
+    const float* wp;           // packed weights: [class][n tile][chunk][hi | lo][NT*32]
+    long long cls_off[FFC_V5_MAXCLS];     // float offset of each class
+    int nt_full;               // N of a full tile (multiple of 16, <= 192)
+    const float* bias; const float* addend; float* y;
+    int B, cout, Hi, Wi, Ho, Wo, k, stride, pad, transposed;
+};
+
+// N (padded to 16) of tile `t` when cout is cut into tiles of nt_full
+__host__ __device__ __forceinline__ int v5_tile_n(int cout, int nt_full, int t) {
+    const int rem = cout - t * nt_full;
+    const int n = rem < nt_full ? rem : nt_full;
+    return (n + 15) / 16 * 16;
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing
+// ---------------------------------------------------------------------------------------------
+struct PackV5Params {
+    const float* w[2]; int cin[2]; int cps[2]; int nseg;
+    float* wp; long long cls_off[FFC_V5_MAXCLS];
+    int nt_full, ntiles, cout, k, stride, pad, transposed;
+};
+
+__global__ void __launch_bounds__(256) pack_v5_kernel(const PackV5Params p) {
+    const int cls = blockIdx.y;
+    const ConvClassGeom g = ffc_conv_class_geom(cls, p.k, p.stride, p.pad, p.transposed);
+    const int T = g.Ta * g.Tb, KK = p.k * p.k;
+    const int nchunks = T * (p.cps[0] + (p.nseg > 1 ? p.cps[1] : 0));
+    // element e of the class: (tile, chunk, half, n, kk) with n-major inside (n/8, kk/4, n%8, kk%4) order
+    long long tile_base = 0;
+    for (int t = 0; t < p.ntiles; ++t) {
+        const int NT = v5_tile_n(p.cout, p.nt_full, t);
+        const long long per_chunk = 2LL * NT * V5_BK;
+        const long long total = (long long)nchunks * NT * V5_BK;
+        for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+            const int kk = (int)(e % V5_BK);
+            const int n = (int)((e / V5_BK) % NT);
+            int chunk = (int)(e / ((long long)V5_BK * NT));
+            const int chunk_all = chunk;
+            int sg = 0;
+            if (chunk >= T * p.cps[0]) { sg = 1; chunk -= T * p.cps[0]; }
+            const int cps = sg ? p.cps[1] : p.cps[0], cin = sg ? p.cin[1] : p.cin[0];
+            const int tap = chunk / cps, ci = (chunk % cps) * V5_BK + kk;
+            const int co = t * p.nt_full + n;
+            float v = 0.f;
+            if (co < p.cout && ci < cin) {
+                const int a = tap / g.Tb, b = tap % g.Tb;
+                const float* w = sg ? p.w[1] : p.w[0];
+                if (p.transposed) v = __ldg(w + ((size_t)ci * p.cout + co) * KK + (g.ky0 + p.stride * a) * p.k + (g.kx0 + p.stride * b));
+                else v = __ldg(w + ((size_t)co * cin + ci) * KK + a * p.k + b);
+            }
+            const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+            float* dst = p.wp + p.cls_off[cls] + tile_base + (long long)chunk_all * per_chunk
+                       + (n / 8) * 256 + (kk / 4) * 32 + (n % 8) * 4 + (kk % 4);
+            dst[0] = hi;
+            dst[(size_t)NT * V5_BK] = v - hi;
+        }
+        tile_base += (long long)nchunks * per_chunk;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(V5_THREADS, 2) conv_v5_kernel(const ConvV5Params p) {
+    extern __shared__ __align__(128) unsigned char v5_smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int s = p.transposed ? p.stride : 1;
+    const int cls = blockIdx.z, py = cls / s, px = cls % s;
+    const int Hc = (p.Ho - py + s - 1) / s, Wc = (p.Wo - px + s - 1) / s;
+    const int Mc = p.B * Hc * Wc;
+    const int m0 = blockIdx.x * 128;
+    if (m0 >= Mc) return;                               // whole CTA exits together
+    const int ntile = blockIdx.y;
+    const int NT = v5_tile_n(p.cout, p.nt_full, ntile);
+    const ConvClassGeom g = ffc_conv_class_geom(cls, p.k, p.stride, p.pad, p.transposed);
+    const int T = g.Ta * g.Tb;
+    const int nchunks = T * (p.cps[0] + (p.nseg > 1 ? p.cps[1] : 0));
+    const uint32_t stage_bytes = (uint32_t)(2 * NT * V5_BK * 4);
+    // packed weights of this (class, tile): tiles before it have nt_full columns
+    const float* wp = p.wp + p.cls_off[cls] + (long long)ntile * nchunks * 2LL * p.nt_full * V5_BK;
+
+    unsigned char* bstage = v5_smem;                                                     // V5_SB stages
+    uint64_t* bars = reinterpret_cast<uint64_t*>(v5_smem + (size_t)V5_SB * stage_bytes);
+    uint64_t* b_full = bars;                    // [V5_SB]
+    uint64_t* b_free = bars + V5_SB;            // [V5_SB]
+    uint64_t* a_ready = bars + 2 * V5_SB;       // [2]
+    uint64_t* a_free = a_ready + 2;             // [2]
+    uint64_t* acc_done = a_free + 2;            // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+
+    // TMEM columns: D_hi [0, NT) | D_lo [NT, 2NT) | A stage st at a_col0 + 64*st (hi 32 | lo 32)
+    const uint32_t tmem_cols = NT > 64 ? 512u : 256u;
+    if (tid == 0) {
+        for (int i = 0; i < V5_SB; ++i) { umma::mbar_init(&b_full[i], 1); umma::mbar_init(&b_free[i], 1); }
+        for (int i = 0; i < 2; ++i) { umma::mbar_init(&a_ready[i], 128); umma::mbar_init(&a_free[i], 1); }
+        umma::mbar_init(acc_done, 1);
+        umma::fence_barrier_init();
+    }
+    if (warp == 8) umma::tmem_alloc(tmem_slot, tmem_cols);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tbase = *tmem_slot;
+    const uint32_t a_col0 = NT > 64 ? 384u : 128u;
+
+    if (warp < 8) {
+        // ===================== A producers (then epilogue) =====================
+        const int wg = warp >> 2;
+        const int row = tid & 127;                          // TMEM lane == pixel of the tile
+        const uint32_t lane_base = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+        const int m = m0 + row;
+        const bool ok = m < Mc;
+        const int xq = m % Wc, yq = (m / Wc) % Hc, b = m / (Wc * Hc);
+        const int HWi = p.Hi * p.Wi;
+        for (int c = wg; c < nchunks; c += 2) {
+            // cursor of chunk c: (segment, tap, first channel)
+            int r = c, sg = 0;
+            if (r >= T * p.cps[0]) { sg = 1; r -= T * p.cps[0]; }
+            const int cps = sg ? p.cps[1] : p.cps[0], cin = sg ? p.cin[1] : p.cin[0];
+            const int tap = r / cps, c0 = (r % cps) * V5_BK;
+            const int ta = tap / g.Tb, tb = tap % g.Tb;
+            int iy, ix;
+            if (p.transposed) { iy = yq + g.qy - ta; ix = xq + g.qx - tb; }
+            else { iy = yq * p.stride - p.pad + ta; ix = xq * p.stride - p.pad + tb; }
+            const bool okp = ok && iy >= 0 && iy < p.Hi && ix >= 0 && ix < p.Wi;
+            const float* xs = sg ? p.x[1] : p.x[0];
+            const float* xp = xs + ((size_t)(b * cin + c0) * HWi + iy * p.Wi + ix);
+            float v[V5_BK];
+#pragma unroll
+            for (int j = 0; j < V5_BK; ++j) v[j] = (okp && c0 + j < cin) ? __ldg(xp + (size_t)j * HWi) : 0.f;
+            const int it = c >> 1;
+            if (it > 0) umma::mbar_wait(&a_free[wg], (uint32_t)((it - 1) & 1));      // the MMAs that read this stage are done
+            umma::fence_after_sync();
+            const uint32_t acol = lane_base + a_col0 + 64u * (uint32_t)wg;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float xv = v[16 * h + j];
+                    const float xh = __uint_as_float(__float_as_uint(xv) & 0xffffe000u);
+                    hi[j] = __float_as_uint(xh);
+                    lo[j] = __float_as_uint(xv - xh);
+                }
+                umma::tmem_st16(acol + 16 * h, hi);
+                umma::tmem_st16(acol + 32 + 16 * h, lo);
+            }
+            umma::wait_st();
+            umma::fence_before_sync();
+            umma::mbar_arrive(&a_ready[wg]);
+        }
+        // ===================== epilogue =====================
+        if (nchunks > 0) { umma::mbar_wait(acc_done, 0); umma::fence_after_sync(); }
+        {
+            const int oy = yq * s + py, ox = xq * s + px;
+            const size_t HWo = (size_t)p.Ho * p.Wo;
+            const int co0 = ntile * p.nt_full;
+            const size_t o0 = ((size_t)b * p.cout + co0) * HWo + (size_t)oy * p.Wo + ox;
+            for (int n0 = 16 * wg; n0 < NT; n0 += 32) {
+                uint32_t r[16];
+                if (nchunks > 0) {                            // warp-wide: every lane takes part
+                    uint32_t q[16];
+                    umma::tmem_ld16(lane_base + (uint32_t)n0, r);
+                    umma::tmem_ld16(lane_base + (uint32_t)(NT + n0), q);
+                    umma::wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(q[j]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) r[j] = 0u;
+                }
+                if (ok) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int co = co0 + n0 + j;
+                        if (co < p.cout) {
+                            float v2 = __uint_as_float(r[j]);
+                            if (p.bias) v2 += __ldg(p.bias + co);
+                            if (p.addend) v2 += __ldg(p.addend + o0 + (size_t)(n0 + j) * HWo);
+                            p.y[o0 + (size_t)(n0 + j) * HWo] = v2;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 8) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma::idesc_tf32(128, NT);
+            for (int c = 0; c < nchunks; ++c) {
+                const int sa = c & 1, sb = c % V5_SB;
+                umma::mbar_wait(&b_full[sb], (uint32_t)((c / V5_SB) & 1));
+                umma::mbar_wait(&a_ready[sa], (uint32_t)((c >> 1) & 1));
+                umma::fence_after_sync();
+                const uint32_t b_hi = umma::smem_u32(bstage + (size_t)sb * stage_bytes), b_lo = b_hi + (uint32_t)(NT * V5_BK * 4);
+                const uint32_t a_hi = tbase + a_col0 + 64u * (uint32_t)sa, a_lo = a_hi + 32u;
+#pragma unroll
+                for (int ks = 0; ks < V5_BK / 8; ++ks) {
+                    const uint64_t dh = umma::smem_desc_kmajor_noswizzle(b_hi + ks * 256, 128, 1024);
+                    const uint64_t dl = umma::smem_desc_kmajor_noswizzle(b_lo + ks * 256, 128, 1024);
+                    umma::mma_tf32_ts(tbase + (uint32_t)NT, a_lo + ks * 8, dh, idesc, (c | ks) ? 1u : 0u);
+                    umma::mma_tf32_ts(tbase + (uint32_t)NT, a_hi + ks * 8, dl, idesc, 1u);
+                    umma::mma_tf32_ts(tbase, a_hi + ks * 8, dh, idesc, (c | ks) ? 1u : 0u);
+                }
+                umma::commit(&a_free[sa]);
+                umma::commit(&b_free[sb]);
+            }
+            umma::commit(acc_done);
+        }
+        __syncwarp();
+    } else {
+        // ===================== B loader =====================
+        if (lane == 0) {
+            for (int c = 0; c < nchunks; ++c) {
+                const int sb = c % V5_SB;
+                if (c >= V5_SB) umma::mbar_wait(&b_free[sb], (uint32_t)((c / V5_SB - 1) & 1));
+                umma::mbar_arrive_expect_tx(&b_full[sb], stage_bytes);
+                umma::bulk_g2s(bstage + (size_t)sb * stage_bytes, wp + (size_t)c * 2 * NT * V5_BK, stage_bytes, &b_full[sb]);
+            }
+        }
+        __syncwarp();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 8) umma::tmem_dealloc(tbase, tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct ConvV5Plan { int nt_full, ntiles, cps[2], ncls; long long cls_off[FFC_V5_MAXCLS]; long long total_floats; };
+
+static ConvV5Plan conv_v5_plan(int cin0, int cin1, int cout, int k, int stride, int pad, int transposed) {
+    ConvV5Plan pl;
+    const int c16 = (cout + 15) / 16 * 16;
+    // widest tile: 2 accumulators of N columns + 128 columns of A stages in the 512 TMEM columns; an even split
+    // (e.g. 384 -> 192 + 192, 512 -> 3 x 176) keeps the tiles alike
+    const int nt_max = 192;
+    const int nsplit = (c16 + nt_max - 1) / nt_max;
+    pl.nt_full = ((c16 + nsplit - 1) / nsplit + 15) / 16 * 16;
+    pl.ntiles = (cout + pl.nt_full - 1) / pl.nt_full;
+    pl.cps[0] = (cin0 + V5_BK - 1) / V5_BK;
+    pl.cps[1] = cin1 ? (cin1 + V5_BK - 1) / V5_BK : 0;
+    pl.ncls = transposed ? stride * stride : 1;
+    long long off = 0, cols = 0;
+    for (int t = 0; t < pl.ntiles; ++t) cols += v5_tile_n(cout, pl.nt_full, t);
+    for (int c = 0; c < FFC_V5_MAXCLS; ++c) {
+        pl.cls_off[c] = off;
+        if (c < pl.ncls) {
+            const ConvClassGeom g = ffc_conv_class_geom(c, k, stride, pad, transposed);
+            off += (long long)g.Ta * g.Tb * (pl.cps[0] + pl.cps[1]) * 2LL * cols * V5_BK;
+        }
+    }
+    pl.total_floats = off;
+    return pl;
+}
+
+size_t conv_v5_workspace_bytes(int cin0, int cin1, int cout, int k, int stride, int pad, int transposed) {
+    return (size_t)conv_v5_plan(cin0, cin1, cout, k, stride, pad, transposed).total_floats * sizeof(float) + 256;
+}
+
+// arguments validated by ffc_conv2d_fwd_ws
+int conv_v5_run(const float* x0, const float* w0, int cin0, const float* x1, const float* w1, int cin1,
+                const float* bias, const float* addend, float* y, int B, int cout, int Hi, int Wi, int Ho, int Wo,
+                int k, int stride, int pad, int transposed, void* workspace, size_t workspace_bytes, ffc_stream_t st) {
+    const ConvV5Plan pl = conv_v5_plan(cin0, cin1, cout, k, stride, pad, transposed);
+    const uintptr_t wsa = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
+    if (!workspace || wsa + (size_t)pl.total_floats * sizeof(float) > (uintptr_t)workspace + workspace_bytes) {
+        ffc_set_error("ffc_conv2d_fwd_ws: workspace too small (%zu bytes needed)", (size_t)pl.total_floats * sizeof(float) + 256);
+        return FFC_ERR_WORKSPACE;
+    }
+    PackV5Params pp;
+    pp.w[0] = w0; pp.w[1] = w1; pp.cin[0] = cin0; pp.cin[1] = cin1; pp.cps[0] = pl.cps[0]; pp.cps[1] = pl.cps[1];
+    pp.nseg = x1 ? 2 : 1; pp.wp = (float*)wsa; pp.nt_full = pl.nt_full; pp.ntiles = pl.ntiles; pp.cout = cout;
+    pp.k = k; pp.stride = stride; pp.pad = pad; pp.transposed = transposed;
+    for (int c = 0; c < FFC_V5_MAXCLS; ++c) pp.cls_off[c] = pl.cls_off[c];
+    const long long per_cls = (long long)k * k * (pl.cps[0] + pl.cps[1]) * V5_BK * ((cout + 15) / 16 * 16);
+    int gx = (int)((per_cls + 255) / 256); if (gx > 148 * 4) gx = 148 * 4; if (gx < 1) gx = 1;
+    pack_v5_kernel<<<dim3(gx, pl.ncls), 256, 0, st>>>(pp);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { ffc_set_error("pack_v5 launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
+    ffc_count_launch();
+
+    ConvV5Params p;
+    p.x[0] = x0; p.x[1] = x1; p.cin[0] = cin0; p.cin[1] = cin1; p.cps[0] = pl.cps[0]; p.cps[1] = pl.cps[1]; p.nseg = x1 ? 2 : 1;
+    p.wp = (const float*)wsa; p.nt_full = pl.nt_full;
+    for (int c = 0; c < FFC_V5_MAXCLS; ++c) p.cls_off[c] = pl.cls_off[c];
+    p.bias = bias; p.addend = addend; p.y = y; p.B = B; p.cout = cout; p.Hi = Hi; p.Wi = Wi; p.Ho = Ho; p.Wo = Wo;
+    p.k = k; p.stride = stride; p.pad = pad; p.transposed = transposed;
+    const int s = transposed ? stride : 1;
+    const int Mc = B * ffc_cdiv(Ho, s) * ffc_cdiv(Wo, s);
+    const size_t smem = (size_t)V5_SB * 2 * pl.nt_full * V5_BK * 4 + 256;
+    static size_t configured = 0;
+    if (smem > configured) {
+        e = cudaFuncSetAttribute(conv_v5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { ffc_set_error("cudaFuncSetAttribute(conv_v5, %zu B): %s", smem, cudaGetErrorString(e)); return FFC_ERR_CUDA; }
+        configured = smem;
+    }
+    conv_v5_kernel<<<dim3(ffc_cdiv(Mc, 128), pl.ntiles, s * s), V5_THREADS, smem, st>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { ffc_set_error("conv_v5 launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
+    ffc_count_launch();
+    return FFC_OK;
+}
+#endif  // !FFC_EMU

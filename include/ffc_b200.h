@@ -174,10 +174,11 @@ int ffc_se_bwd(const float* x, const float* dy, const float* w1, const float* w2
                void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- test hook ---------------------------------------------------------------------------------
- * Kernel family used by the convolution entry points: 3 (default) ffc_conv2d_fwd_ws runs the packed-weight
- * cp.async-pipelined tensor-core kernel (3xTF32 mma at FP32 accuracy) and ffc_conv2d_fwd the register-prefetch
- * tensor-core kernel; 0 both run the register-prefetch tensor-core kernel; 1 the simple single-buffered FP32 forms
- * of the same math; 2 the tuned FP32 SIMT kernels.  Tests compare all four. */
+ * Kernel family used by the convolution entry points.  5 (default): ffc_conv2d_fwd_ws picks, by output width, the
+ * tcgen05 / tensor-memory implicit-GEMM kernel (ConvFwdV5) or the packed-weight cp.async-pipelined mma.sync kernel
+ * (ConvFwdV4), both 3xTF32 at FP32 accuracy, and plain ffc_conv2d_fwd runs the register-prefetch mma.sync kernel;
+ * 4 / 3 force ConvFwdV5 / ConvFwdV4; 0 the register-prefetch mma.sync kernel everywhere; 1 the simple single-buffered
+ * FP32 forms of the same math; 2 the tuned FP32 SIMT kernels.  Tests compare all of them. */
 void ffc_debug_conv_reference(int mode);
 /* Training-mode ffc_fu_fwd runs as ONE cooperative kernel (spectrum held in shared memory across a grid barrier)
  * when all image tiles are co-resident, else as two passes over x; on = 1 forces the two-pass form. */

@@ -93,25 +93,29 @@ CONV_CASES = [
     (1, [17], 1, 4, 4, 1, 0, False, False, False, 0),
     (3, [40, 24], 100, 6, 4, 2, 1, True, True, True, 0),
     (2, [33], 20, 9, 3, 1, 1, False, True, False, 0),
+    (1, [40], 400, 5, 3, 1, 1, False, True, False, 0),       # several output-channel tiles
+    (2, [70, 10], 200, 4, 4, 2, 1, True, False, True, 0),
+    (40, [36], 24, 6, 3, 1, 1, False, False, False, 0),      # several pixel tiles
 ]
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
-@pytest.mark.parametrize("reference_form", [0, 1, 2, 3])
+@pytest.mark.parametrize("reference_form", [0, 1, 2, 3, 4])
 def test_conv_forward_dgrad_wgrad(lib, case, reference_form):
     """0: tensor-core 3xTF32 kernels; 1: the simple single-buffered forms; 2: tuned FP32 SIMT kernels;
-    3: tensor-core 3xTF32 with packed weights and a cp.async ring (ffc_conv2d_fwd_ws)."""
+    3: tensor-core 3xTF32 with packed weights and a cp.async ring (ffc_conv2d_fwd_ws); 4: tcgen05 / TMEM implicit GEMM
+    (device build only; the emulation build runs family 3 for it)."""
     lib[0].ffc_debug_conv_reference(reference_form)
     _conv_mode[0] = reference_form if lib[1] != "cpu" else 1      # the emulation build computes every family in FP32
     try:
         _conv_case(lib, case)
     finally:
-        lib[0].ffc_debug_conv_reference(3)
+        lib[0].ffc_debug_conv_reference(5)
 
 
 # 3xTF32 on the tensor cores: the dropped lo*lo term and the MMA's internal accumulation leave ~1e-5
 # (still an order of magnitude inside the 1e-4 FP32 parity bound); the FP32 FMA families reach ~1e-7.
-CONV_TOL = {0: 4e-5, 1: 3e-6, 2: 3e-6, 3: 4e-5}
+CONV_TOL = {0: 4e-5, 1: 3e-6, 2: 3e-6, 3: 4e-5, 4: 4e-5}
 _conv_mode = [0]
 
 

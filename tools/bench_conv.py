@@ -48,7 +48,7 @@ def main():
         flops = 2.0 * B * Ho * Ho * cout * cin * taps
         row = {"shape": name, "GFLOP": round(flops / 1e9, 2)}
         ref = (F.conv_transpose2d(x.double(), w.double(), None, s, p) if tr else F.conv2d(x.double(), w.double(), None, s, p))
-        for mode in (0, 3):
+        for mode in (3, 4):
             L.ffc_debug_conv_reference(mode)
             y = ops.conv2d(x, w, stride=s, pad=p, transposed=tr)
             err = ((y.double() - ref).abs().max() / ref.abs().max()).item()
@@ -60,7 +60,7 @@ def main():
                 return torch.autograd.grad(out, (xg, wg), dy)
             t_b = graph_time(fwd_bwd) - t_f
             row[f"m{mode}"] = f"fwd {1000 * t_f:.0f}us {flops / t_f / 1e9:.1f}TF err {err:.1e} | bwd {1000 * t_b:.0f}us {2 * flops / t_b / 1e9:.1f}TF"
-        L.ffc_debug_conv_reference(3)
+        L.ffc_debug_conv_reference(5)
         for tf32 in (False, True):
             torch.backends.cudnn.allow_tf32 = tf32
             fn = (lambda: F.conv_transpose2d(x, w, None, s, p)) if tr else (lambda: F.conv2d(x, w, None, s, p))
