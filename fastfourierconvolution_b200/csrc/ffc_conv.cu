@@ -864,6 +864,12 @@ extern "C" int ffc_conv2d_fwd(const float* x0, const float* w0, int cin0,
 // kernels, 2 tuned FP32 SIMT kernels
 extern "C" void ffc_debug_conv_reference(int on) { ffc_conv_use_reference_kernel = on; }
 
+#ifndef FFC_EMU
+bool wgrad_v5_supported(int SC, int LC, int Hs, int Ws, int k);
+int wgrad_v5_run(const float* S, const float* L, float* dW, int B, int SC, int LC, int Hs, int Ws, int Hl, int Wl,
+                 int k, int stride, int pad, ffc_stream_t st);
+#endif
+
 extern "C" int ffc_conv2d_wgrad(const float* S, const float* L, float* dW,
                                 int B, int SC, int LC, int Hs, int Ws, int Hl, int Wl,
                                 int k, int stride, int pad, void* stream) {
@@ -875,6 +881,11 @@ extern "C" int ffc_conv2d_wgrad(const float* S, const float* L, float* dW,
     const size_t nW = (size_t)SC * LC * k * k;
     FFC_CHECK(ffc_memset_async(dW, 0, nW * sizeof(float), st));
     if (B == 0) return FFC_OK;
+#ifndef FFC_EMU
+    // tcgen05 kernel (ffc_wgrad_v5.cu) for the shapes that fill its 128 x N tile; kernel families 4 and 5 (default)
+    if (ffc_conv_use_reference_kernel >= 4 && wgrad_v5_supported(SC, LC, Hs, Ws, k))
+        return wgrad_v5_run(S, L, dW, B, SC, LC, Hs, Ws, Hl, Wl, k, stride, pad, st);
+#endif
     WgradParams p{S, L, dW, B, SC, LC, Hs, Ws, Hl, Wl, k, stride, pad, 0};
     const int Ktot = B * Hs * Ws;
     const bool ref = ffc_conv_use_reference_kernel == 1;

@@ -96,6 +96,9 @@ CONV_CASES = [
     (1, [40], 400, 5, 3, 1, 1, False, True, False, 0),       # several output-channel tiles
     (2, [70, 10], 200, 4, 4, 2, 1, True, False, True, 0),
     (40, [36], 24, 6, 3, 1, 1, False, False, False, 0),      # several pixel tiles
+    (9, [48], 40, 8, 4, 2, 1, True, False, False, 0),        # tcgen05 weight-gradient shapes (both directions)
+    (9, [40], 48, 8, 4, 2, 1, False, True, False, 0),
+    (33, [26], 30, 4, 3, 1, 1, False, False, False, 0),
 ]
 
 
@@ -156,7 +159,8 @@ def _conv_case(lib, case):
             call(lib, "ffc_conv2d_wgrad", x, dy, dW, B, x.shape[1], cout, Hi, Hi, Ho, Ho, k, s, p, None)
         else:
             call(lib, "ffc_conv2d_wgrad", dy, x, dW, B, cout, x.shape[1], Ho, Ho, Hi, Hi, k, s, p, None)
-        assert parity.relerr(dW, wd.grad) < 3e-6          # wgrad is FP32 FMA in every family
+        # wgrad is FP32 FMA in families 0-3; family 4 (and the default 5) use the tcgen05 3xTF32 kernel where it applies
+        assert parity.relerr(dW, wd.grad) < (4e-5 if _conv_mode[0] >= 4 else 3e-6)
         _conv_fwd(lib, dy, w, cout, None, None, 0, None, None, dx, B, x.shape[1], Ho, Ho, Hi, Hi, k, s, p, int(not tr))
         assert parity.relerr(dx, xd.grad) < CONV_TOL[_conv_mode[0]]
 
