@@ -866,6 +866,9 @@ extern "C" void ffc_debug_conv_reference(int on) { ffc_conv_use_reference_kernel
 
 #ifndef FFC_EMU
 bool wgrad_v5_supported(int SC, int LC, int Hs, int Ws, int k);
+bool wgrad_small_supported(int SC, int k);
+int wgrad_small_run(const float* S, const float* L, float* dW, int B, int SC, int LC, int Hs, int Ws, int Hl, int Wl,
+                    int k, int stride, int pad, ffc_stream_t st);
 int wgrad_v5_run(const float* S, const float* L, float* dW, int B, int SC, int LC, int Hs, int Ws, int Hl, int Wl,
                  int k, int stride, int pad, ffc_stream_t st);
 #endif
@@ -883,6 +886,8 @@ extern "C" int ffc_conv2d_wgrad(const float* S, const float* L, float* dW,
     if (B == 0) return FFC_OK;
 #ifndef FFC_EMU
     // tcgen05 kernel (ffc_wgrad_v5.cu) for the shapes that fill its 128 x N tile; kernel families 4 and 5 (default)
+    if (ffc_conv_use_reference_kernel >= 5 && wgrad_small_supported(SC, k))
+        return wgrad_small_run(S, L, dW, B, SC, LC, Hs, Ws, Hl, Wl, k, stride, pad, st);
     if (ffc_conv_use_reference_kernel >= 4 && wgrad_v5_supported(SC, LC, Hs, Ws, k))
         return wgrad_v5_run(S, L, dW, B, SC, LC, Hs, Ws, Hl, Wl, k, stride, pad, st);
 #endif

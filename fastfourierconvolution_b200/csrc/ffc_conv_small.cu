@@ -1,0 +1,244 @@
+// Direct (SIMT, FP32 FMA) convolution kernels for layers with at most 4 channels on one side -- the RGB output
+// convolution of every generator (fgan_complete.py:110-113: FFC_BN_ACT(ngf, 3, ...)) and its gradients.  A 128 x N
+// tensor-core tile is >90 % padding there and the work is bandwidth bound, so one thread per output pixel with the few
+// channels in registers is the right shape:
+//   ConvSmallCout : cout <= 4, any cin (two summed segments), acc[4] per pixel, weights broadcast from shared memory
+//   ConvSmallCin  : cin  <= 4 (one segment), the k*k*cin gathered inputs of a pixel stay in registers across all cout
+//   WgradSmallSc  : SC   <= 4 small-side channels, thread = pixel walker with SC*k*k partial sums in registers,
+//                   warp-shuffle + shared-memory reduction, one atomic per weight entry and CTA
+// Same contracts as ffc_conv2d_fwd / ffc_conv2d_wgrad (gather form, transposed by tap validity).  Device build only.
+#include "ffc_common.cuh"
+
+#ifndef FFC_EMU
+
+struct SmallConvParams {
+    const float* x[2]; const float* w[2]; int cin[2]; int nseg;
+    const float* bias; const float* addend; float* y;
+    int B, cout, Hi, Wi, Ho, Wo, k, stride, pad, transposed;
+};
+
+// input offset (iy*Wi + ix) of tap (ky,kx) for output pixel (oy,ox), or -1 when the tap does not contribute
+__device__ __forceinline__ int small_tap_off(const SmallConvParams& p, int oy, int ox, int ky, int kx) {
+    int iy, ix;
+    if (!p.transposed) { iy = oy * p.stride - p.pad + ky; ix = ox * p.stride - p.pad + kx; }
+    else {
+        const int ty = oy + p.pad - ky, tx = ox + p.pad - kx;
+        if (ty < 0 || tx < 0 || ty % p.stride || tx % p.stride) return -1;
+        iy = ty / p.stride; ix = tx / p.stride;
+    }
+    return (iy >= 0 && iy < p.Hi && ix >= 0 && ix < p.Wi) ? iy * p.Wi + ix : -1;
+}
+// weight element [co][ci][ky][kx] (conv) or [ci][co][ky][kx] (transposed)
+__device__ __forceinline__ float small_w(const SmallConvParams& p, const float* w, int cin, int co, int ci, int t) {
+    const int KK = p.k * p.k;
+    return p.transposed ? __ldg(w + ((size_t)ci * p.cout + co) * KK + t) : __ldg(w + ((size_t)co * cin + ci) * KK + t);
+}
+
+template <int K>
+__global__ void __launch_bounds__(256) conv_small_cout_kernel(const SmallConvParams p) {
+    extern __shared__ float4 scw[];                 // [seg ci][tap] -> (w of co 0..3)
+    constexpr int KK = K * K;
+    const int ctot = p.cin[0] + (p.nseg > 1 ? p.cin[1] : 0);
+    for (int e = threadIdx.x; e < ctot * KK; e += blockDim.x) {
+        const int c = e / KK, t = e % KK;
+        const int sg = c >= p.cin[0], ci = sg ? c - p.cin[0] : c;
+        float q[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int co = 0; co < p.cout; ++co) q[co] = small_w(p, p.w[sg], p.cin[sg], co, ci, t);
+        scw[e] = make_float4(q[0], q[1], q[2], q[3]);
+    }
+    __syncthreads();
+    const int HWo = p.Ho * p.Wo, HWi = p.Hi * p.Wi;
+    const long long total = (long long)p.B * HWo;
+    for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < total; m += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(m / HWo), r = (int)(m % HWo), oy = r / p.Wo, ox = r % p.Wo;
+        int off[KK];
+#pragma unroll
+        for (int t = 0; t < KK; ++t) off[t] = small_tap_off(p, oy, ox, t / K, t % K);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        int cbase = 0;
+        for (int sg = 0; sg < p.nseg; ++sg) {
+            const float* xp = p.x[sg] + (size_t)b * p.cin[sg] * HWi;
+            for (int ci = 0; ci < p.cin[sg]; ++ci, xp += HWi) {
+                const float4* wq = scw + (size_t)(cbase + ci) * KK;
+#pragma unroll
+                for (int t = 0; t < KK; ++t) {
+                    if (off[t] >= 0) {
+                        const float v = __ldg(xp + off[t]);
+                        const float4 q = wq[t];
+                        acc[0] = fmaf(v, q.x, acc[0]); acc[1] = fmaf(v, q.y, acc[1]);
+                        acc[2] = fmaf(v, q.z, acc[2]); acc[3] = fmaf(v, q.w, acc[3]);
+                    }
+                }
+            }
+            cbase += p.cin[sg];
+        }
+        for (int co = 0; co < p.cout; ++co) {
+            const size_t o = ((size_t)b * p.cout + co) * HWo + r;
+            float v = acc[co];
+            if (p.bias) v += __ldg(p.bias + co);
+            if (p.addend) v += __ldg(p.addend + o);
+            p.y[o] = v;
+        }
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(256) conv_small_cin_kernel(const SmallConvParams p) {
+    extern __shared__ float scv[];                  // [co][ci][tap]
+    constexpr int KK = K * K;
+    const int cin = p.cin[0];
+    for (int e = threadIdx.x; e < p.cout * cin * KK; e += blockDim.x) {
+        const int t = e % KK, ci = (e / KK) % cin, co = e / (KK * cin);
+        scv[e] = small_w(p, p.w[0], cin, co, ci, t);
+    }
+    __syncthreads();
+    const int HWo = p.Ho * p.Wo, HWi = p.Hi * p.Wi;
+    const long long total = (long long)p.B * HWo;
+    for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < total; m += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(m / HWo), r = (int)(m % HWo), oy = r / p.Wo, ox = r % p.Wo;
+        float v[4][KK];
+        const float* xp = p.x[0] + (size_t)b * cin * HWi;
+#pragma unroll
+        for (int t = 0; t < KK; ++t) {
+            const int off = small_tap_off(p, oy, ox, t / K, t % K);
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci) v[ci][t] = (off >= 0 && ci < cin) ? __ldg(xp + (size_t)ci * HWi + off) : 0.f;
+        }
+        for (int co = 0; co < p.cout; ++co) {
+            const float* wr = scv + (size_t)co * cin * KK;
+            float acc = 0.f;
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci) {
+                if (ci < cin) {
+#pragma unroll
+                    for (int t = 0; t < KK; ++t) acc = fmaf(v[ci][t], wr[ci * KK + t], acc);
+                }
+            }
+            const size_t o = ((size_t)b * p.cout + co) * HWo + r;
+            if (p.bias) acc += __ldg(p.bias + co);
+            if (p.addend) acc += __ldg(p.addend + o);
+            p.y[o] = acc;
+        }
+    }
+}
+
+bool conv_small_supported(int cin0, int cin1, int cout, int k) {
+    if (k != 1 && k != 3 && k != 4) return false;
+    if (cout <= 4) return (size_t)(cin0 + cin1) * k * k * 16 <= 96 * 1024;
+    return cin1 == 0 && cin0 <= 4 && (size_t)cout * cin0 * k * k * 4 <= 96 * 1024;
+}
+
+template <int K>
+static int conv_small_launch(const SmallConvParams& p, ffc_stream_t st) {
+    const long long total = (long long)p.B * p.Ho * p.Wo;
+    int grid = (int)((total + 255) / 256); if (grid > 148 * 16) grid = 148 * 16; if (grid < 1) grid = 1;
+    cudaError_t e;
+    if (p.cout <= 4) {
+        const size_t smem = (size_t)(p.cin[0] + (p.nseg > 1 ? p.cin[1] : 0)) * K * K * 16;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(conv_small_cout_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        conv_small_cout_kernel<K><<<grid, 256, smem, st>>>(p);
+    } else {
+        const size_t smem = (size_t)p.cout * p.cin[0] * K * K * 4;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(conv_small_cin_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        conv_small_cin_kernel<K><<<grid, 256, smem, st>>>(p);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { ffc_set_error("conv_small launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
+    ffc_count_launch();
+    return FFC_OK;
+}
+
+int conv_small_run(const float* x0, const float* w0, int cin0, const float* x1, const float* w1, int cin1,
+                   const float* bias, const float* addend, float* y, int B, int cout, int Hi, int Wi, int Ho, int Wo,
+                   int k, int stride, int pad, int transposed, ffc_stream_t st) {
+    SmallConvParams p;
+    p.x[0] = x0; p.x[1] = x1; p.w[0] = w0; p.w[1] = w1; p.cin[0] = cin0; p.cin[1] = cin1; p.nseg = x1 ? 2 : 1;
+    p.bias = bias; p.addend = addend; p.y = y; p.B = B; p.cout = cout; p.Hi = Hi; p.Wi = Wi; p.Ho = Ho; p.Wo = Wo;
+    p.k = k; p.stride = stride; p.pad = pad; p.transposed = transposed;
+    if (k == 1) return conv_small_launch<1>(p, st);
+    if (k == 3) return conv_small_launch<3>(p, st);
+    return conv_small_launch<4>(p, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight gradient with SC <= 4:  dW[sc][lc][ky][kx] = sum_{b,y,x} S[b,sc,y,x] * L[b,lc,y*s-pad+ky,x*s-pad+kx]
+// grid = (LC, image groups); a thread walks pixels of its images with SC*K*K partial sums in registers
+// ---------------------------------------------------------------------------------------------
+struct SmallWgradParams { const float* S; const float* L; float* dW; int B, SC, LC, Hs, Ws, Hl, Wl, stride, pad, imgs; };
+
+template <int K>
+__global__ void __launch_bounds__(256) wgrad_small_sc_kernel(const SmallWgradParams p) {
+    constexpr int KK = K * K;
+    __shared__ float red[8][4 * KK];
+    const int lc = blockIdx.x;
+    const int HWs = p.Hs * p.Ws, HWl = p.Hl * p.Wl;
+    const int b0 = blockIdx.y * p.imgs;
+    const int b1 = (b0 + p.imgs) < p.B ? (b0 + p.imgs) : p.B;
+    float acc[4][KK];
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int t = 0; t < KK; ++t) acc[s][t] = 0.f;
+    for (int r = threadIdx.x; r < HWs; r += blockDim.x) {
+        const int y = r / p.Ws, x = r % p.Ws;
+        int off[KK];
+#pragma unroll
+        for (int t = 0; t < KK; ++t) {
+            const int ly = y * p.stride - p.pad + t / K, lx = x * p.stride - p.pad + t % K;
+            off[t] = (ly >= 0 && ly < p.Hl && lx >= 0 && lx < p.Wl) ? ly * p.Wl + lx : -1;
+        }
+        for (int b = b0; b < b1; ++b) {
+            const float* lp = p.L + ((size_t)b * p.LC + lc) * HWl;
+            const float* sp = p.S + (size_t)b * p.SC * HWs + r;
+            float sv[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) sv[s] = s < p.SC ? __ldg(sp + (size_t)s * HWs) : 0.f;
+#pragma unroll
+            for (int t = 0; t < KK; ++t) {
+                if (off[t] >= 0) {
+                    const float v = __ldg(lp + off[t]);
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) acc[s][t] = fmaf(sv[s], v, acc[s][t]);
+                }
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int t = 0; t < KK; ++t) {
+            float v = acc[s][t];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+            if (lane == 0) red[warp][s * KK + t] = v;
+        }
+    __syncthreads();
+    for (int e = threadIdx.x; e < p.SC * KK; e += blockDim.x) {
+        float v = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w][e];
+        const int s = e / KK, t = e % KK;
+        atomicAdd(p.dW + ((size_t)s * p.LC + lc) * KK + t, v);
+    }
+}
+
+bool wgrad_small_supported(int SC, int k) { return SC <= 4 && (k == 1 || k == 3 || k == 4); }
+
+// dW zeroed by the caller
+int wgrad_small_run(const float* S, const float* L, float* dW, int B, int SC, int LC, int Hs, int Ws, int Hl, int Wl,
+                    int k, int stride, int pad, ffc_stream_t st) {
+    SmallWgradParams p{S, L, dW, B, SC, LC, Hs, Ws, Hl, Wl, stride, pad, 1};
+    // ~4 CTAs per SM; each CTA reduces `imgs` images of one large-side channel
+    int groups = ffc_cdiv(4 * 148, LC); if (groups > B) groups = B; if (groups < 1) groups = 1;
+    p.imgs = ffc_cdiv(B, groups);
+    groups = ffc_cdiv(B, p.imgs);
+    const dim3 grid(LC, groups);
+    if (k == 1) wgrad_small_sc_kernel<1><<<grid, 256, 0, st>>>(p);
+    else if (k == 3) wgrad_small_sc_kernel<3><<<grid, 256, 0, st>>>(p);
+    else wgrad_small_sc_kernel<4><<<grid, 256, 0, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { ffc_set_error("wgrad_small launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
+    ffc_count_launch();
+    return FFC_OK;
+}
+#endif  // !FFC_EMU

@@ -289,6 +289,10 @@ static const int ffc_conv_v4_mode = 3;      // value of ffc_debug_conv_reference
 static const int ffc_conv_auto_mode = 5;    // default: V5 or V4 by output width
 static const int ffc_conv_v5_mode = 4;      // ... ConvFwdV5 (tcgen05; device build only -- the emulation build runs V4 instead)
 #ifndef FFC_EMU
+bool conv_small_supported(int cin0, int cin1, int cout, int k);
+int conv_small_run(const float* x0, const float* w0, int cin0, const float* x1, const float* w1, int cin1,
+                   const float* bias, const float* addend, float* y, int B, int cout, int Hi, int Wi, int Ho, int Wo,
+                   int k, int stride, int pad, int transposed, ffc_stream_t st);
 size_t conv_v5_workspace_bytes(int cin0, int cin1, int cout, int k, int stride, int pad, int transposed);
 int conv_v5_run(const float* x0, const float* w0, int cin0, const float* x1, const float* w1, int cin1,
                 const float* bias, const float* addend, float* y, int B, int cout, int Hi, int Wi, int Ho, int Wo,
@@ -344,6 +348,16 @@ extern "C" int ffc_conv2d_fwd_ws(const float* x0, const float* w0, int cin0,
                                  int k, int stride, int pad, int transposed,
                                  void* workspace, size_t workspace_bytes, void* stream) {
     int mode = ffc_conv_use_reference_kernel;
+#ifndef FFC_EMU
+    if (mode == ffc_conv_auto_mode && conv_small_supported(cin0, cin1, cout, k)) {
+        // <= 4 channels on one side (the RGB output layer and its data gradient): direct FP32 kernel
+        FFC_REQUIRE(x0 && w0 && y && cin0 > 0 && B >= 0 && cout > 0, "ffc_conv2d_fwd_ws: null pointer / bad sizes");
+        FFC_REQUIRE((x1 == nullptr) == (cin1 == 0) && (x1 == nullptr) == (w1 == nullptr), "ffc_conv2d_fwd_ws: inconsistent second segment");
+        FFC_REQUIRE(stride == 1 || stride == 2, "ffc_conv2d_fwd_ws: unsupported stride %d", stride);
+        if (B == 0) return FFC_OK;
+        return conv_small_run(x0, w0, cin0, x1, w1, cin1, bias, addend, y, B, cout, Hi, Wi, Ho, Wo, k, stride, pad, transposed, (ffc_stream_t)stream);
+    }
+#endif
     if (mode == ffc_conv_auto_mode) {
         // tcgen05 kernel wherever its 128 x N tile is reasonably filled; the mma.sync kernel for narrow outputs
 #ifndef FFC_EMU

@@ -99,15 +99,20 @@ CONV_CASES = [
     (9, [48], 40, 8, 4, 2, 1, True, False, False, 0),        # tcgen05 weight-gradient shapes (both directions)
     (9, [40], 48, 8, 4, 2, 1, False, True, False, 0),
     (33, [26], 30, 4, 3, 1, 1, False, False, False, 0),
+    (5, [20, 12], 3, 12, 3, 1, 1, False, True, True, 0),     # <= 4 channels on one side: direct kernels
+    (4, [3], 24, 8, 4, 2, 1, False, True, False, 0),
+    (4, [4], 10, 6, 4, 2, 1, True, False, False, 0),
+    (4, [10], 2, 6, 4, 2, 1, True, False, False, 0),
 ]
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
-@pytest.mark.parametrize("reference_form", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("reference_form", [0, 1, 2, 3, 4, 5])
 def test_conv_forward_dgrad_wgrad(lib, case, reference_form):
     """0: tensor-core 3xTF32 kernels; 1: the simple single-buffered forms; 2: tuned FP32 SIMT kernels;
     3: tensor-core 3xTF32 with packed weights and a cp.async ring (ffc_conv2d_fwd_ws); 4: tcgen05 / TMEM implicit GEMM
-    (device build only; the emulation build runs family 3 for it)."""
+    (device build only; the emulation build runs family 3 for it); 5: the default automatic choice, which adds the
+    direct kernels for <= 4 channels and the tcgen05 weight gradient."""
     lib[0].ffc_debug_conv_reference(reference_form)
     _conv_mode[0] = reference_form if lib[1] != "cpu" else 1      # the emulation build computes every family in FP32
     try:
@@ -118,7 +123,7 @@ def test_conv_forward_dgrad_wgrad(lib, case, reference_form):
 
 # 3xTF32 on the tensor cores: the dropped lo*lo term and the MMA's internal accumulation leave ~1e-5
 # (still an order of magnitude inside the 1e-4 FP32 parity bound); the FP32 FMA families reach ~1e-7.
-CONV_TOL = {0: 4e-5, 1: 3e-6, 2: 3e-6, 3: 4e-5, 4: 4e-5}
+CONV_TOL = {0: 4e-5, 1: 3e-6, 2: 3e-6, 3: 4e-5, 4: 4e-5, 5: 4e-5}
 _conv_mode = [0]
 
 

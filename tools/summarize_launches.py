@@ -12,8 +12,13 @@ def main(path, top=30):
     agg = collections.defaultdict(lambda: [0, 0.0])
     for row in csv.DictReader(lines):
         full = row["Kernel Name"]
-        m = re.search(r"ffc_kernel<(\w+)(<[^>]*>)?", full)
-        name = "ffc_b200:" + m.group(1) + (m.group(2) or "") if m else re.sub(r"<.*", "", full)[:70]
+        m = re.search(r"ffc_kernel(?:_coop)?<(\w+)(<[^>]*>)?", full)
+        if m:
+            name = "ffc_b200:" + m.group(1) + (m.group(2) or "")
+        elif re.match(r"(conv_v5|wgrad_v5|pack_v5)_kernel", full):
+            name = "ffc_b200:" + re.sub(r"\(.*", "", full)
+        else:
+            name = re.sub(r"<.*", "", full)[:70]
         v = float(row["Metric Value"].replace(",", ""))
         unit = row["Metric Unit"]
         v = v / 1000 if unit.startswith("n") else (v * 1000 if unit.startswith("m") else v)
