@@ -11,7 +11,8 @@
 //   * A (im2col of the NCHW activations) is never staged in shared memory: each of 128 gather threads owns one output
 //     pixel (= one TMEM lane), loads the 32 channels of the current K chunk with coalesced 4-byte loads (consecutive lanes
 //     = consecutive pixels), splits hi/lo in registers and writes both straight into TMEM (tcgen05.st); the MMA reads A
-//     from TMEM (the .ts form).  Two gather warpgroups alternate over two TMEM stages.
+//     from TMEM (the .ts form).  Up to four gather warpgroups rotate over as many TMEM stages, so the global-load
+//     latency of one chunk hides behind the others.
 //   * B (weights) is re-packed once per call by PackV5 into the exact shared-memory image of a K-major no-swizzle UMMA
 //     operand tile, hi and lo halves adjacent, zero padded; one 1-D bulk copy (cp.async.bulk) per K chunk and stage,
 //     completion counted on an mbarrier.
@@ -20,8 +21,9 @@
 //   * Epilogue: both warpgroups read their lanes of D from TMEM (tcgen05.ld), add bias / addend and store; for a fixed
 //     output channel consecutive lanes are consecutive pixels.
 //
-// Warp roles (320 threads): warps 0-3 gather even chunks, warps 4-7 gather odd chunks, warp 8 issues MMAs and owns the
-// TMEM allocation, warp 9 streams B.
+// Warp roles (576 threads): four gather warpgroups (warps 0-15) rotate over the K chunks, each with its own TMEM stage
+// (two of them when N > 128 leaves room for two stages only); warp 16 issues MMAs and owns the TMEM allocation, warp 17
+// streams B.  One CTA per SM (all 512 TMEM columns).
 #include "ffc_conv_geom.cuh"
 
 #ifndef FFC_EMU
@@ -30,7 +32,9 @@
 #define FFC_V5_MAXCLS 4
 static constexpr int V5_BK = 32;          // K per chunk (= 4 MMA K-steps of 8)
 static constexpr int V5_SB = 3;           // B stages
-static constexpr int V5_THREADS = 320;
+// V5_GW = gather warpgroups = A stages in TMEM is a template parameter of the kernel: 2 (320 threads; two CTAs per SM
+// when N <= 64 so that one CTA's prologue / epilogue overlaps the other's main loop; also N > 128, where only two
+// stages fit beside the accumulators) or 4 (576 threads, one CTA per SM, 64 < N <= 128).
 
 struct ConvV5Params {
     const float* x[2]; int cin[2]; int cps[2];     // segments: input, channels, 32-channel chunks per tap
@@ -99,7 +103,9 @@ __global__ void __launch_bounds__(256) pack_v5_kernel(const PackV5Params p) {
 // ---------------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(V5_THREADS, 2) conv_v5_kernel(const ConvV5Params p) {
+template <int V5_GW>
+__global__ void __launch_bounds__(V5_GW * 128 + 64, V5_GW == 2 ? 2 : 1) conv_v5_kernel(const ConvV5Params p) {
+    constexpr int V5_MMAWARP = V5_GW * 4;
     extern __shared__ __align__(128) unsigned char v5_smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int s = p.transposed ? p.stride : 1;
@@ -121,27 +127,29 @@ __global__ void __launch_bounds__(V5_THREADS, 2) conv_v5_kernel(const ConvV5Para
     uint64_t* bars = reinterpret_cast<uint64_t*>(v5_smem + (size_t)V5_SB * stage_bytes);
     uint64_t* b_full = bars;                    // [V5_SB]
     uint64_t* b_free = bars + V5_SB;            // [V5_SB]
-    uint64_t* a_ready = bars + 2 * V5_SB;       // [2]
-    uint64_t* a_free = a_ready + 2;             // [2]
-    uint64_t* acc_done = a_free + 2;            // [1]
+    uint64_t* a_ready = bars + 2 * V5_SB;       // [V5_GW]
+    uint64_t* a_free = a_ready + V5_GW;         // [V5_GW]
+    uint64_t* acc_done = a_free + V5_GW;        // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
 
-    // TMEM columns: D_hi [0, NT) | D_lo [NT, 2NT) | A stage st at a_col0 + 64*st (hi 32 | lo 32)
-    const uint32_t tmem_cols = NT > 64 ? 512u : 256u;
+    // TMEM columns: D_hi [0, NT) | D_lo [NT, 2NT) | A stage st at a_col0 + 64*st (hi 32 | lo 32), one stage per
+    // gather warpgroup
+    const uint32_t tmem_cols = (2 * NT + 64 * V5_GW <= 256) ? 256u : 512u;
+    constexpr int nstage = V5_GW;
     if (tid == 0) {
         for (int i = 0; i < V5_SB; ++i) { umma::mbar_init(&b_full[i], 1); umma::mbar_init(&b_free[i], 1); }
-        for (int i = 0; i < 2; ++i) { umma::mbar_init(&a_ready[i], 128); umma::mbar_init(&a_free[i], 1); }
+        for (int i = 0; i < V5_GW; ++i) { umma::mbar_init(&a_ready[i], 128); umma::mbar_init(&a_free[i], 1); }
         umma::mbar_init(acc_done, 1);
         umma::fence_barrier_init();
     }
-    if (warp == 8) umma::tmem_alloc(tmem_slot, tmem_cols);
+    if (warp == V5_MMAWARP) umma::tmem_alloc(tmem_slot, tmem_cols);
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tbase = *tmem_slot;
-    const uint32_t a_col0 = NT > 64 ? 384u : 128u;
+    const uint32_t a_col0 = tmem_cols - 64u * V5_GW;
 
-    if (warp < 8) {
+    if (warp < V5_MMAWARP) {
         // ===================== A producers (then epilogue) =====================
         const int wg = warp >> 2;
         const int row = tid & 127;                          // TMEM lane == pixel of the tile
@@ -150,7 +158,7 @@ __global__ void __launch_bounds__(V5_THREADS, 2) conv_v5_kernel(const ConvV5Para
         const bool ok = m < Mc;
         const int xq = m % Wc, yq = (m / Wc) % Hc, b = m / (Wc * Hc);
         const int HWi = p.Hi * p.Wi;
-        for (int c = wg; c < nchunks; c += 2) {
+        for (int c = wg; c < nchunks; c += nstage) {
             // cursor of chunk c: (segment, tap, first channel)
             int r = c, sg = 0;
             if (r >= T * p.cps[0]) { sg = 1; r -= T * p.cps[0]; }
@@ -166,7 +174,7 @@ __global__ void __launch_bounds__(V5_THREADS, 2) conv_v5_kernel(const ConvV5Para
             float v[V5_BK];
 #pragma unroll
             for (int j = 0; j < V5_BK; ++j) v[j] = (okp && c0 + j < cin) ? __ldg(xp + (size_t)j * HWi) : 0.f;
-            const int it = c >> 1;
+            const int it = c / nstage;
             if (it > 0) umma::mbar_wait(&a_free[wg], (uint32_t)((it - 1) & 1));      // the MMAs that read this stage are done
             umma::fence_after_sync();
             const uint32_t acol = lane_base + a_col0 + 64u * (uint32_t)wg;
@@ -194,7 +202,7 @@ __global__ void __launch_bounds__(V5_THREADS, 2) conv_v5_kernel(const ConvV5Para
             const size_t HWo = (size_t)p.Ho * p.Wo;
             const int co0 = ntile * p.nt_full;
             const size_t o0 = ((size_t)b * p.cout + co0) * HWo + (size_t)oy * p.Wo + ox;
-            for (int n0 = 16 * wg; n0 < NT; n0 += 32) {
+            for (int n0 = 16 * wg; n0 < NT; n0 += 16 * V5_GW) {
                 uint32_t r[16];
                 if (nchunks > 0) {                            // warp-wide: every lane takes part
                     uint32_t q[16];
@@ -221,14 +229,14 @@ __global__ void __launch_bounds__(V5_THREADS, 2) conv_v5_kernel(const ConvV5Para
                 }
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == V5_MMAWARP) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = umma::idesc_tf32(128, NT);
             for (int c = 0; c < nchunks; ++c) {
-                const int sa = c & 1, sb = c % V5_SB;
+                const int sa = c % nstage, sb = c % V5_SB;
                 umma::mbar_wait(&b_full[sb], (uint32_t)((c / V5_SB) & 1));
-                umma::mbar_wait(&a_ready[sa], (uint32_t)((c >> 1) & 1));
+                umma::mbar_wait(&a_ready[sa], (uint32_t)((c / nstage) & 1));
                 umma::fence_after_sync();
                 const uint32_t b_hi = umma::smem_u32(bstage + (size_t)sb * stage_bytes), b_lo = b_hi + (uint32_t)(NT * V5_BK * 4);
                 const uint32_t a_hi = tbase + a_col0 + 64u * (uint32_t)sa, a_lo = a_hi + 32u;
@@ -260,7 +268,7 @@ __global__ void __launch_bounds__(V5_THREADS, 2) conv_v5_kernel(const ConvV5Para
     }
     umma::fence_before_sync();
     __syncthreads();
-    if (warp == 8) umma::tmem_dealloc(tbase, tmem_cols);
+    if (warp == V5_MMAWARP) umma::tmem_dealloc(tbase, tmem_cols);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -330,11 +338,14 @@ int conv_v5_run(const float* x0, const float* w0, int cin0, const float* x1, con
     const size_t smem = (size_t)V5_SB * 2 * pl.nt_full * V5_BK * 4 + 256;
     static size_t configured = 0;
     if (smem > configured) {
-        e = cudaFuncSetAttribute(conv_v5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(conv_v5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_v5_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { ffc_set_error("cudaFuncSetAttribute(conv_v5, %zu B): %s", smem, cudaGetErrorString(e)); return FFC_ERR_CUDA; }
         configured = smem;
     }
-    conv_v5_kernel<<<dim3(ffc_cdiv(Mc, 128), pl.ntiles, s * s), V5_THREADS, smem, st>>>(p);
+    const dim3 grid(ffc_cdiv(Mc, 128), pl.ntiles, s * s);
+    if (pl.nt_full > 64 && pl.nt_full <= 128) conv_v5_kernel<4><<<grid, 4 * 128 + 64, smem, st>>>(p);
+    else conv_v5_kernel<2><<<grid, 2 * 128 + 64, smem, st>>>(p);
     e = cudaGetLastError();
     if (e != cudaSuccess) { ffc_set_error("conv_v5 launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
     ffc_count_launch();

@@ -138,16 +138,25 @@ struct Fu2Fwd {
         else mix_impl<BNF, false>(p, ctx, l, tid);
     }
 
-    // per-image statistics of the mixed spectrum: thread = (complex channel, slice), partial sums kept in registers
+    // per-image statistics of the mixed spectrum: thread = (complex channel, slice) sums whole rows (float4 reads,
+    // no per-bin index math); partial sums stay in registers
     static FFC_DEVICE void stats_accumulate(const Params& p, const BlockCtx& ctx, const Lay& l, int tid, Acc& acc) {
         const int S = ctx.nt / p.Cout;
         const int c2 = tid / S, sl = tid % S;
         if (c2 < p.Cout) {
-            const float2* yp = reinterpret_cast<const float2*>(l.yreg + (size_t)c2 * G::REGION);
-            for (int bin = sl; bin < BINS; bin += S) {
-                const float2 y = yp[fu2_bin_off<N>(bin)];
-                acc.v[0] += y.x; acc.v[1] = fmaf(y.x, y.x, acc.v[1]);
-                acc.v[2] += y.y; acc.v[3] = fmaf(y.y, y.y, acc.v[3]);
+            const float* plane = l.yreg + (size_t)c2 * G::REGION;
+            for (int u = sl; u < N; u += S) {
+                const float4* row = reinterpret_cast<const float4*>(plane + u * G::RS);
+                FFC_UNROLL
+                for (int j = 0; j < G::RS / 4; ++j) {
+                    const float4 a = row[j];
+                    acc.v[0] += a.x; acc.v[1] = fmaf(a.x, a.x, acc.v[1]);
+                    acc.v[2] += a.y; acc.v[3] = fmaf(a.y, a.y, acc.v[3]);
+                    if (2 * j + 1 < Wf) {                   // the last float4 of a row holds one bin and one pad
+                        acc.v[0] += a.z; acc.v[1] = fmaf(a.z, a.z, acc.v[1]);
+                        acc.v[2] += a.w; acc.v[3] = fmaf(a.w, a.w, acc.v[3]);
+                    }
+                }
             }
         }
     }

@@ -104,12 +104,13 @@ class SNDiscriminator(nn.Module):
             setattr(self, f"conv{i}", sn_fn(nn.Conv2d(ci, co, k, stride=s, padding=(1, 1))))
         self.fc = sn_fn(nn.Linear(mg * mg * 512, 1))
         self.act = nn.LeakyReLU(0.1)
+        self.channels_last = False      # PyTorch-side tuning knob: run cuDNN in NHWC (same math, no layout round trips)
 
     def forward(self, x):
-        m = x
+        m = x.contiguous(memory_format=torch.channels_last) if self.channels_last else x
         for i in range(1, self.n_convs + 1):
             m = self.act(getattr(self, f"conv{i}")(m))
-        return self.fc(m.view(-1, self.mg * self.mg * 512))
+        return self.fc(m.reshape(-1, self.mg * self.mg * 512))
 
 
 class FDiscriminator(nn.Module):

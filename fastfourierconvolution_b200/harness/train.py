@@ -64,6 +64,8 @@ class GanTrainer:
             # whole-step CUDA-graph capture: the optimiser keeps step counters and the learning rate on the device
             dev = next(G.parameters()).device
             kw = dict(capturable=True)
+            if dev.type == "cuda":
+                kw["fused"] = True          # one multi-tensor kernel per optimiser step instead of ~10 per parameter
             lr = torch.tensor(float(lr), device=dev)
         self.optim_G = opt(G.parameters(), lr=lr.clone() if capturable else lr, betas=betas, **kw)
         self.optim_D = opt(D.parameters(), lr=lr.clone() if capturable else lr, betas=betas, **kw)
