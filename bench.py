@@ -218,6 +218,35 @@ def time_fourier_unit(workload, per_rank_batch, dev):
     return out
 
 
+# largest local-branch convolution of each generator: (cin, cout, input size) of conv2.ffc.convl2l, ConvTranspose2d k4 s2 p1
+CONV_SHAPES = {"fgan32": (512, 192, 4), "fgan64": (512, 192, 4), "fgan128": (1024, 256, 4)}
+
+
+def tensor_peak_tf32():
+    """Dense TF32 tensor peak: half of the measured BF16 cuBLAS burst figure (MEASURED_PEAKS.json), else of the fallback."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return 0.5 * float(json.load(f)["bf16_tflops"]), "0.5 x measured bf16_tflops (MEASURED_PEAKS.json)"
+    return 0.5 * 1590.0, "0.5 x fallback bf16 (B200_PROFILING.md)"
+
+
+def time_conv_layer(workload, per_rank_batch, dev):
+    """The tcgen05 implicit-GEMM convolution (ConvFwdV5, 3xTF32) on the generator's largest local convolution."""
+    from fastfourierconvolution_b200 import ops
+    cin, cout, hi = CONV_SHAPES[workload]
+    B = per_rank_batch
+    torch.manual_seed(0)
+    w = torch.randn(cin, cout, 4, 4, device=dev) * 0.02
+    nbuf = min(max(2, int(160e6 // (4 * B * cout * 4 * hi * hi)) + 1), 16)
+    xs = [torch.randn(B, cin, hi, hi, device=dev) for _ in range(nbuf)]
+    with torch.no_grad():
+        ms = _graph_time(lambda x: ops.conv2d(x, w, stride=2, pad=1, transposed=True), xs)
+    flops = 2.0 * B * (2 * hi) ** 2 * cout * cin * 4            # 16 taps / 4 parity classes per output pixel
+    return {"ms": ms, "flops": flops, "shape": f"ConvTranspose2d({cin}->{cout}, k4 s2 p1) {hi}x{hi}->{2 * hi}x{2 * hi}, batch {B}",
+            "rotating_buffers": nbuf}
+
+
 def run_ours(args):
     import torch.distributed as dist
     rank, local_rank, world = dist_env()
@@ -312,6 +341,7 @@ def run_ours(args):
     clocks = clk.summary()
 
     fu = time_fourier_unit(workload, pb, dev) if rank == 0 else None
+    cv = time_conv_layer(workload, pb, dev) if rank == 0 else None
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, ms, cores = cpu_reference_step_rate(workload, min(gb, args.cpu_batch), args.cpu_steps, 1)
@@ -357,6 +387,15 @@ def run_ours(args):
                          "timing": "CUDA events around CUDA-graph replays of the op over %d rotating inputs (> L2)" % fu["rotating_buffers"]},
             "clocks": clocks,
         }
+        tpeak, tpeak_src = tensor_peak_tf32()
+        issued = 3.0 * cv["flops"] / cv["ms"] / 1e9          # three TF32 MMAs per FP32-accurate product (3xTF32)
+        line["roofline_tensor"] = {
+            "bound": "tensor", "achieved": issued, "peak": tpeak, "unit": "TFLOP/s", "frac": issued / tpeak, "traffic": None,
+            "peak_source": tpeak_src,
+            "kernel": "conv_v5_kernel (tcgen05.mma kind::tf32, A in TMEM, 3xTF32 at FP32 accuracy) + pack_v5_kernel, " + cv["shape"],
+            "effective_fp32_tflops": cv["flops"] / cv["ms"] / 1e9, "algorithmic_flops_per_launch": cv["flops"],
+            "us_per_launch": 1000 * cv["ms"],
+            "timing": "CUDA events around CUDA-graph replays over %d rotating inputs; includes the per-call weight packing kernel" % cv["rotating_buffers"]}
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

@@ -58,7 +58,8 @@ __global__ void __launch_bounds__(256) conv_small_cout_kernel(const SmallConvPar
         int cbase = 0;
         for (int sg = 0; sg < p.nseg; ++sg) {
             const float* xp = p.x[sg] + (size_t)b * p.cin[sg] * HWi;
-            for (int ci = 0; ci < p.cin[sg]; ++ci, xp += HWi) {
+#pragma unroll 4
+            for (int ci = 0; ci < p.cin[sg]; ++ci, xp += HWi) {            // 4 channels x k*k loads in flight per thread
                 const float4* wq = scw + (size_t)(cbase + ci) * KK;
 #pragma unroll
                 for (int t = 0; t < KK; ++t) {

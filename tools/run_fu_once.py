@@ -1,5 +1,5 @@
 """Runs the FourierUnit forward a few times on one shape (for ncu captures).
-usage: python tools/run_fu_once.py B C N [train|eval] [general]"""
+usage: python tools/run_fu_once.py B C N [train|eval] [general] [bwd]"""
 import os
 import sys
 
@@ -13,8 +13,13 @@ mode = sys.argv[4] if len(sys.argv) > 4 else "eval"
 m = ffc.FourierUnitSN(C, C).to("cuda:0").train(mode == "train")
 m.fused = "general" not in sys.argv
 xs = [torch.randn(B, C, N, N, device="cuda:0") for _ in range(4)]
-with torch.no_grad():
-    for i in range(8):
-        m(xs[i % 4])
+if "bwd" in sys.argv:
+    for i in range(4):
+        x = xs[i].requires_grad_(True)
+        m(x).square().sum().backward()
+else:
+    with torch.no_grad():
+        for i in range(8):
+            m(xs[i % 4])
 torch.cuda.synchronize()
 print("ok")

@@ -15,8 +15,8 @@ def main(path, top=30):
         m = re.search(r"ffc_kernel(?:_coop)?<(\w+)(<[^>]*>)?", full)
         if m:
             name = "ffc_b200:" + m.group(1) + (m.group(2) or "")
-        elif re.match(r"(conv_v5|wgrad_v5|pack_v5)_kernel", full):
-            name = "ffc_b200:" + re.sub(r"\(.*", "", full)
+        elif re.match(r"(void )?(conv_v5|wgrad_v5|pack_v5|conv_small\w*|wgrad_small\w*)_kernel", full):
+            name = "ffc_b200:" + re.sub(r"\(.*", "", full).replace("void ", "")
         else:
             name = re.sub(r"<.*", "", full)[:70]
         v = float(row["Metric Value"].replace(",", ""))
