@@ -37,22 +37,51 @@ struct ChanReduceKernel {
         double* red = reinterpret_cast<double*>(smem);
         const int c = ctx.bx, split = ctx.by;
         const long long total = (long long)p.B * p.HW;
-        const long long per = (total + p.nsplit - 1) / p.nsplit;
+        const long long per = ((total + p.nsplit - 1) / p.nsplit + 3) / 4 * 4;       // multiple of 4: float4 items never straddle splits
         const long long beg = split * per, end = (beg + per) < total ? (beg + per) : total;
         FFC_PHASE {
             double s0 = 0.0, s1 = 0.0;
             float mu = 0.f, is = 1.f, ga = 1.f, be = 0.f;
             if (MODE == 1 && p.mean) { mu = p.mean[c]; is = p.invstd[c]; ga = p.gamma[c]; be = p.beta[c]; }
-            for (long long i = beg + tid; i < end; i += kThreads) {
-                const int b = (int)(i / p.HW), r = (int)(i % p.HW);
-                const size_t o = ((size_t)b * p.C + c) * p.HW + r;
-                if (MODE == 0) { const float v = FFC_LDG(p.x + o); s0 += v; s1 += (double)v * v; }
-                else if (MODE == 2) { s0 += FFC_LDG(p.x + o); }
-                else {
-                    const float xh = (FFC_LDG(p.x + o) - mu) * is;
-                    const float z = xh * ga + be;
-                    const float g = FFC_LDG(p.dy + o) * ffc_act_bwd(z, p.act, p.slope);
-                    s0 += g; s1 += (double)g * xh;
+            const bool vec = (p.HW % 4 == 0) && (((uintptr_t)p.x | (uintptr_t)p.dy) & 15) == 0;
+            if (vec) {
+                // float4 items of channel c, numbered over (image, quarter-row); the (image, offset) pair of a thread is
+                // advanced incrementally (no per-element division); FP32 partial sums of 4 values feed the doubles
+                const int q = p.HW / 4;
+                const long long beg4 = beg / 4, end4 = (end + 3) / 4 < (total / 4) ? (end + 3) / 4 : total / 4;
+                long long i = beg4 + tid;
+                int b = (int)(i / q), r = (int)(i % q);
+                for (; i < end4; i += kThreads) {
+                    const size_t o4 = ((size_t)b * p.C + c) * q + r;
+                    const float4 v = FFC_LDG(reinterpret_cast<const float4*>(p.x) + o4);
+                    if (MODE == 0) {
+                        s0 += (double)((v.x + v.y) + (v.z + v.w));
+                        s1 += (double)(fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w));
+                    } else if (MODE == 2) {
+                        s0 += (double)((v.x + v.y) + (v.z + v.w));
+                    } else {
+                        const float4 d = FFC_LDG(reinterpret_cast<const float4*>(p.dy) + o4);
+                        const float x0 = (v.x - mu) * is, x1 = (v.y - mu) * is, x2 = (v.z - mu) * is, x3 = (v.w - mu) * is;
+                        const float g0 = d.x * ffc_act_bwd(x0 * ga + be, p.act, p.slope), g1 = d.y * ffc_act_bwd(x1 * ga + be, p.act, p.slope);
+                        const float g2 = d.z * ffc_act_bwd(x2 * ga + be, p.act, p.slope), g3 = d.w * ffc_act_bwd(x3 * ga + be, p.act, p.slope);
+                        s0 += (double)((g0 + g1) + (g2 + g3));
+                        s1 += (double)(fmaf(g0, x0, g1 * x1) + fmaf(g2, x2, g3 * x3));
+                    }
+                    r += kThreads;
+                    if (r >= q) { b += r / q; r %= q; }
+                }
+            } else {
+                for (long long i = beg + tid; i < end; i += kThreads) {
+                    const int b = (int)(i / p.HW), r = (int)(i % p.HW);
+                    const size_t o = ((size_t)b * p.C + c) * p.HW + r;
+                    if (MODE == 0) { const float v = FFC_LDG(p.x + o); s0 += v; s1 += (double)v * v; }
+                    else if (MODE == 2) { s0 += FFC_LDG(p.x + o); }
+                    else {
+                        const float xh = (FFC_LDG(p.x + o) - mu) * is;
+                        const float z = xh * ga + be;
+                        const float g = FFC_LDG(p.dy + o) * ffc_act_bwd(z, p.act, p.slope);
+                        s0 += g; s1 += (double)g * xh;
+                    }
                 }
             }
             red[tid] = s0; red[kThreads + tid] = s1;
@@ -131,8 +160,8 @@ struct BnApplyKernel {
             const bool vec = (p.HW % 4 == 0);
             const long long n = vec ? p.total / 4 : p.total;
             for (long long i = (long long)ctx.bx * kThreads + tid; i < n; i += (long long)ctx.gx * kThreads) {
-                const long long e0 = vec ? i * 4 : i;
-                const int c = (int)((e0 / p.HW) % p.C);
+                const int c = vec ? (int)((unsigned long long)i / (unsigned)(p.HW / 4) % (unsigned)p.C)
+                                  : (int)((unsigned long long)i / (unsigned)p.HW % (unsigned)p.C);
                 float mu = 0.f, a = 1.f, be = 0.f;
                 if (p.mean) { mu = FFC_LDG(p.mean + c); a = FFC_LDG(p.invstd + c) * FFC_LDG(p.gamma + c); be = FFC_LDG(p.beta + c); }
                 if (vec) {
@@ -167,25 +196,43 @@ struct BnBwdApplyParams {
 struct BnBwdApplyKernel {
     typedef BnBwdApplyParams Params;
     static constexpr int kThreads = 256;
+    // gradient of one element; k1 = sum_g / N, k2 = sum_gx / N (0 in eval mode), a = gamma * invstd
+    static FFC_DEVICE float one(const Params& p, float xv, float g0, float mu, float is, float ga, float be, float a, float k1, float k2) {
+        const float xh = (xv - mu) * is;
+        const float g = g0 * ffc_act_bwd(xh * ga + be, p.act, p.slope);
+        return a * (g - k1 - xh * k2);
+    }
     static FFC_DEVICE void run(const Params& p, const BlockCtx& ctx, float*) {
         FFC_PHASE {
-            for (long long i = (long long)ctx.bx * kThreads + tid; i < p.total; i += (long long)ctx.gx * kThreads) {
-                const long long plane = i / p.HW;
-                const int c = (int)(plane % p.C);
-                const float xv = FFC_LDG(p.x + i), g0 = FFC_LDG(p.dy + i);
+            const bool vec = (p.HW % 4 == 0) && (((uintptr_t)p.x | (uintptr_t)p.dy | (uintptr_t)p.dx) & 15) == 0;
+            const long long n = vec ? p.total / 4 : p.total;
+            const unsigned per_plane = vec ? (unsigned)(p.HW / 4) : (unsigned)p.HW;
+            const float inv_count = (float)(1.0 / p.count);
+            for (long long i = (long long)ctx.bx * kThreads + tid; i < n; i += (long long)ctx.gx * kThreads) {
+                const unsigned long long plane = (unsigned long long)i / per_plane;
+                const int c = (int)(plane % (unsigned)p.C);
                 if (!p.mean) {
-                    p.dx[i] = g0 * ffc_act_bwd(xv, p.act, p.slope);
+                    if (vec) {
+                        const float4 xv = FFC_LDG(reinterpret_cast<const float4*>(p.x) + i), g = FFC_LDG(reinterpret_cast<const float4*>(p.dy) + i);
+                        reinterpret_cast<float4*>(p.dx)[i] = make_float4(g.x * ffc_act_bwd(xv.x, p.act, p.slope), g.y * ffc_act_bwd(xv.y, p.act, p.slope),
+                                                                         g.z * ffc_act_bwd(xv.z, p.act, p.slope), g.w * ffc_act_bwd(xv.w, p.act, p.slope));
+                    } else {
+                        p.dx[i] = FFC_LDG(p.dy + i) * ffc_act_bwd(FFC_LDG(p.x + i), p.act, p.slope);
+                    }
                     continue;
                 }
                 const float mu = FFC_LDG(p.mean + c), is = FFC_LDG(p.invstd + c), ga = FFC_LDG(p.gamma + c), be = FFC_LDG(p.beta + c);
-                const float xh = (xv - mu) * is;
-                const float g = g0 * ffc_act_bwd(xh * ga + be, p.act, p.slope);
                 const double sg = p.sums[c], sgx = p.sums[p.C + c];
-                float d;
-                if (p.training) d = ga * is * (g - (float)(sg / p.count) - xh * (float)(sgx / p.count));
-                else d = ga * is * g;
-                p.dx[i] = d;
-                if (i == (long long)c * p.HW) {       // first element of plane (b = 0, c)
+                const float k1 = p.training ? (float)sg * inv_count : 0.f, k2 = p.training ? (float)sgx * inv_count : 0.f;
+                const float a = ga * is;
+                if (vec) {
+                    const float4 xv = FFC_LDG(reinterpret_cast<const float4*>(p.x) + i), g = FFC_LDG(reinterpret_cast<const float4*>(p.dy) + i);
+                    reinterpret_cast<float4*>(p.dx)[i] = make_float4(one(p, xv.x, g.x, mu, is, ga, be, a, k1, k2), one(p, xv.y, g.y, mu, is, ga, be, a, k1, k2),
+                                                                     one(p, xv.z, g.z, mu, is, ga, be, a, k1, k2), one(p, xv.w, g.w, mu, is, ga, be, a, k1, k2));
+                } else {
+                    p.dx[i] = one(p, FFC_LDG(p.x + i), FFC_LDG(p.dy + i), mu, is, ga, be, a, k1, k2);
+                }
+                if ((unsigned long long)i == (unsigned long long)c * per_plane) {       // first item of plane (b = 0, c)
                     if (p.dgamma) p.dgamma[c] = (float)sgx;
                     if (p.dbeta) p.dbeta[c] = (float)sg;
                 }
@@ -461,7 +508,8 @@ extern "C" int ffc_bn_act_bwd(const float* x, const float* dy, float* dx, const 
         FFC_CHECK((ffc_launch<ChanReduceKernel<1>>(C, rp.nsplit, 1, FFC_RED_THREADS, ChanReduceKernel<1>::smem_bytes(), st, rp)));
         ap.mean = save_mean; ap.invstd = save_invstd; ap.gamma = gamma; ap.beta = beta; ap.sums = sums;
     }
-    return ffc_launch<BnBwdApplyKernel>(ew_grid(total, 256), 1, 1, 256, 0, st, ap);
+    const bool vec = (HW % 4 == 0) && ((((uintptr_t)x) | ((uintptr_t)dy) | ((uintptr_t)dx)) & 15) == 0;
+    return ffc_launch<BnBwdApplyKernel>(ew_grid(vec ? total / 4 : total, 256), 1, 1, 256, 0, st, ap);
 }
 
 // db[c] = sum_{b,hw} dy.  Workspace: C doubles.

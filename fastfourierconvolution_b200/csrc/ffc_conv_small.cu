@@ -83,6 +83,62 @@ __global__ void __launch_bounds__(256) conv_small_cout_kernel(const SmallConvPar
     }
 }
 
+// The RGB layer itself (k3, stride 1, pad 1, width a multiple of 4): a thread computes 4 consecutive output pixels of a
+// row, so a (channel, row) costs one aligned float4 plus two edge loads for 4 x 3 taps instead of 12 loads.
+__global__ void __launch_bounds__(256) conv_small_cout_k3s1_kernel(const SmallConvParams p) {
+    extern __shared__ float4 scw[];                 // [seg ci][tap] -> (w of co 0..3)
+    const int ctot = p.cin[0] + (p.nseg > 1 ? p.cin[1] : 0);
+    for (int e = threadIdx.x; e < ctot * 9; e += blockDim.x) {
+        const int c = e / 9, t = e % 9;
+        const int sg = c >= p.cin[0], ci = sg ? c - p.cin[0] : c;
+        float q[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int co = 0; co < p.cout; ++co) q[co] = small_w(p, p.w[sg], p.cin[sg], co, ci, t);
+        scw[e] = make_float4(q[0], q[1], q[2], q[3]);
+    }
+    __syncthreads();
+    const int W = p.Wi, H = p.Hi, HW = H * W, W4 = W / 4;
+    const long long total = (long long)p.B * H * W4;
+    for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < total; m += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(m / (H * W4)), r = (int)(m % (H * W4)), oy = r / W4, ox0 = 4 * (r % W4);
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+        int cbase = 0;
+        for (int sg = 0; sg < p.nseg; ++sg) {
+            const float* xp = p.x[sg] + (size_t)b * p.cin[sg] * HW + ox0;
+#pragma unroll 2
+            for (int ci = 0; ci < p.cin[sg]; ++ci, xp += HW) {
+                const float4* wq = scw + (size_t)(cbase + ci) * 9;
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+                    const int iy = oy - 1 + dy;
+                    if (iy < 0 || iy >= H) continue;
+                    const float* row = xp + iy * W;
+                    const float4 c4 = __ldg(reinterpret_cast<const float4*>(row));
+                    const float v[6] = {ox0 > 0 ? __ldg(row - 1) : 0.f, c4.x, c4.y, c4.z, c4.w, ox0 + 4 < W ? __ldg(row + 4) : 0.f};
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const float4 q = wq[dy * 3 + kx];
+#pragma unroll
+                        for (int px = 0; px < 4; ++px) {
+                            acc[px][0] = fmaf(v[px + kx], q.x, acc[px][0]); acc[px][1] = fmaf(v[px + kx], q.y, acc[px][1]);
+                            acc[px][2] = fmaf(v[px + kx], q.z, acc[px][2]); acc[px][3] = fmaf(v[px + kx], q.w, acc[px][3]);
+                        }
+                    }
+                }
+            }
+            cbase += p.cin[sg];
+        }
+        for (int co = 0; co < p.cout; ++co) {
+            const size_t o = ((size_t)b * p.cout + co) * HW + (size_t)oy * W + ox0;
+            float4 v = make_float4(acc[0][co], acc[1][co], acc[2][co], acc[3][co]);
+            if (p.bias) { const float bb = __ldg(p.bias + co); v.x += bb; v.y += bb; v.z += bb; v.w += bb; }
+            if (p.addend) { const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.addend + o)); v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w; }
+            *reinterpret_cast<float4*>(p.y + o) = v;
+        }
+    }
+}
+
 template <int K>
 __global__ void __launch_bounds__(256) conv_small_cin_kernel(const SmallConvParams p) {
     extern __shared__ float scv[];                  // [co][ci][tap]
@@ -134,7 +190,13 @@ static int conv_small_launch(const SmallConvParams& p, ffc_stream_t st) {
     const long long total = (long long)p.B * p.Ho * p.Wo;
     int grid = (int)((total + 255) / 256); if (grid > 148 * 16) grid = 148 * 16; if (grid < 1) grid = 1;
     cudaError_t e;
-    if (p.cout <= 4) {
+    const uintptr_t al = (uintptr_t)p.x[0] | (uintptr_t)p.x[1] | (uintptr_t)p.y | (uintptr_t)p.addend;
+    if (p.cout <= 4 && K == 3 && p.stride == 1 && p.pad == 1 && !p.transposed && p.Wi % 4 == 0 && (al & 15) == 0) {
+        const size_t smem = (size_t)(p.cin[0] + (p.nseg > 1 ? p.cin[1] : 0)) * 9 * 16;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(conv_small_cout_k3s1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int g4 = (int)((total / 4 + 255) / 256); if (g4 > 148 * 16) g4 = 148 * 16; if (g4 < 1) g4 = 1;
+        conv_small_cout_k3s1_kernel<<<g4, 256, smem, st>>>(p);
+    } else if (p.cout <= 4) {
         const size_t smem = (size_t)(p.cin[0] + (p.nseg > 1 ? p.cin[1] : 0)) * K * K * 16;
         if (smem > 48 * 1024) cudaFuncSetAttribute(conv_small_cout_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         conv_small_cout_kernel<K><<<grid, 256, smem, st>>>(p);
@@ -223,6 +285,59 @@ __global__ void __launch_bounds__(256) wgrad_small_sc_kernel(const SmallWgradPar
     }
 }
 
+// k3, stride 1, pad 1, width a multiple of 4 (the RGB layer): 4 consecutive pixels per thread, see conv_small_cout_k3s1_kernel
+__global__ void __launch_bounds__(256) wgrad_small_sc_k3s1_kernel(const SmallWgradParams p) {
+    __shared__ float red[8][4 * 9];
+    const int lc = blockIdx.x;
+    const int W = p.Ws, H = p.Hs, HW = H * W, W4 = W / 4;
+    const int b0 = blockIdx.y * p.imgs;
+    const int b1 = (b0 + p.imgs) < p.B ? (b0 + p.imgs) : p.B;
+    float acc[4][9];
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc[s][t] = 0.f;
+    for (int r = threadIdx.x; r < H * W4; r += blockDim.x) {
+        const int y = r / W4, x0 = 4 * (r % W4);
+        for (int b = b0; b < b1; ++b) {
+            const float* lp = p.L + ((size_t)b * p.LC + lc) * HW + x0;
+            const float* sp = p.S + (size_t)b * p.SC * HW + (size_t)y * W + x0;
+            float4 sv[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) sv[s] = s < p.SC ? __ldg(reinterpret_cast<const float4*>(sp + (size_t)s * HW)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+                const int ly = y - 1 + dy;
+                if (ly < 0 || ly >= H) continue;
+                const float* row = lp + ly * W;
+                const float4 c4 = __ldg(reinterpret_cast<const float4*>(row));
+                const float v[6] = {x0 > 0 ? __ldg(row - 1) : 0.f, c4.x, c4.y, c4.z, c4.w, x0 + 4 < W ? __ldg(row + 4) : 0.f};
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                    for (int s = 0; s < 4; ++s)
+                        acc[s][dy * 3 + kx] += sv[s].x * v[kx] + sv[s].y * v[kx + 1] + sv[s].z * v[kx + 2] + sv[s].w * v[kx + 3];
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            float v = acc[s][t];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+            if (lane == 0) red[warp][s * 9 + t] = v;
+        }
+    __syncthreads();
+    for (int e = threadIdx.x; e < p.SC * 9; e += blockDim.x) {
+        float v = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w][e];
+        atomicAdd(p.dW + ((size_t)(e / 9) * p.LC + lc) * 9 + e % 9, v);
+    }
+}
+
 bool wgrad_small_supported(int SC, int k) { return SC <= 4 && (k == 1 || k == 3 || k == 4); }
 
 // dW zeroed by the caller
@@ -234,7 +349,9 @@ int wgrad_small_run(const float* S, const float* L, float* dW, int B, int SC, in
     p.imgs = ffc_cdiv(B, groups);
     groups = ffc_cdiv(B, p.imgs);
     const dim3 grid(LC, groups);
-    if (k == 1) wgrad_small_sc_kernel<1><<<grid, 256, 0, st>>>(p);
+    if (k == 3 && stride == 1 && pad == 1 && Hs == Hl && Ws == Wl && Ws % 4 == 0 && (((uintptr_t)S | (uintptr_t)L) & 15) == 0)
+        wgrad_small_sc_k3s1_kernel<<<grid, 256, 0, st>>>(p);
+    else if (k == 1) wgrad_small_sc_kernel<1><<<grid, 256, 0, st>>>(p);
     else if (k == 3) wgrad_small_sc_kernel<3><<<grid, 256, 0, st>>>(p);
     else wgrad_small_sc_kernel<4><<<grid, 256, 0, st>>>(p);
     cudaError_t e = cudaGetLastError();

@@ -103,6 +103,7 @@ CONV_CASES = [
     (4, [3], 24, 8, 4, 2, 1, False, True, False, 0),
     (4, [4], 10, 6, 4, 2, 1, True, False, False, 0),
     (4, [10], 2, 6, 4, 2, 1, True, False, False, 0),
+    (3, [9, 5], 3, 16, 3, 1, 1, False, False, True, 0),      # the 4-pixel strip forms (k3 s1 p1, width % 4 == 0)
 ]
 
 

@@ -25,7 +25,9 @@ def _model_case(fn):
             "cfg1": lambda: H.FFCGenerator(100, 1, 32)}[fn]()
 
 
-def run_model_fixture(name, fn, device):
+def run_model_fixture(name, fn, device, grad_l2=False):
+    """Max-norm relative errors of the model's output, gradients and buffers against the reference fixture; with
+    grad_l2 the gradients are measured in the relative L2 norm instead (robust to one flipped ReLU element)."""
     fx = parity.load_fixture(name)
     mod = _model_case(fn)
     sd = mod.state_dict()
@@ -45,7 +47,10 @@ def run_model_fixture(name, fn, device):
             got[k] = params[k[5:]].grad
         if k.startswith("post/"):
             got[k] = bufs[k[5:]]
-    return {k: parity.relerr(got[k], fx[k]) for k in got}
+    def l2(a, b):
+        a, b = a.detach().double().cpu(), torch.as_tensor(b).double()
+        return ((a - b).norm() / max(b.norm().item(), 1e-30)).item()
+    return {k: (l2(got[k], fx[k]) if grad_l2 and (k == "din0" or k.startswith("grad/")) else parity.relerr(got[k], fx[k])) for k in got}
 
 
 @pytest.mark.parametrize("name,fn", [("model_fgan32_G", "fgan32"), ("model_sngan_FD", "fd"), ("model_ffcgen_cfg1", "cfg1")])
