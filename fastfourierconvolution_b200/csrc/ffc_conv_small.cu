@@ -84,10 +84,13 @@ __global__ void __launch_bounds__(256) conv_small_cout_kernel(const SmallConvPar
 }
 
 // The RGB layer itself (k3, stride 1, pad 1, width a multiple of 4): a thread computes 4 consecutive output pixels of a
-// row, so a (channel, row) costs one aligned float4 plus two edge loads for 4 x 3 taps instead of 12 loads.
+// row, so a (channel, row) costs one aligned float4 plus two edge loads for 4 x 3 taps instead of 12 loads.  The input
+// channels are dealt round-robin to 4 thread groups of the CTA (64 strips x 4 groups) and summed through shared memory:
+// 4x the threads of a pixel-only mapping, which this latency-bound loop needs to fill the SMs.
 __global__ void __launch_bounds__(256) conv_small_cout_k3s1_kernel(const SmallConvParams p) {
-    extern __shared__ float4 scw[];                 // [seg ci][tap] -> (w of co 0..3)
+    extern __shared__ float4 scw[];                 // [seg ci][tap] -> (w of co 0..3), then 64 x 4 x 4 float4 partials
     const int ctot = p.cin[0] + (p.nseg > 1 ? p.cin[1] : 0);
+    float4* part = scw + (size_t)ctot * 9;
     for (int e = threadIdx.x; e < ctot * 9; e += blockDim.x) {
         const int c = e / 9, t = e % 9;
         const int sg = c >= p.cin[0], ci = sg ? c - p.cin[0] : c;
@@ -98,16 +101,19 @@ __global__ void __launch_bounds__(256) conv_small_cout_k3s1_kernel(const SmallCo
     __syncthreads();
     const int W = p.Wi, H = p.Hi, HW = H * W, W4 = W / 4;
     const long long total = (long long)p.B * H * W4;
-    for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < total; m += (long long)gridDim.x * blockDim.x) {
-        const int b = (int)(m / (H * W4)), r = (int)(m % (H * W4)), oy = r / W4, ox0 = 4 * (r % W4);
+    const int strip = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    for (long long m0 = (long long)blockIdx.x * 64; m0 < total; m0 += (long long)gridDim.x * 64) {
+        const long long m = m0 + strip;
+        const bool ok = m < total;
+        const int b = ok ? (int)(m / (H * W4)) : 0, r = ok ? (int)(m % (H * W4)) : 0, oy = r / W4, ox0 = 4 * (r % W4);
         float acc[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
         int cbase = 0;
         for (int sg = 0; sg < p.nseg; ++sg) {
-            const float* xp = p.x[sg] + (size_t)b * p.cin[sg] * HW + ox0;
+            const float* xp = p.x[sg] + ((size_t)b * p.cin[sg] + grp) * HW + ox0;
 #pragma unroll 2
-            for (int ci = 0; ci < p.cin[sg]; ++ci, xp += HW) {
+            for (int ci = grp; ci < p.cin[sg] && ok; ci += 4, xp += 4 * (size_t)HW) {
                 const float4* wq = scw + (size_t)(cbase + ci) * 9;
 #pragma unroll
                 for (int dy = 0; dy < 3; ++dy) {
@@ -129,9 +135,26 @@ __global__ void __launch_bounds__(256) conv_small_cout_k3s1_kernel(const SmallCo
             }
             cbase += p.cin[sg];
         }
-        for (int co = 0; co < p.cout; ++co) {
+        // sum the 4 channel groups: partial [group][pixel of strip][strip] as float4 over co
+        __syncthreads();
+#pragma unroll
+        for (int px = 0; px < 4; ++px) part[(grp * 4 + px) * 64 + strip] = make_float4(acc[px][0], acc[px][1], acc[px][2], acc[px][3]);
+        __syncthreads();
+        if (ok && grp < p.cout) {                   // group g finishes output channel g
+            const int co = grp;
+            float o4[4];
+#pragma unroll
+            for (int px = 0; px < 4; ++px) {
+                float sum = 0.f;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const float4 q = part[(g * 4 + px) * 64 + strip];
+                    sum += co == 0 ? q.x : (co == 1 ? q.y : (co == 2 ? q.z : q.w));
+                }
+                o4[px] = sum;
+            }
             const size_t o = ((size_t)b * p.cout + co) * HW + (size_t)oy * W + ox0;
-            float4 v = make_float4(acc[0][co], acc[1][co], acc[2][co], acc[3][co]);
+            float4 v = make_float4(o4[0], o4[1], o4[2], o4[3]);
             if (p.bias) { const float bb = __ldg(p.bias + co); v.x += bb; v.y += bb; v.z += bb; v.w += bb; }
             if (p.addend) { const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.addend + o)); v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w; }
             *reinterpret_cast<float4*>(p.y + o) = v;
@@ -192,9 +215,9 @@ static int conv_small_launch(const SmallConvParams& p, ffc_stream_t st) {
     cudaError_t e;
     const uintptr_t al = (uintptr_t)p.x[0] | (uintptr_t)p.x[1] | (uintptr_t)p.y | (uintptr_t)p.addend;
     if (p.cout <= 4 && K == 3 && p.stride == 1 && p.pad == 1 && !p.transposed && p.Wi % 4 == 0 && (al & 15) == 0) {
-        const size_t smem = (size_t)(p.cin[0] + (p.nseg > 1 ? p.cin[1] : 0)) * 9 * 16;
+        const size_t smem = (size_t)(p.cin[0] + (p.nseg > 1 ? p.cin[1] : 0)) * 9 * 16 + 64 * 16 * 16;
         if (smem > 48 * 1024) cudaFuncSetAttribute(conv_small_cout_k3s1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int g4 = (int)((total / 4 + 255) / 256); if (g4 > 148 * 16) g4 = 148 * 16; if (g4 < 1) g4 = 1;
+        int g4 = (int)((total / 4 + 63) / 64); if (g4 > 148 * 16) g4 = 148 * 16; if (g4 < 1) g4 = 1;
         conv_small_cout_k3s1_kernel<<<g4, 256, smem, st>>>(p);
     } else if (p.cout <= 4) {
         const size_t smem = (size_t)(p.cin[0] + (p.nseg > 1 ? p.cin[1] : 0)) * K * K * 16;

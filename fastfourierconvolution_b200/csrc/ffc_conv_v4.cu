@@ -361,7 +361,7 @@ extern "C" int ffc_conv2d_fwd_ws(const float* x0, const float* w0, int cin0,
     if (mode == ffc_conv_auto_mode) {
         // tcgen05 kernel wherever its 128 x N tile is reasonably filled; the mma.sync kernel for narrow outputs
 #ifndef FFC_EMU
-        mode = cout >= 24 ? ffc_conv_v5_mode : ffc_conv_v4_mode;
+        mode = (cout >= 24 || (cout >= 16 && k >= 3)) ? ffc_conv_v5_mode : ffc_conv_v4_mode;
 #else
         mode = ffc_conv_v4_mode;
 #endif
