@@ -265,13 +265,16 @@ def run_ours(args):
     assert gb % world == 0
     pb = gb // world
     torch.manual_seed(1234 + rank)
-    # the reference's convolutions run in TF32 on GPUs by default (cudnn.allow_tf32); the FFC path here is
-    # true FP32, and the (out-of-scope, PyTorch) discriminator is kept at PyTorch's defaults
+    # Everything on the step's critical path is FP32-accurate: the FFC generator AND the SN conv
+    # discriminator run on libffc_b200's kernels.  FFC_BENCH_D=torch keeps the discriminator on nn.Conv2d.forward
+    # (cuDNN, autotuned, NHWC, TF32 allowed -- PyTorch's GPU defaults) for an A/B comparison only.
+    d_backend = os.environ.get("FFC_BENCH_D", "ffc_b200")
     G = H.FGenerator(128, 4, variant).to(dev).train(); G.apply(H.weights_init)
-    D = H.SNDiscriminator(True, 4, n_convs).to(dev).train(); D.apply(H.weights_init)
-    if os.environ.get("FFC_BENCH_D_NHWC", "1") == "1":
-        # PyTorch-side tuning of the out-of-scope discriminator only: cuDNN autotuning and NHWC activations, which
-        # removes cuDNN's per-convolution NCHW<->NHWC transposes and its FP32 dgrad fallback
+    D = H.SNDiscriminator(True, 4, n_convs, backend="ffc_b200" if d_backend == "ffc_b200" else "torch").to(dev).train()
+    D.apply(H.weights_init)
+    if d_backend != "ffc_b200":                      # "torch" (TF32 allowed) or "torch_fp32" (cuDNN held to FP32 like the product)
+        torch.backends.cudnn.allow_tf32 = d_backend != "torch_fp32"
+        torch.backends.cuda.matmul.allow_tf32 = d_backend != "torch_fp32"
         torch.backends.cudnn.benchmark = True
         D = D.to(memory_format=torch.channels_last); D.channels_last = True
     if world > 1:                                    # identical replicas
@@ -367,7 +370,8 @@ def run_ours(args):
                        "l2": "per-step working set (activations of batch %d, > 400 MB) exceeds the 126 MB L2; FourierUnit timing rotates %d input buffers"
                              % (pb, fu["rotating_buffers"]),
                        "launch": "whole step replayed as one CUDA graph" if use_graph else "eager launches",
-                       "discriminator": "plain SN conv net (no FFC layer; PyTorch kernels, out of the hot-path scope; cuDNN autotuned, NHWC activations)",
+                       "discriminator": ("plain SN conv net on libffc_b200 kernels (tcgen05 conv / dgrad / wgrad at FP32 accuracy, fused bias, LeakyReLU kernel)"
+                                         if d_backend == "ffc_b200" else "plain SN conv net on PyTorch kernels (cuDNN autotuned, NHWC, %s)" % ("FP32" if d_backend == "torch_fp32" else "TF32")),
                        "generator_params_MB": round(act_mb, 1)},
             "e2e": {"value": gb / ms_e2e * 1000.0, "unit": "images/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": world * (h_zg.numel() + h_zd.numel() + h_real.numel()) * 4,

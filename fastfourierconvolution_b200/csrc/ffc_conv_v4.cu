@@ -297,6 +297,9 @@ size_t conv_v5_workspace_bytes(int cin0, int cin1, int cout, int k, int stride, 
 int conv_v5_run(const float* x0, const float* w0, int cin0, const float* x1, const float* w1, int cin1,
                 const float* bias, const float* addend, float* y, int B, int cout, int Hi, int Wi, int Ho, int Wo,
                 int k, int stride, int pad, int transposed, void* workspace, size_t workspace_bytes, ffc_stream_t st);
+int conv_v5_run_block(const float* x0, const float* w0, const float* w0b, int cin0, const float* x1, const float* w1, int cin1,
+                      const float* bias, const float* addend, float* y, float* y1, int cout0, int B, int cout, int Hi, int Wi, int Ho, int Wo,
+                      int k, int stride, int pad, int transposed, void* workspace, size_t workspace_bytes, ffc_stream_t st);
 #endif
 
 static int conv_v4_bn(int cout) { return (cout <= 32 || (cout > 64 && cout % 64 != 0 && cout % 64 <= 32 && cout < 128)) ? 32 : 64; }
@@ -409,4 +412,40 @@ extern "C" int ffc_conv2d_fwd_ws(const float* x0, const float* w0, int cin0,
     p.bias = bias; p.addend = addend; p.y = y; p.B = B; p.cout = cout; p.Hi = Hi; p.Wi = Wi; p.Ho = Ho; p.Wo = Wo;
     p.k = k; p.stride = stride; p.pad = pad; p.transposed = transposed;
     return pl.bn == 32 ? conv_v4_launch<32>(p, st) : conv_v4_launch<64>(p, st);
+}
+
+// Block form of the local branches of FFC.forward (ffc.py:91-96; ffc_transpose.py:98-106):
+//   y0 (cout0 channels) = conv(x0, w00) + conv(x1, w10) [+ bias[0:cout0]]          convl2l(x_l) + convg2l(x_g)
+//   y1 (cout1 channels) = conv(x0, w01)                 [+ bias[cout0:cout0+cout1]]  convl2g(x_l)
+// On the tcgen05 path this is ONE implicit GEMM over the concatenated output channels (the operand gathered from x0 is
+// shared); otherwise it is two calls of ffc_conv2d_fwd_ws.  x1 / w10 may be null (no second segment).
+extern "C" int ffc_conv2d_block_fwd_ws(const float* x0, const float* w00, const float* w01, int cin0,
+                                       const float* x1, const float* w10, int cin1, const float* bias,
+                                       float* y0, int cout0, float* y1, int cout1,
+                                       int B, int Hi, int Wi, int Ho, int Wo, int k, int stride, int pad, int transposed,
+                                       void* workspace, size_t workspace_bytes, void* stream) {
+    FFC_REQUIRE(x0 && w00 && w01 && y0 && y1 && cin0 > 0 && cout0 > 0 && cout1 > 0, "ffc_conv2d_block_fwd_ws: null pointer / empty block");
+    FFC_REQUIRE((x1 == nullptr) == (cin1 == 0) && (x1 == nullptr) == (w10 == nullptr), "ffc_conv2d_block_fwd_ws: inconsistent second segment");
+#ifndef FFC_EMU
+    const int cout = cout0 + cout1;
+    if ((ffc_conv_use_reference_kernel == ffc_conv_auto_mode || ffc_conv_use_reference_kernel == ffc_conv_v5_mode) && cout >= 16) {
+        FFC_REQUIRE(k >= 1 && k <= 7 && (stride == 1 || stride == 2) && pad >= 0 && pad < 8, "ffc_conv2d_block_fwd_ws: unsupported k=%d stride=%d pad=%d", k, stride, pad);
+        FFC_REQUIRE(B >= 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0, "ffc_conv2d_block_fwd_ws: bad sizes");
+        if (!transposed) {
+            FFC_REQUIRE(Ho == (Hi + 2 * pad - k) / stride + 1 && Wo == (Wi + 2 * pad - k) / stride + 1, "ffc_conv2d_block_fwd_ws: inconsistent output size");
+        } else {
+            const int hmin = (Hi - 1) * stride - 2 * pad + k, wmin = (Wi - 1) * stride - 2 * pad + k;
+            FFC_REQUIRE(Ho >= hmin && Ho < hmin + stride && Wo >= wmin && Wo < wmin + stride, "ffc_conv2d_block_fwd_ws: inconsistent transposed output size");
+        }
+        if (B == 0) return FFC_OK;
+        const int cmax = cin0 > cin1 ? cin0 : cin1;
+        FFC_REQUIRE((long long)B * cout * Ho * Wo < (1LL << 31) && (long long)B * cmax * Hi * Wi < (1LL << 31), "ffc_conv2d_block_fwd_ws: tensor too large for 32-bit element offsets");
+        return conv_v5_run_block(x0, w00, w01, cin0, x1, w10, cin1, bias, nullptr, y0, y1, cout0, B, cout, Hi, Wi, Ho, Wo,
+                                 k, stride, pad, transposed, workspace, workspace_bytes, (ffc_stream_t)stream);
+    }
+#endif
+    FFC_CHECK(ffc_conv2d_fwd_ws(x0, w00, cin0, x1, w10, cin1, bias, nullptr, y0, B, cout0, Hi, Wi, Ho, Wo, k, stride, pad, transposed,
+                                workspace, workspace_bytes, stream));
+    return ffc_conv2d_fwd_ws(x0, w01, cin0, nullptr, nullptr, 0, bias ? bias + cout0 : nullptr, nullptr, y1, B, cout1, Hi, Wi, Ho, Wo,
+                             k, stride, pad, transposed, workspace, workspace_bytes, stream);
 }

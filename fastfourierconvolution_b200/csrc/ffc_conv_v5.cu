@@ -43,6 +43,7 @@ struct ConvV5Params {
     long long cls_off[FFC_V5_MAXCLS];     // float offset of each class
     int nt_full;               // N of a full tile (multiple of 16, <= 192)
     const float* bias; const float* addend; float* y;
+    float* y1; int cout0;      // block form: output channels [cout0, cout) go to y1 (cout - cout0 channels); else y1 == null, cout0 == cout
     int B, cout, Hi, Wi, Ho, Wo, k, stride, pad, transposed;
 };
 
@@ -58,6 +59,7 @@ __host__ __device__ __forceinline__ int v5_tile_n(int cout, int nt_full, int t) 
 // ---------------------------------------------------------------------------------------------
 struct PackV5Params {
     const float* w[2]; int cin[2]; int cps[2]; int nseg;
+    const float* w0b; int cout0;   // block form: segment 0 uses w[0] for co < cout0 and w0b for the rest, segment 1 is zero there
     float* wp; long long cls_off[FFC_V5_MAXCLS];
     int nt_full, ntiles, cout, k, stride, pad, transposed;
 };
@@ -86,9 +88,14 @@ __global__ void __launch_bounds__(256) pack_v5_kernel(const PackV5Params p) {
             float v = 0.f;
             if (co < p.cout && ci < cin) {
                 const int a = tap / g.Tb, b = tap % g.Tb;
+                // weight tensor that holds (segment, co) and its own channel count / local channel index
                 const float* w = sg ? p.w[1] : p.w[0];
-                if (p.transposed) v = __ldg(w + ((size_t)ci * p.cout + co) * KK + (g.ky0 + p.stride * a) * p.k + (g.kx0 + p.stride * b));
-                else v = __ldg(w + ((size_t)co * cin + ci) * KK + a * p.k + b);
+                int wc = p.cout0, cl = co;
+                if (co >= p.cout0) { w = sg ? nullptr : p.w0b; wc = p.cout - p.cout0; cl = co - p.cout0; }
+                if (w) {
+                    if (p.transposed) v = __ldg(w + ((size_t)ci * wc + cl) * KK + (g.ky0 + p.stride * a) * p.k + (g.kx0 + p.stride * b));
+                    else v = __ldg(w + ((size_t)cl * cin + ci) * KK + a * p.k + b);
+                }
             }
             const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
             float* dst = p.wp + p.cls_off[cls] + tile_base + (long long)chunk_all * per_chunk
@@ -201,7 +208,7 @@ __global__ void __launch_bounds__(V5_GW * 128 + 64, V5_GW == 2 ? 2 : 1) conv_v5_
             const int oy = yq * s + py, ox = xq * s + px;
             const size_t HWo = (size_t)p.Ho * p.Wo;
             const int co0 = ntile * p.nt_full;
-            const size_t o0 = ((size_t)b * p.cout + co0) * HWo + (size_t)oy * p.Wo + ox;
+            const size_t pix = (size_t)oy * p.Wo + ox;
             for (int n0 = 16 * wg; n0 < NT; n0 += 16 * V5_GW) {
                 uint32_t r[16];
                 if (nchunks > 0) {                            // warp-wide: every lane takes part
@@ -222,8 +229,13 @@ __global__ void __launch_bounds__(V5_GW * 128 + 64, V5_GW == 2 ? 2 : 1) conv_v5_
                         if (co < p.cout) {
                             float v2 = __uint_as_float(r[j]);
                             if (p.bias) v2 += __ldg(p.bias + co);
-                            if (p.addend) v2 += __ldg(p.addend + o0 + (size_t)(n0 + j) * HWo);
-                            p.y[o0 + (size_t)(n0 + j) * HWo] = v2;
+                            if (co < p.cout0) {
+                                const size_t o = ((size_t)b * p.cout0 + co) * HWo + pix;
+                                if (p.addend) v2 += __ldg(p.addend + o);
+                                p.y[o] = v2;
+                            } else {
+                                p.y1[((size_t)b * (p.cout - p.cout0) + (co - p.cout0)) * HWo + pix] = v2;
+                            }
                         }
                     }
                 }
@@ -306,9 +318,23 @@ size_t conv_v5_workspace_bytes(int cin0, int cin1, int cout, int k, int stride, 
 }
 
 // arguments validated by ffc_conv2d_fwd_ws
+int conv_v5_run_block(const float* x0, const float* w0, const float* w0b, int cin0, const float* x1, const float* w1, int cin1,
+                      const float* bias, const float* addend, float* y, float* y1, int cout0, int B, int cout, int Hi, int Wi, int Ho, int Wo,
+                      int k, int stride, int pad, int transposed, void* workspace, size_t workspace_bytes, ffc_stream_t st);
+
 int conv_v5_run(const float* x0, const float* w0, int cin0, const float* x1, const float* w1, int cin1,
                 const float* bias, const float* addend, float* y, int B, int cout, int Hi, int Wi, int Ho, int Wo,
                 int k, int stride, int pad, int transposed, void* workspace, size_t workspace_bytes, ffc_stream_t st) {
+    return conv_v5_run_block(x0, w0, nullptr, cin0, x1, w1, cin1, bias, addend, y, nullptr, cout, B, cout, Hi, Wi, Ho, Wo,
+                             k, stride, pad, transposed, workspace, workspace_bytes, st);
+}
+
+// Block form: y (cout0 channels) = conv(x0, w0) + conv(x1, w1) [+ bias[:cout0]] [+ addend];  y1 (cout - cout0 channels) =
+// conv(x0, w0b) [+ bias[cout0:]] -- ONE implicit GEMM over the concatenated output channels, so the operand gathered from x0
+// is shared by both outputs (the convl2l | convl2g pair of FFC.forward, ffc.py:91-96).  y1 == null: the plain form.
+int conv_v5_run_block(const float* x0, const float* w0, const float* w0b, int cin0, const float* x1, const float* w1, int cin1,
+                      const float* bias, const float* addend, float* y, float* y1, int cout0, int B, int cout, int Hi, int Wi, int Ho, int Wo,
+                      int k, int stride, int pad, int transposed, void* workspace, size_t workspace_bytes, ffc_stream_t st) {
     const ConvV5Plan pl = conv_v5_plan(cin0, cin1, cout, k, stride, pad, transposed);
     const uintptr_t wsa = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
     if (!workspace || wsa + (size_t)pl.total_floats * sizeof(float) > (uintptr_t)workspace + workspace_bytes) {
@@ -318,7 +344,7 @@ int conv_v5_run(const float* x0, const float* w0, int cin0, const float* x1, con
     PackV5Params pp;
     pp.w[0] = w0; pp.w[1] = w1; pp.cin[0] = cin0; pp.cin[1] = cin1; pp.cps[0] = pl.cps[0]; pp.cps[1] = pl.cps[1];
     pp.nseg = x1 ? 2 : 1; pp.wp = (float*)wsa; pp.nt_full = pl.nt_full; pp.ntiles = pl.ntiles; pp.cout = cout;
-    pp.k = k; pp.stride = stride; pp.pad = pad; pp.transposed = transposed;
+    pp.k = k; pp.stride = stride; pp.pad = pad; pp.transposed = transposed; pp.w0b = w0b; pp.cout0 = cout0;
     for (int c = 0; c < FFC_V5_MAXCLS; ++c) pp.cls_off[c] = pl.cls_off[c];
     const long long per_cls = (long long)k * k * (pl.cps[0] + pl.cps[1]) * V5_BK * ((cout + 15) / 16 * 16);
     int gx = (int)((per_cls + 255) / 256); if (gx > 148 * 4) gx = 148 * 4; if (gx < 1) gx = 1;
@@ -331,7 +357,7 @@ int conv_v5_run(const float* x0, const float* w0, int cin0, const float* x1, con
     p.x[0] = x0; p.x[1] = x1; p.cin[0] = cin0; p.cin[1] = cin1; p.cps[0] = pl.cps[0]; p.cps[1] = pl.cps[1]; p.nseg = x1 ? 2 : 1;
     p.wp = (const float*)wsa; p.nt_full = pl.nt_full;
     for (int c = 0; c < FFC_V5_MAXCLS; ++c) p.cls_off[c] = pl.cls_off[c];
-    p.bias = bias; p.addend = addend; p.y = y; p.B = B; p.cout = cout; p.Hi = Hi; p.Wi = Wi; p.Ho = Ho; p.Wo = Wo;
+    p.bias = bias; p.addend = addend; p.y = y; p.y1 = y1; p.cout0 = cout0; p.B = B; p.cout = cout; p.Hi = Hi; p.Wi = Wi; p.Ho = Ho; p.Wo = Wo;
     p.k = k; p.stride = stride; p.pad = pad; p.transposed = transposed;
     const int s = transposed ? stride : 1;
     const int Mc = B * ffc_cdiv(Ho, s) * ffc_cdiv(Wo, s);

@@ -91,12 +91,18 @@ class FGenerator(nn.Module):
 class SNDiscriminator(nn.Module):
     """The plain spectral-norm conv discriminator the fgan scripts train against
     (fgan_complete.py:142-171 n_convs=7, fgan64_complete.py:159-191 n_convs=8,
-    fgan128_complete.py:525-562 n_convs=9).  It contains no FFC layer and is outside the hot path
-    (SURVEY.md section 8(f) rank 1): it stays on PyTorch's own kernels."""
+    fgan128_complete.py:525-562 n_convs=9): SN Conv2d + LeakyReLU(0.1) stack, SN Linear head.
 
-    def __init__(self, sn=True, mg: int = 4, n_convs: int = 7):
+    SURVEY.md section 8(f) rank 1 -- it is more than half of a training step.  ``backend="ffc_b200"`` (default) runs
+    every convolution, its data / weight / bias gradients and the LeakyReLU on the FP32-accurate sm_100a kernels of the
+    local branches (same ``ops.conv2d`` as FFC.convl2l); the ``nn.Conv2d`` objects stay as parameter holders, so the
+    state_dict (``convN.weight_orig / weight_u / weight_v / bias``) is the reference's.  ``backend="torch"`` is the
+    reference's own arithmetic (nn.Conv2d.forward) and is what the parity tests compare against."""
+
+    def __init__(self, sn=True, mg: int = 4, n_convs: int = 7, backend: str = "ffc_b200"):
         super().__init__()
-        self.mg, self.n_convs = mg, n_convs
+        assert backend in ("ffc_b200", "torch")
+        self.mg, self.n_convs, self.backend = mg, n_convs, backend
         sn_fn = torch.nn.utils.spectral_norm if sn else (lambda m: m)
         spec = [(3, 64, 3, 1), (64, 64, 4, 2), (64, 128, 3, 1), (128, 128, 4, 2), (128, 256, 3, 1),
                 (256, 256, 4, 2), (256, 512, 3, 1), (512, 512, 4, 2), (512, 512, 4, 2)][:n_convs]
@@ -104,9 +110,18 @@ class SNDiscriminator(nn.Module):
             setattr(self, f"conv{i}", sn_fn(nn.Conv2d(ci, co, k, stride=s, padding=(1, 1))))
         self.fc = sn_fn(nn.Linear(mg * mg * 512, 1))
         self.act = nn.LeakyReLU(0.1)
-        self.channels_last = False      # PyTorch-side tuning knob: run cuDNN in NHWC (same math, no layout round trips)
+        self.channels_last = False      # backend="torch" only: run cuDNN in NHWC (same math, no layout round trips)
 
     def forward(self, x):
+        if self.backend == "ffc_b200":
+            from .. import ops
+            from ..layers import _util
+            m = x
+            for i in range(1, self.n_convs + 1):
+                conv = getattr(self, f"conv{i}")
+                w = _util.effective_weight(conv)          # spectral_norm pre-forward hook: W / sigma, one power iteration
+                m = ops.conv2d_act(m, w, conv.bias, conv.stride[0], conv.padding[0], ops.ACT_LEAKY, self.act.negative_slope)
+            return self.fc(m.reshape(-1, self.mg * self.mg * 512))
         m = x.contiguous(memory_format=torch.channels_last) if self.channels_last else x
         for i in range(1, self.n_convs + 1):
             m = self.act(getattr(self, f"conv{i}")(m))

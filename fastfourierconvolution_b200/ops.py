@@ -71,40 +71,92 @@ class Conv2dFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x0, w0, x1, w1 = ctx.saved_tensors
-        stride, pad, transposed, k, cout, has_bias, has_addend = ctx.cfg
-        dy = dy.contiguous()
-        B, _, Ho, Wo = dy.shape
-        L = _C.lib()
-        st = _C.current_stream(dy.device)
-        grads = [None] * 10
-        for slot, (x, w) in enumerate(((x0, w0), (x1, w1))):
-            if x is None:
-                continue
-            cin, Hi, Wi = x.shape[1], x.shape[2], x.shape[3]
-            if ctx.needs_input_grad[2 * slot]:
-                dx = torch.empty_like(x)
-                # data gradient = the opposite gather form over dy with the same weight tensor
-                _conv_launch(dy, w, cout, None, None, 0, None, None, dx, B, cin, Ho, Wo, Hi, Wi, k, stride, pad, not transposed)
-                grads[2 * slot] = dx
-            if ctx.needs_input_grad[2 * slot + 1]:
-                dw = torch.empty_like(w)
-                if transposed:   # S = x (cin, Hi), L = dy (cout, Ho) -> [cin][cout][k][k]
-                    _C.check(L.ffc_conv2d_wgrad(_C.ptr(x), _C.ptr(dy), _C.ptr(dw), B, cin, cout, Hi, Wi, Ho, Wo, k, stride, pad, st))
-                else:            # S = dy, L = x -> [cout][cin][k][k]
-                    _C.check(L.ffc_conv2d_wgrad(_C.ptr(dy), _C.ptr(x), _C.ptr(dw), B, cout, cin, Ho, Wo, Hi, Wi, k, stride, pad, st))
-                grads[2 * slot + 1] = dw
-        if has_bias and ctx.needs_input_grad[4]:
-            db = torch.empty(cout, device=dy.device, dtype=torch.float32)
-            ws = _C.workspace(2 * cout * 8, dy.device)
-            _C.check(L.ffc_bias_grad(_C.ptr(dy), _C.ptr(db), B, cout, Ho * Wo, _C.ptr(ws), ws.numel(), st))
-            grads[4] = db
-        if has_addend and ctx.needs_input_grad[5]:
-            grads[5] = dy
-        return tuple(grads)
+        return _conv_backward(ctx.cfg, x0, w0, x1, w1, dy, ctx.needs_input_grad)
+
+
+def _conv_backward(cfg, x0, w0, x1, w1, dy, needs):
+    """Gradients of Conv2dFn's ten inputs (None where not needed)."""
+    stride, pad, transposed, k, cout, has_bias, has_addend = cfg
+    dy = dy.contiguous()
+    B, _, Ho, Wo = dy.shape
+    L = _C.lib()
+    st = _C.current_stream(dy.device)
+    grads = [None] * 10
+    for slot, (x, w) in enumerate(((x0, w0), (x1, w1))):
+        if x is None:
+            continue
+        cin, Hi, Wi = x.shape[1], x.shape[2], x.shape[3]
+        if needs[2 * slot]:
+            dx = torch.empty_like(x)
+            # data gradient = the opposite gather form over dy with the same weight tensor
+            _conv_launch(dy, w, cout, None, None, 0, None, None, dx, B, cin, Ho, Wo, Hi, Wi, k, stride, pad, not transposed)
+            grads[2 * slot] = dx
+        if needs[2 * slot + 1]:
+            dw = torch.empty_like(w)
+            if transposed:   # S = x (cin, Hi), L = dy (cout, Ho) -> [cin][cout][k][k]
+                _C.check(L.ffc_conv2d_wgrad(_C.ptr(x), _C.ptr(dy), _C.ptr(dw), B, cin, cout, Hi, Wi, Ho, Wo, k, stride, pad, st))
+            else:            # S = dy, L = x -> [cout][cin][k][k]
+                _C.check(L.ffc_conv2d_wgrad(_C.ptr(dy), _C.ptr(x), _C.ptr(dw), B, cout, cin, Ho, Wo, Hi, Wi, k, stride, pad, st))
+            grads[2 * slot + 1] = dw
+    if has_bias and needs[4]:
+        db = torch.empty(cout, device=dy.device, dtype=torch.float32)
+        ws = _C.workspace(2 * cout * 8, dy.device)
+        _C.check(L.ffc_bias_grad(_C.ptr(dy), _C.ptr(db), B, cout, Ho * Wo, _C.ptr(ws), ws.numel(), st))
+        grads[4] = db
+    if has_addend and needs[5]:
+        grads[5] = dy
+    return tuple(grads)
 
 
 def conv2d(x0, w0, x1=None, w1=None, bias=None, addend=None, stride=1, pad=0, transposed=False, out_pad=0):
     return Conv2dFn.apply(x0, w0, x1, w1, bias, addend, stride, pad, transposed, out_pad)
+
+
+class ConvActFn(torch.autograd.Function):
+    """a = act(conv(x, w) + bias) for act in {LeakyReLU, ReLU}: the SN-conv + LeakyReLU(0.1) stage of the fgan
+    discriminators (fgan_complete.py:160-169).  Only the activated output is kept: both activations preserve the
+    sign of their argument, so the backward mask is read from ``a`` itself."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, stride, pad, act, slope):
+        if act not in (ACT_LEAKY, ACT_RELU) or (act == ACT_LEAKY and not slope > 0):
+            raise ValueError("conv2d_act: LeakyReLU (slope > 0) or ReLU only")
+        _C.require_device(x, w, bias)
+        x, w, bias = _c(x), _c(w), _c(bias)
+        B, cin, Hi, Wi = x.shape
+        cout, k = w.shape[0], w.shape[-1]
+        if w.shape[1] != cin or w.shape[-2] != k:
+            raise ValueError(f"weight {tuple(w.shape)} does not match input channels {cin} (groups=1, square kernels only)")
+        Ho, Wo = conv_out_size(Hi, k, stride, pad, False), conv_out_size(Wi, k, stride, pad, False)
+        a = torch.empty((B, cout, Ho, Wo), device=x.device, dtype=torch.float32)
+        _conv_launch(x, w, cin, None, None, 0, bias, None, a, B, cout, Hi, Wi, Ho, Wo, k, stride, pad, False)
+        L = _C.lib()
+        ws = _C.workspace(2 * cout * 8, x.device)
+        _C.check(L.ffc_bn_act_fwd(_C.ptr(a), _C.ptr(a), None, None, None, None, None, None, B, cout, Ho * Wo, 0, 0, 0.0, 0.0,
+                                  int(act), float(slope), _C.ptr(ws), ws.numel(), _C.current_stream(x.device)))
+        ctx.save_for_backward(x, w, a)
+        ctx.cfg = (stride, pad, False, k, cout, bias is not None, False)
+        ctx.act = (int(act), float(slope))
+        return a
+
+    @staticmethod
+    def backward(ctx, da):
+        x, w, a = ctx.saved_tensors
+        act, slope = ctx.act
+        da = da.contiguous()
+        B, cout, Ho, Wo = a.shape
+        dpre = torch.empty_like(a)
+        L = _C.lib()
+        ws = _C.workspace(2 * cout * 8, a.device)
+        _C.check(L.ffc_bn_act_bwd(_C.ptr(a), _C.ptr(da), _C.ptr(dpre), None, None, None, None, None, None,
+                                  B, cout, Ho * Wo, 0, 0, act, slope, _C.ptr(ws), ws.numel(), _C.current_stream(a.device)))
+        n = ctx.needs_input_grad
+        g = _conv_backward(ctx.cfg, x, w, None, None, dpre, (n[0], n[1], False, False, n[2], False))
+        return g[0], g[1], g[4], None, None, None, None
+
+
+def conv2d_act(x, w, bias=None, stride=1, pad=0, act=ACT_LEAKY, slope=0.1):
+    return ConvActFn.apply(x, w, bias, stride, pad, act, slope)
 
 
 # ---------------------------------------------------------------------------------------------

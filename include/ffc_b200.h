@@ -128,6 +128,17 @@ int ffc_conv2d_fwd_ws(const float* x0, const float* w0, int cin0,
                       int k, int stride, int pad, int transposed,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* ffc_conv2d_block_fwd_ws: the local branches of FFC.forward (ffc.py:91-96, ffc_transpose.py:98-106) in one call:
+ *   y0 (cout0 channels) = conv(x0, w00) + conv(x1, w10) [+ bias[0:cout0]]            convl2l(x_l) + convg2l(x_g)
+ *   y1 (cout1 channels) = conv(x0, w01)                 [+ bias[cout0:cout0+cout1]]   convl2g(x_l)
+ * On the tcgen05 path both outputs come from ONE implicit GEMM over the concatenated output channels, so the operand
+ * gathered from x0 is shared.  x1 / w10 may be NULL.  workspace: ffc_conv2d_workspace_bytes(cin0, cin1, cout0 + cout1, ...). */
+int ffc_conv2d_block_fwd_ws(const float* x0, const float* w00, const float* w01, int cin0,
+                            const float* x1, const float* w10, int cin1, const float* bias,
+                            float* y0, int cout0, float* y1, int cout1,
+                            int B, int Hi, int Wi, int Ho, int Wo, int k, int stride, int pad, int transposed,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
 /* dW[sc][lc][ky][kx] = sum_{b,y,x} S[b,sc,y,x] * L[b,lc,y*stride-pad+ky,x*stride-pad+kx]
  * nn.Conv2d:          S = dy (cout, Ho x Wo), L = x  (cin,  Hi x Wi)  -> dW [cout][cin][k][k]
  * nn.ConvTranspose2d: S = x  (cin,  Hi x Wi), L = dy (cout, Ho x Wo)  -> dW [cin][cout][k][k]

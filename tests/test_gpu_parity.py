@@ -318,3 +318,25 @@ def test_graph_captured_step_matches_eager_step():
     w1 = G1.conv3.ffc.convg2g.fu.conv_layer.weight
     w2 = G2.conv3.ffc.convg2g.fu.conv_layer.weight
     assert (w1 - w2).abs().max().item() < 1.5e-3 and t2.launches_per_step > 100
+
+
+@pytest.mark.parametrize("n_convs,size,batch", [(7, 32, 16), (8, 64, 4), (9, 128, 2)])
+def test_sn_discriminator_on_product_kernels_matches_torch_convs(n_convs, size, batch):
+    """the plain SN conv discriminators of fgan / fgan64 / fgan128 on the sm_100a kernels against
+    nn.Conv2d.forward in float64 on the same device: output 1e-4 in the max norm, gradients 2e-2 in the relative L2 norm (one
+    LeakyReLU element on the other side of the kink moves the max norm; per-layer 1e-4 bounds: test_conv2d_act_matches_float64)."""
+    from test_layers_emu import _sn_discriminator_pair, _check_discriminator_errs
+    _check_discriminator_errs(_sn_discriminator_pair(DEV, n_convs, size, batch))
+
+
+def _conv_act_cases():
+    from test_layers_emu import CONV_ACT_CASES
+    return CONV_ACT_CASES + [(64, 64, 64, 32, 4, 2), (64, 256, 256, 8, 4, 2), (16, 512, 512, 8, 4, 2)]
+
+
+@pytest.mark.parametrize("case", _conv_act_cases())
+def test_conv2d_act_matches_float64(case):
+    """One SN-discriminator stage (conv + bias + LeakyReLU(0.1), forward and all gradients) at 1e-4 in the max norm."""
+    from test_layers_emu import conv2d_act_errs
+    errs = conv2d_act_errs(DEV, case)
+    assert max(errs.values()) < parity.TOL, errs
