@@ -34,6 +34,7 @@ _SIGNATURES = {
     "ffc_conv2d_workspace_bytes": (c_size_t, [c_int] * 7),
     "ffc_conv2d_block_fwd_ws": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                         c_void_p, c_int, c_void_p, c_int] + [c_int] * 9 + [c_void_p, c_size_t, c_void_p]),
+    "ffc_conv2d_act_fwd_ws": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p] + [c_int] * 9 + [c_int, c_float, c_void_p, c_size_t, c_void_p]),
     "ffc_conv2d_wgrad": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 10 + [c_void_p]),
     "ffc_bias_grad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "ffc_bn_act_fwd": (c_int, [c_void_p] * 8 + [c_int] * 5 + [c_float, c_float, c_int, c_float, c_void_p, c_size_t, c_void_p]),

@@ -299,7 +299,7 @@ int conv_v5_run(const float* x0, const float* w0, int cin0, const float* x1, con
                 int k, int stride, int pad, int transposed, void* workspace, size_t workspace_bytes, ffc_stream_t st);
 int conv_v5_run_block(const float* x0, const float* w0, const float* w0b, int cin0, const float* x1, const float* w1, int cin1,
                       const float* bias, const float* addend, float* y, float* y1, int cout0, int B, int cout, int Hi, int Wi, int Ho, int Wo,
-                      int k, int stride, int pad, int transposed, void* workspace, size_t workspace_bytes, ffc_stream_t st);
+                      int k, int stride, int pad, int transposed, float slope, void* workspace, size_t workspace_bytes, ffc_stream_t st);
 #endif
 
 static int conv_v4_bn(int cout) { return (cout <= 32 || (cout > 64 && cout % 64 != 0 && cout % 64 <= 32 && cout < 128)) ? 32 : 64; }
@@ -441,11 +441,43 @@ extern "C" int ffc_conv2d_block_fwd_ws(const float* x0, const float* w00, const 
         const int cmax = cin0 > cin1 ? cin0 : cin1;
         FFC_REQUIRE((long long)B * cout * Ho * Wo < (1LL << 31) && (long long)B * cmax * Hi * Wi < (1LL << 31), "ffc_conv2d_block_fwd_ws: tensor too large for 32-bit element offsets");
         return conv_v5_run_block(x0, w00, w01, cin0, x1, w10, cin1, bias, nullptr, y0, y1, cout0, B, cout, Hi, Wi, Ho, Wo,
-                                 k, stride, pad, transposed, workspace, workspace_bytes, (ffc_stream_t)stream);
+                                 k, stride, pad, transposed, 1.f, workspace, workspace_bytes, (ffc_stream_t)stream);
     }
 #endif
     FFC_CHECK(ffc_conv2d_fwd_ws(x0, w00, cin0, x1, w10, cin1, bias, nullptr, y0, B, cout0, Hi, Wi, Ho, Wo, k, stride, pad, transposed,
                                 workspace, workspace_bytes, stream));
     return ffc_conv2d_fwd_ws(x0, w01, cin0, nullptr, nullptr, 0, bias ? bias + cout0 : nullptr, nullptr, y1, B, cout1, Hi, Wi, Ho, Wo,
                              k, stride, pad, transposed, workspace, workspace_bytes, stream);
+}
+
+extern "C" int ffc_bn_act_fwd(const float* x, float* y, const float* gamma, const float* beta,
+                              float* running_mean, float* running_var, float* save_mean, float* save_invstd,
+                              int B, int C, int HW, int norm, int training, float eps, float momentum,
+                              int act, float slope, void* workspace, size_t workspace_bytes, void* stream);    // ffc_bnact.cu
+
+// y = act(conv(x, w) + bias), act = LeakyReLU(slope) or ReLU: one stage of the SN conv discriminators of the fgan scripts
+// (fgan_complete.py:160-169: ``self.activation(self.convN(m))``).  The activation rides in the epilogue of the tcgen05
+// kernel; shapes that kernel does not take (<= 4 input channels: the RGB stage) run the convolution and then the
+// elementwise kernel in place.  workspace: ffc_conv2d_workspace_bytes(cin, 0, cout, k, stride, pad, 0), at least 2*cout*8 bytes.
+extern "C" int ffc_conv2d_act_fwd_ws(const float* x, const float* w, int cin, const float* bias, float* y,
+                                     int B, int cout, int Hi, int Wi, int Ho, int Wo, int k, int stride, int pad,
+                                     int act, float slope, void* workspace, size_t workspace_bytes, void* stream) {
+    FFC_REQUIRE(act == FFC_ACT_LEAKY || act == FFC_ACT_RELU, "ffc_conv2d_act_fwd_ws: LeakyReLU or ReLU only (code %d)", act);
+    FFC_REQUIRE(act == FFC_ACT_RELU || slope > 0.f, "ffc_conv2d_act_fwd_ws: LeakyReLU needs slope > 0");
+#ifndef FFC_EMU
+    if (ffc_conv_use_reference_kernel == ffc_conv_auto_mode && !conv_small_supported(cin, 0, cout, k) && (cout >= 24 || (cout >= 16 && k >= 3))) {
+        FFC_REQUIRE(x && w && y && cin > 0, "ffc_conv2d_act_fwd_ws: null pointer / empty input");
+        FFC_REQUIRE(k >= 1 && k <= 7 && (stride == 1 || stride == 2) && pad >= 0 && pad < 8, "ffc_conv2d_act_fwd_ws: unsupported k=%d stride=%d pad=%d", k, stride, pad);
+        FFC_REQUIRE(B >= 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0, "ffc_conv2d_act_fwd_ws: bad sizes");
+        FFC_REQUIRE(Ho == (Hi + 2 * pad - k) / stride + 1 && Wo == (Wi + 2 * pad - k) / stride + 1, "ffc_conv2d_act_fwd_ws: inconsistent output size");
+        if (B == 0) return FFC_OK;
+        FFC_REQUIRE((long long)B * cout * Ho * Wo < (1LL << 31) && (long long)B * cin * Hi * Wi < (1LL << 31), "ffc_conv2d_act_fwd_ws: tensor too large for 32-bit element offsets");
+        return conv_v5_run_block(x, w, nullptr, cin, nullptr, nullptr, 0, bias, nullptr, y, nullptr, cout, B, cout, Hi, Wi, Ho, Wo,
+                                 k, stride, pad, 0, act == FFC_ACT_RELU ? 0.f : slope, workspace, workspace_bytes, (ffc_stream_t)stream);
+    }
+#endif
+    FFC_CHECK(ffc_conv2d_fwd_ws(x, w, cin, nullptr, nullptr, 0, bias, nullptr, y, B, cout, Hi, Wi, Ho, Wo, k, stride, pad, 0,
+                                workspace, workspace_bytes, stream));
+    return ffc_bn_act_fwd(y, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, B, cout, Ho * Wo, 0, 0, 0.f, 0.f, act, slope,
+                          workspace, workspace_bytes, stream);
 }

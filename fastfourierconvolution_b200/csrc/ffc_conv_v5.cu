@@ -31,7 +31,7 @@
 
 #define FFC_V5_MAXCLS 4
 static constexpr int V5_BK = 32;          // K per chunk (= 4 MMA K-steps of 8)
-static constexpr int V5_SB = 3;           // B stages
+static constexpr int V5_SB_MAX = 8;       // B stages: as many as fit the shared-memory budget (ConvV5Params::nsb), at most 8
 // V5_GW = gather warpgroups = A stages in TMEM is a template parameter of the kernel: 2 (320 threads; two CTAs per SM
 // when N <= 64 so that one CTA's prologue / epilogue overlaps the other's main loop; also N > 128, where only two
 // stages fit beside the accumulators) or 4 (576 threads, one CTA per SM, 64 < N <= 128).
@@ -42,7 +42,9 @@ struct ConvV5Params {
     const float* wp;           // packed weights: [class][n tile][chunk][hi | lo][NT*32]
     long long cls_off[FFC_V5_MAXCLS];     // float offset of each class
     int nt_full;               // N of a full tile (multiple of 16, <= 192)
+    int nsb;                   // B stages in shared memory (2 .. V5_SB_MAX)
     const float* bias; const float* addend; float* y;
+    float slope;               // epilogue activation x > 0 ? x : slope * x (1 = none, 0.1 = LeakyReLU(0.1), 0 = ReLU)
     float* y1; int cout0;      // block form: output channels [cout0, cout) go to y1 (cout - cout0 channels); else y1 == null, cout0 == cout
     int B, cout, Hi, Wi, Ho, Wo, k, stride, pad, transposed;
 };
@@ -130,11 +132,12 @@ __global__ void __launch_bounds__(V5_GW * 128 + 64, V5_GW == 2 ? 2 : 1) conv_v5_
     // packed weights of this (class, tile): tiles before it have nt_full columns
     const float* wp = p.wp + p.cls_off[cls] + (long long)ntile * nchunks * 2LL * p.nt_full * V5_BK;
 
-    unsigned char* bstage = v5_smem;                                                     // V5_SB stages
-    uint64_t* bars = reinterpret_cast<uint64_t*>(v5_smem + (size_t)V5_SB * stage_bytes);
-    uint64_t* b_full = bars;                    // [V5_SB]
-    uint64_t* b_free = bars + V5_SB;            // [V5_SB]
-    uint64_t* a_ready = bars + 2 * V5_SB;       // [V5_GW]
+    const int nsb = p.nsb;
+    unsigned char* bstage = v5_smem;                                                     // nsb stages
+    uint64_t* bars = reinterpret_cast<uint64_t*>(v5_smem + (size_t)nsb * stage_bytes);
+    uint64_t* b_full = bars;                    // [V5_SB_MAX]
+    uint64_t* b_free = bars + V5_SB_MAX;        // [V5_SB_MAX]
+    uint64_t* a_ready = bars + 2 * V5_SB_MAX;   // [V5_GW]
     uint64_t* a_free = a_ready + V5_GW;         // [V5_GW]
     uint64_t* acc_done = a_free + V5_GW;        // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
@@ -144,8 +147,8 @@ __global__ void __launch_bounds__(V5_GW * 128 + 64, V5_GW == 2 ? 2 : 1) conv_v5_
     const uint32_t tmem_cols = (2 * NT + 64 * V5_GW <= 256) ? 256u : 512u;
     constexpr int nstage = V5_GW;
     if (tid == 0) {
-        for (int i = 0; i < V5_SB; ++i) { umma::mbar_init(&b_full[i], 1); umma::mbar_init(&b_free[i], 1); }
-        for (int i = 0; i < V5_GW; ++i) { umma::mbar_init(&a_ready[i], 128); umma::mbar_init(&a_free[i], 1); }
+        for (int i = 0; i < nsb; ++i) { umma::mbar_init(&b_full[i], 1); umma::mbar_init(&b_free[i], 1); }
+        for (int i = 0; i < V5_GW; ++i) { umma::mbar_init(&a_ready[i], 4); umma::mbar_init(&a_free[i], 1); }
         umma::mbar_init(acc_done, 1);
         umma::fence_barrier_init();
     }
@@ -200,7 +203,8 @@ __global__ void __launch_bounds__(V5_GW * 128 + 64, V5_GW == 2 ? 2 : 1) conv_v5_
             }
             umma::wait_st();
             umma::fence_before_sync();
-            umma::mbar_arrive(&a_ready[wg]);
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive(&a_ready[wg]);       // one arrival per warp: 128 arrivals on one mbarrier serialise
         }
         // ===================== epilogue =====================
         if (nchunks > 0) { umma::mbar_wait(acc_done, 0); umma::fence_after_sync(); }
@@ -232,9 +236,9 @@ __global__ void __launch_bounds__(V5_GW * 128 + 64, V5_GW == 2 ? 2 : 1) conv_v5_
                             if (co < p.cout0) {
                                 const size_t o = ((size_t)b * p.cout0 + co) * HWo + pix;
                                 if (p.addend) v2 += __ldg(p.addend + o);
-                                p.y[o] = v2;
+                                p.y[o] = v2 > 0.f ? v2 : v2 * p.slope;
                             } else {
-                                p.y1[((size_t)b * (p.cout - p.cout0) + (co - p.cout0)) * HWo + pix] = v2;
+                                p.y1[((size_t)b * (p.cout - p.cout0) + (co - p.cout0)) * HWo + pix] = v2 > 0.f ? v2 : v2 * p.slope;
                             }
                         }
                     }
@@ -245,9 +249,10 @@ __global__ void __launch_bounds__(V5_GW * 128 + 64, V5_GW == 2 ? 2 : 1) conv_v5_
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = umma::idesc_tf32(128, NT);
+            int sb = 0; uint32_t sb_phase = 0;
             for (int c = 0; c < nchunks; ++c) {
-                const int sa = c % nstage, sb = c % V5_SB;
-                umma::mbar_wait(&b_full[sb], (uint32_t)((c / V5_SB) & 1));
+                const int sa = c % nstage;
+                umma::mbar_wait(&b_full[sb], sb_phase);
                 umma::mbar_wait(&a_ready[sa], (uint32_t)((c / nstage) & 1));
                 umma::fence_after_sync();
                 const uint32_t b_hi = umma::smem_u32(bstage + (size_t)sb * stage_bytes), b_lo = b_hi + (uint32_t)(NT * V5_BK * 4);
@@ -262,6 +267,7 @@ __global__ void __launch_bounds__(V5_GW * 128 + 64, V5_GW == 2 ? 2 : 1) conv_v5_
                 }
                 umma::commit(&a_free[sa]);
                 umma::commit(&b_free[sb]);
+                if (++sb == nsb) { sb = 0; sb_phase ^= 1u; }
             }
             umma::commit(acc_done);
         }
@@ -269,11 +275,12 @@ __global__ void __launch_bounds__(V5_GW * 128 + 64, V5_GW == 2 ? 2 : 1) conv_v5_
     } else {
         // ===================== B loader =====================
         if (lane == 0) {
+            int sb = 0; uint32_t free_phase = 1;               // first pass over the ring: nothing to wait for
             for (int c = 0; c < nchunks; ++c) {
-                const int sb = c % V5_SB;
-                if (c >= V5_SB) umma::mbar_wait(&b_free[sb], (uint32_t)((c / V5_SB - 1) & 1));
+                if (c >= nsb) umma::mbar_wait(&b_free[sb], free_phase);
                 umma::mbar_arrive_expect_tx(&b_full[sb], stage_bytes);
                 umma::bulk_g2s(bstage + (size_t)sb * stage_bytes, wp + (size_t)c * 2 * NT * V5_BK, stage_bytes, &b_full[sb]);
+                if (++sb == nsb) { sb = 0; free_phase ^= 1u; }
             }
         }
         __syncwarp();
@@ -320,13 +327,13 @@ size_t conv_v5_workspace_bytes(int cin0, int cin1, int cout, int k, int stride, 
 // arguments validated by ffc_conv2d_fwd_ws
 int conv_v5_run_block(const float* x0, const float* w0, const float* w0b, int cin0, const float* x1, const float* w1, int cin1,
                       const float* bias, const float* addend, float* y, float* y1, int cout0, int B, int cout, int Hi, int Wi, int Ho, int Wo,
-                      int k, int stride, int pad, int transposed, void* workspace, size_t workspace_bytes, ffc_stream_t st);
+                      int k, int stride, int pad, int transposed, float slope, void* workspace, size_t workspace_bytes, ffc_stream_t st);
 
 int conv_v5_run(const float* x0, const float* w0, int cin0, const float* x1, const float* w1, int cin1,
                 const float* bias, const float* addend, float* y, int B, int cout, int Hi, int Wi, int Ho, int Wo,
                 int k, int stride, int pad, int transposed, void* workspace, size_t workspace_bytes, ffc_stream_t st) {
     return conv_v5_run_block(x0, w0, nullptr, cin0, x1, w1, cin1, bias, addend, y, nullptr, cout, B, cout, Hi, Wi, Ho, Wo,
-                             k, stride, pad, transposed, workspace, workspace_bytes, st);
+                             k, stride, pad, transposed, 1.f, workspace, workspace_bytes, st);
 }
 
 // Block form: y (cout0 channels) = conv(x0, w0) + conv(x1, w1) [+ bias[:cout0]] [+ addend];  y1 (cout - cout0 channels) =
@@ -334,7 +341,7 @@ int conv_v5_run(const float* x0, const float* w0, int cin0, const float* x1, con
 // is shared by both outputs (the convl2l | convl2g pair of FFC.forward, ffc.py:91-96).  y1 == null: the plain form.
 int conv_v5_run_block(const float* x0, const float* w0, const float* w0b, int cin0, const float* x1, const float* w1, int cin1,
                       const float* bias, const float* addend, float* y, float* y1, int cout0, int B, int cout, int Hi, int Wi, int Ho, int Wo,
-                      int k, int stride, int pad, int transposed, void* workspace, size_t workspace_bytes, ffc_stream_t st) {
+                      int k, int stride, int pad, int transposed, float slope, void* workspace, size_t workspace_bytes, ffc_stream_t st) {
     const ConvV5Plan pl = conv_v5_plan(cin0, cin1, cout, k, stride, pad, transposed);
     const uintptr_t wsa = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
     if (!workspace || wsa + (size_t)pl.total_floats * sizeof(float) > (uintptr_t)workspace + workspace_bytes) {
@@ -357,11 +364,21 @@ int conv_v5_run_block(const float* x0, const float* w0, const float* w0b, int ci
     p.x[0] = x0; p.x[1] = x1; p.cin[0] = cin0; p.cin[1] = cin1; p.cps[0] = pl.cps[0]; p.cps[1] = pl.cps[1]; p.nseg = x1 ? 2 : 1;
     p.wp = (const float*)wsa; p.nt_full = pl.nt_full;
     for (int c = 0; c < FFC_V5_MAXCLS; ++c) p.cls_off[c] = pl.cls_off[c];
-    p.bias = bias; p.addend = addend; p.y = y; p.y1 = y1; p.cout0 = cout0; p.B = B; p.cout = cout; p.Hi = Hi; p.Wi = Wi; p.Ho = Ho; p.Wo = Wo;
+    p.bias = bias; p.addend = addend; p.y = y; p.y1 = y1; p.cout0 = cout0; p.slope = slope; p.B = B; p.cout = cout; p.Hi = Hi; p.Wi = Wi; p.Ho = Ho; p.Wo = Wo;
     p.k = k; p.stride = stride; p.pad = pad; p.transposed = transposed;
     const int s = transposed ? stride : 1;
     const int Mc = B * ffc_cdiv(Ho, s) * ffc_cdiv(Wo, s);
-    const size_t smem = (size_t)V5_SB * 2 * pl.nt_full * V5_BK * 4 + 256;
+    // B ring: as deep as shared memory allows (the weight stream of a CTA is 2x its activation stream and arrives by
+    // bulk copies of one stage each; with 3 stages the MMA warp waited on b_full half of the time, ncu r01n).  The
+    // narrow-tile kernel keeps 2 CTAs per SM, and ~60 KB stay with the L1 for the gather loads.
+    const bool four_wg = pl.nt_full > 64 && pl.nt_full <= 128;
+    const size_t stage_b = (size_t)2 * pl.nt_full * V5_BK * 4;
+    const size_t budget = (!four_wg && pl.nt_full <= 64) ? 96 * 1024 : 196 * 1024;
+    int nsb = (int)(budget / stage_b);
+    if (nsb > V5_SB_MAX) nsb = V5_SB_MAX;
+    if (nsb < 2) nsb = 2;
+    p.nsb = nsb;
+    const size_t smem = (size_t)nsb * stage_b + 256;
     static size_t configured = 0;
     if (smem > configured) {
         e = cudaFuncSetAttribute(conv_v5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -370,7 +387,7 @@ int conv_v5_run_block(const float* x0, const float* w0, const float* w0b, int ci
         configured = smem;
     }
     const dim3 grid(ffc_cdiv(Mc, 128), pl.ntiles, s * s);
-    if (pl.nt_full > 64 && pl.nt_full <= 128) conv_v5_kernel<4><<<grid, 4 * 128 + 64, smem, st>>>(p);
+    if (four_wg) conv_v5_kernel<4><<<grid, 4 * 128 + 64, smem, st>>>(p);
     else conv_v5_kernel<2><<<grid, 2 * 128 + 64, smem, st>>>(p);
     e = cudaGetLastError();
     if (e != cudaSuccess) { ffc_set_error("conv_v5 launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }

@@ -46,16 +46,16 @@ __global__ void __launch_bounds__(WG5_THREADS, 1) wgrad_v5_kernel(const WgradV5P
 
     unsigned char* bstage = wg5_smem;
     uint64_t* bars = reinterpret_cast<uint64_t*>(wg5_smem + (size_t)WG5_SB * stage_bytes);
-    uint64_t* b_full = bars;                    // [SB] count 128
+    uint64_t* b_full = bars;                    // [SB] count 4 (one arrival per builder warp)
     uint64_t* b_free = bars + WG5_SB;           // [SB]
-    uint64_t* a_ready = bars + 2 * WG5_SB;      // [GW] count 128
+    uint64_t* a_ready = bars + 2 * WG5_SB;      // [GW] count 4 (one arrival per gather warp)
     uint64_t* a_free = a_ready + WG5_GW;        // [GW]
     uint64_t* acc_done = a_free + WG5_GW;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
     const uint32_t tmem_cols = 512u;
     if (tid == 0) {
-        for (int i = 0; i < WG5_SB; ++i) { umma::mbar_init(&b_full[i], 128); umma::mbar_init(&b_free[i], 1); }
-        for (int i = 0; i < WG5_GW; ++i) { umma::mbar_init(&a_ready[i], 128); umma::mbar_init(&a_free[i], 1); }
+        for (int i = 0; i < WG5_SB; ++i) { umma::mbar_init(&b_full[i], 4); umma::mbar_init(&b_free[i], 1); }
+        for (int i = 0; i < WG5_GW; ++i) { umma::mbar_init(&a_ready[i], 4); umma::mbar_init(&a_free[i], 1); }
         umma::mbar_init(acc_done, 1);
         umma::fence_barrier_init();
     }
@@ -121,7 +121,8 @@ __global__ void __launch_bounds__(WG5_THREADS, 1) wgrad_v5_kernel(const WgradV5P
             }
             umma::wait_st();
             umma::fence_before_sync();
-            umma::mbar_arrive(&a_ready[wg]);
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive(&a_ready[wg]);       // one arrival per warp
         }
         // ===================== epilogue =====================
         umma::mbar_wait(acc_done, 0);
@@ -178,7 +179,8 @@ __global__ void __launch_bounds__(WG5_THREADS, 1) wgrad_v5_kernel(const WgradV5P
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core
-            umma::mbar_arrive(&b_full[sb]);
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive(&b_full[sb]);
         }
     } else {
         // ===================== MMA issuer =====================

@@ -62,9 +62,38 @@ class _FFCBase(nn.Module):
                 out = out + t
         return out
 
+    def _local_block(self, x_l, x_g):
+        """(convl2l(x_l) + convg2l(x_g), convl2g(x_l)) in ONE launch when all of them are convolutions of one geometry
+        (every FFC layer of the reference's generators / discriminators except the first and the last); else None."""
+        l2l, l2g, g2l = self.convl2l, self.convl2g, self.convg2l
+        if isinstance(l2l, nn.Identity) or isinstance(l2g, nn.Identity) or not torch.is_tensor(x_l):
+            return None
+        has_g = not isinstance(g2l, nn.Identity)
+        if has_g != torch.is_tensor(x_g) or (not has_g and not (type(x_g) is int and x_g == 0)):
+            return None
+        geo = lambda c: (c.kernel_size, c.stride, c.padding, c.dilation, c.groups, getattr(c, "output_padding", (0, 0)))
+        if geo(l2l) != geo(l2g) or (has_g and geo(g2l) != geo(l2l)):
+            return None
+        if l2l.kernel_size[0] != l2l.kernel_size[1] or l2l.dilation != (1, 1) or l2l.groups != 1:
+            raise NotImplementedError("only square kernels, dilation 1, groups 1 are supported")
+        w00, w01 = _util.effective_weight(l2l), _util.effective_weight(l2g)
+        w10 = _util.effective_weight(g2l) if has_g else None
+        bias0 = l2l.bias
+        if has_g and g2l.bias is not None:
+            bias0 = g2l.bias if bias0 is None else bias0 + g2l.bias
+        op = l2l.output_padding[0] if self._transposed else 0
+        return ops.conv2d_block(x_l, w00, w01, x_g if has_g else None, w10, bias0, l2g.bias,
+                                l2l.stride[0], l2l.padding[0], self._transposed, op)
+
     def forward(self, x, y=None):
         x_l, x_g = x if type(x) is tuple else (x, 0)
         out_xl, out_xg = 0, 0
+        blk = self._local_block(x_l, x_g)
+        if blk is not None:
+            out_xl, base = blk
+            if type(self.convg2g) is not nn.Identity:
+                return out_xl, self.convg2g._run(x_g, y, base)
+            return out_xl, base
         if self.ratio_gout != 1:
             out_xl = self._local_sum([(self.convl2l, x_l), (self.convg2l, x_g)])
         if self.ratio_gout != 0:

@@ -112,6 +112,99 @@ def conv2d(x0, w0, x1=None, w1=None, bias=None, addend=None, stride=1, pad=0, tr
     return Conv2dFn.apply(x0, w0, x1, w1, bias, addend, stride, pad, transposed, out_pad)
 
 
+class ConvBlockFn(torch.autograd.Function):
+    """The local branches of FFC.forward in one launch (ffc.py:91-96, ffc_transpose.py:98-106):
+        y0 = conv(x0, w00) [+ conv(x1, w10)] [+ bias0]      convl2l(x_l) + convg2l(x_g)
+        y1 = conv(x0, w01) [+ bias1]                         convl2g(x_l)
+    On the tcgen05 path the operand gathered from x0 feeds one implicit GEMM over the concatenated output channels; in the
+    backward, dx0 = conv^T(dy0, w00) + conv^T(dy1, w01) is one two-segment launch as well."""
+
+    @staticmethod
+    def forward(ctx, x0, w00, w01, x1, w10, bias0, bias1, stride, pad, transposed, out_pad):
+        _C.require_device(x0, w00, w01, x1, w10, bias0, bias1)
+        x0, w00, w01, x1, w10 = _c(x0), _c(w00), _c(w01), _c(x1), _c(w10)
+        B, cin0, Hi, Wi = x0.shape
+        k = w00.shape[-1]
+        co_dim, ci_dim = (1, 0) if transposed else (0, 1)
+        cout0, cout1 = w00.shape[co_dim], w01.shape[co_dim]
+        if w00.shape[ci_dim] != cin0 or w01.shape[ci_dim] != cin0 or w01.shape[-1] != k or w00.shape[-2] != k:
+            raise ValueError("conv2d_block: weights do not match the input channels (groups=1, square kernels only)")
+        cin1 = 0
+        if x1 is not None:
+            cin1 = x1.shape[1]
+            if x1.shape[0] != B or x1.shape[2:] != x0.shape[2:] or w10.shape[ci_dim] != cin1 or w10.shape[co_dim] != cout0 or w10.shape[-1] != k:
+                raise ValueError("conv2d_block: second input segment is inconsistent with the first")
+        Ho = conv_out_size(Hi, k, stride, pad, transposed, out_pad)
+        Wo = conv_out_size(Wi, k, stride, pad, transposed, out_pad)
+        y0 = torch.empty((B, cout0, Ho, Wo), device=x0.device, dtype=torch.float32)
+        y1 = torch.empty((B, cout1, Ho, Wo), device=x0.device, dtype=torch.float32)
+        bias = None
+        if bias0 is not None or bias1 is not None:
+            z = lambda n: torch.zeros(n, device=x0.device, dtype=torch.float32)
+            bias = torch.cat([bias0 if bias0 is not None else z(cout0), bias1 if bias1 is not None else z(cout1)]).contiguous()
+        L = _C.lib()
+        nbytes = L.ffc_conv2d_workspace_bytes(cin0, cin1, cout0 + cout1, k, stride, pad, int(transposed))
+        ws = _C.workspace(nbytes, y0.device)
+        _C.check(L.ffc_conv2d_block_fwd_ws(_C.ptr(x0), _C.ptr(w00), _C.ptr(w01), cin0, _C.ptr(x1), _C.ptr(w10), cin1, _C.ptr(bias),
+                                           _C.ptr(y0), cout0, _C.ptr(y1), cout1, B, Hi, Wi, Ho, Wo, k, stride, pad, int(transposed),
+                                           _C.ptr(ws), ws.numel(), _C.current_stream(y0.device)))
+        ctx.save_for_backward(x0, w00, w01, x1, w10)
+        ctx.cfg = (stride, pad, bool(transposed), k, cout0, cout1, bias0 is not None, bias1 is not None)
+        return y0, y1
+
+    @staticmethod
+    def backward(ctx, dy0, dy1):
+        x0, w00, w01, x1, w10 = ctx.saved_tensors
+        stride, pad, transposed, k, cout0, cout1, has_b0, has_b1 = ctx.cfg
+        dy0, dy1 = dy0.contiguous(), dy1.contiguous()
+        B, _, Ho, Wo = dy0.shape
+        cin0, Hi, Wi = x0.shape[1], x0.shape[2], x0.shape[3]
+        L = _C.lib()
+        st = _C.current_stream(dy0.device)
+        need = ctx.needs_input_grad
+        g = [None] * 11
+
+        def wgrad(x, dy, w, cin, cout):
+            dw = torch.empty_like(w)
+            if transposed:
+                _C.check(L.ffc_conv2d_wgrad(_C.ptr(x), _C.ptr(dy), _C.ptr(dw), B, cin, cout, Hi, Wi, Ho, Wo, k, stride, pad, st))
+            else:
+                _C.check(L.ffc_conv2d_wgrad(_C.ptr(dy), _C.ptr(x), _C.ptr(dw), B, cout, cin, Ho, Wo, Hi, Wi, k, stride, pad, st))
+            return dw
+
+        def bgrad(dy, cout):
+            db = torch.empty(cout, device=dy.device, dtype=torch.float32)
+            ws = _C.workspace(2 * cout * 8, dy.device)
+            _C.check(L.ffc_bias_grad(_C.ptr(dy), _C.ptr(db), B, cout, Ho * Wo, _C.ptr(ws), ws.numel(), st))
+            return db
+
+        if need[0]:     # both output blocks flow back into x0: one two-segment launch of the opposite gather form
+            dx0 = torch.empty_like(x0)
+            _conv_launch(dy0, w00, cout0, dy1, w01, cout1, None, None, dx0, B, cin0, Ho, Wo, Hi, Wi, k, stride, pad, not transposed)
+            g[0] = dx0
+        if need[1]:
+            g[1] = wgrad(x0, dy0, w00, cin0, cout0)
+        if need[2]:
+            g[2] = wgrad(x0, dy1, w01, cin0, cout1)
+        if x1 is not None:
+            cin1 = x1.shape[1]
+            if need[3]:
+                dx1 = torch.empty_like(x1)
+                _conv_launch(dy0, w10, cout0, None, None, 0, None, None, dx1, B, cin1, Ho, Wo, Hi, Wi, k, stride, pad, not transposed)
+                g[3] = dx1
+            if need[4]:
+                g[4] = wgrad(x1, dy0, w10, cin1, cout0)
+        if has_b0 and need[5]:
+            g[5] = bgrad(dy0, cout0)
+        if has_b1 and need[6]:
+            g[6] = bgrad(dy1, cout1)
+        return tuple(g)
+
+
+def conv2d_block(x0, w00, w01, x1=None, w10=None, bias0=None, bias1=None, stride=1, pad=0, transposed=False, out_pad=0):
+    return ConvBlockFn.apply(x0, w00, w01, x1, w10, bias0, bias1, stride, pad, transposed, out_pad)
+
+
 class ConvActFn(torch.autograd.Function):
     """a = act(conv(x, w) + bias) for act in {LeakyReLU, ReLU}: the SN-conv + LeakyReLU(0.1) stage of the fgan
     discriminators (fgan_complete.py:160-169).  Only the activated output is kept: both activations preserve the
@@ -129,11 +222,11 @@ class ConvActFn(torch.autograd.Function):
             raise ValueError(f"weight {tuple(w.shape)} does not match input channels {cin} (groups=1, square kernels only)")
         Ho, Wo = conv_out_size(Hi, k, stride, pad, False), conv_out_size(Wi, k, stride, pad, False)
         a = torch.empty((B, cout, Ho, Wo), device=x.device, dtype=torch.float32)
-        _conv_launch(x, w, cin, None, None, 0, bias, None, a, B, cout, Hi, Wi, Ho, Wo, k, stride, pad, False)
         L = _C.lib()
-        ws = _C.workspace(2 * cout * 8, x.device)
-        _C.check(L.ffc_bn_act_fwd(_C.ptr(a), _C.ptr(a), None, None, None, None, None, None, B, cout, Ho * Wo, 0, 0, 0.0, 0.0,
-                                  int(act), float(slope), _C.ptr(ws), ws.numel(), _C.current_stream(x.device)))
+        nbytes = max(L.ffc_conv2d_workspace_bytes(cin, 0, cout, k, stride, pad, 0), 2 * cout * 8)
+        ws = _C.workspace(nbytes, x.device)
+        _C.check(L.ffc_conv2d_act_fwd_ws(_C.ptr(x), _C.ptr(w), cin, _C.ptr(bias), _C.ptr(a), B, cout, Hi, Wi, Ho, Wo, k, stride, pad,
+                                         int(act), float(slope), _C.ptr(ws), ws.numel(), _C.current_stream(x.device)))
         ctx.save_for_backward(x, w, a)
         ctx.cfg = (stride, pad, False, k, cout, bias is not None, False)
         ctx.act = (int(act), float(slope))

@@ -139,6 +139,16 @@ int ffc_conv2d_block_fwd_ws(const float* x0, const float* w00, const float* w01,
                             int B, int Hi, int Wi, int Ho, int Wo, int k, int stride, int pad, int transposed,
                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* ffc_conv2d_act_fwd_ws: y = act(conv(x, w) + bias), act = FFC_ACT_LEAKY (slope > 0) or FFC_ACT_RELU -- one stage of the
+ * SN conv discriminators the FFC generators are trained against (fgan_complete.py:160-169, ``activation(convN(m))``;
+ * SURVEY.md 8(f) rank 1).  nn.Conv2d semantics (not transposed, one segment).  The activation rides in the epilogue of the
+ * tcgen05 kernel; the <= 4-input-channel RGB stage runs the convolution and then the elementwise kernel in place.
+ * Both activations keep the sign of their argument, so the backward mask is taken from y (ffc_bn_act_bwd with x := y).
+ * workspace: max(ffc_conv2d_workspace_bytes(cin, 0, cout, k, stride, pad, 0), 2*cout*8) bytes. */
+int ffc_conv2d_act_fwd_ws(const float* x, const float* w, int cin, const float* bias, float* y,
+                          int B, int cout, int Hi, int Wi, int Ho, int Wo, int k, int stride, int pad,
+                          int act, float slope, void* workspace, size_t workspace_bytes, void* stream);
+
 /* dW[sc][lc][ky][kx] = sum_{b,y,x} S[b,sc,y,x] * L[b,lc,y*stride-pad+ky,x*stride-pad+kx]
  * nn.Conv2d:          S = dy (cout, Ho x Wo), L = x  (cin,  Hi x Wi)  -> dW [cout][cin][k][k]
  * nn.ConvTranspose2d: S = x  (cin,  Hi x Wi), L = dy (cout, Ho x Wo)  -> dW [cin][cout][k][k]

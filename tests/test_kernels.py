@@ -171,6 +171,58 @@ def _conv_case(lib, case):
         assert parity.relerr(dx, xd.grad) < CONV_TOL[_conv_mode[0]]
 
 
+# (B, cin0, cin1, cout0, cout1, Hi, k, stride, pad, transposed, bias)
+BLOCK_CASES = [
+    (3, 48, 16, 24, 8, 8, 4, 2, 1, True, False),      # an upsampling FFC stage: l2l | g2l and l2g
+    (2, 36, 12, 40, 24, 8, 4, 2, 1, False, True),     # a downsampling stage with biases (sngan FDiscriminator)
+    (2, 20, 0, 130, 70, 6, 3, 1, 1, False, True),     # no global input (first layer); several output tiles
+    (2, 6, 3, 5, 4, 5, 3, 1, 1, True, True),          # narrow: falls back to two plain launches
+]
+
+
+@pytest.mark.parametrize("case", BLOCK_CASES)
+def test_conv_block_forward(lib, case):
+    """ffc_conv2d_block_fwd_ws: y0 = conv(x0, w00) + conv(x1, w10) + bias[:cout0], y1 = conv(x0, w01) + bias[cout0:]."""
+    B, cin0, cin1, cout0, cout1, Hi, k, s, p, tr, bias = case
+    torch.manual_seed(1)
+    shp = (lambda ci, co: (ci, co, k, k)) if tr else (lambda ci, co: (co, ci, k, k))
+    x0 = torch.randn(B, cin0, Hi, Hi)
+    w00, w01 = torch.randn(shp(cin0, cout0)) * 0.1, torch.randn(shp(cin0, cout1)) * 0.1
+    x1 = torch.randn(B, cin1, Hi, Hi) if cin1 else None
+    w10 = torch.randn(shp(cin1, cout0)) * 0.1 if cin1 else None
+    b = torch.randn(cout0 + cout1) if bias else None
+    op_ref = (lambda x, w: F.conv_transpose2d(x.double(), w.double(), None, s, p)) if tr else (lambda x, w: F.conv2d(x.double(), w.double(), None, s, p))
+    r0, r1 = op_ref(x0, w00), op_ref(x0, w01)
+    if cin1:
+        r0 = r0 + op_ref(x1, w10)
+    if bias:
+        r0 = r0 + b[:cout0].double().view(1, -1, 1, 1)
+        r1 = r1 + b[cout0:].double().view(1, -1, 1, 1)
+    Ho = r0.shape[-1]
+    y0, y1 = torch.empty(B, cout0, Ho, Ho), torch.empty(B, cout1, Ho, Ho)
+    nbytes = lib[0].ffc_conv2d_workspace_bytes(cin0, cin1, cout0 + cout1, k, s, p, int(tr))
+    ws = torch.zeros(nbytes + 64, dtype=torch.uint8)
+    call(lib, "ffc_conv2d_block_fwd_ws", x0, w00, w01, cin0, x1, w10, cin1, b, y0, cout0, y1, cout1,
+         B, Hi, Hi, Ho, Ho, k, s, p, int(tr), ws, ws.numel(), None)
+    tol = 4e-5 if lib[1] != "cpu" else 3e-6
+    assert parity.relerr(y0, r0) < tol and parity.relerr(y1, r1) < tol
+
+
+@pytest.mark.parametrize("case", [(3, 40, 48, 8, 4, 2, 2, 0.1), (2, 24, 130, 6, 3, 1, 2, 0.2), (2, 3, 20, 8, 3, 1, 2, 0.1), (2, 33, 32, 6, 3, 1, 1, 0.0)])
+def test_conv_act_forward(lib, case):
+    """ffc_conv2d_act_fwd_ws: LeakyReLU / ReLU of conv + bias (fused epilogue on the tcgen05 path, two kernels otherwise)."""
+    B, cin, cout, Hi, k, s, act, slope = case
+    torch.manual_seed(2)
+    x, w, b = torch.randn(B, cin, Hi, Hi), torch.randn(cout, cin, k, k) * 0.1, torch.randn(cout)
+    ref = ACTS[act](F.conv2d(x.double(), w.double(), b.double(), s, 1)) if act == 1 else F.leaky_relu(F.conv2d(x.double(), w.double(), b.double(), s, 1), slope)
+    Ho = ref.shape[-1]
+    y = torch.empty(B, cout, Ho, Ho)
+    nbytes = max(lib[0].ffc_conv2d_workspace_bytes(cin, 0, cout, k, s, 1, 0), 2 * cout * 8)
+    ws = torch.zeros(nbytes + 64, dtype=torch.uint8)
+    call(lib, "ffc_conv2d_act_fwd_ws", x, w, cin, b, y, B, cout, Hi, Hi, Ho, Ho, k, s, 1, act, slope, ws, ws.numel(), None)
+    assert parity.relerr(y, ref) < (4e-5 if lib[1] != "cpu" else 3e-6)
+
+
 ACTS = {0: lambda z: z, 1: F.relu, 2: lambda z: F.leaky_relu(z, 0.1), 3: F.gelu, 4: torch.tanh, 5: torch.sigmoid}
 
 
