@@ -247,31 +247,42 @@ __global__ void __launch_bounds__(V5_GW * 128 + 64, V5_GW == 2 ? 2 : 1) conv_v5_
         }
     } else if (warp == V5_MMAWARP) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // The whole warp walks the loop converged (uniform values stay in uniform registers) and one elected lane issues:
+        // inside an `if (lane == 0)` region every tcgen05 instruction was wrapped in its own elect / branch sequence and
+        // the issue rate, not the tensor pipe, set the pace (~150 cycles per MMA against a 64-96 cycle floor, ncu r01n).
+        {
             const uint32_t idesc = umma::idesc_tf32(128, NT);
+            const uint32_t b0 = umma::smem_u32(bstage);
             int sb = 0; uint32_t sb_phase = 0;
             for (int c = 0; c < nchunks; ++c) {
                 const int sa = c % nstage;
                 umma::mbar_wait(&b_full[sb], sb_phase);
                 umma::mbar_wait(&a_ready[sa], (uint32_t)((c / nstage) & 1));
                 umma::fence_after_sync();
-                const uint32_t b_hi = umma::smem_u32(bstage + (size_t)sb * stage_bytes), b_lo = b_hi + (uint32_t)(NT * V5_BK * 4);
-                const uint32_t a_hi = tbase + a_col0 + 64u * (uint32_t)sa, a_lo = a_hi + 32u;
+                if (umma::elect_one()) {
+                    const uint32_t b_hi = b0 + (uint32_t)sb * stage_bytes, b_lo = b_hi + (uint32_t)(NT * V5_BK * 4);
+                    const uint32_t a_hi = tbase + a_col0 + 64u * (uint32_t)sa, a_lo = a_hi + 32u;
 #pragma unroll
-                for (int ks = 0; ks < V5_BK / 8; ++ks) {
-                    const uint64_t dh = umma::smem_desc_kmajor_noswizzle(b_hi + ks * 256, 128, 1024);
-                    const uint64_t dl = umma::smem_desc_kmajor_noswizzle(b_lo + ks * 256, 128, 1024);
-                    umma::mma_tf32_ts(tbase + (uint32_t)NT, a_lo + ks * 8, dh, idesc, (c | ks) ? 1u : 0u);
-                    umma::mma_tf32_ts(tbase + (uint32_t)NT, a_hi + ks * 8, dl, idesc, 1u);
-                    umma::mma_tf32_ts(tbase, a_hi + ks * 8, dh, idesc, (c | ks) ? 1u : 0u);
+                    for (int ks = 0; ks < V5_BK / 8; ++ks) {        // cross terms first, then the main products: two
+                        const uint64_t dh = umma::smem_desc_kmajor_noswizzle(b_hi + ks * 256, 128, 1024);   // accumulator switches per chunk
+                        const uint64_t dl = umma::smem_desc_kmajor_noswizzle(b_lo + ks * 256, 128, 1024);
+                        umma::mma_tf32_ts(tbase + (uint32_t)NT, a_lo + ks * 8, dh, idesc, (c | ks) ? 1u : 0u);
+                        umma::mma_tf32_ts(tbase + (uint32_t)NT, a_hi + ks * 8, dl, idesc, 1u);
+                    }
+#pragma unroll
+                    for (int ks = 0; ks < V5_BK / 8; ++ks) {
+                        const uint64_t dh = umma::smem_desc_kmajor_noswizzle(b_hi + ks * 256, 128, 1024);
+                        umma::mma_tf32_ts(tbase, a_hi + ks * 8, dh, idesc, (c | ks) ? 1u : 0u);
+                    }
+                    umma::commit(&a_free[sa]);
+                    umma::commit(&b_free[sb]);
                 }
-                umma::commit(&a_free[sa]);
-                umma::commit(&b_free[sb]);
+                __syncwarp();
                 if (++sb == nsb) { sb = 0; sb_phase ^= 1u; }
             }
-            umma::commit(acc_done);
+            if (umma::elect_one()) umma::commit(acc_done);
+            __syncwarp();
         }
-        __syncwarp();
     } else {
         // ===================== B loader =====================
         if (lane == 0) {

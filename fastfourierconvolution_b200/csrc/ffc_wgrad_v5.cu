@@ -17,11 +17,12 @@
 #include "ffc_umma.cuh"
 
 static constexpr int WG5_BK = 32;
-static constexpr int WG5_SB = 3;
-static constexpr int WG5_GW = 4;              // gather warpgroups == A stages in TMEM
-static constexpr int WG5_THREADS = WG5_GW * 128 + 128 + 32;       // gather warps, 4 B-builder warps, 1 MMA warp
+static constexpr int WG5_SB = 4;
+static constexpr int WG5_GW = 3;              // gather warpgroups == A stages in TMEM
+static constexpr int WG5_BW = 3;              // B-builder warpgroups, alternating over the chunks
+static constexpr int WG5_THREADS = WG5_GW * 128 + WG5_BW * 128 + 32;       // gather warps, B-builder warps, 1 MMA warp
 static constexpr int WG5_BUILD0 = WG5_GW * 128;                   // first B-builder thread
-static constexpr int WG5_MMAWARP = WG5_GW * 4 + 4;
+static constexpr int WG5_MMAWARP = WG5_GW * 4 + WG5_BW * 4;
 
 struct WgradV5Params {
     const float* S; const float* L; float* dW;
@@ -143,11 +144,12 @@ __global__ void __launch_bounds__(WG5_THREADS, 1) wgrad_v5_kernel(const WgradV5P
         }
     } else if (warp < WG5_MMAWARP) {
         // ===================== B builders: S tile -> K-major no-swizzle UMMA image (hi | lo) =====================
-        const int bt = tid - WG5_BUILD0;                // 0..127
+        const int bt = (tid - WG5_BUILD0) & 127;        // 0..127 within the builder warpgroup
+        const int bw = (tid - WG5_BUILD0) >> 7;         // builder warpgroup: chunks bw, bw + WG5_BW, ...
         const int n8 = bt & 7, qs = (bt >> 3) & 3, grp0 = bt >> 5;       // lane -> (row in 8-group, 16-byte piece), warp -> group
         const int ngroups = (NT / 8) * 2;
         constexpr int MAXG = (128 / 8) * 2 / 4;         // groups per builder warp at the widest tile (NT = 128)
-        for (int c = 0; c < nchunks; ++c) {
+        for (int c = bw; c < nchunks; c += WG5_BW) {
             const int sb = c % WG5_SB;
             const int kk0 = kbeg + c * WG5_BK;
             // all loads of the chunk are in flight before the first is used (and before the stage wait)
@@ -184,28 +186,36 @@ __global__ void __launch_bounds__(WG5_THREADS, 1) wgrad_v5_kernel(const WgradV5P
         }
     } else {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = umma::idesc_tf32(128, NT);
-            for (int c = 0; c < nchunks; ++c) {
-                const int sa = c % WG5_GW, sb = c % WG5_SB;
-                umma::mbar_wait(&b_full[sb], (uint32_t)((c / WG5_SB) & 1));
-                umma::mbar_wait(&a_ready[sa], (uint32_t)((c / WG5_GW) & 1));
-                umma::fence_after_sync();
-                const uint32_t b_hi = umma::smem_u32(bstage + (size_t)sb * stage_bytes), b_lo = b_hi + half_bytes;
+        // whole warp converged, one elected lane issues (see ffc_conv_v5.cu: inside `if (lane == 0)` each tcgen05
+        // instruction got its own elect / branch sequence and the issue rate set the pace)
+        const uint32_t idesc = umma::idesc_tf32(128, NT);
+        const uint32_t b0 = umma::smem_u32(bstage);
+        for (int c = 0; c < nchunks; ++c) {
+            const int sa = c % WG5_GW, sb = c % WG5_SB;
+            umma::mbar_wait(&b_full[sb], (uint32_t)((c / WG5_SB) & 1));
+            umma::mbar_wait(&a_ready[sa], (uint32_t)((c / WG5_GW) & 1));
+            umma::fence_after_sync();
+            if (umma::elect_one()) {
+                const uint32_t b_hi = b0 + (uint32_t)sb * stage_bytes, b_lo = b_hi + half_bytes;
                 const uint32_t a_hi = tbase + a_col0 + 64u * (uint32_t)sa, a_lo = a_hi + 32u;
 #pragma unroll
-                for (int ks = 0; ks < WG5_BK / 8; ++ks) {
-                    const uint64_t dh = umma::smem_desc_kmajor_noswizzle(b_hi + ks * 256, 128, 1024);
+                for (int ks = 0; ks < WG5_BK / 8; ++ks) {          // cross terms first, then the main products: two
+                    const uint64_t dh = umma::smem_desc_kmajor_noswizzle(b_hi + ks * 256, 128, 1024);   // accumulator switches per chunk
                     const uint64_t dl = umma::smem_desc_kmajor_noswizzle(b_lo + ks * 256, 128, 1024);
                     umma::mma_tf32_ts(tbase + (uint32_t)NT, a_lo + ks * 8, dh, idesc, (c | ks) ? 1u : 0u);
                     umma::mma_tf32_ts(tbase + (uint32_t)NT, a_hi + ks * 8, dl, idesc, 1u);
+                }
+#pragma unroll
+                for (int ks = 0; ks < WG5_BK / 8; ++ks) {
+                    const uint64_t dh = umma::smem_desc_kmajor_noswizzle(b_hi + ks * 256, 128, 1024);
                     umma::mma_tf32_ts(tbase, a_hi + ks * 8, dh, idesc, (c | ks) ? 1u : 0u);
                 }
                 umma::commit(&a_free[sa]);
                 umma::commit(&b_free[sb]);
             }
-            umma::commit(acc_done);
+            __syncwarp();
         }
+        if (umma::elect_one()) umma::commit(acc_done);
         __syncwarp();
     }
     umma::fence_before_sync();

@@ -2,6 +2,8 @@ import os, sys, json
 sys.path.insert(0, os.getcwd())
 import torch
 from fastfourierconvolution_b200 import _C
+if os.environ.get('FFC_LIB'):
+    _C._lib = _C.Library(os.environ['FFC_LIB'])
 L = _C.lib()
 shapes = {"d2": (64, 64, 32, 4, 2), "d3": (64, 128, 16, 3, 1), "d4": (128, 128, 16, 4, 2), "d5": (128, 256, 8, 3, 1),
           "d6": (256, 256, 8, 4, 2), "d7": (256, 512, 4, 3, 1)}
@@ -23,4 +25,4 @@ for name, (cin, cout, Hi, k, s) in shapes.items():
     us = e0.elapsed_time(e1) / 20 * 1000
     gf = 2.0 * B * Ho * Ho * cout * cin * k * k / 1e9
     out[name] = f"{us:.0f}us {gf / us * 1e-3 * 1e3:.0f}TF"
-print(os.environ.get("FFC_WG5_DBG", "0"), json.dumps(out))
+print(os.environ.get("FFC_LIB", "base"), json.dumps(out))
