@@ -51,24 +51,38 @@ struct ChanReduceKernel {
                 const long long beg4 = beg / 4, end4 = (end + 3) / 4 < (total / 4) ? (end + 3) / 4 : total / 4;
                 long long i = beg4 + tid;
                 int b = (int)(i / q), r = (int)(i % q);
-                for (; i < end4; i += kThreads) {
-                    const size_t o4 = ((size_t)b * p.C + c) * q + r;
-                    const float4 v = FFC_LDG(reinterpret_cast<const float4*>(p.x) + o4);
-                    if (MODE == 0) {
-                        s0 += (double)((v.x + v.y) + (v.z + v.w));
-                        s1 += (double)(fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w));
-                    } else if (MODE == 2) {
-                        s0 += (double)((v.x + v.y) + (v.z + v.w));
-                    } else {
-                        const float4 d = FFC_LDG(reinterpret_cast<const float4*>(p.dy) + o4);
-                        const float x0 = (v.x - mu) * is, x1 = (v.y - mu) * is, x2 = (v.z - mu) * is, x3 = (v.w - mu) * is;
-                        const float g0 = d.x * ffc_act_bwd(x0 * ga + be, p.act, p.slope), g1 = d.y * ffc_act_bwd(x1 * ga + be, p.act, p.slope);
-                        const float g2 = d.z * ffc_act_bwd(x2 * ga + be, p.act, p.slope), g3 = d.w * ffc_act_bwd(x3 * ga + be, p.act, p.slope);
-                        s0 += (double)((g0 + g1) + (g2 + g3));
-                        s1 += (double)(fmaf(g0, x0, g1 * x1) + fmaf(g2, x2, g3 * x3));
+                const int db = kThreads / q, dr = kThreads % q;          // one thread-block stride in (image, offset) form
+                // four independent float4 loads per thread and iteration (one load in flight per thread left the kernel
+                // latency bound at ~30 % of the HBM rate); out-of-range slots read as zeros, which add nothing
+                constexpr int U = 4;
+                for (; i < end4; i += (long long)U * kThreads) {
+                    float4 v[U], d[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        v[u] = make_float4(0.f, 0.f, 0.f, 0.f); d[u] = v[u];
+                        if (i + (long long)u * kThreads < end4) {
+                            const size_t o4 = ((size_t)b * p.C + c) * q + r;
+                            v[u] = FFC_LDG(reinterpret_cast<const float4*>(p.x) + o4);
+                            if (MODE == 1) d[u] = FFC_LDG(reinterpret_cast<const float4*>(p.dy) + o4);
+                        }
+                        b += db; r += dr;
+                        if (r >= q) { r -= q; ++b; }
                     }
-                    r += kThreads;
-                    if (r >= q) { b += r / q; r %= q; }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (MODE == 0) {
+                            s0 += (double)((v[u].x + v[u].y) + (v[u].z + v[u].w));
+                            s1 += (double)(fmaf(v[u].x, v[u].x, v[u].y * v[u].y) + fmaf(v[u].z, v[u].z, v[u].w * v[u].w));
+                        } else if (MODE == 2) {
+                            s0 += (double)((v[u].x + v[u].y) + (v[u].z + v[u].w));
+                        } else {
+                            const float x0 = (v[u].x - mu) * is, x1 = (v[u].y - mu) * is, x2 = (v[u].z - mu) * is, x3 = (v[u].w - mu) * is;
+                            const float g0 = d[u].x * ffc_act_bwd(x0 * ga + be, p.act, p.slope), g1 = d[u].y * ffc_act_bwd(x1 * ga + be, p.act, p.slope);
+                            const float g2 = d[u].z * ffc_act_bwd(x2 * ga + be, p.act, p.slope), g3 = d[u].w * ffc_act_bwd(x3 * ga + be, p.act, p.slope);
+                            s0 += (double)((g0 + g1) + (g2 + g3));
+                            s1 += (double)(fmaf(g0, x0, g1 * x1) + fmaf(g2, x2, g3 * x3));
+                        }
+                    }
                 }
             } else {
                 for (long long i = beg + tid; i < end; i += kThreads) {
