@@ -10,7 +10,7 @@ import torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import fastfourierconvolution_b200 as ffc
 from fastfourierconvolution_b200 import _C, ops
-from oracle import ffc_ref as R
+import torch.nn.functional as F
 
 DEV = "cuda:0"
 PEAK = 6545.6
@@ -43,14 +43,93 @@ def timeit(fn, xs, iters=10, warm=2):
     return e0.elapsed_time(e1) / (iters * len(xs))
 
 
+def ref_fourier_unit(x, P, training):
+    """The reference's op sequence (layers/ffc/fourier_unity.py:32-58) on PyTorch's GPU kernels (cuFFT, cuDNN): the
+    comparison arm of this benchmark.  Restated here so that tools/ does not import the test oracle."""
+    b, c, h, w = x.shape
+    s = torch.fft.rfftn(x, dim=(-2, -1), norm="ortho")                                       # :38
+    s = torch.stack((s.real, s.imag), dim=2).reshape(b, 2 * c, h, s.shape[-1])               # :40-42
+    y = F.conv2d(s, P["conv_layer.weight"])                                                  # :45
+    y = F.relu(F.batch_norm(y, P["bn.running_mean"], P["bn.running_var"], P["bn.weight"], P["bn.bias"], training, 0.1, 1e-5))   # :49
+    y = y.reshape(b, -1, 2, h, y.shape[-1])
+    yc = torch.complex(y[:, :, 0].contiguous(), y[:, :, 1].contiguous())                     # :51-53
+    return torch.fft.irfftn(yc, s=(h, w), dim=(-2, -1), norm="ortho")                        # :56
+
+
 def torch_fu(mod):
     P = dict(mod.state_dict())
     def f(x, training):
-        return R.fourier_unit(x, P, "", training)        # the reference's op sequence on cuFFT/cuDNN
+        return ref_fourier_unit(x, P, training)
     return f
 
 
+def timeit_fwd_bwd(fn, xs, iters=5):
+    """fn(x) -> output; times forward + backward (all gradients) per call, graph-captured like timeit."""
+    gs = [torch.randn_like(fn(xs[0]).detach())]
+    def step(x):
+        x.grad = None
+        fn(x).backward(gs[0])
+    for i in range(2):
+        step(xs[i % len(xs)])
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    stream = torch.cuda.Stream()
+    stream.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(stream):
+        with torch.cuda.graph(g, stream=stream):
+            for x in xs:
+                step(x)
+    torch.cuda.synchronize()
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / (iters * len(xs))
+
+
+def sweep_config5(out_path):
+    """BASELINE.json configs[4]: FourierUnitSN(Cf, Cf), Cf = int(C * r) // 2 for C in {64, 256, 512}, r in {.25, .5, .75},
+    H = W in {16, 32, 64, 128}, batch 32, training mode, forward and forward + backward, against the reference's op
+    sequence on the same GPU (cuFFT + cuDNN, TF32 off).  Algorithmic bytes: 8*B*C*H*W forward, 20*B*C*H*W fwd + bwd."""
+    import copy
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    B = 32
+    cfs = sorted({int(C * r) // 2 for C in (64, 256, 512) for r in (0.25, 0.5, 0.75)})
+    with open(out_path, "w") as f:
+        for Cf in cfs:
+            for N in (16, 32, 64, 128):
+                torch.manual_seed(0)
+                m = ffc.FourierUnitSN(Cf, Cf).to(DEV).train()
+                nbytes = 4 * B * Cf * N * N
+                nbuf = min(max(2, int(200e6 // nbytes) + 1), 8)
+                xs = [torch.randn(B, Cf, N, N, device=DEV, requires_grad=True) for _ in range(nbuf)]
+                P = {k: v.detach().clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in m.state_dict().items()}
+                ref = lambda x: ref_fourier_unit(x, P, True)
+                row = {"B": B, "C": Cf, "N": N, "fused": bool(ops.fu_fused_supported(B, Cf, Cf, N, N))}
+                with torch.no_grad():
+                    row["ours_fwd_us"] = 1000 * timeit(m, xs, iters=5)
+                    row["torch_fwd_us"] = 1000 * timeit(ref, xs, iters=5)
+                row["ours_fwd_bwd_us"] = 1000 * timeit_fwd_bwd(m, xs)
+                row["torch_fwd_bwd_us"] = 1000 * timeit_fwd_bwd(ref, xs)
+                row["fwd_frac_hbm"] = 2.0 * nbytes / row["ours_fwd_us"] / 1e3 / PEAK
+                row["fwd_bwd_frac_hbm"] = 5.0 * nbytes / row["ours_fwd_bwd_us"] / 1e3 / PEAK
+                row["speedup_fwd"] = row["torch_fwd_us"] / row["ours_fwd_us"]
+                row["speedup_fwd_bwd"] = row["torch_fwd_bwd_us"] / row["ours_fwd_bwd_us"]
+                line = json.dumps({k: (round(v, 3) if isinstance(v, float) else v) for k, v in row.items()})
+                print(line, flush=True)
+                f.write(line + "\n")
+                del xs, m, P
+                torch.cuda.empty_cache()
+
+
 def main():
+    if "--config5" in sys.argv:
+        return sweep_config5(sys.argv[sys.argv.index("--config5") + 1])
     shapes = [(256, 8, 32), (256, 16, 16), (256, 32, 8), (128, 8, 64), (128, 16, 16), (64, 64, 16), (64, 32, 32),
               (64, 32, 64), (64, 32, 128), (32, 32, 16), (32, 16, 32), (32, 8, 32), (32, 24, 16), (32, 96, 32)]
     if "--quick" in sys.argv:
