@@ -456,7 +456,7 @@ extern "C" int ffc_bn_act_fwd(const float* x, float* y, const float* gamma, cons
                               int act, float slope, void* workspace, size_t workspace_bytes, void* stream);    // ffc_bnact.cu
 
 // y = act(conv(x, w) + bias), act = LeakyReLU(slope) or ReLU: one stage of the SN conv discriminators of the fgan scripts
-// (fgan_complete.py:160-169: ``self.activation(self.convN(m))``).  The activation rides in the epilogue of the tcgen05
+// (fgan_complete.py:162-168: ``self.act(self.convN(m))``).  The activation rides in the epilogue of the tcgen05
 // kernel; shapes that kernel does not take (<= 4 input channels: the RGB stage) run the convolution and then the
 // elementwise kernel in place.  workspace: ffc_conv2d_workspace_bytes(cin, 0, cout, k, stride, pad, 0), at least 2*cout*8 bytes.
 extern "C" int ffc_conv2d_act_fwd_ws(const float* x, const float* w, int cin, const float* bias, float* y,

@@ -207,7 +207,7 @@ def conv2d_block(x0, w00, w01, x1=None, w10=None, bias0=None, bias1=None, stride
 
 class ConvActFn(torch.autograd.Function):
     """a = act(conv(x, w) + bias) for act in {LeakyReLU, ReLU}: the SN-conv + LeakyReLU(0.1) stage of the fgan
-    discriminators (fgan_complete.py:160-169).  Only the activated output is kept: both activations preserve the
+    discriminators (fgan_complete.py:162-168).  Only the activated output is kept: both activations preserve the
     sign of their argument, so the backward mask is read from ``a`` itself."""
 
     @staticmethod

@@ -140,7 +140,7 @@ int ffc_conv2d_block_fwd_ws(const float* x0, const float* w00, const float* w01,
                             void* workspace, size_t workspace_bytes, void* stream);
 
 /* ffc_conv2d_act_fwd_ws: y = act(conv(x, w) + bias), act = FFC_ACT_LEAKY (slope > 0) or FFC_ACT_RELU -- one stage of the
- * SN conv discriminators the FFC generators are trained against (fgan_complete.py:160-169, ``activation(convN(m))``;
+ * SN conv discriminators the FFC generators are trained against (fgan_complete.py:162-168, ``act(convN(m))``;
  * SURVEY.md 8(f) rank 1).  nn.Conv2d semantics (not transposed, one segment).  The activation rides in the epilogue of the
  * tcgen05 kernel; the <= 4-input-channel RGB stage runs the convolution and then the elementwise kernel in place.
  * Both activations keep the sign of their argument, so the backward mask is taken from y (ffc_bn_act_bwd with x := y).
