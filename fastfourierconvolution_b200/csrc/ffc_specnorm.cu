@@ -1,0 +1,193 @@
+// Spectral normalisation of a convolution weight in three small kernels ("a fused
+// spectral-norm power iteration").
+//
+// torch.nn.utils.spectral_norm (layers/snffc/snffc.py:8, 23-33; fgan_complete.py:147-156) runs, before every forward,
+//     v = normalize(W^T u);  u = normalize(W v)        (one power iteration, training mode only, no gradient)
+//     sigma = u . (W v);     weight = W / sigma
+// on W = weight_orig viewed as (h = out channels, w = the rest).  As PyTorch ops that is ~14 launches of a few
+// microseconds per layer and forward (3 discriminator forwards x 7-9 layers per GAN step); here it is
+//     SnColKernel    t = W^T u                       (column sums, split over rows with atomics)
+//     SnRowKernel    v = t / max(|t|, eps);  s = W v  (one 32-thread group per row)
+//     SnScaleKernel  u = s / max(|s|, eps);  sigma = u . s;  weight = W / sigma
+// The matrix (<= 16 MB) stays in L2 between the three passes.  Without a power iteration (eval mode) the first kernel
+// is skipped and u, v are read as they are.
+#include "ffc_common.cuh"
+
+struct SnParams {
+    const float* W;        // (h, w) row-major
+    float* u;              // (h)   in/out
+    float* v;              // (w)   in/out
+    float* u_save;         // (h)   copy of the u used for sigma (for the backward), or null
+    float* v_save;         // (w)
+    float* w_eff;          // (h, w)
+    float* sigma;          // (1)
+    float* t;              // workspace (w)
+    float* s;              // workspace (h)
+    int h, w, power_iteration, rows_per_split;
+    float eps;
+};
+
+static constexpr int SN_THREADS = 256;
+
+// t[j] += sum over the rows of this split of W[i][j] * u[i]
+struct SnColKernel {
+    typedef SnParams Params;
+    static constexpr int kThreads = SN_THREADS;
+    static FFC_DEVICE void run(const Params& p, const BlockCtx& ctx, float*) {
+        FFC_PHASE {
+            const int j = ctx.bx * kThreads + tid;
+            if (j < p.w) {
+                const int i0 = ctx.by * p.rows_per_split;
+                const int i1 = (i0 + p.rows_per_split) < p.h ? (i0 + p.rows_per_split) : p.h;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                int i = i0;
+                for (; i + 4 <= i1; i += 4) {
+                    const float* r = p.W + (size_t)i * p.w + j;
+                    a0 = fmaf(FFC_LDG(r), FFC_LDG(p.u + i), a0);
+                    a1 = fmaf(FFC_LDG(r + p.w), FFC_LDG(p.u + i + 1), a1);
+                    a2 = fmaf(FFC_LDG(r + 2 * (size_t)p.w), FFC_LDG(p.u + i + 2), a2);
+                    a3 = fmaf(FFC_LDG(r + 3 * (size_t)p.w), FFC_LDG(p.u + i + 3), a3);
+                }
+                for (; i < i1; ++i) a0 = fmaf(FFC_LDG(p.W + (size_t)i * p.w + j), FFC_LDG(p.u + i), a0);
+                ffc_atomic_add(p.t + j, (a0 + a1) + (a2 + a3));
+            }
+        } FFC_SYNC;
+    }
+};
+
+// every CTA: inv = 1 / max(|t|, eps) (recomputed per CTA, t is <= 32 KB in L2); rows bx*8 .. +7: s[r] = W[r] . v
+struct SnRowKernel {
+    typedef SnParams Params;
+    static constexpr int kThreads = SN_THREADS;
+    static constexpr int kRows = SN_THREADS / 32;
+    static size_t smem_bytes() { return (size_t)SN_THREADS * sizeof(double); }
+    static FFC_DEVICE void run(const Params& p, const BlockCtx& ctx, float* smem) {
+        double* red = reinterpret_cast<double*>(smem);
+        const float* vin = p.power_iteration ? p.t : p.v;
+        FFC_PHASE {
+            double a = 0.0;
+            if (p.power_iteration)
+                for (int j = tid; j < p.w; j += kThreads) { const float x = FFC_LDG(p.t + j); a += (double)x * x; }
+            red[tid] = a;
+        } FFC_SYNC;
+        for (int wd = kThreads / 2; wd >= 1; wd >>= 1) {
+            FFC_PHASE { if (tid < wd) red[tid] += red[tid + wd]; } FFC_SYNC;
+        }
+        FFC_TLS(float, inv);
+        FFC_PHASE {
+            FFC_TLS_REF(float, inv);
+            inv = 1.f;
+            if (p.power_iteration) { const float n = sqrtf((float)red[0]); inv = 1.f / (n > p.eps ? n : p.eps); }
+        } FFC_SYNC;
+        FFC_PHASE {
+            FFC_TLS_REF(float, inv);
+            // this CTA's slice of v (normalised t) goes back to the caller's buffer and to the saved copy
+            const int per = (p.w + ctx.gx - 1) / ctx.gx;
+            const int j0 = ctx.bx * per, j1 = (j0 + per) < p.w ? (j0 + per) : p.w;
+            for (int j = j0 + tid; j < j1; j += kThreads) {
+                const float x = FFC_LDG(vin + j) * inv;
+                if (p.power_iteration) p.v[j] = x;
+                if (p.v_save) p.v_save[j] = x;
+            }
+            const int r = ctx.bx * kRows + tid / 32, lane = tid % 32;
+            float a0 = 0.f, a1 = 0.f;
+            if (r < p.h) {
+                const float* row = p.W + (size_t)r * p.w;
+                int j = lane;
+                for (; j + 32 < p.w; j += 64) {
+                    a0 = fmaf(FFC_LDG(row + j), FFC_LDG(vin + j) * inv, a0);
+                    a1 = fmaf(FFC_LDG(row + j + 32), FFC_LDG(vin + j + 32) * inv, a1);
+                }
+                for (; j < p.w; j += 32) a0 = fmaf(FFC_LDG(row + j), FFC_LDG(vin + j) * inv, a0);
+            }
+            red[tid] = (double)(a0 + a1);
+        } FFC_SYNC;
+        for (int wd = 16; wd >= 1; wd >>= 1) {
+            FFC_PHASE { if (tid % 32 < wd) red[tid] += red[tid + wd]; } FFC_SYNC;
+        }
+        FFC_PHASE {
+            const int r = ctx.bx * kRows + tid / 32;
+            if (tid % 32 == 0 && r < p.h) p.s[r] = (float)red[tid];
+        } FFC_SYNC;
+    }
+};
+
+// every CTA: sigma from s (and u); CTA 0 publishes u / sigma; all: w_eff = W / sigma
+struct SnScaleKernel {
+    typedef SnParams Params;
+    static constexpr int kThreads = SN_THREADS;
+    static size_t smem_bytes() { return (size_t)SN_THREADS * sizeof(double); }
+    static FFC_DEVICE void run(const Params& p, const BlockCtx& ctx, float* smem) {
+        double* red = reinterpret_cast<double*>(smem);
+        FFC_PHASE {
+            double a = 0.0;
+            for (int i = tid; i < p.h; i += kThreads) {
+                const float x = FFC_LDG(p.s + i);
+                a += p.power_iteration ? (double)x * x : (double)x * FFC_LDG(p.u + i);
+            }
+            red[tid] = a;
+        } FFC_SYNC;
+        for (int wd = kThreads / 2; wd >= 1; wd >>= 1) {
+            FFC_PHASE { if (tid < wd) red[tid] += red[tid + wd]; } FFC_SYNC;
+        }
+        FFC_TLS(float, sg);
+        FFC_PHASE {
+            FFC_TLS_REF(float, sg);
+            float inv = 1.f;
+            if (p.power_iteration) {
+                const float n = sqrtf((float)red[0]);
+                inv = 1.f / (n > p.eps ? n : p.eps);
+                sg = (float)red[0] * inv;                    // u . s with u = s * inv
+            } else {
+                sg = (float)red[0];
+            }
+            if (ctx.bx == 0) {
+                for (int i = tid; i < p.h; i += kThreads) {
+                    const float x = p.power_iteration ? FFC_LDG(p.s + i) * inv : FFC_LDG(p.u + i);
+                    if (p.u_save) p.u_save[i] = x;
+                    if (p.power_iteration) p.u[i] = x;
+                }
+                if (tid == 0) p.sigma[0] = sg;
+            }
+        } FFC_SYNC;
+        FFC_PHASE {
+            FFC_TLS_REF(float, sg);
+            const long long n = (long long)p.h * p.w;
+            for (long long i = (long long)ctx.bx * kThreads + tid; i < n; i += (long long)ctx.gx * kThreads)
+                p.w_eff[i] = FFC_LDG(p.W + i) / sg;
+        } FFC_SYNC;
+    }
+};
+
+extern "C" size_t ffc_spectral_norm_workspace_bytes(int h, int w) { return (size_t)(h + w) * sizeof(float) + 64; }
+
+// W (h, w) row-major = weight_orig viewed as (out channels, rest) (SpectralNorm.dim == 0).  u (h), v (w): the module's
+// weight_u / weight_v buffers, updated in place when power_iteration != 0.  u_save / v_save (nullable) receive the
+// vectors sigma was computed with, sigma (1 float) the value itself: ffc consumers keep them for the backward
+//     dW = g / sigma - (sum(g * W) / sigma^2) * u v^T.
+extern "C" int ffc_spectral_norm_fwd(const float* w_orig, float* u, float* v, float* u_save, float* v_save,
+                                     float* w_eff, float* sigma, int h, int w, int power_iteration, float eps,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+    FFC_REQUIRE(w_orig && u && v && w_eff && sigma, "ffc_spectral_norm_fwd: null pointer");
+    FFC_REQUIRE(h > 0 && w > 0, "ffc_spectral_norm_fwd: bad sizes");
+    FFC_REQUIRE(workspace && workspace_bytes >= ffc_spectral_norm_workspace_bytes(h, w), "ffc_spectral_norm_fwd: workspace too small");
+    ffc_stream_t st = (ffc_stream_t)stream;
+    SnParams p;
+    p.W = w_orig; p.u = u; p.v = v; p.u_save = u_save; p.v_save = v_save; p.w_eff = w_eff; p.sigma = sigma;
+    p.t = (float*)(((uintptr_t)workspace + 15) & ~(uintptr_t)15); p.s = p.t + w;
+    p.h = h; p.w = w; p.power_iteration = power_iteration ? 1 : 0; p.eps = eps;
+    const int colblocks = ffc_cdiv(w, SN_THREADS);
+    int rsplit = ffc_cdiv(2 * 148, colblocks);
+    if (rsplit > ffc_cdiv(h, 16)) rsplit = ffc_cdiv(h, 16);
+    if (rsplit < 1) rsplit = 1;
+    p.rows_per_split = ffc_cdiv(h, rsplit);
+    rsplit = ffc_cdiv(h, p.rows_per_split);
+    if (p.power_iteration) {
+        FFC_CHECK(ffc_memset_async(p.t, 0, (size_t)w * sizeof(float), st));
+        FFC_CHECK((ffc_launch<SnColKernel>(colblocks, rsplit, 1, SN_THREADS, 0, st, p)));
+    }
+    FFC_CHECK((ffc_launch<SnRowKernel>(ffc_cdiv(h, SnRowKernel::kRows), 1, 1, SN_THREADS, SnRowKernel::smem_bytes(), st, p)));
+    long long items = ((long long)h * w + SN_THREADS - 1) / SN_THREADS;
+    if (items > 148 * 8) items = 148 * 8;
+    return ffc_launch<SnScaleKernel>((int)items, 1, 1, SN_THREADS, SnScaleKernel::smem_bytes(), st, p);
+}

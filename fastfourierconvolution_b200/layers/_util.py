@@ -3,6 +3,7 @@ from __future__ import annotations
 
 import torch
 import torch.nn as nn
+from torch.nn.utils.spectral_norm import SpectralNorm as _SpectralNorm
 
 from .. import ops
 
@@ -12,9 +13,15 @@ def effective_weight(mod: nn.Module) -> torch.Tensor:
 
     ``torch.nn.utils.spectral_norm`` (layers/snffc/snffc.py:23-33) installs a forward-pre-hook that
     recomputes ``mod.weight = weight_orig / sigma`` (one power iteration in training mode).  The
-    B200 path never calls ``mod.forward``, so the hooks are run here, exactly once per forward.
+    B200 path never calls ``mod.forward``, so the hook's computation is done here, exactly once per forward: by
+    ``ops.spectral_norm_weight`` (three kernels) for the standard configuration -- ``dim == 0`` (nn.Conv2d), one power
+    iteration -- and by running the hook itself otherwise (nn.ConvTranspose2d has ``dim == 1``).
     """
     for hook in mod._forward_pre_hooks.values():
+        if isinstance(hook, _SpectralNorm) and hook.name == "weight" and hook.dim == 0 and hook.n_power_iterations == 1:
+            w = ops.spectral_norm_weight(mod.weight_orig, mod.weight_u, mod.weight_v, mod.training, hook.eps)
+            setattr(mod, "weight", w)                 # what the hook leaves behind for other readers of mod.weight
+            return w
         hook(mod, (None,))
     return mod.weight
 

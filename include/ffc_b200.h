@@ -178,6 +178,19 @@ int ffc_bn_act_bwd(const float* x, const float* dy, float* dx, const float* gamm
                    int B, int C, int HW, int norm, int training, int act, float slope,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- spectral normalisation ----------------------------------------------------------------------
+ * torch.nn.utils.spectral_norm's pre-forward computation (layers/snffc/snffc.py:8, 23-33; fgan_complete.py:147-156) on
+ * W = weight_orig viewed as (h = out channels, w = the rest), SpectralNorm.dim == 0, one power iteration:
+ *     power_iteration != 0:  v = normalize(W^T u);  u = normalize(W v)     (u, v updated in place, eps as in torch)
+ *     sigma = u . (W v);     w_eff = W / sigma
+ * u_save (h) / v_save (w) (nullable) receive the vectors sigma was computed with and sigma[0] its value: the caller keeps
+ * them for the backward  dW = g / sigma - (sum(g * W) / sigma^2) * u v^T.
+ * workspace: ffc_spectral_norm_workspace_bytes(h, w). */
+size_t ffc_spectral_norm_workspace_bytes(int h, int w);
+int ffc_spectral_norm_fwd(const float* w_orig, float* u, float* v, float* u_save, float* v_save,
+                          float* w_eff, float* sigma, int h, int w, int power_iteration, float eps,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- SE gate + resampling ---------------------------------------------------------------------
  * y = r(x) * sigmoid(W2 relu(W1 mean_hw(r(x)))): SpectralTransform.downsample followed by SELayer
  * (spectral_transform.py:79, 87 -> :12-28).  w1 [hid][C], w2 [C][hid] (hid = C // 16, may be 0).

@@ -340,3 +340,13 @@ def test_conv2d_act_matches_float64(case):
     from test_layers_emu import conv2d_act_errs
     errs = conv2d_act_errs(DEV, case)
     assert max(errs.values()) < parity.TOL, errs
+
+
+@pytest.mark.parametrize("shape,training", [((64, 3, 3), True), ((128, 64, 3), True), ((512, 256, 3), True), ((512, 512, 4), True),
+                                            ((256, 256, 4), False), ((130, 70, 3), True)])
+def test_spectral_norm_weight_matches_torch_hook(shape, training):
+    """The fused spectral-norm kernels against torch.nn.utils.spectral_norm's own hook (float64) for the discriminator's
+    weight shapes: normalised weight, gradient through sigma, and the updated weight_u / weight_v."""
+    from test_layers_emu import spectral_norm_errs
+    errs = spectral_norm_errs(DEV, shape, training)
+    assert max(errs.values()) < 1e-5, errs

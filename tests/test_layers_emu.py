@@ -180,3 +180,30 @@ def conv2d_act_errs(device, case, seed=0):
 def test_conv2d_act_matches_float64(case, emu):
     errs = conv2d_act_errs("cpu", case)
     assert max(errs.values()) < parity.TOL, errs
+
+
+def spectral_norm_errs(device, shape, training, seed=0):
+    """ops.spectral_norm_weight (three kernels) against torch.nn.utils.spectral_norm's own hook in float64: the weight,
+    its gradient with respect to weight_orig, and the power-iteration vectors left in the buffers."""
+    import copy
+    from fastfourierconvolution_b200 import ops
+    torch.manual_seed(seed)
+    conv = torch.nn.utils.spectral_norm(torch.nn.Conv2d(shape[1], shape[0], shape[2], bias=False))
+    conv.train(training)
+    ref = copy.deepcopy(conv).double()
+    conv.to(device)
+    u, v = conv.weight_u.detach().clone(), conv.weight_v.detach().clone()
+    w = ops.spectral_norm_weight(conv.weight_orig, u, v, training, 1e-12)
+    for hook in ref._forward_pre_hooks.values():
+        hook(ref, (None,))
+    cot = torch.randn(w.shape)
+    (w * cot.to(device)).sum().backward()
+    (ref.weight * cot.double()).sum().backward()
+    return {"w": parity.relerr(w, ref.weight.detach()), "dw": parity.relerr(conv.weight_orig.grad, ref.weight_orig.grad),
+            "u": parity.relerr(u, ref.weight_u), "v": parity.relerr(v, ref.weight_v)}
+
+
+@pytest.mark.parametrize("shape,training", [((64, 3, 3), True), ((40, 24, 4), True), ((40, 24, 4), False), ((130, 70, 3), True)])
+def test_spectral_norm_weight_matches_torch_hook(shape, training, emu):
+    errs = spectral_norm_errs("cpu", shape, training)
+    assert max(errs.values()) < 1e-5, errs
