@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(256) conv_small_cout_k3s1_kernel(const SmallCo
         const int c = e / 9, t = e % 9;
         const int sg = c >= p.cin[0], ci = sg ? c - p.cin[0] : c;
         float q[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int co = 0; co < p.cout; ++co) q[co] = small_w(p, p.w[sg], p.cin[sg], co, ci, t);
+        // a transposed k3 s1 p1 convolution is the plain one with the taps mirrored (ky -> 2 - ky, kx -> 2 - kx)
+        for (int co = 0; co < p.cout; ++co) q[co] = small_w(p, p.w[sg], p.cin[sg], co, ci, p.transposed ? 8 - t : t);
         scw[e] = make_float4(q[0], q[1], q[2], q[3]);
     }
     __syncthreads();
@@ -164,12 +165,18 @@ __global__ void __launch_bounds__(256) conv_small_cout_k3s1_kernel(const SmallCo
 
 template <int K>
 __global__ void __launch_bounds__(256) conv_small_cin_kernel(const SmallConvParams p) {
-    extern __shared__ float scv[];                  // [co][ci][tap]
+    // weights as float4 over 4 consecutive output channels: [co / 4][ci][tap] -> one broadcast LDS.128 feeds 4 FMAs (with
+    // scalar weights the loop issued one shared-memory load per FMA and ran at the LDS rate)
+    extern __shared__ float4 scv4[];
     constexpr int KK = K * K;
     const int cin = p.cin[0];
-    for (int e = threadIdx.x; e < p.cout * cin * KK; e += blockDim.x) {
-        const int t = e % KK, ci = (e / KK) % cin, co = e / (KK * cin);
-        scv[e] = small_w(p, p.w[0], cin, co, ci, t);
+    const int co4n = (p.cout + 3) / 4;
+    for (int e = threadIdx.x; e < co4n * cin * KK; e += blockDim.x) {
+        const int t = e % KK, ci = (e / KK) % cin, c4 = e / (KK * cin);
+        float q[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) q[j] = (4 * c4 + j < p.cout) ? small_w(p, p.w[0], cin, 4 * c4 + j, ci, t) : 0.f;
+        scv4[e] = make_float4(q[0], q[1], q[2], q[3]);
     }
     __syncthreads();
     const int HWo = p.Ho * p.Wo, HWi = p.Hi * p.Wi;
@@ -184,20 +191,32 @@ __global__ void __launch_bounds__(256) conv_small_cin_kernel(const SmallConvPara
 #pragma unroll
             for (int ci = 0; ci < 4; ++ci) v[ci][t] = (off >= 0 && ci < cin) ? __ldg(xp + (size_t)ci * HWi + off) : 0.f;
         }
-        for (int co = 0; co < p.cout; ++co) {
-            const float* wr = scv + (size_t)co * cin * KK;
-            float acc = 0.f;
+        for (int c4 = 0; c4 < co4n; ++c4) {
+            const float4* wr = scv4 + (size_t)c4 * cin * KK;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
             for (int ci = 0; ci < 4; ++ci) {
                 if (ci < cin) {
 #pragma unroll
-                    for (int t = 0; t < KK; ++t) acc = fmaf(v[ci][t], wr[ci * KK + t], acc);
+                    for (int t = 0; t < KK; ++t) {
+                        const float4 q = wr[ci * KK + t];
+                        a0 = fmaf(v[ci][t], q.x, a0); a1 = fmaf(v[ci][t], q.y, a1);
+                        a2 = fmaf(v[ci][t], q.z, a2); a3 = fmaf(v[ci][t], q.w, a3);
+                    }
                 }
             }
-            const size_t o = ((size_t)b * p.cout + co) * HWo + r;
-            if (p.bias) acc += __ldg(p.bias + co);
-            if (p.addend) acc += __ldg(p.addend + o);
-            p.y[o] = acc;
+            const float acc[4] = {a0, a1, a2, a3};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int co = 4 * c4 + j;
+                if (co < p.cout) {
+                    const size_t o = ((size_t)b * p.cout + co) * HWo + r;
+                    float a = acc[j];
+                    if (p.bias) a += __ldg(p.bias + co);
+                    if (p.addend) a += __ldg(p.addend + o);
+                    p.y[o] = a;
+                }
+            }
         }
     }
 }
@@ -205,7 +224,7 @@ __global__ void __launch_bounds__(256) conv_small_cin_kernel(const SmallConvPara
 bool conv_small_supported(int cin0, int cin1, int cout, int k) {
     if (k != 1 && k != 3 && k != 4) return false;
     if (cout <= 4) return (size_t)(cin0 + cin1) * k * k * 16 <= 96 * 1024;
-    return cin1 == 0 && cin0 <= 4 && (size_t)cout * cin0 * k * k * 4 <= 96 * 1024;
+    return cin1 == 0 && cin0 <= 4 && (size_t)((cout + 3) / 4) * cin0 * k * k * 16 <= 96 * 1024;
 }
 
 template <int K>
@@ -214,7 +233,7 @@ static int conv_small_launch(const SmallConvParams& p, ffc_stream_t st) {
     int grid = (int)((total + 255) / 256); if (grid > 148 * 16) grid = 148 * 16; if (grid < 1) grid = 1;
     cudaError_t e;
     const uintptr_t al = (uintptr_t)p.x[0] | (uintptr_t)p.x[1] | (uintptr_t)p.y | (uintptr_t)p.addend;
-    if (p.cout <= 4 && K == 3 && p.stride == 1 && p.pad == 1 && !p.transposed && p.Wi % 4 == 0 && (al & 15) == 0) {
+    if (p.cout <= 4 && K == 3 && p.stride == 1 && p.pad == 1 && p.Ho == p.Hi && p.Wo == p.Wi && p.Wi % 4 == 0 && (al & 15) == 0) {
         const size_t smem = (size_t)(p.cin[0] + (p.nseg > 1 ? p.cin[1] : 0)) * 9 * 16 + 64 * 16 * 16;
         if (smem > 48 * 1024) cudaFuncSetAttribute(conv_small_cout_k3s1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int g4 = (int)((total / 4 + 63) / 64); if (g4 > 148 * 16) g4 = 148 * 16; if (g4 < 1) g4 = 1;
@@ -224,7 +243,7 @@ static int conv_small_launch(const SmallConvParams& p, ffc_stream_t st) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(conv_small_cout_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         conv_small_cout_kernel<K><<<grid, 256, smem, st>>>(p);
     } else {
-        const size_t smem = (size_t)p.cout * p.cin[0] * K * K * 4;
+        const size_t smem = (size_t)((p.cout + 3) / 4) * p.cin[0] * K * K * 16;
         if (smem > 48 * 1024) cudaFuncSetAttribute(conv_small_cin_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         conv_small_cin_kernel<K><<<grid, 256, smem, st>>>(p);
     }

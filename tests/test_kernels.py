@@ -104,6 +104,8 @@ CONV_CASES = [
     (4, [4], 10, 6, 4, 2, 1, True, False, False, 0),
     (4, [10], 2, 6, 4, 2, 1, True, False, False, 0),
     (3, [9, 5], 3, 16, 3, 1, 1, False, False, True, 0),      # the 4-pixel strip forms (k3 s1 p1, width % 4 == 0)
+    (3, [9], 3, 16, 3, 1, 1, True, True, False, 0),          # ... and the transposed one (mirrored taps): dgrad of a 3 -> C conv
+    (2, [24, 8], 2, 8, 3, 1, 1, True, False, True, 0),
 ]
 
 
