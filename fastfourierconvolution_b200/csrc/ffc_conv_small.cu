@@ -221,6 +221,87 @@ __global__ void __launch_bounds__(256) conv_small_cin_kernel(const SmallConvPara
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 1x1 convolution with a narrow output (5 <= cout <= 24): conv1 / conv2 of SpectralTransform (spectral_transform.py:52-53,
+// 70-71: in_cg -> out_cg / 2 -> out_cg with 8-48 channels) and their data gradients.  Pure bandwidth: a thread owns 4
+// consecutive pixels, reads one float4 per input channel (coalesced) and keeps 4 x cout accumulators in registers; the
+// weights sit in shared memory as float4 over 4 output channels (one broadcast LDS.128 per 16 FMAs).
+// ---------------------------------------------------------------------------------------------
+template <int C4>           // groups of 4 output channels
+__global__ void __launch_bounds__(256) conv1x1_narrow_kernel(const SmallConvParams p) {
+    extern __shared__ float4 w4[];                  // [ci][C4]
+    const int cin = p.cin[0];
+    for (int e = threadIdx.x; e < cin * C4; e += blockDim.x) {
+        const int ci = e / C4, g = e % C4;
+        float q[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) q[j] = (4 * g + j < p.cout) ? small_w(p, p.w[0], cin, 4 * g + j, ci, 0) : 0.f;
+        w4[e] = make_float4(q[0], q[1], q[2], q[3]);
+    }
+    __syncthreads();
+    const int HW = p.Hi * p.Wi, HW4 = HW / 4;
+    const long long total = (long long)p.B * HW4;
+    for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < total; m += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(m / HW4), r4 = (int)(m % HW4);
+        const float4* xp = reinterpret_cast<const float4*>(p.x[0] + (size_t)b * cin * HW) + r4;
+        float4 acc[4 * C4];
+#pragma unroll
+        for (int i = 0; i < 4 * C4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int ci = 0; ci < cin; ++ci) {
+            const float4 v = __ldg(xp + (size_t)ci * HW4);
+#pragma unroll
+            for (int g = 0; g < C4; ++g) {
+                const float4 q = w4[ci * C4 + g];
+                float4& a0 = acc[4 * g], &a1 = acc[4 * g + 1], &a2 = acc[4 * g + 2], &a3 = acc[4 * g + 3];
+                a0.x = fmaf(v.x, q.x, a0.x); a0.y = fmaf(v.y, q.x, a0.y); a0.z = fmaf(v.z, q.x, a0.z); a0.w = fmaf(v.w, q.x, a0.w);
+                a1.x = fmaf(v.x, q.y, a1.x); a1.y = fmaf(v.y, q.y, a1.y); a1.z = fmaf(v.z, q.y, a1.z); a1.w = fmaf(v.w, q.y, a1.w);
+                a2.x = fmaf(v.x, q.z, a2.x); a2.y = fmaf(v.y, q.z, a2.y); a2.z = fmaf(v.z, q.z, a2.z); a2.w = fmaf(v.w, q.z, a2.w);
+                a3.x = fmaf(v.x, q.w, a3.x); a3.y = fmaf(v.y, q.w, a3.y); a3.z = fmaf(v.z, q.w, a3.z); a3.w = fmaf(v.w, q.w, a3.w);
+            }
+        }
+#pragma unroll
+        for (int co = 0; co < 4 * C4; ++co) {
+            if (co < p.cout) {
+                float4 a = acc[co];
+                const size_t o4 = ((size_t)b * p.cout + co) * HW4 + r4;
+                if (p.bias) { const float bb = __ldg(p.bias + co); a.x += bb; a.y += bb; a.z += bb; a.w += bb; }
+                if (p.addend) { const float4 d = __ldg(reinterpret_cast<const float4*>(p.addend) + o4); a.x += d.x; a.y += d.y; a.z += d.z; a.w += d.w; }
+                reinterpret_cast<float4*>(p.y)[o4] = a;
+            }
+        }
+    }
+}
+
+bool conv1x1_narrow_supported(int cin0, int cin1, int cout, int k, int stride, int pad, int Hi, int Wi, int Ho, int Wo,
+                              const void* x, const void* y, const void* addend) {
+    return k == 1 && stride == 1 && pad == 0 && cin1 == 0 && cout >= 5 && cout <= 24 && cin0 >= 1 && cin0 <= 512 && Ho == Hi && Wo == Wi &&
+           (Hi * Wi) % 4 == 0 && ((((uintptr_t)x) | ((uintptr_t)y) | ((uintptr_t)addend)) & 15) == 0;
+}
+
+int conv1x1_narrow_run(const float* x, const float* w, int cin, const float* bias, const float* addend, float* y,
+                       int B, int cout, int Hi, int Wi, int transposed, ffc_stream_t st) {
+    SmallConvParams p;
+    p.x[0] = x; p.x[1] = nullptr; p.w[0] = w; p.w[1] = nullptr; p.cin[0] = cin; p.cin[1] = 0; p.nseg = 1;
+    p.bias = bias; p.addend = addend; p.y = y; p.B = B; p.cout = cout; p.Hi = Hi; p.Wi = Wi; p.Ho = Hi; p.Wo = Wi;
+    p.k = 1; p.stride = 1; p.pad = 0; p.transposed = transposed;
+    const long long total = (long long)B * (Hi * Wi / 4);
+    int grid = (int)((total + 255) / 256); if (grid > 148 * 8) grid = 148 * 8; if (grid < 1) grid = 1;
+    const int c4 = (cout + 3) / 4;
+    const size_t smem = (size_t)cin * c4 * 16;
+    switch (c4) {
+        case 2: conv1x1_narrow_kernel<2><<<grid, 256, smem, st>>>(p); break;
+        case 3: conv1x1_narrow_kernel<3><<<grid, 256, smem, st>>>(p); break;
+        case 4: conv1x1_narrow_kernel<4><<<grid, 256, smem, st>>>(p); break;
+        case 5: conv1x1_narrow_kernel<5><<<grid, 256, smem, st>>>(p); break;
+        default: conv1x1_narrow_kernel<6><<<grid, 256, smem, st>>>(p); break;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { ffc_set_error("conv1x1_narrow launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
+    ffc_count_launch();
+    return FFC_OK;
+}
+
 bool conv_small_supported(int cin0, int cin1, int cout, int k) {
     if (k != 1 && k != 3 && k != 4) return false;
     if (cout <= 4) return (size_t)(cin0 + cin1) * k * k * 16 <= 96 * 1024;

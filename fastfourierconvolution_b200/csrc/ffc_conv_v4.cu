@@ -290,6 +290,10 @@ static const int ffc_conv_auto_mode = 5;    // default: V5 or V4 by output width
 static const int ffc_conv_v5_mode = 4;      // ... ConvFwdV5 (tcgen05; device build only -- the emulation build runs V4 instead)
 #ifndef FFC_EMU
 bool conv_small_supported(int cin0, int cin1, int cout, int k);
+bool conv1x1_narrow_supported(int cin0, int cin1, int cout, int k, int stride, int pad, int Hi, int Wi, int Ho, int Wo,
+                              const void* x, const void* y, const void* addend);
+int conv1x1_narrow_run(const float* x, const float* w, int cin, const float* bias, const float* addend, float* y,
+                       int B, int cout, int Hi, int Wi, int transposed, ffc_stream_t st);
 int conv_small_run(const float* x0, const float* w0, int cin0, const float* x1, const float* w1, int cin1,
                    const float* bias, const float* addend, float* y, int B, int cout, int Hi, int Wi, int Ho, int Wo,
                    int k, int stride, int pad, int transposed, ffc_stream_t st);
@@ -359,6 +363,12 @@ extern "C" int ffc_conv2d_fwd_ws(const float* x0, const float* w0, int cin0,
         FFC_REQUIRE(stride == 1 || stride == 2, "ffc_conv2d_fwd_ws: unsupported stride %d", stride);
         if (B == 0) return FFC_OK;
         return conv_small_run(x0, w0, cin0, x1, w1, cin1, bias, addend, y, B, cout, Hi, Wi, Ho, Wo, k, stride, pad, transposed, (ffc_stream_t)stream);
+    }
+    if (mode == ffc_conv_auto_mode && x0 && w0 && y && B > 0 &&
+        conv1x1_narrow_supported(cin0, cin1, cout, k, stride, pad, Hi, Wi, Ho, Wo, x0, y, addend)) {
+        // narrow 1x1 (SpectralTransform conv1 / conv2 and their data gradients): bandwidth-bound direct kernel
+        FFC_REQUIRE((long long)B * cout * Ho * Wo < (1LL << 31) && (long long)B * cin0 * Hi * Wi < (1LL << 31), "ffc_conv2d_fwd_ws: tensor too large for 32-bit element offsets");
+        return conv1x1_narrow_run(x0, w0, cin0, bias, addend, y, B, cout, Hi, Wi, transposed, (ffc_stream_t)stream);
     }
 #endif
     if (mode == ffc_conv_auto_mode) {

@@ -104,6 +104,10 @@ CONV_CASES = [
     (4, [4], 10, 6, 4, 2, 1, True, False, False, 0),
     (4, [10], 2, 6, 4, 2, 1, True, False, False, 0),
     (3, [9, 5], 3, 16, 3, 1, 1, False, False, True, 0),      # the 4-pixel strip forms (k3 s1 p1, width % 4 == 0)
+    (3, [24], 8, 8, 1, 1, 0, False, False, True, 0),         # narrow 1x1 (SpectralTransform conv1 / conv2 and their dgrads)
+    (2, [8], 16, 16, 1, 1, 0, False, True, False, 0),
+    (2, [33], 20, 6, 1, 1, 0, True, False, False, 0),
+    (2, [16], 23, 4, 1, 1, 0, False, True, True, 0),
     (3, [9], 3, 16, 3, 1, 1, True, True, False, 0),          # ... and the transposed one (mirrored taps): dgrad of a 3 -> C conv
     (2, [24, 8], 2, 8, 3, 1, 1, True, False, True, 0),
 ]
