@@ -343,6 +343,12 @@ def run_ours(args):
         ms_e2e, _ = timed(step_e2e)
     clocks = clk.summary()
 
+    if args.profile_step:                            # launch lists under ncu: the timed steps only, no micro-benchmarks
+        if rank == 0:
+            print(json.dumps({"profile_step": True, "ms_per_step": ms_res, "gpu_launches_per_step": launches}), flush=True)
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize(dev); sys.stdout.flush(); os._exit(0)
+        return
     fu = time_fourier_unit(workload, pb, dev) if rank == 0 else None
     cv = time_conv_layer(workload, pb, dev) if rank == 0 else None
     cpu = None
@@ -422,6 +428,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=64, help="batch of the bounded CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true", help="run the warm-up and the timed steps only (for ncu launch lists)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
