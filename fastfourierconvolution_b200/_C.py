@@ -40,7 +40,7 @@ _SIGNATURES = {
     "ffc_bn_act_fwd": (c_int, [c_void_p] * 8 + [c_int] * 5 + [c_float, c_float, c_int, c_float, c_void_p, c_size_t, c_void_p]),
     "ffc_bn_act_bwd": (c_int, [c_void_p] * 9 + [c_int] * 6 + [c_float, c_void_p, c_size_t, c_void_p]),
     "ffc_spectral_norm_workspace_bytes": (c_size_t, [c_int, c_int]),
-    "ffc_spectral_norm_fwd": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
+    "ffc_spectral_norm_fwd": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
     "ffc_se_fwd": (c_int, [c_void_p] * 7 + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
     "ffc_se_bwd": (c_int, [c_void_p] * 10 + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
     "ffc_fu_fwd": (c_int, [c_void_p] * 10 + [c_int] * 6 + [c_float, c_float, c_void_p, c_size_t, c_void_p]),

@@ -24,8 +24,16 @@ struct SnParams {
     float* t;              // workspace (w)
     float* s;              // workspace (h)
     int h, w, power_iteration, rows_per_split;
+    int kk;                // 0: W is (h, w) row-major (SpectralNorm.dim == 0, nn.Conv2d / nn.Linear);
+                           // > 0: the weight is stored (w / kk, h, kk) (dim == 1, nn.ConvTranspose2d with kk = k * k)
     float eps;
 };
+
+// element (i, j) of the matrix view
+FFC_HD size_t sn_at(const SnParams& p, int i, int j) {
+    if (p.kk == 0) return (size_t)i * p.w + j;
+    return ((size_t)(j / p.kk) * p.h + i) * p.kk + j % p.kk;
+}
 
 static constexpr int SN_THREADS = 256;
 
@@ -41,14 +49,17 @@ struct SnColKernel {
                 const int i1 = (i0 + p.rows_per_split) < p.h ? (i0 + p.rows_per_split) : p.h;
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
                 int i = i0;
+                // column j of the matrix view: rows are `rs` floats apart
+                const size_t rs = p.kk == 0 ? (size_t)p.w : (size_t)p.kk;
+                const float* col = p.W + sn_at(p, 0, j);
                 for (; i + 4 <= i1; i += 4) {
-                    const float* r = p.W + (size_t)i * p.w + j;
+                    const float* r = col + (size_t)i * rs;
                     a0 = fmaf(FFC_LDG(r), FFC_LDG(p.u + i), a0);
-                    a1 = fmaf(FFC_LDG(r + p.w), FFC_LDG(p.u + i + 1), a1);
-                    a2 = fmaf(FFC_LDG(r + 2 * (size_t)p.w), FFC_LDG(p.u + i + 2), a2);
-                    a3 = fmaf(FFC_LDG(r + 3 * (size_t)p.w), FFC_LDG(p.u + i + 3), a3);
+                    a1 = fmaf(FFC_LDG(r + rs), FFC_LDG(p.u + i + 1), a1);
+                    a2 = fmaf(FFC_LDG(r + 2 * rs), FFC_LDG(p.u + i + 2), a2);
+                    a3 = fmaf(FFC_LDG(r + 3 * rs), FFC_LDG(p.u + i + 3), a3);
                 }
-                for (; i < i1; ++i) a0 = fmaf(FFC_LDG(p.W + (size_t)i * p.w + j), FFC_LDG(p.u + i), a0);
+                for (; i < i1; ++i) a0 = fmaf(FFC_LDG(col + (size_t)i * rs), FFC_LDG(p.u + i), a0);
                 ffc_atomic_add(p.t + j, (a0 + a1) + (a2 + a3));
             }
         } FFC_SYNC;
@@ -91,7 +102,7 @@ struct SnRowKernel {
             }
             const int r = ctx.bx * kRows + tid / 32, lane = tid % 32;
             float a0 = 0.f, a1 = 0.f;
-            if (r < p.h) {
+            if (r < p.h && p.kk == 0) {
                 const float* row = p.W + (size_t)r * p.w;
                 int j = lane;
                 for (; j + 32 < p.w; j += 64) {
@@ -99,6 +110,8 @@ struct SnRowKernel {
                     a1 = fmaf(FFC_LDG(row + j + 32), FFC_LDG(vin + j + 32) * inv, a1);
                 }
                 for (; j < p.w; j += 32) a0 = fmaf(FFC_LDG(row + j), FFC_LDG(vin + j) * inv, a0);
+            } else if (r < p.h) {
+                for (int j = lane; j < p.w; j += 32) a0 = fmaf(FFC_LDG(p.W + sn_at(p, r, j)), FFC_LDG(vin + j) * inv, a0);
             }
             red[tid] = (double)(a0 + a1);
         } FFC_SYNC;
@@ -161,21 +174,23 @@ struct SnScaleKernel {
 
 extern "C" size_t ffc_spectral_norm_workspace_bytes(int h, int w) { return (size_t)(h + w) * sizeof(float) + 64; }
 
-// W (h, w) row-major = weight_orig viewed as (out channels, rest) (SpectralNorm.dim == 0).  u (h), v (w): the module's
+// W = weight_orig viewed as (h = out channels, w = the rest): row-major (h, w) when kk == 0 (SpectralNorm.dim == 0:
+// nn.Conv2d, nn.Linear), stored as (w / kk, h, kk) when kk = k * k > 0 (dim == 1: nn.ConvTranspose2d, whose weight is
+// (in, out, k, k) and whose matrix view is weight.permute(1, 0, 2, 3).reshape(out, -1)).  u (h), v (w): the module's
 // weight_u / weight_v buffers, updated in place when power_iteration != 0.  u_save / v_save (nullable) receive the
 // vectors sigma was computed with, sigma (1 float) the value itself: ffc consumers keep them for the backward
 //     dW = g / sigma - (sum(g * W) / sigma^2) * u v^T.
 extern "C" int ffc_spectral_norm_fwd(const float* w_orig, float* u, float* v, float* u_save, float* v_save,
-                                     float* w_eff, float* sigma, int h, int w, int power_iteration, float eps,
+                                     float* w_eff, float* sigma, int h, int w, int kk, int power_iteration, float eps,
                                      void* workspace, size_t workspace_bytes, void* stream) {
     FFC_REQUIRE(w_orig && u && v && w_eff && sigma, "ffc_spectral_norm_fwd: null pointer");
-    FFC_REQUIRE(h > 0 && w > 0, "ffc_spectral_norm_fwd: bad sizes");
+    FFC_REQUIRE(h > 0 && w > 0 && kk >= 0 && (kk == 0 || w % kk == 0), "ffc_spectral_norm_fwd: bad sizes");
     FFC_REQUIRE(workspace && workspace_bytes >= ffc_spectral_norm_workspace_bytes(h, w), "ffc_spectral_norm_fwd: workspace too small");
     ffc_stream_t st = (ffc_stream_t)stream;
     SnParams p;
     p.W = w_orig; p.u = u; p.v = v; p.u_save = u_save; p.v_save = v_save; p.w_eff = w_eff; p.sigma = sigma;
     p.t = (float*)(((uintptr_t)workspace + 15) & ~(uintptr_t)15); p.s = p.t + w;
-    p.h = h; p.w = w; p.power_iteration = power_iteration ? 1 : 0; p.eps = eps;
+    p.h = h; p.w = w; p.kk = kk; p.power_iteration = power_iteration ? 1 : 0; p.eps = eps;
     const int colblocks = ffc_cdiv(w, SN_THREADS);
     int rsplit = ffc_cdiv(2 * 148, colblocks);
     if (rsplit > ffc_cdiv(h, 16)) rsplit = ffc_cdiv(h, 16);

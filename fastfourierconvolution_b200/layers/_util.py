@@ -14,12 +14,13 @@ def effective_weight(mod: nn.Module) -> torch.Tensor:
     ``torch.nn.utils.spectral_norm`` (layers/snffc/snffc.py:23-33) installs a forward-pre-hook that
     recomputes ``mod.weight = weight_orig / sigma`` (one power iteration in training mode).  The
     B200 path never calls ``mod.forward``, so the hook's computation is done here, exactly once per forward: by
-    ``ops.spectral_norm_weight`` (three kernels) for the standard configuration -- ``dim == 0`` (nn.Conv2d), one power
-    iteration -- and by running the hook itself otherwise (nn.ConvTranspose2d has ``dim == 1``).
+    ``ops.spectral_norm_weight`` (three kernels) for the standard configurations -- one power iteration, ``dim == 0``
+    (nn.Conv2d) or ``dim == 1`` (nn.ConvTranspose2d) -- and by running the hook itself otherwise.
     """
     for hook in mod._forward_pre_hooks.values():
-        if isinstance(hook, _SpectralNorm) and hook.name == "weight" and hook.dim == 0 and hook.n_power_iterations == 1:
-            w = ops.spectral_norm_weight(mod.weight_orig, mod.weight_u, mod.weight_v, mod.training, hook.eps)
+        if isinstance(hook, _SpectralNorm) and hook.name == "weight" and hook.n_power_iterations == 1 and \
+                (hook.dim == 0 or (hook.dim == 1 and mod.weight_orig.dim() == 4)):
+            w = ops.spectral_norm_weight(mod.weight_orig, mod.weight_u, mod.weight_v, mod.training, hook.eps, hook.dim)
             setattr(mod, "weight", w)                 # what the hook leaves behind for other readers of mod.weight
             return w
         hook(mod, (None,))

@@ -52,7 +52,7 @@ class NoiseInjection(nn.Module):
         if noise is None:
             b, _, h, w = x.shape
             noise = x.new_empty(b, 1, h, w).normal_()
-        return x + self.weight * noise
+        return torch.addcmul(x, self.weight, noise)          # x + weight * noise in one pass over the activation
 
 
 class GaussianNoise(nn.Module):

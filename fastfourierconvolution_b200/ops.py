@@ -257,17 +257,20 @@ def conv2d_act(x, w, bias=None, stride=1, pad=0, act=ACT_LEAKY, slope=0.1):
 # ---------------------------------------------------------------------------------------------
 class SpectralNormFn(torch.autograd.Function):
     """weight = weight_orig / sigma with sigma = u . (W v) after one power iteration in training mode
-    (torch.nn.utils.spectral_norm.SpectralNorm.compute_weight, dim 0; layers/snffc/snffc.py:23-33,
+    (torch.nn.utils.spectral_norm.SpectralNorm.compute_weight, dim 0 or 1; layers/snffc/snffc.py:23-33,
     fgan_complete.py:147-156) in three kernels instead of ~14 PyTorch launches.  ``uv`` = (weight_u, weight_v) buffers,
     updated in place like the hook does; the vectors sigma was computed with are kept for the backward."""
 
     @staticmethod
-    def forward(ctx, w_orig, uv, power_iteration, eps):
+    def forward(ctx, w_orig, uv, power_iteration, eps, dim):
         u, v = uv
         _C.require_device(w_orig, u, v)
+        if dim not in (0, 1) or (dim == 1 and w_orig.dim() < 3):
+            raise ValueError("spectral_norm: dim 0 (Conv2d / Linear) or dim 1 (ConvTranspose2d) only")
         w_orig = w_orig.contiguous()
-        h = w_orig.shape[0]
+        h = w_orig.shape[dim]
         wd = w_orig.numel() // h
+        kk = w_orig[0, 0].numel() if dim == 1 else 0          # k * k
         if u.numel() != h or v.numel() != wd or not (u.is_contiguous() and v.is_contiguous()):
             raise ValueError("spectral_norm: weight_u / weight_v do not match weight_orig viewed as (out channels, rest)")
         w_eff = torch.empty_like(w_orig)
@@ -276,9 +279,10 @@ class SpectralNormFn(torch.autograd.Function):
         L = _C.lib()
         ws = _C.workspace(L.ffc_spectral_norm_workspace_bytes(h, wd), w_orig.device)
         _C.check(L.ffc_spectral_norm_fwd(_C.ptr(w_orig), _C.ptr(u), _C.ptr(v), _C.ptr(u_s), _C.ptr(v_s), _C.ptr(w_eff), _C.ptr(sigma),
-                                         h, wd, int(bool(power_iteration)), float(eps), _C.ptr(ws), ws.numel(),
+                                         h, wd, kk, int(bool(power_iteration)), float(eps), _C.ptr(ws), ws.numel(),
                                          _C.current_stream(w_orig.device)))
         ctx.save_for_backward(w_orig, u_s, v_s, sigma)
+        ctx.dim = dim
         return w_eff
 
     @staticmethod
@@ -286,12 +290,18 @@ class SpectralNormFn(torch.autograd.Function):
         w_orig, u_s, v_s, sigma = ctx.saved_tensors
         g = g.contiguous()
         coef = (g * w_orig).sum() / (sigma * sigma)                    # sum(g * W) / sigma^2, a one-element tensor
-        dw = g / sigma - (coef * torch.outer(u_s, v_s)).view_as(w_orig)
-        return dw, None, None, None
+        uv = torch.outer(u_s, v_s)                                     # d sigma / d W in the (out channels, rest) view
+        if ctx.dim == 1:
+            s = w_orig.shape
+            uv = uv.view(s[1], s[0], *s[2:]).transpose(0, 1)
+        else:
+            uv = uv.view_as(w_orig)
+        dw = g / sigma - coef * uv
+        return dw, None, None, None, None
 
 
-def spectral_norm_weight(w_orig, u, v, power_iteration=True, eps=1e-12):
-    return SpectralNormFn.apply(w_orig, (u, v), power_iteration, eps)
+def spectral_norm_weight(w_orig, u, v, power_iteration=True, eps=1e-12, dim=0):
+    return SpectralNormFn.apply(w_orig, (u, v), power_iteration, eps, dim)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -180,7 +180,9 @@ int ffc_bn_act_bwd(const float* x, const float* dy, float* dx, const float* gamm
 
 /* ---- spectral normalisation ----------------------------------------------------------------------
  * torch.nn.utils.spectral_norm's pre-forward computation (layers/snffc/snffc.py:8, 23-33; fgan_complete.py:147-156) on
- * W = weight_orig viewed as (h = out channels, w = the rest), SpectralNorm.dim == 0, one power iteration:
+ * W = weight_orig viewed as (h = out channels, w = the rest), one power iteration.  kk == 0: the weight is that matrix,
+ * row-major (SpectralNorm.dim == 0: nn.Conv2d, nn.Linear); kk = k*k > 0: the weight is stored (w / kk, h, kk)
+ * (dim == 1: nn.ConvTranspose2d, matrix view weight.permute(1, 0, 2, 3).reshape(out, -1)):
  *     power_iteration != 0:  v = normalize(W^T u);  u = normalize(W v)     (u, v updated in place, eps as in torch)
  *     sigma = u . (W v);     w_eff = W / sigma
  * u_save (h) / v_save (w) (nullable) receive the vectors sigma was computed with and sigma[0] its value: the caller keeps
@@ -188,7 +190,7 @@ int ffc_bn_act_bwd(const float* x, const float* dy, float* dx, const float* gamm
  * workspace: ffc_spectral_norm_workspace_bytes(h, w). */
 size_t ffc_spectral_norm_workspace_bytes(int h, int w);
 int ffc_spectral_norm_fwd(const float* w_orig, float* u, float* v, float* u_save, float* v_save,
-                          float* w_eff, float* sigma, int h, int w, int power_iteration, float eps,
+                          float* w_eff, float* sigma, int h, int w, int kk, int power_iteration, float eps,
                           void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- SE gate + resampling ---------------------------------------------------------------------

@@ -182,18 +182,20 @@ def test_conv2d_act_matches_float64(case, emu):
     assert max(errs.values()) < parity.TOL, errs
 
 
-def spectral_norm_errs(device, shape, training, seed=0):
+def spectral_norm_errs(device, shape, training, seed=0, transposed=False):
     """ops.spectral_norm_weight (three kernels) against torch.nn.utils.spectral_norm's own hook in float64: the weight,
-    its gradient with respect to weight_orig, and the power-iteration vectors left in the buffers."""
+    its gradient with respect to weight_orig, and the power-iteration vectors left in the buffers.  ``transposed``: an
+    nn.ConvTranspose2d holder (SpectralNorm.dim == 1)."""
     import copy
     from fastfourierconvolution_b200 import ops
     torch.manual_seed(seed)
-    conv = torch.nn.utils.spectral_norm(torch.nn.Conv2d(shape[1], shape[0], shape[2], bias=False))
+    cls = torch.nn.ConvTranspose2d if transposed else torch.nn.Conv2d
+    conv = torch.nn.utils.spectral_norm(cls(shape[1], shape[0], shape[2], bias=False))
     conv.train(training)
     ref = copy.deepcopy(conv).double()
     conv.to(device)
     u, v = conv.weight_u.detach().clone(), conv.weight_v.detach().clone()
-    w = ops.spectral_norm_weight(conv.weight_orig, u, v, training, 1e-12)
+    w = ops.spectral_norm_weight(conv.weight_orig, u, v, training, 1e-12, 1 if transposed else 0)
     for hook in ref._forward_pre_hooks.values():
         hook(ref, (None,))
     cot = torch.randn(w.shape)
@@ -206,4 +208,10 @@ def spectral_norm_errs(device, shape, training, seed=0):
 @pytest.mark.parametrize("shape,training", [((64, 3, 3), True), ((40, 24, 4), True), ((40, 24, 4), False), ((130, 70, 3), True)])
 def test_spectral_norm_weight_matches_torch_hook(shape, training, emu):
     errs = spectral_norm_errs("cpu", shape, training)
+    assert max(errs.values()) < 1e-5, errs
+
+
+@pytest.mark.parametrize("shape,training", [((24, 40, 4), True), ((24, 40, 4), False), ((7, 130, 3), True)])
+def test_spectral_norm_weight_dim1_matches_torch_hook(shape, training, emu):
+    errs = spectral_norm_errs("cpu", shape, training, transposed=True)
     assert max(errs.values()) < 1e-5, errs
