@@ -291,6 +291,30 @@ def test_empty_batch_is_a_noop(lib):
     y = torch.zeros(0, 3, 8, 8)
     w = torch.randn(3, 4, 3, 3)
     call(lib, "ffc_conv2d_fwd", torch.zeros(4), w, 4, None, None, 0, None, None, torch.zeros(4), 0, 3, 8, 8, 8, 8, 3, 1, 1, 0, None)
+    # the entry points added for the block form and the discriminator stages
+    ws = torch.zeros(1 << 16, dtype=torch.uint8)
+    w32 = torch.randn(32, 4, 3, 3)
+    call(lib, "ffc_conv2d_act_fwd_ws", torch.zeros(4), w32, 4, None, torch.zeros(4), 0, 32, 8, 8, 8, 8, 3, 1, 1, 2, ctypes.c_float(0.1),
+         ws, ws.numel(), None)
+    call(lib, "ffc_conv2d_block_fwd_ws", torch.zeros(4), w32, w32, 4, None, None, 0, None, torch.zeros(4), 32, torch.zeros(4), 32,
+         0, 8, 8, 8, 8, 3, 1, 1, 0, ws, ws.numel(), None)
+
+
+def test_new_entry_points_reject_bad_arguments(lib):
+    """Error behaviour of the C ABI: non-zero status + message, nothing launched."""
+    library = lib[0]
+    ws = torch.zeros(1 << 12, dtype=torch.uint8)
+    z = ctypes.c_void_p(0)
+    p = ctypes.c_void_p(ws.data_ptr())
+    # activation other than LeakyReLU / ReLU
+    assert library.ffc_conv2d_act_fwd_ws(p, p, 4, z, p, 1, 8, 4, 4, 4, 4, 3, 1, 1, 3, ctypes.c_float(0.1), p, ws.numel(), z) != 0
+    assert "LeakyReLU" in library.last_error()
+    # LeakyReLU with a non-positive slope (the backward mask is read from the output's sign)
+    assert library.ffc_conv2d_act_fwd_ws(p, p, 4, z, p, 1, 8, 4, 4, 4, 4, 3, 1, 1, 2, ctypes.c_float(0.0), p, ws.numel(), z) != 0
+    # spectral norm: workspace too small, bad matrix view
+    assert library.ffc_spectral_norm_fwd(p, p, p, z, z, p, p, 8, 16, 0, 1, ctypes.c_float(1e-12), p, 4, z) != 0
+    assert "workspace" in library.last_error()
+    assert library.ffc_spectral_norm_fwd(p, p, p, z, z, p, p, 8, 15, 4, 1, ctypes.c_float(1e-12), p, ws.numel(), z) != 0
 
 
 def _fu_reference(x, w, gamma, beta, rmean, rvar, training, eps=1e-5):

@@ -1,3 +1,5 @@
+"""Weight-gradient micro-benchmark (wgrad_v5_kernel) on the SN-discriminator layer shapes of fgan32, batch 256.
+usage: python tools/bench_wgrad.py      (FFC_LIB=<path to an alternative libffc_b200.so> to A/B builds)"""
 import os, sys, json
 sys.path.insert(0, os.getcwd())
 import torch
@@ -24,5 +26,5 @@ for name, (cin, cout, Hi, k, s) in shapes.items():
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / 20 * 1000
     gf = 2.0 * B * Ho * Ho * cout * cin * k * k / 1e9
-    out[name] = f"{us:.0f}us {gf / us * 1e-3 * 1e3:.0f}TF"
-print(os.environ.get("FFC_LIB", "base"), json.dumps(out))
+    out[name] = f"{us:.0f}us {gf / us * 1e3 / 1e3:.0f}TF"
+print(os.environ.get("FFC_LIB", "in-tree"), json.dumps(out))
