@@ -39,6 +39,8 @@ _SIGNATURES = {
     "ffc_bias_grad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "ffc_bn_act_fwd": (c_int, [c_void_p] * 8 + [c_int] * 5 + [c_float, c_float, c_int, c_float, c_void_p, c_size_t, c_void_p]),
     "ffc_bn_act_bwd": (c_int, [c_void_p] * 9 + [c_int] * 6 + [c_float, c_void_p, c_size_t, c_void_p]),
+    "ffc_bn_stats": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_float, c_float, c_void_p, c_size_t, c_void_p]),
+    "ffc_irfft2_bn_relu": (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p] * 5),
     "ffc_spectral_norm_workspace_bytes": (c_size_t, [c_int, c_int]),
     "ffc_spectral_norm_fwd": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
     "ffc_se_fwd": (c_int, [c_void_p] * 7 + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),

@@ -502,6 +502,30 @@ extern "C" int ffc_bn_act_fwd(const float* x, float* y, const float* gamma, cons
     return ffc_launch<BnApplyKernel>(ew_grid(items, 256), 1, 1, 256, 0, st, ap);
 }
 
+// The statistics half of ffc_bn_act_fwd on its own: save_mean / save_invstd from the batch (training, running statistics
+// updated in place) or from the running statistics (eval).  Consumers that apply the normalisation themselves
+// (ffc_irfft2_bn_relu) call this first.  Workspace: 2*C doubles.
+extern "C" int ffc_bn_stats(const float* x, float* running_mean, float* running_var, float* save_mean, float* save_invstd,
+                            int B, int C, int HW, int training, float eps, float momentum,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+    FFC_REQUIRE(x && save_mean && save_invstd, "ffc_bn_stats: null pointer");
+    FFC_REQUIRE(B >= 0 && C > 0 && HW > 0, "ffc_bn_stats: bad sizes");
+    ffc_stream_t st = (ffc_stream_t)stream;
+    if ((long long)B * C * HW == 0) return FFC_OK;
+    if (training) {
+        FFC_REQUIRE(workspace && workspace_bytes >= (size_t)2 * C * sizeof(double), "ffc_bn_stats: workspace too small");
+        double* sums = (double*)workspace;
+        FFC_CHECK(ffc_memset_async(sums, 0, (size_t)2 * C * sizeof(double), st));
+        ChanReduceParams rp{x, nullptr, nullptr, nullptr, nullptr, nullptr, sums, B, C, HW, 0, reduce_split(C, (long long)B * HW), 0.f};
+        FFC_CHECK((ffc_launch<ChanReduceKernel<0>>(C, rp.nsplit, 1, FFC_RED_THREADS, ChanReduceKernel<0>::smem_bytes(), st, rp)));
+        BnFinalizeParams fp{sums, save_mean, save_invstd, running_mean, running_var, C, (double)B * HW, eps, momentum};
+        return ffc_launch<BnFinalizeKernel>(ffc_cdiv(C, 256), 1, 1, 256, 0, st, fp);
+    }
+    FFC_REQUIRE(running_mean && running_var, "ffc_bn_stats: eval mode needs running statistics");
+    BnEvalStatsParams ep{running_mean, running_var, save_mean, save_invstd, C, eps};
+    return ffc_launch<BnEvalStatsKernel>(ffc_cdiv(C, 256), 1, 1, 256, 0, st, ep);
+}
+
 // Workspace: 2*C doubles.
 extern "C" int ffc_bn_act_bwd(const float* x, const float* dy, float* dx, const float* gamma, const float* beta,
                               const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta,

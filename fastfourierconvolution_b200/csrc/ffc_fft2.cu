@@ -76,6 +76,9 @@ struct Irfft2Kernel {
         int nplanes, P;
         int colscale;            // 0: torch c2r semantics;  1: interior columns pre-multiplied by 1/2
         float scale;
+        // optional BatchNorm + ReLU applied to the spectrum as it is loaded (fourier_unity.py:49 folded into :51-56):
+        // per spectrum channel 2c / 2c+1 of plane (b, c), c = plane % cout;  null mean = none
+        const float* mean; const float* invstd; const float* gamma; const float* beta; int cout;
     };
     static constexpr int kThreads = 512;
     typedef Fft2Plan<H, W> PL;
@@ -110,7 +113,14 @@ struct Irfft2Kernel {
                     if (i < total) {
                         const int pl = i / per, rem = i % per, v = rem % PL::Wf;
                         const float a = (p.colscale && v != 0 && v != W / 2) ? 0.5f : 1.0f;
-                        reinterpret_cast<float2*>(S + pl * PL::REGION)[rem] = make_float2(re[u] * a, im[u] * a);
+                        float xr = re[u], xi = im[u];
+                        if (p.mean) {            // same arithmetic as BnApplyKernel: relu((x - mean) * (invstd * gamma) + beta)
+                            const int c0 = 2 * ((plane0 + pl) % p.cout), c1 = c0 + 1;
+                            xr = (xr - FFC_LDG(p.mean + c0)) * (FFC_LDG(p.invstd + c0) * FFC_LDG(p.gamma + c0)) + FFC_LDG(p.beta + c0);
+                            xi = (xi - FFC_LDG(p.mean + c1)) * (FFC_LDG(p.invstd + c1) * FFC_LDG(p.gamma + c1)) + FFC_LDG(p.beta + c1);
+                            xr = xr > 0.f ? xr : 0.f; xi = xi > 0.f ? xi : 0.f;
+                        }
+                        reinterpret_cast<float2*>(S + pl * PL::REGION)[rem] = make_float2(xr * a, xi * a);
                     }
                 }
             }
@@ -175,11 +185,14 @@ static int rfft2_launch(const float* x, float* spec, int nplanes, int colscale, 
     typename K::Params p{x, spec, nplanes, P, colscale, 1.0f / sqrtf((float)N * (float)N)};
     return ffc_launch<K>(ffc_cdiv(nplanes, P), 1, 1, nt, K::smem_bytes(P), st, p);
 }
+struct IrfftBn { const float* mean; const float* invstd; const float* gamma; const float* beta; int cout; };
 template <int N>
-static int irfft2_launch(const float* spec, const float* residual, float* out, int nplanes, int colscale, ffc_stream_t st) {
+static int irfft2_launch(const float* spec, const float* residual, float* out, int nplanes, int colscale, ffc_stream_t st,
+                         IrfftBn bn = IrfftBn{nullptr, nullptr, nullptr, nullptr, 1}) {
     typedef Irfft2Kernel<N, N> K;
     int P, nt; fft2_tile_config<N, N>(nplanes, &P, &nt);
-    typename K::Params p{spec, residual, out, nplanes, P, colscale, 1.0f / sqrtf((float)N * (float)N)};
+    typename K::Params p{spec, residual, out, nplanes, P, colscale, 1.0f / sqrtf((float)N * (float)N),
+                         bn.mean, bn.invstd, bn.gamma, bn.beta, bn.cout};
     return ffc_launch<K>(ffc_cdiv(nplanes, P), 1, 1, nt, K::smem_bytes(P), st, p);
 }
 
@@ -217,5 +230,28 @@ extern "C" int ffc_irfft2(const float* spec, const float* residual, float* out, 
         case 32: return irfft2_launch<32>(spec, residual, out, nplanes, colscale, st);
         case 64: return irfft2_launch<64>(spec, residual, out, nplanes, colscale, st);
         default: return irfft2_launch<128>(spec, residual, out, nplanes, colscale, st);
+    }
+}
+
+// irfft2 of relu(batchnorm(spec)) [+ residual]: the BatchNorm + ReLU of FourierUnitSN.forward (fourier_unity.py:49) applied
+// while the spectrum is loaded, so the normalised spectrum never exists in memory (one read + one write of the spectrum
+// less than bn_act followed by irfft2).  spec (nplanes, 2, H, W/2+1) with nplanes = B * cout; mean / invstd / gamma / beta
+// over the 2*cout spectrum channels (mean / invstd as written by ffc_bn_stats).
+extern "C" int ffc_irfft2_bn_relu(const float* spec, const float* residual, float* out, int nplanes, int cout, int H, int W,
+                                  const float* mean, const float* invstd, const float* gamma, const float* beta, void* stream) {
+    FFC_REQUIRE(spec && out && mean && invstd && gamma && beta, "ffc_irfft2_bn_relu: null pointer");
+    FFC_REQUIRE(fft2_supported(H, W), "ffc_irfft2_bn_relu: unsupported plane %dx%d (square powers of two 4..128 only)", H, W);
+    FFC_REQUIRE(((uintptr_t)out & 15) == 0 && ((uintptr_t)residual & 15) == 0, "ffc_irfft2_bn_relu: out/residual must be 16-byte aligned");
+    FFC_REQUIRE(nplanes >= 0 && cout > 0 && nplanes % cout == 0, "ffc_irfft2_bn_relu: plane count must be a multiple of cout");
+    if (nplanes == 0) return FFC_OK;
+    ffc_stream_t st = (ffc_stream_t)stream;
+    const IrfftBn bn{mean, invstd, gamma, beta, cout};
+    switch (H) {
+        case 4: return irfft2_launch<4>(spec, residual, out, nplanes, 0, st, bn);
+        case 8: return irfft2_launch<8>(spec, residual, out, nplanes, 0, st, bn);
+        case 16: return irfft2_launch<16>(spec, residual, out, nplanes, 0, st, bn);
+        case 32: return irfft2_launch<32>(spec, residual, out, nplanes, 0, st, bn);
+        case 64: return irfft2_launch<64>(spec, residual, out, nplanes, 0, st, bn);
+        default: return irfft2_launch<128>(spec, residual, out, nplanes, 0, st, bn);
     }
 }

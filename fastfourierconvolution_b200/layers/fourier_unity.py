@@ -4,7 +4,7 @@ Same constructor, same submodules (``conv_layer``, ``bn``, ``relu``; they only h
 buffers so ``state_dict`` / ``apply(weights_init)`` / optimizers see the reference layout), same
 ``forward(x, y=None)``.  The forward runs hand-written sm_100a kernels: a fused shared-memory
 rfft2 -> channel mix -> BatchNorm + ReLU -> irfft2 kernel where one image's spectrum fits in a
-CTA's shared memory, otherwise the general form rfft2 | 1x1 mix | BN+ReLU | irfft2 with the
+CTA's shared memory, otherwise the general form rfft2 | 1x1 mix | BN statistics | (BN+ReLU)->irfft2 with the
 spectrum staged through L2 in the reference's (B, 2C, H, W/2+1) channel layout (no layout copies).
 """
 from __future__ import annotations
@@ -53,5 +53,10 @@ class FourierUnitSN(nn.Module):
                                           bn.running_var, residual, bn.training, bn.eps, bn.momentum)
         spec = ops.rfft2(x)                                            # fourier_unity.py:38-42
         mixed = ops.conv2d(spec, weight)                               # :45
+        if plain_bn:                                                   # :49 applied inside the load of :51-56
+            if bn.training:
+                bn.num_batches_tracked.add_(1)
+            return ops.bn_relu_irfft2(mixed, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual,
+                                      bn.training, bn.eps, bn.momentum)
         act = _util.bn_act(mixed, self.bn, (ops.ACT_RELU, 0.0))        # :49
         return ops.irfft2(act, residual)                               # :51-56

@@ -409,6 +409,54 @@ class Irfft2Fn(torch.autograd.Function):
         return dspec, (dout if ctx.has_res and ctx.needs_input_grad[1] else None)
 
 
+class BnReluIrfft2Fn(torch.autograd.Function):
+    """irfft2(relu(batchnorm(spec))) [+ residual] with the BatchNorm + ReLU applied as the spectrum is loaded
+    (fourier_unity.py:49 folded into :51-56): statistics kernel, then one kernel; the normalised spectrum is never
+    written.  Backward: adjoint transform of dout, then the ordinary BN + ReLU backward on the saved spectrum."""
+
+    @staticmethod
+    def forward(ctx, spec, gamma, beta, running_mean, running_var, residual, training, eps, momentum):
+        _C.require_device(spec, gamma, beta, running_mean, running_var, residual)
+        spec, residual = spec.contiguous(), _c(residual)
+        B, C2, H, Wf = spec.shape
+        W = 2 * (Wf - 1)
+        if not training and (running_mean is None or running_var is None):
+            raise ValueError("BatchNorm in eval mode needs running statistics")
+        L = _C.lib()
+        st = _C.current_stream(spec.device)
+        save_mean = torch.empty(C2, device=spec.device, dtype=torch.float32)
+        save_invstd = torch.empty(C2, device=spec.device, dtype=torch.float32)
+        ws = _C.workspace(2 * C2 * 8, spec.device)
+        _C.check(L.ffc_bn_stats(_C.ptr(spec), _C.ptr(running_mean), _C.ptr(running_var), _C.ptr(save_mean), _C.ptr(save_invstd),
+                                B, C2, H * Wf, int(training), float(eps), float(momentum), _C.ptr(ws), ws.numel(), st))
+        out = torch.empty((B, C2 // 2, H, W), device=spec.device, dtype=torch.float32)
+        _C.check(L.ffc_irfft2_bn_relu(_C.ptr(spec), _C.ptr(residual), _C.ptr(out), B * (C2 // 2), C2 // 2, H, W,
+                                      _C.ptr(save_mean), _C.ptr(save_invstd), _C.ptr(gamma), _C.ptr(beta), st))
+        ctx.save_for_backward(spec, gamma, beta, save_mean, save_invstd)
+        ctx.cfg = (bool(training), residual is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        spec, gamma, beta, save_mean, save_invstd = ctx.saved_tensors
+        training, has_res = ctx.cfg
+        dout = dout.contiguous()
+        B, C2, H, Wf = spec.shape
+        dact = _rfft2(dout, 1)                                  # gradient with respect to relu(bn(spec))
+        dspec = torch.empty_like(spec)
+        dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(beta)
+        ws = _C.workspace(2 * C2 * 8, spec.device)
+        _C.check(_C.lib().ffc_bn_act_bwd(_C.ptr(spec), _C.ptr(dact), _C.ptr(dspec), _C.ptr(gamma), _C.ptr(beta),
+                                         _C.ptr(save_mean), _C.ptr(save_invstd), _C.ptr(dgamma), _C.ptr(dbeta),
+                                         B, C2, H * Wf, 1, int(training), ACT_RELU, 0.0,
+                                         _C.ptr(ws), ws.numel(), _C.current_stream(spec.device)))
+        return dspec, dgamma, dbeta, None, None, (dout if has_res and ctx.needs_input_grad[5] else None), None, None, None
+
+
+def bn_relu_irfft2(spec, gamma, beta, running_mean, running_var, residual, training, eps, momentum):
+    return BnReluIrfft2Fn.apply(spec, gamma, beta, running_mean, running_var, residual, training, eps, momentum)
+
+
 def rfft2(x):
     return Rfft2Fn.apply(x)
 

@@ -178,6 +178,17 @@ int ffc_bn_act_bwd(const float* x, const float* dy, float* dx, const float* gamm
                    int B, int C, int HW, int norm, int training, int act, float slope,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* ffc_bn_stats: the statistics half of ffc_bn_act_fwd (batch statistics + running-stat update in training mode, running
+ * statistics in eval mode) -> save_mean / save_invstd [C].  workspace >= 2*C*8 bytes.
+ * ffc_irfft2_bn_relu: out = irfft2(relu(batchnorm(spec))) [+ residual] -- fourier_unity.py:49 folded into :51-56, the
+ * normalised spectrum never exists in memory.  spec (nplanes = B*cout, 2, H, W/2+1); mean / invstd / gamma / beta over the
+ * 2*cout spectrum channels.  The backward is ffc_rfft2(colscale = 1) followed by ffc_bn_act_bwd on the saved spec. */
+int ffc_bn_stats(const float* x, float* running_mean, float* running_var, float* save_mean, float* save_invstd,
+                 int B, int C, int HW, int training, float eps, float momentum,
+                 void* workspace, size_t workspace_bytes, void* stream);
+int ffc_irfft2_bn_relu(const float* spec, const float* residual, float* out, int nplanes, int cout, int H, int W,
+                       const float* mean, const float* invstd, const float* gamma, const float* beta, void* stream);
+
 /* ---- spectral normalisation ----------------------------------------------------------------------
  * torch.nn.utils.spectral_norm's pre-forward computation (layers/snffc/snffc.py:8, 23-33; fgan_complete.py:147-156) on
  * W = weight_orig viewed as (h = out channels, w = the rest), one power iteration.  kk == 0: the weight is that matrix,
