@@ -401,8 +401,14 @@ def run_ours(args):
         }
         tpeak, tpeak_src = tensor_peak_tf32()
         issued = 3.0 * cv["flops"] / cv["ms"] / 1e9          # three TF32 MMAs per FP32-accurate product (3xTF32)
+        ctraffic = None                                   # DRAM bytes per launch from the committed ncu capture (same shape only)
+        cpath = os.path.join(ROOT, "profiles", "roofline_traffic_conv.json")
+        if os.path.exists(cpath):
+            cj = json.load(open(cpath))
+            if cj.get("shape") == {"workload": workload, "B": pb}:
+                ctraffic = cj["traffic"]
         line["roofline_tensor"] = {
-            "bound": "tensor", "achieved": issued, "peak": tpeak, "unit": "TFLOP/s", "frac": issued / tpeak, "traffic": None,
+            "bound": "tensor", "achieved": issued, "peak": tpeak, "unit": "TFLOP/s", "frac": issued / tpeak, "traffic": ctraffic,
             "peak_source": tpeak_src,
             "kernel": "conv_v5_kernel (tcgen05.mma kind::tf32, A in TMEM, 3xTF32 at FP32 accuracy) + pack_v5_kernel, " + cv["shape"],
             "effective_fp32_tflops": cv["flops"] / cv["ms"] / 1e9, "algorithmic_flops_per_launch": cv["flops"],
