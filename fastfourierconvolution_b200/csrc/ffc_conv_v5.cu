@@ -43,6 +43,8 @@ struct ConvV5Params {
     long long cls_off[FFC_V5_MAXCLS];     // float offset of each class
     int nt_full;               // N of a full tile (multiple of 16, <= 192)
     int nsb;                   // B stages in shared memory (2 .. V5_SB_MAX)
+    int ksplit;                // K chunks of a tile are dealt to ksplit CTAs (gridDim.z = classes * ksplit), which add their
+                               // partial sums into a zeroed y with float atomics; 1 = one CTA per tile, plain stores
     const float* bias; const float* addend; float* y;
     float slope;               // epilogue activation x > 0 ? x : slope * x (1 = none, 0.1 = LeakyReLU(0.1), 0 = ReLU)
     float* y1; int cout0;      // block form: output channels [cout0, cout) go to y1 (cout - cout0 channels); else y1 == null, cout0 == cout
@@ -118,7 +120,8 @@ __global__ void __launch_bounds__(V5_GW * 128 + 64, V5_GW == 2 ? 2 : 1) conv_v5_
     extern __shared__ __align__(128) unsigned char v5_smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int s = p.transposed ? p.stride : 1;
-    const int cls = blockIdx.z, py = cls / s, px = cls % s;
+    const int ncls = s * s;
+    const int cls = blockIdx.z % ncls, ksp = blockIdx.z / ncls, py = cls / s, px = cls % s;
     const int Hc = (p.Ho - py + s - 1) / s, Wc = (p.Wo - px + s - 1) / s;
     const int Mc = p.B * Hc * Wc;
     const int m0 = blockIdx.x * 128;
@@ -127,10 +130,16 @@ __global__ void __launch_bounds__(V5_GW * 128 + 64, V5_GW == 2 ? 2 : 1) conv_v5_
     const int NT = v5_tile_n(p.cout, p.nt_full, ntile);
     const ConvClassGeom g = ffc_conv_class_geom(cls, p.k, p.stride, p.pad, p.transposed);
     const int T = g.Ta * g.Tb;
-    const int nchunks = T * (p.cps[0] + (p.nseg > 1 ? p.cps[1] : 0));
+    const int nchunks_all = T * (p.cps[0] + (p.nseg > 1 ? p.cps[1] : 0));
+    // this CTA's share of the K chunks: [cb, cb + nchunks)
+    const int per_split = (nchunks_all + p.ksplit - 1) / p.ksplit;
+    const int cb = ksp * per_split;
+    const int nchunks = (cb + per_split <= nchunks_all) ? per_split : (nchunks_all > cb ? nchunks_all - cb : 0);
+    if (p.ksplit > 1 && nchunks == 0) return;           // nothing to add (whole CTA)
     const uint32_t stage_bytes = (uint32_t)(2 * NT * V5_BK * 4);
     // packed weights of this (class, tile): tiles before it have nt_full columns
-    const float* wp = p.wp + p.cls_off[cls] + (long long)ntile * nchunks * 2LL * p.nt_full * V5_BK;
+    const float* wp = p.wp + p.cls_off[cls] + (long long)ntile * nchunks_all * 2LL * p.nt_full * V5_BK
+                      + (long long)cb * 2LL * NT * V5_BK;
 
     const int nsb = p.nsb;
     unsigned char* bstage = v5_smem;                                                     // nsb stages
@@ -169,8 +178,8 @@ __global__ void __launch_bounds__(V5_GW * 128 + 64, V5_GW == 2 ? 2 : 1) conv_v5_
         const int xq = m % Wc, yq = (m / Wc) % Hc, b = m / (Wc * Hc);
         const int HWi = p.Hi * p.Wi;
         for (int c = wg; c < nchunks; c += nstage) {
-            // cursor of chunk c: (segment, tap, first channel)
-            int r = c, sg = 0;
+            // cursor of chunk cb + c: (segment, tap, first channel)
+            int r = cb + c, sg = 0;
             if (r >= T * p.cps[0]) { sg = 1; r -= T * p.cps[0]; }
             const int cps = sg ? p.cps[1] : p.cps[0], cin = sg ? p.cin[1] : p.cin[0];
             const int tap = r / cps, c0 = (r % cps) * V5_BK;
@@ -232,14 +241,17 @@ __global__ void __launch_bounds__(V5_GW * 128 + 64, V5_GW == 2 ? 2 : 1) conv_v5_
                         const int co = co0 + n0 + j;
                         if (co < p.cout) {
                             float v2 = __uint_as_float(r[j]);
-                            if (p.bias) v2 += __ldg(p.bias + co);
+                            if (p.bias && ksp == 0) v2 += __ldg(p.bias + co);
+                            float* dst;
                             if (co < p.cout0) {
                                 const size_t o = ((size_t)b * p.cout0 + co) * HWo + pix;
-                                if (p.addend) v2 += __ldg(p.addend + o);
-                                p.y[o] = v2 > 0.f ? v2 : v2 * p.slope;
+                                if (p.addend && ksp == 0) v2 += __ldg(p.addend + o);
+                                dst = p.y + o;
                             } else {
-                                p.y1[((size_t)b * (p.cout - p.cout0) + (co - p.cout0)) * HWo + pix] = v2 > 0.f ? v2 : v2 * p.slope;
+                                dst = p.y1 + ((size_t)b * (p.cout - p.cout0) + (co - p.cout0)) * HWo + pix;
                             }
+                            if (p.ksplit > 1) atomicAdd(dst, v2);                 // slope == 1 in this mode (host)
+                            else *dst = v2 > 0.f ? v2 : v2 * p.slope;
                         }
                     }
                 }
@@ -397,7 +409,32 @@ int conv_v5_run_block(const float* x0, const float* w0, const float* w0b, int ci
         if (e != cudaSuccess) { ffc_set_error("cudaFuncSetAttribute(conv_v5, %zu B): %s", smem, cudaGetErrorString(e)); return FFC_ERR_CUDA; }
         configured = smem;
     }
-    const dim3 grid(ffc_cdiv(Mc, 128), pl.ntiles, s * s);
+    // small grids (deep layers on small planes, small batch shards): split K over CTAs until the SMs are covered; the
+    // partial sums meet in a zeroed output through float atomics.  Not with a fused activation.
+    int ksplit = 1;
+    {
+        const int ctas = ffc_cdiv(Mc, 128) * pl.ntiles * s * s;
+        int min_chunks = 1 << 30;
+        for (int c = 0; c < pl.ncls; ++c) {
+            const ConvClassGeom g = ffc_conv_class_geom(c, k, stride, pad, transposed);
+            const int n = g.Ta * g.Tb * (pl.cps[0] + pl.cps[1]);
+            if (n < min_chunks) min_chunks = n;
+        }
+        if (slope == 1.f && ctas * 2 <= 148) {
+            ksplit = 148 / ctas;
+            if (ksplit > min_chunks / 8) ksplit = min_chunks / 8;
+            if (ksplit > 16) ksplit = 16;
+            if (ksplit < 1) ksplit = 1;
+        }
+    }
+    p.ksplit = ksplit;
+    if (ksplit > 1) {
+        const size_t HWo = (size_t)Ho * Wo;
+        e = cudaMemsetAsync(y, 0, (size_t)B * cout0 * HWo * sizeof(float), st);
+        if (e == cudaSuccess && y1) e = cudaMemsetAsync(y1, 0, (size_t)B * (cout - cout0) * HWo * sizeof(float), st);
+        if (e != cudaSuccess) { ffc_set_error("conv_v5 memset: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
+    }
+    const dim3 grid(ffc_cdiv(Mc, 128), pl.ntiles, s * s * ksplit);
     if (four_wg) conv_v5_kernel<4><<<grid, 4 * 128 + 64, smem, st>>>(p);
     else conv_v5_kernel<2><<<grid, 2 * 128 + 64, smem, st>>>(p);
     e = cudaGetLastError();

@@ -183,6 +183,8 @@ BLOCK_CASES = [
     (2, 36, 12, 40, 24, 8, 4, 2, 1, False, True),     # a downsampling stage with biases (sngan FDiscriminator)
     (2, 20, 0, 130, 70, 6, 3, 1, 1, False, True),     # no global input (first layer); several output tiles
     (2, 6, 3, 5, 4, 5, 3, 1, 1, True, True),          # narrow: falls back to two plain launches
+    (2, 96, 32, 24, 8, 8, 4, 2, 1, True, True),       # deep K on a small grid: split-K with atomics into both outputs
+    (1, 160, 0, 40, 24, 6, 3, 1, 1, False, True),
 ]
 
 
