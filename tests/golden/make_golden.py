@@ -131,7 +131,7 @@ def main():
         for k in keep_grads:
             fx["grad/" + k] = params[k].grad.numpy()
         for k, b in mod.named_buffers():
-            if k.endswith("running_mean") and b.numel() <= 64:
+            if (k.endswith("running_mean") and b.numel() <= 64) or (k.endswith("weight_u") and b.numel() <= 512):
                 fx["post/" + k] = b.detach().clone().numpy()
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **fx)
@@ -141,6 +141,9 @@ def main():
     record_model("model_fgan32_G", quiet(lambda: ns["FGenerator"](z_size=128, mg=4)), t(2, 128), 3,
                  ["conv3.ffc.convg2g.fu.conv_layer.weight", "conv4.ffc.convg2g.conv1.weight", "conv4.bn_g.weight",
                   "conv3.ffc.convg2g.se_block.fc.0.weight", "conv5.ffc.convg2l.weight"])
+    # the plain SN conv discriminator the FFC generators are trained against
+    record_model("model_fgan32_D", quiet(lambda: ns["Discriminator"](sn=True, mg=4)), t(4, 3, 32, 32) * 0.5, 9,
+                 ["conv1.weight_orig", "conv1.bias", "conv2.weight_orig", "conv7.bias", "fc.weight_orig"])
     ns = load_script_classes("/root/reference/sngan_complete.py")
     record_model("model_sngan_FD", quiet(lambda: ns["FDiscriminator"](sn=True, mg=4)), t(2, 3, 32, 32), 5,
                  ["main.1.ffc.convg2g.fu.conv_layer.weight", "main.2.ffc.convg2g.conv2.weight", "main.0.ffc.convl2g.weight"])
