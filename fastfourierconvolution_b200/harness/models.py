@@ -4,7 +4,7 @@ The reference defines these inline in its training scripts, which run ``main()``
 datasets at import time, and its ``models/*`` classes do not construct (FFCModel.__init__ rejects
 ``inplanes=``); neither can be imported on the GPU box.  They are therefore restated here,
 table-driven, on top of ``fastfourierconvolution_b200.layers`` with the reference's attribute names so
-that a reference ``state_dict`` loads with ``strict=True`` (tests/test_golden_models.py checks the
+that a reference ``state_dict`` loads with ``strict=True`` (tests/test_layers_emu.py and tests/test_gpu_parity.py check the
 key lists and the outputs against fixtures generated from the reference classes themselves).
 """
 from __future__ import annotations

@@ -144,6 +144,12 @@ def main():
     # the plain SN conv discriminator the FFC generators are trained against
     record_model("model_fgan32_D", quiet(lambda: ns["Discriminator"](sn=True, mg=4)), t(4, 3, 32, 32) * 0.5, 9,
                  ["conv1.weight_orig", "conv1.bias", "conv2.weight_orig", "conv7.bias", "fc.weight_orig"])
+    # fgan64: one more upsampling stage and a 64x64 Fourier unit (general form: rfft2 | mix | BN statistics | BN+ReLU->irfft2).
+    # (uses_sn=True is stored and ignored by the reference's FFC_BN_ACT, ffc_bn_act.py:39: the generator has plain weights)
+    ns64 = load_script_classes("/root/reference/fgan64_complete.py")
+    record_model("model_fgan64_G", quiet(lambda: ns64["FGenerator"](z_size=128, mg=4)), t(2, 128), 11,
+                 ["conv3.ffc.convg2g.fu.conv_layer.weight", "conv5.ffc.convg2g.fu.conv_layer.weight", "conv5.ffc.convl2g.weight",
+                  "conv5.ffc.convg2g.conv1.weight", "conv6.ffc.convg2l.weight", "conv5.bn_g.weight"])
     ns = load_script_classes("/root/reference/sngan_complete.py")
     record_model("model_sngan_FD", quiet(lambda: ns["FDiscriminator"](sn=True, mg=4)), t(2, 3, 32, 32), 5,
                  ["main.1.ffc.convg2g.fu.conv_layer.weight", "main.2.ffc.convg2g.conv2.weight", "main.0.ffc.convl2g.weight"])

@@ -354,7 +354,7 @@ def test_spectral_norm_weight_matches_torch_hook(shape, training):
 
 @pytest.mark.parametrize("shape,training", [((256, 512, 4), True), ((48, 96, 4), True), ((64, 64, 4), False)])
 def test_spectral_norm_weight_dim1_matches_torch_hook(shape, training):
-    """... and for nn.ConvTranspose2d holders (SpectralNorm.dim == 1: the SN generators of fgan64 / fgan128)."""
+    """... and for nn.ConvTranspose2d holders (SpectralNorm.dim == 1: SNFFCTranspose, layers/snffc/snffc_transpose.py)."""
     from test_layers_emu import spectral_norm_errs
     errs = spectral_norm_errs(DEV, shape, training, transposed=True)
     assert max(errs.values()) < 1e-5, errs
