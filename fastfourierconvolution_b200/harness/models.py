@@ -151,6 +151,43 @@ class FDiscriminator(nn.Module):
         return self.fc(m.view(-1, self.mg * self.mg * 512))
 
 
+# stages of the SNFFC discriminator below: (in, out, kernel, ratio_gin, ratio_gout, stride, padding, norm)
+FD_SN64_STAGES = [(3, 64, 3, 0.0, 0.25, 1, 1, nn.Identity), (64, 128, 4, 0.25, 0.25, 2, 1, nn.BatchNorm2d),
+                  (128, 256, 4, 0.25, 0.25, 2, 1, nn.BatchNorm2d), (256, 512, 4, 0.25, 0.25, 2, 1, nn.BatchNorm2d),
+                  (512, 512, 4, 0.25, 0.0, 2, 1, nn.BatchNorm2d)]
+
+
+def build_fd_sn64(layers, sn_fn, mg=4):
+    """(main, fc) of the 64x64 SNFFC discriminator from a ``layers`` package -- this one or the reference's own (the
+    golden fixture tests/golden/model_fgan64_FD.npz is built from the reference's classes by this same function)."""
+    stages = []
+    for ci, co, k, rgi, rgo, s, p, norm in FD_SN64_STAGES:
+        blk = layers.FFC_BN_ACT(ci, co, k, rgi, rgo, stride=s, padding=p, bias=True, uses_noise=False, uses_sn=True,
+                                activation_layer=nn.LeakyReLU, norm_layer=norm)
+        blk.ffc = layers.SNFFC(ci, co, k, rgi, rgo, s, p, 1, 1, True)       # FFC -> its spectral-norm twin (layers/snffc/snffc.py:12-33)
+        stages.append(blk)
+    return nn.Sequential(*stages), sn_fn(nn.Linear(mg * mg * 512, 1))
+
+
+class FDiscriminatorSN64(nn.Module):
+    """BASELINE configs[2] names a "spectral-norm snffc discriminator" for the 64x64 workload; the reference ships none
+    (its only FFC discriminator, sngan_complete.py:116-157, takes 32x32 images and leaves ``uses_sn`` unused).  This is
+    SURVEY.md 8(d)'s construction: sngan's FDiscriminator extended by one stride-2 stage, with every FFC replaced by
+    the reference's SNFFC, so that ``layers/snffc`` runs at the CelebA shape and an oracle built from the reference's
+    own classes exists."""
+
+    def __init__(self, sn=True, mg: int = 4):
+        super().__init__()
+        from .. import layers
+        self.mg = mg
+        self.resizer = Resizer()
+        self.main, self.fc = build_fd_sn64(layers, torch.nn.utils.spectral_norm if sn else (lambda m: m), mg)
+
+    def forward(self, x):
+        m = self.resizer(self.main(x))
+        return self.fc(m.view(-1, self.mg * self.mg * 512))
+
+
 class FFCGenerator(nn.Module):
     """models/ffc_generator.py:14-45 (config 1: nz=100, nc=1, ngf=32, g_factor=0.5)."""
 

@@ -348,6 +348,21 @@ def sngan_fdiscriminator(x: Tensor, P: Params, training: bool, mg: int = 4) -> T
     return F.linear(m.reshape(-1, mg * mg * 512), w, P["fc.bias"])
 
 
+def fdiscriminator_sn64(x: Tensor, P: Params, training: bool, mg: int = 4) -> Tensor:
+    """The 64x64 SNFFC discriminator of SURVEY.md 8(d) config 3 (harness FDiscriminatorSN64): sngan's FDiscriminator
+    (sngan_complete.py:125-157) with one more stride-2 stage and SNFFC (layers/snffc/snffc.py:12-33) in place of FFC."""
+    A = dict(bias=True, act="leaky_relu", spectral_norm=True)
+    cfgs = [FFCConfig(3, 64, 3, 0.0, 0.25, 1, 1, norm="identity", **A), FFCConfig(64, 128, 4, 0.25, 0.25, 2, 1, norm="bn", **A),
+            FFCConfig(128, 256, 4, 0.25, 0.25, 2, 1, norm="bn", **A), FFCConfig(256, 512, 4, 0.25, 0.25, 2, 1, norm="bn", **A),
+            FFCConfig(512, 512, 4, 0.25, 0.0, 2, 1, norm="bn", **A)]
+    m = x
+    for i, cfg in enumerate(cfgs):
+        m = ffc_bn_act(m, P, f"main.{i}.", cfg, training)
+    m = resizer(m)
+    w = spectral_norm_weight(P, "fc.", training)
+    return F.linear(m.reshape(-1, mg * mg * 512), w, P["fc.bias"])
+
+
 # hinge losses, fgan_complete.py:216-235
 def hinge_loss_dis(fake: Tensor, real: Tensor) -> Tensor:
     return F.relu(1.0 - real).mean() + F.relu(1.0 + fake).mean()

@@ -150,6 +150,26 @@ def main():
     record_model("model_fgan64_G", quiet(lambda: ns64["FGenerator"](z_size=128, mg=4)), t(2, 128), 11,
                  ["conv3.ffc.convg2g.fu.conv_layer.weight", "conv5.ffc.convg2g.fu.conv_layer.weight", "conv5.ffc.convl2g.weight",
                   "conv5.ffc.convg2g.conv1.weight", "conv6.ffc.convg2l.weight", "conv5.bn_g.weight"])
+    # BASELINE configs[2] / SURVEY.md 8(d): the 64x64 SNFFC discriminator, assembled from the REFERENCE's FFC_BN_ACT and
+    # SNFFC classes by the same builder the harness uses on its own layers
+    from fastfourierconvolution_b200.harness.models import build_fd_sn64
+
+    class RefFDiscriminatorSN64(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.mg = 4
+            self.resizer = ref_layers.Resizer()
+            self.main, self.fc = build_fd_sn64(ref_layers, torch.nn.utils.spectral_norm)
+
+        def forward(self, x):
+            return self.fc(self.resizer(self.main(x)).view(-1, 16 * 512))
+
+    # batch 4, and a seed for which neither FP32 evaluation order puts an activation on the other side of its kink: with
+    # BatchNorm over 32-64 values per channel in the last stages about every third (seed, batch) choice does, and then the
+    # reference's own FP32 gradients sit 1e-3..1e-2 away from its float64 ones (SURVEY.md 8(c) caveat 1)
+    record_model("model_fgan64_FD", quiet(RefFDiscriminatorSN64), t(4, 3, 64, 64) * 0.5, 15,
+                 ["main.0.ffc.convl2l.weight_orig", "main.1.ffc.convg2g.conv1.weight_orig", "main.1.ffc.convg2g.fu.conv_layer.weight",
+                  "main.1.ffc.convl2g.weight_orig", "main.0.ffc.convl2l.bias", "main.0.ffc.convl2g.weight_orig"])   # (biases in front of a BatchNorm have gradient 0)
     ns = load_script_classes("/root/reference/sngan_complete.py")
     record_model("model_sngan_FD", quiet(lambda: ns["FDiscriminator"](sn=True, mg=4)), t(2, 3, 32, 32), 5,
                  ["main.1.ffc.convg2g.fu.conv_layer.weight", "main.2.ffc.convg2g.conv2.weight", "main.0.ffc.convl2g.weight"])

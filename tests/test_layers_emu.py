@@ -23,7 +23,7 @@ def test_module_matches_reference_golden(name, emu):
 def _model_case(fn):
     return {"fgan32": lambda: H.FGenerator(128, 4, "fgan32"), "fd": lambda: H.FDiscriminator(True, 4),
             "cfg1": lambda: H.FFCGenerator(100, 1, 32), "d32": lambda: H.SNDiscriminator(True, 4, 7),
-            "fgan64": lambda: H.FGenerator(128, 4, "fgan64")}[fn]()
+            "fgan64": lambda: H.FGenerator(128, 4, "fgan64"), "fd64": lambda: H.FDiscriminatorSN64(True, 4)}[fn]()
 
 
 def run_model_fixture(name, fn, device, grad_l2=False):
@@ -55,7 +55,8 @@ def run_model_fixture(name, fn, device, grad_l2=False):
 
 
 @pytest.mark.parametrize("name,fn", [("model_fgan32_G", "fgan32"), ("model_sngan_FD", "fd"), ("model_ffcgen_cfg1", "cfg1"),
-                                     ("model_fgan32_D", "d32"), ("model_fgan64_G", "fgan64")])
+                                     ("model_fgan32_D", "d32"), ("model_fgan64_G", "fgan64"),
+                                     ("model_fgan64_FD", "fd64")])
 def test_model_matches_reference_golden(name, fn, emu):
     errs = run_model_fixture(name, fn, "cpu")
     # whole networks at batch 2: the reference's own FP32-vs-FP64 spread is ~6e-5 here
