@@ -36,10 +36,14 @@ WORKLOADS = {
     "fgan32": ("fgan32", 7, 32, 256, False),     # configs[1]: global batch 256 on 1/2/4/8 GPUs (strong)
     "fgan64": ("fgan64", 8, 64, 128, True),      # configs[2]: 128 per GPU (weak)
     "fgan128": ("fgan128", 9, 128, 64, True),    # configs[3]: 64 per GPU (weak)
+    # configs[2] with the "spectral-norm snffc discriminator" it names (harness.FDiscriminatorSN64):
+    # the reference ships no such class; it is assembled from FFC_BN_ACT + SNFFC and pinned by tests/golden/model_fgan64_FD.npz
+    "fgan64_snffc": ("fgan64", "fd64", 64, 128, True),
 }
 # FourierUnit instances inside each generator: (channels, plane size) -- SURVEY.md appendix A.2/A.3
 FU_SHAPES = {"fgan32": [(16, 16), (8, 32)], "fgan64": [(16, 16), (8, 32), (8, 64)],
              "fgan128": [(64, 16), (32, 32), (32, 64), (32, 128)]}
+FU_SHAPES["fgan64_snffc"] = FU_SHAPES["fgan64"]
 
 
 def measured_peaks():
@@ -113,7 +117,8 @@ def cpu_reference_step_rate(workload, batch, steps, warmup, seed=1234):
     torch.manual_seed(seed)
     torch.set_num_threads(os.cpu_count() or 1)
     G = H.FGenerator(128, 4, variant); G.apply(H.weights_init)
-    D = H.SNDiscriminator(True, 4, n_convs); D.apply(H.weights_init)
+    D = H.FDiscriminatorSN64(True, 4) if n_convs == "fd64" else H.SNDiscriminator(True, 4, n_convs)
+    D.apply(H.weights_init)
     tr = RefTrainer(G.state_dict(), D.state_dict(), variant, n_convs)
     def data():
         return torch.randn(batch, 128), torch.randn(batch, 128), torch.rand(batch, 3, size, size) * 2 - 1
@@ -219,7 +224,7 @@ def time_fourier_unit(workload, per_rank_batch, dev):
 
 
 # largest local-branch convolution of each generator: (cin, cout, input size) of conv2.ffc.convl2l, ConvTranspose2d k4 s2 p1
-CONV_SHAPES = {"fgan32": (512, 192, 4), "fgan64": (512, 192, 4), "fgan128": (1024, 256, 4)}
+CONV_SHAPES = {"fgan32": (512, 192, 4), "fgan64": (512, 192, 4), "fgan128": (1024, 256, 4), "fgan64_snffc": (512, 192, 4)}
 
 
 def tensor_peak_tf32():
@@ -272,7 +277,11 @@ def run_ours(args):
     # (cuDNN, autotuned, NHWC, TF32 allowed -- PyTorch's GPU defaults) for an A/B comparison only.
     d_backend = os.environ.get("FFC_BENCH_D", "ffc_b200")
     G = H.FGenerator(128, 4, variant).to(dev).train(); G.apply(H.weights_init)
-    D = H.SNDiscriminator(True, 4, n_convs, backend="ffc_b200" if d_backend == "ffc_b200" else "torch").to(dev).train()
+    if n_convs == "fd64":
+        D = H.FDiscriminatorSN64(True, 4).to(dev).train()        # an FFC discriminator: on the product's kernels by construction
+        d_backend = "ffc_b200"
+    else:
+        D = H.SNDiscriminator(True, 4, n_convs, backend="ffc_b200" if d_backend == "ffc_b200" else "torch").to(dev).train()
     D.apply(H.weights_init)
     if d_backend != "ffc_b200":                      # "torch" (TF32 allowed) or "torch_fp32" (cuDNN held to FP32 like the product)
         torch.backends.cudnn.allow_tf32 = d_backend != "torch_fp32"
@@ -378,7 +387,7 @@ def run_ours(args):
                        "l2": "per-step working set (activations of batch %d, > 400 MB) exceeds the 126 MB L2; FourierUnit timing rotates %d input buffers"
                              % (pb, fu["rotating_buffers"]),
                        "launch": "whole step replayed as one CUDA graph" if use_graph else "eager launches",
-                       "discriminator": ("plain SN conv net on libffc_b200 kernels (tcgen05 conv / dgrad / wgrad at FP32 accuracy, fused bias, LeakyReLU kernel)"
+                       "discriminator": ("SNFFC discriminator (harness.FDiscriminatorSN64) on libffc_b200 kernels" if n_convs == "fd64" else "plain SN conv net on libffc_b200 kernels (tcgen05 conv / dgrad / wgrad at FP32 accuracy, fused bias, LeakyReLU kernel)"
                                          if d_backend == "ffc_b200" else "plain SN conv net on PyTorch kernels (cuDNN autotuned, NHWC, %s)" % ("FP32" if d_backend == "torch_fp32" else "TF32")),
                        "generator_params_MB": round(act_mb, 1)},
             "e2e": {"value": gb / ms_e2e * 1000.0, "unit": "images/s", "ms_per_step": ms_e2e,

@@ -45,6 +45,8 @@ class RefTrainer:
         return R.fgenerator(z, self.PG, True, self.variant, self.mg)
 
     def D(self, x):
+        if self.n_convs == "fd64":                       # the 64x64 SNFFC discriminator (harness.FDiscriminatorSN64)
+            return R.fdiscriminator_sn64(x, self.PD, True, self.mg)
         return R.sn_discriminator(x, self.PD, True, self.n_convs, self.mg)
 
     @staticmethod

@@ -25,3 +25,12 @@ def test_reference_arm_other_ranks_exit_without_work():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_reference_arm_runs_the_snffc_discriminator_workload():
+    """BASELINE configs[2] with the SNFFC discriminator it names (bench.py --workload fgan64_snffc)."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "fgan64_snffc",
+                        "--steps", "1", "--warmup", "0", "--cpu-batch", "2"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert d["impl"] == "reference" and d["config"]["workload"].startswith("fgan64_snffc") and d["scaling"] == "weak"
