@@ -150,6 +150,11 @@ def main():
     record_model("model_fgan64_G", quiet(lambda: ns64["FGenerator"](z_size=128, mg=4)), t(2, 128), 11,
                  ["conv3.ffc.convg2g.fu.conv_layer.weight", "conv5.ffc.convg2g.fu.conv_layer.weight", "conv5.ffc.convl2g.weight",
                   "conv5.ffc.convg2g.conv1.weight", "conv6.ffc.convg2l.weight", "conv5.bn_g.weight"])
+    # fgan128: ngf 128, ratio 0.5, five upsampling stages, Fourier units up to 32 channels @ 128x128 (the largest spectrum)
+    ns128 = load_script_classes("/root/reference/fgan128_complete.py")
+    record_model("model_fgan128_G", quiet(lambda: ns128["FGenerator"](z_size=128, mg=4)), t(1, 128), 21,
+                 ["conv6.ffc.convg2g.fu.conv_layer.weight", "conv6.ffc.convg2g.conv1.weight", "conv6.bn_g.weight",
+                  "conv7.ffc.convg2l.weight", "conv4.ffc.convg2g.fu.bn.weight"])
     # BASELINE configs[2] / SURVEY.md 8(d): the 64x64 SNFFC discriminator, assembled from the REFERENCE's FFC_BN_ACT and
     # SNFFC classes by the same builder the harness uses on its own layers
     from fastfourierconvolution_b200.harness.models import build_fd_sn64
