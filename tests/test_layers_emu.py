@@ -218,3 +218,31 @@ def test_spectral_norm_weight_matches_torch_hook(shape, training, emu):
 def test_spectral_norm_weight_dim1_matches_torch_hook(shape, training, emu):
     errs = spectral_norm_errs("cpu", shape, training, transposed=True)
     assert max(errs.values()) < 1e-5, errs
+
+
+@pytest.mark.parametrize("B,C,N", [(2, 64, 16), (2, 24, 32), (1, 96, 16), (2, 8, 64)])
+def test_fourier_unit_sweep_shapes_general_form(B, C, N, emu):
+    """BASELINE configs[4] shapes that take the general form (rfft2 | 1x1 mix | BN statistics | BN+ReLU->irfft2), training
+    mode, forward and backward against the float64 oracle.  Output in the max norm; gradients in the relative L2 norm
+    (a ReLU element on the other side of its kink moves the max norm, SURVEY.md 8(c) caveat 1)."""
+    torch.manual_seed(C + N)
+    m = ffc.FourierUnitSN(C, C).train()
+    with torch.no_grad():
+        m.bn.weight.uniform_(0.5, 1.5); m.bn.bias.normal_(0, 0.2)
+    P = {k: (v.double().clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else
+             (v.double().clone() if v.is_floating_point() else v.clone())) for k, v in m.state_dict().items()}
+    x = torch.randn(B, C, N, N)
+    xr = x.double().requires_grad_(True)
+    ref = R.fourier_unit(xr, P, "", True)
+    cot = torch.randn(ref.shape, dtype=torch.float64)
+    (ref * cot).sum().backward()
+    xo = x.clone().requires_grad_(True)
+    out = m(xo)
+    (out * cot.float()).sum().backward()
+
+    def l2(a, b):
+        return ((a.detach().double() - b.detach().double()).norm() / b.detach().double().norm()).item()
+    assert parity.relerr(out, ref.detach()) < 1e-5
+    assert l2(xo.grad, xr.grad) < 1e-3 and l2(m.conv_layer.weight.grad, P["conv_layer.weight"].grad) < 1e-3
+    assert l2(m.bn.weight.grad, P["bn.weight"].grad) < 1e-3 and l2(m.bn.bias.grad, P["bn.bias"].grad) < 1e-3
+    assert parity.relerr(m.bn.running_var, P["bn.running_var"]) < 1e-5
