@@ -46,6 +46,17 @@ FU_SHAPES = {"fgan32": [(16, 16), (8, 32)], "fgan64": [(16, 16), (8, 32), (8, 64
 FU_SHAPES["fgan64_snffc"] = FU_SHAPES["fgan64"]
 
 
+def workload_config(workload, gb):
+    """The ``config`` object of the JSON line: identical for our arm and the reference arm (same workload, same batch)."""
+    _, n_convs, size, _, _ = WORKLOADS[workload]
+    d = "SNFFC discriminator (FFC_BN_ACT + SNFFC stages)" if n_convs == "fd64" else f"SN conv Discriminator ({n_convs} convs)"
+    return {"workload": f"{workload}: fgan_complete-style FGenerator + {d} GAN training step (G fwd x2, G bwd, D fwd x3, D bwd x2, "
+                        f"2 optimiser steps), synthetic 3x{size}x{size}, global batch {gb}",
+            "global_batch": gb,
+            "l2": "per-step working set (activations + gradients of the global batch, > 400 MB) exceeds the 126 MB L2; "
+                  "isolated-kernel timings rotate input buffers whose total exceeds L2"}
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -140,16 +151,16 @@ def run_reference(args):
         return
     workload = args.workload
     gb = args.batch or WORKLOADS[workload][3] * (args.gpus if WORKLOADS[workload][4] else 1)
-    # bounded sample: the CPU step is run at a capped batch so K+W steps end within minutes
-    sample = min(gb, args.cpu_batch)
+    # the CPU step runs the workload's own global batch (same config as our arm); --cpu-batch N caps it for a quick look
+    sample = min(gb, args.cpu_batch) if args.cpu_batch else gb
     rate, ms, cores = cpu_reference_step_rate(workload, sample, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": "FFC-GAN training images/s", "value": rate, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak" if WORKLOADS[workload][4] else "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{workload}: fgan_complete FGenerator + SN Discriminator GAN step, 3x{WORKLOADS[workload][2]}x{WORKLOADS[workload][2]}, global batch {gb}",
-                   "cpu_step_batch": sample},
+        "config": workload_config(workload, gb),
+        "notes": {"cpu_step_batch": sample, "threads": cores},
         "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} steps at batch {sample} (of global batch {gb}) of the same G+D step, oracle/train_ref.py on PyTorch CPU kernels"},
         "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -187,11 +198,27 @@ def _graph_time(fn, xs, replays=10):
 
 
 def time_fourier_unit(workload, per_rank_batch, dev):
-    """The fused FourierUnit kernels on the workload's largest unit, timed alone on the device."""
+    """The FourierUnit kernels on the workload's largest unit, timed alone on the device."""
+    C, N = max(FU_SHAPES[workload], key=lambda s: s[0] * s[1] * s[1])
+    return time_fourier_unit_shape(C, N, per_rank_batch, dev)
+
+
+def fu_roofline(fu, peak, peak_src, traffic):
+    kern = (f"fused FourierUnit forward ({fu['launches_fwd_train']} launch(es))" if fu["fused"] else
+            f"L2-staged FourierUnit forward ({fu['launches_fwd_train']} launches: rfft2 | tensor-core mix + BN statistics | BN+ReLU -> irfft2)")
+    return {"bound": "hbm", "achieved": fu["gbs_fwd_train"], "peak": peak, "unit": "GB/s", "frac": fu["gbs_fwd_train"] / peak,
+            "traffic": traffic, "peak_source": peak_src,
+            "kernel": f"{kern}, FourierUnitSN({fu['C']},{fu['C']}) @ {fu['N']}x{fu['N']}, batch {fu['B']}, training mode",
+            "algorithmic_bytes_per_launch": fu["alg_bytes_fwd"], "us_per_launch": 1000 * fu["ms_fwd_train"],
+            "eval_mode_single_pass": {"us": 1000 * fu["ms_fwd_eval"], "achieved": fu["gbs_fwd_eval"], "frac": fu["gbs_fwd_eval"] / peak},
+            "fwd_plus_bwd": {"us": 1000 * fu["ms_fwd_bwd_train"], "achieved": fu["gbs_fwd_bwd_train"], "frac": fu["gbs_fwd_bwd_train"] / peak,
+                             "algorithmic_bytes": 20.0 * fu["B"] * fu["C"] * fu["N"] * fu["N"]},
+            "timing": "CUDA events around CUDA-graph replays of the op over %d rotating inputs (> L2)" % fu["rotating_buffers"]}
+
+
+def time_fourier_unit_shape(C, N, B, dev):
     import fastfourierconvolution_b200 as ffc
     from fastfourierconvolution_b200 import _C
-    C, N = max(FU_SHAPES[workload], key=lambda s: s[0] * s[1] * s[1])
-    B = per_rank_batch
     torch.manual_seed(0)
     fu = ffc.FourierUnitSN(C, C).to(dev)
     bytes_in = 4 * B * C * N * N
@@ -221,6 +248,182 @@ def time_fourier_unit(workload, per_rank_batch, dev):
     out["gbs_fwd_eval"] = alg_f / out["ms_fwd_eval"] / 1e6
     out["gbs_fwd_bwd_train"] = alg_fb / out["ms_fwd_bwd_train"] / 1e6
     return out
+
+
+def time_generation(G, z, steps, dev, world):
+    """Pure generation (G.eval() forward, uint8 images out for the fgan generators): batch shards, no collective.  Eager launches
+    (the fgan64 / fgan128 eval epilogue reads min / max on the host, fgan64_complete.py:150-153), CUDA events, max over ranks."""
+    import torch.distributed as dist
+    was_training = G.training
+    G.eval()
+    with torch.no_grad():
+        for _ in range(3):
+            G(z)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = G(z)
+        e1.record()
+        torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    G.train(was_training)
+    return {"value": z.shape[0] * world / ms * 1000.0, "unit": "images/s", "ms_per_batch": ms, "per_gpu_batch": z.shape[0],
+            "out_dtype": str(out.dtype).replace("torch.", ""), "collectives": 0,
+            "what": "G.eval() forward on resident latents, batch sharded over the ranks (fgan_complete.py:413-427 path)"}
+
+
+# ---------------------------------------------------------------------------------------------
+# configs[0]: FFC-DCGAN generator (models/ffc_generator.py) forward + backward, batch 128 per GPU
+# ---------------------------------------------------------------------------------------------
+CFG1_BATCH = 128
+
+
+def cfg1_config(gb):
+    return {"workload": "ffcgen_cfg1: models/ffc_generator.py FFCGenerator(nz=100, nc=1, ngf=32, g_factor=0.5) forward + backward of "
+                        f"out.mean(), z (B,100,1,1) -> (B,1,64,64), batch {gb}",
+            "global_batch": gb,
+            "l2": "activations + gradients of the batch (> 200 MB) exceed the 126 MB L2"}
+
+
+def run_reference_cfg1(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    from fastfourierconvolution_b200 import harness as H
+    from oracle import ffc_ref as R
+    gb = args.batch or CFG1_BATCH * args.gpus
+    sample = min(gb, args.cpu_batch) if args.cpu_batch else gb
+    torch.manual_seed(1234)
+    torch.set_num_threads(os.cpu_count() or 1)
+    G = H.FFCGenerator(100, 1, 32); G.apply(H.weights_init)
+    P = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in G.state_dict().items()}
+    leaves = [v for v in P.values() if v.requires_grad]
+
+    def step():
+        z = torch.randn(sample, 100, 1, 1)
+        t0 = time.perf_counter()
+        out = R.ffc_generator(z, P, True)
+        torch.autograd.grad(out.mean(), leaves, allow_unused=True)
+        return time.perf_counter() - t0
+    for _ in range(args.warmup):
+        step()
+    total = sum(step() for _ in range(args.steps))
+    rate, ms, cores = sample * args.steps / total, 1000.0 * total / args.steps, torch.get_num_threads()
+    print(json.dumps({
+        "impl": "reference", "metric": "FFC-DCGAN generator fwd+bwd images/s", "value": rate, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": cfg1_config(gb), "notes": {"cpu_step_batch": sample, "threads": cores},
+        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} fwd+bwd passes at batch {sample}, oracle/ffc_ref.py ffc_generator on PyTorch CPU kernels"},
+        "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+
+
+def run_ours_cfg1(args):
+    import torch.distributed as dist
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: libffc_b200 has no CPU fallback")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    from fastfourierconvolution_b200 import _C, harness as H
+    from fastfourierconvolution_b200.harness.train import FlatGradAllReduce
+    L = _C.lib()
+    gb = args.batch or CFG1_BATCH * world
+    pb = gb // world
+    torch.manual_seed(1234 + rank)
+    G = H.FFCGenerator(100, 1, 32).to(dev).train(); G.apply(H.weights_init)
+    if world > 1:
+        for p in list(G.parameters()) + list(G.buffers()):
+            dist.broadcast(p.data, 0)
+    reduce_G = FlatGradAllReduce(G.parameters())
+    h_z = torch.randn(pb, 100, 1, 1).pin_memory()
+    z = h_z.to(dev)
+    h_loss = torch.zeros(1).pin_memory()
+
+    def step():
+        G.zero_grad(set_to_none=True)
+        loss = G(z).mean()
+        loss.backward()
+        reduce_G()
+        return loss.detach()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize(dev)
+    n0 = L.ffc_launch_count()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        static_loss = step()
+    launches = L.ffc_launch_count() - n0
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize(dev)
+
+    def resident():
+        graph.replay()
+
+    def e2e():
+        z.copy_(h_z, non_blocking=True)
+        graph.replay()
+        h_loss.copy_(static_loss.reshape(1), non_blocking=False)
+    for _ in range(max(args.warmup, 3)):
+        resident()
+
+    def timed(fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        e0.record()
+        for _ in range(args.steps):
+            fn()
+        e1.record()
+        sync_all()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms / args.steps
+    with ClockSampler(local_rank) as clk:
+        ms_res = timed(resident)
+        ms_e2e = timed(e2e)
+    gen = time_generation(G, z, args.steps, dev, world)
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        fu = time_fourier_unit_shape(32, 8, pb, dev)
+        line = {"metric": "FFC-DCGAN generator fwd+bwd images/s", "value": gb / ms_res * 1000.0, "unit": "images/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg1_config(gb),
+                "notes": {"per_gpu_batch": pb, "launch": "forward + backward replayed as one CUDA graph"},
+                "e2e": {"value": gb / ms_e2e * 1000.0, "unit": "images/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": world * h_z.numel() * 4,
+                        "d2h_bytes_per_step": world * 4},
+                "gpu_launches": int(launches * args.steps), "gpu_launches_per_step": launches, "generation": gen,
+                "roofline": fu_roofline(fu, peak, peak_src, None), "clocks": clk.summary()}
+        if not args.no_cpu_baseline and world == 1:
+            import subprocess as sp
+            r = sp.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", "ffcgen_cfg1", "--steps", str(args.cpu_steps),
+                        "--warmup", "1"], capture_output=True, text=True)
+            try:
+                line["cpu_baseline"] = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])["cpu_baseline"]
+            except Exception:
+                line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier(); torch.cuda.synchronize(dev); sys.stdout.flush(); os._exit(0)
 
 
 # largest local-branch convolution of each generator: (cin, cout, input size) of conv2.ffc.convl2l, ConvTranspose2d k4 s2 p1
@@ -360,13 +563,24 @@ def run_ours(args):
         if world > 1:
             dist.barrier(); torch.cuda.synchronize(dev); sys.stdout.flush(); os._exit(0)
         return
+    gen = time_generation(G, d_zg, args.steps, dev, world)         # every rank: generation shards the batch, no collective
     fu = time_fourier_unit(workload, pb, dev) if rank == 0 else None
     cv = time_conv_layer(workload, pb, dev) if rank == 0 else None
+    fu_all = []
+    if rank == 0:                                     # every Fourier unit of the generator at this batch, next to the headline one
+        peak0, _ = measured_peaks()
+        for (c, n) in FU_SHAPES[workload]:
+            f = fu if (c, n) == (fu["C"], fu["N"]) else time_fourier_unit_shape(c, n, pb, dev)
+            fu_all.append({"C": c, "N": n, "B": pb, "fused_single_kernel": f["fused"], "launches": f["launches_fwd_train"],
+                           "us_fwd_train": 1000 * f["ms_fwd_train"], "frac_fwd_train": f["gbs_fwd_train"] / peak0,
+                           "us_fwd_eval": 1000 * f["ms_fwd_eval"], "frac_fwd_eval": f["gbs_fwd_eval"] / peak0,
+                           "us_fwd_bwd": 1000 * f["ms_fwd_bwd_train"], "frac_fwd_bwd": f["gbs_fwd_bwd_train"] / peak0})
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, ms, cores = cpu_reference_step_rate(workload, min(gb, args.cpu_batch), args.cpu_steps, 1)
+        cb = min(gb, args.cpu_batch) if args.cpu_batch else gb
+        rate, ms, cores = cpu_reference_step_rate(workload, cb, args.cpu_steps, 1)
         cpu = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_steps} steps at batch {min(gb, args.cpu_batch)} of the same G+D training step "
+               "sample": f"{args.cpu_steps} steps at batch {cb} (the global batch) of the same G+D training step "
                          f"(oracle/train_ref.py, PyTorch CPU kernels, {ms:.0f} ms/step)"}
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -382,30 +596,20 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_res,
             "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{workload}: fgan_complete FGenerator + SN Discriminator GAN step, 3x{size}x{size}, global batch {gb}",
-                       "global_batch": gb, "per_gpu_batch": pb, "parallelism": f"dp{world} (batch shards, per-rank BatchNorm, flat-grad NCCL all-reduce)",
-                       "l2": "per-step working set (activations of batch %d, > 400 MB) exceeds the 126 MB L2; FourierUnit timing rotates %d input buffers"
-                             % (pb, fu["rotating_buffers"]),
-                       "launch": "whole step replayed as one CUDA graph" if use_graph else "eager launches",
-                       "discriminator": ("SNFFC discriminator (harness.FDiscriminatorSN64) on libffc_b200 kernels" if n_convs == "fd64" else "plain SN conv net on libffc_b200 kernels (tcgen05 conv / dgrad / wgrad at FP32 accuracy, fused bias, LeakyReLU kernel)"
-                                         if d_backend == "ffc_b200" else "plain SN conv net on PyTorch kernels (cuDNN autotuned, NHWC, %s)" % ("FP32" if d_backend == "torch_fp32" else "TF32")),
-                       "generator_params_MB": round(act_mb, 1)},
+            "config": workload_config(workload, gb),
+            "notes": {"per_gpu_batch": pb, "parallelism": f"dp{world} (batch shards, per-rank BatchNorm, flat-grad NCCL all-reduce)",
+                      "launch": "whole step replayed as one CUDA graph" if use_graph else "eager launches",
+                      "discriminator": ("SNFFC discriminator (harness.FDiscriminatorSN64) on libffc_b200 kernels" if n_convs == "fd64" else "plain SN conv net on libffc_b200 kernels (tcgen05 conv / dgrad / wgrad at FP32 accuracy, fused bias, LeakyReLU kernel)"
+                                        if d_backend == "ffc_b200" else "plain SN conv net on PyTorch kernels (cuDNN autotuned, NHWC, %s)" % ("FP32" if d_backend == "torch_fp32" else "TF32")),
+                      "generator_params_MB": round(act_mb, 1)},
             "e2e": {"value": gb / ms_e2e * 1000.0, "unit": "images/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": world * (h_zg.numel() + h_zd.numel() + h_real.numel()) * 4,
                     "d2h_bytes_per_step": world * 8},
             "gpu_launches": int(round(launches * args.steps)),
             "gpu_launches_per_step": launches,
-            "roofline": {"bound": "hbm", "achieved": fu["gbs_fwd_train"], "peak": peak, "unit": "GB/s",
-                         "frac": fu["gbs_fwd_train"] / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": f"fused FourierUnit forward ({'cooperative single-pass FuFwdCoop' if fu['launches_fwd_train'] == 1 else 'FuFwdKernel stats pass + apply pass'}, {fu['launches_fwd_train']} launch(es)) "
-                                   f"FourierUnitSN({fu['C']},{fu['C']}) @ {fu['N']}x{fu['N']}, batch {fu['B']}, training mode"
-                                   if fu["fused"] else "general-form FourierUnit forward (rfft2 | mix | BN+ReLU | irfft2)",
-                         "algorithmic_bytes_per_launch": fu["alg_bytes_fwd"],
-                         "us_per_launch": 1000 * fu["ms_fwd_train"],
-                         "eval_mode_single_pass": {"us": 1000 * fu["ms_fwd_eval"], "achieved": fu["gbs_fwd_eval"], "frac": fu["gbs_fwd_eval"] / peak},
-                         "fwd_plus_bwd": {"us": 1000 * fu["ms_fwd_bwd_train"], "achieved": fu["gbs_fwd_bwd_train"], "frac": fu["gbs_fwd_bwd_train"] / peak,
-                                          "algorithmic_bytes": 20.0 * fu["B"] * fu["C"] * fu["N"] * fu["N"]},
-                         "timing": "CUDA events around CUDA-graph replays of the op over %d rotating inputs (> L2)" % fu["rotating_buffers"]},
+            "roofline": fu_roofline(fu, peak, peak_src, traffic),
+            "fourier_units": fu_all,
+            "generation": gen,
             "clocks": clocks,
         }
         tpeak, tpeak_src = tensor_peak_tf32()
@@ -440,15 +644,17 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
-    ap.add_argument("--workload", default="fgan32", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="fgan32", choices=sorted(WORKLOADS) + ["ffcgen_cfg1"])
     ap.add_argument("--batch", type=int, default=0, help="global batch (default: the workload's)")
-    ap.add_argument("--cpu-batch", type=int, default=64, help="batch of the bounded CPU sample")
-    ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--cpu-batch", type=int, default=0, help="cap on the batch of the CPU step (default 0: the workload's global batch)")
+    ap.add_argument("--cpu-steps", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-step", action="store_true", help="run the warm-up and the timed steps only (for ncu launch lists)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "ffcgen_cfg1":
+        (run_reference_cfg1 if args.impl == "reference" else run_ours_cfg1)(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -83,21 +83,30 @@ _lib: Optional[Library] = None
 _lock = threading.Lock()
 
 
+ABI_VERSION = 200          # ffc_version() of the library this binding was written for (csrc/ffc_api.cu)
+
+
 def lib() -> Library:
-    """The CUDA library; built in-tree with nvcc on first use when missing or stale."""
+    """The CUDA library; (re)built in-tree with nvcc on first use when it is missing or was built from other sources
+    than the ones present (content hash, build.is_stale).  A stale library that cannot be rebuilt is an error: the
+    ctypes signatures below would otherwise be applied to whatever symbols the old binary has."""
     global _lib
     if _lib is None:
         with _lock:
             if _lib is None:
-                if not os.path.exists(LIB_PATH):
-                    from . import build as _build
+                from . import build as _build
+                if _build.is_stale():
                     try:
                         _build.build()
                     except Exception as e:  # no nvcc either: nothing can run
                         raise RuntimeError(
-                            f"libffc_b200.so is missing ({LIB_PATH}) and could not be built: {e}. "
+                            f"libffc_b200.so is missing or stale ({LIB_PATH}) and could not be built: {e}. "
                             "This package has no CPU or PyTorch fallback.") from e
-                _lib = Library(LIB_PATH)
+                L = Library(LIB_PATH)
+                if L.ffc_version() != ABI_VERSION:
+                    raise RuntimeError(f"{LIB_PATH} reports ABI version {L.ffc_version()}, this binding needs {ABI_VERSION}: "
+                                       "rebuild with `python -m fastfourierconvolution_b200.build --force`")
+                _lib = L
     return _lib
 
 
@@ -124,13 +133,21 @@ def ptr(t: Optional[torch.Tensor]) -> c_void_p:
 
 
 _workspaces = {}
+_retired = []      # buffers a CUDA-graph capture has seen: replays keep using them, so they are never freed
 
 
 def workspace(nbytes: int, device) -> torch.Tensor:
-    """Scratch buffer owned by PyTorch's allocator, one per (device, stream), grown on demand."""
-    key = (str(device), current_stream(device).value)
+    """Scratch buffer owned by PyTorch's allocator, one per (device, stream, capturing?), grown on demand.
+
+    Buffers requested while a CUDA graph is being captured live in the graph's private pool and are baked into the graph:
+    they get their own cache entries (an eager call never writes into them) and are kept alive for the life of the
+    process when a later, larger request replaces them."""
+    capturing = torch.cuda.is_current_stream_capturing() if torch.cuda.is_available() else False
+    key = (str(device), current_stream(device).value, capturing)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
+        if ws is not None and capturing:
+            _retired.append(ws)
         ws = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws

@@ -32,11 +32,26 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
 
 
+def source_hash() -> str:
+    """Content hash of every source the library is built from (independent of file times, which a copy of the working
+    tree to another machine does not preserve)."""
+    import hashlib
+    h = hashlib.sha256()
+    for s in sources():
+        h.update(os.path.basename(s).encode())
+        with open(s, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def is_stale(target: str = LIB) -> bool:
-    if not os.path.exists(target):
+    """True when the library is missing or was built from other sources than the ones present (hash stamp beside it)."""
+    stamp = target + ".stamp"
+    if not os.path.exists(target) or not os.path.exists(stamp):
         return True
-    t = os.path.getmtime(target)
-    return any(os.path.getmtime(s) > t for s in sources() + [os.path.abspath(__file__)])
+    with open(stamp) as f:
+        return f.read().strip() != source_hash()
 
 
 def find_nvcc() -> str:
@@ -74,6 +89,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if r.returncode != 0:
         raise RuntimeError("nvcc link failed:\n" + r.stdout + r.stderr)
     os.replace(LIB + ".tmp", LIB)
+    with open(LIB + ".stamp", "w") as f:
+        f.write(source_hash() + "\n")
     if verbose:
         sys.stderr.write(log)
     return LIB

@@ -14,7 +14,7 @@ void ffc_set_error(const char* fmt, ...) {
 
 extern "C" const char* ffc_last_error(void) { return g_ffc_error; }
 
-extern "C" int ffc_version(void) { return 100; }   // 0.1.0
+extern "C" int ffc_version(void) { return 200; }   // 0.2.0 (ABI version: _C.ABI_VERSION must match)
 
 // 1 when this shared object is the host emulation build used by tests/ (never shipped as product)
 extern "C" int ffc_is_emulation(void) {

@@ -454,13 +454,13 @@ struct SeDxKernel {
 // ---------------------------------------------------------------------------------------------
 static int ew_grid(long long work_items, int threads) {
     long long g = (work_items + threads - 1) / threads;
-    const long long cap = 148LL * 16;            // grid-stride beyond 16 CTAs per SM
+    const long long cap = (long long)ffc_sm_count() * 16;            // grid-stride beyond 16 CTAs per SM
     if (g > cap) g = cap;
     if (g < 1) g = 1;
     return (int)g;
 }
 static int reduce_split(int C, long long per_channel) {
-    int ns = (int)((2 * 148 + C - 1) / C);       // aim at >= 2 CTAs per SM in total
+    int ns = (int)((2 * ffc_sm_count() + C - 1) / C);       // aim at >= 2 CTAs per SM in total
     const long long maxs = (per_channel + 4 * FFC_RED_THREADS - 1) / (4 * FFC_RED_THREADS);
     if (ns > maxs) ns = (int)maxs;
     if (ns < 1) ns = 1;

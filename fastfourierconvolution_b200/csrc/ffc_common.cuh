@@ -112,10 +112,33 @@ static int ffc_launch_coop(int gx, int nt, size_t smem_bytes, ffc_stream_t, cons
     return FFC_OK;
 }
 template <class K> static int ffc_coop_capacity_blocks(int, size_t) { return 1 << 30; }
+static inline int ffc_sm_count() { return 148; }
 static inline int ffc_memset_async(void* p, int v, size_t n, ffc_stream_t) { memset(p, v, n); return FFC_OK; }
 #else
 // ------------------------------------------------------------------ launch (device)
 #include <type_traits>
+// Per-device launch state.  cudaFuncSetAttribute applies to the CURRENT device only, so the "already raised to N bytes"
+// high-water marks are kept per device (one process may drive several GPUs, e.g. nn.DataParallel, train_cond.py:67-68).
+#define FFC_MAX_DEVICES 64
+struct FfcPerDevice { size_t v[FFC_MAX_DEVICES]; };
+static inline size_t* ffc_device_slot(FfcPerDevice& s) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    return &s.v[dev % FFC_MAX_DEVICES];
+}
+// multiprocessors of the current device (grids are sized in multiples of it)
+static inline int ffc_sm_count() {
+    static int cached[FFC_MAX_DEVICES] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    int& c = cached[dev % FFC_MAX_DEVICES];
+    if (c <= 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        c = n;
+    }
+    return c;
+}
 // optional K::kMinBlocks (resident CTAs per SM the register allocation must allow); default 1
 template <class K, class = void> struct FfcMinBlocks { static constexpr int v = 1; };
 template <class K> struct FfcMinBlocks<K, std::void_t<decltype(K::kMinBlocks)>> { static constexpr int v = K::kMinBlocks; };
@@ -137,8 +160,9 @@ static int ffc_launch(int gx, int gy, int gz, int nt, size_t smem_bytes, ffc_str
     }
     // Kernels that stage tiles in shared memory: raise the dynamic limit and ask for the largest shared
     // carve-out so that occupancy is not capped by the default L1/shared split (set once per high-water mark;
-    // a benign race if two host threads launch the same kernel for the first time).
-    static size_t configured_smem = 0;
+    // per device; a benign race if two host threads launch the same kernel for the first time).
+    static FfcPerDevice configured = {};
+    size_t& configured_smem = *ffc_device_slot(configured);
     if (smem_bytes > 16 * 1024 && smem_bytes > configured_smem) {
         cudaError_t e = cudaSuccess;
         if (smem_bytes > 48 * 1024)
@@ -167,7 +191,8 @@ __global__ void __launch_bounds__(K::kThreads, FfcMinBlocks<K>::v) ffc_kernel_co
 // how many CTAs of this kernel can be resident at once on the current device (0 on error)
 template <class K>
 static int ffc_coop_capacity_blocks(int nt, size_t smem_bytes) {
-    static size_t configured_smem = 0;
+    static FfcPerDevice configured = {};
+    size_t& configured_smem = *ffc_device_slot(configured);
     if (smem_bytes > configured_smem) {
         if (smem_bytes > 48 * 1024 &&
             cudaFuncSetAttribute(ffc_kernel_coop<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) return 0;

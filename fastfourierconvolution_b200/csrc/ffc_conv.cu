@@ -897,7 +897,7 @@ extern "C" int ffc_conv2d_wgrad(const float* S, const float* L, float* dW,
     const int BMt = 64, BNt = ref ? 64 : 128;
     const int gx = ffc_cdiv(SC, BMt), gy = ffc_cdiv(LC * k * k, BNt);
     // split K so that the grid has ~3 CTAs per SM (148 SMs), at least 8 K-steps per CTA
-    int nsplit = ffc_cdiv(3 * 148, gx * gy);
+    int nsplit = ffc_cdiv(3 * ffc_sm_count(), gx * gy);
     const int max_split = ffc_cdiv(Ktot, 8 * FFC_CONV_BK);
     if (nsplit > max_split) nsplit = max_split;
     if (nsplit < 1) nsplit = 1;

@@ -286,7 +286,7 @@ int conv1x1_narrow_run(const float* x, const float* w, int cin, const float* bia
     p.bias = bias; p.addend = addend; p.y = y; p.B = B; p.cout = cout; p.Hi = Hi; p.Wi = Wi; p.Ho = Hi; p.Wo = Wi;
     p.k = 1; p.stride = 1; p.pad = 0; p.transposed = transposed;
     const long long total = (long long)B * (Hi * Wi / 4);
-    int grid = (int)((total + 255) / 256); if (grid > 148 * 8) grid = 148 * 8; if (grid < 1) grid = 1;
+    int grid = (int)((total + 255) / 256); if (grid > ffc_sm_count() * 8) grid = ffc_sm_count() * 8; if (grid < 1) grid = 1;
     const int c4 = (cout + 3) / 4;
     const size_t smem = (size_t)cin * c4 * 16;
     switch (c4) {
@@ -311,13 +311,13 @@ bool conv_small_supported(int cin0, int cin1, int cout, int k) {
 template <int K>
 static int conv_small_launch(const SmallConvParams& p, ffc_stream_t st) {
     const long long total = (long long)p.B * p.Ho * p.Wo;
-    int grid = (int)((total + 255) / 256); if (grid > 148 * 16) grid = 148 * 16; if (grid < 1) grid = 1;
+    int grid = (int)((total + 255) / 256); if (grid > ffc_sm_count() * 16) grid = ffc_sm_count() * 16; if (grid < 1) grid = 1;
     cudaError_t e;
     const uintptr_t al = (uintptr_t)p.x[0] | (uintptr_t)p.x[1] | (uintptr_t)p.y | (uintptr_t)p.addend;
     if (p.cout <= 4 && K == 3 && p.stride == 1 && p.pad == 1 && p.Ho == p.Hi && p.Wo == p.Wi && p.Wi % 4 == 0 && (al & 15) == 0) {
         const size_t smem = (size_t)(p.cin[0] + (p.nseg > 1 ? p.cin[1] : 0)) * 9 * 16 + 64 * 16 * 16;
         if (smem > 48 * 1024) cudaFuncSetAttribute(conv_small_cout_k3s1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int g4 = (int)((total / 4 + 63) / 64); if (g4 > 148 * 16) g4 = 148 * 16; if (g4 < 1) g4 = 1;
+        int g4 = (int)((total / 4 + 63) / 64); if (g4 > ffc_sm_count() * 16) g4 = ffc_sm_count() * 16; if (g4 < 1) g4 = 1;
         conv_small_cout_k3s1_kernel<<<g4, 256, smem, st>>>(p);
     } else if (p.cout <= 4) {
         const size_t smem = (size_t)(p.cin[0] + (p.nseg > 1 ? p.cin[1] : 0)) * K * K * 16;
@@ -468,7 +468,7 @@ int wgrad_small_run(const float* S, const float* L, float* dW, int B, int SC, in
                     int k, int stride, int pad, ffc_stream_t st) {
     SmallWgradParams p{S, L, dW, B, SC, LC, Hs, Ws, Hl, Wl, stride, pad, 1};
     // ~4 CTAs per SM; each CTA reduces `imgs` images of one large-side channel
-    int groups = ffc_cdiv(4 * 148, LC); if (groups > B) groups = B; if (groups < 1) groups = 1;
+    int groups = ffc_cdiv(4 * ffc_sm_count(), LC); if (groups > B) groups = B; if (groups < 1) groups = 1;
     p.imgs = ffc_cdiv(B, groups);
     groups = ffc_cdiv(B, p.imgs);
     const dim3 grid(LC, groups);

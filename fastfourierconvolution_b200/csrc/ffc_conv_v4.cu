@@ -413,7 +413,7 @@ extern "C" int ffc_conv2d_fwd_ws(const float* x0, const float* w0, int cin0,
     pp.transposed = transposed; pp.ncls = pl.ncls;
     for (int c = 0; c < FFC_V4_MAXCLS; ++c) pp.cls_off[c] = pl.cls_off[c];
     const long long per_cls = (long long)k * k * (pl.cpad[0] + pl.cpad[1]) * pl.npad;
-    int gx = (int)((per_cls + 255) / 256); if (gx > 148 * 8) gx = 148 * 8; if (gx < 1) gx = 1;
+    int gx = (int)((per_cls + 255) / 256); if (gx > ffc_sm_count() * 8) gx = ffc_sm_count() * 8; if (gx < 1) gx = 1;
     FFC_CHECK((ffc_launch<PackWeightsKernel>(gx, pl.ncls, 1, 256, 0, st, pp)));
     ConvV4Params p;
     p.x[0] = x0; p.x[1] = x1; p.cin[0] = cin0; p.cin[1] = cin1; p.cpad[0] = pl.cpad[0]; p.cpad[1] = pl.cpad[1]; p.nseg = x1 ? 2 : 1;

@@ -377,7 +377,7 @@ int conv_v5_run_block(const float* x0, const float* w0, const float* w0b, int ci
     pp.k = k; pp.stride = stride; pp.pad = pad; pp.transposed = transposed; pp.w0b = w0b; pp.cout0 = cout0;
     for (int c = 0; c < FFC_V5_MAXCLS; ++c) pp.cls_off[c] = pl.cls_off[c];
     const long long per_cls = (long long)k * k * (pl.cps[0] + pl.cps[1]) * V5_BK * ((cout + 15) / 16 * 16);
-    int gx = (int)((per_cls + 255) / 256); if (gx > 148 * 4) gx = 148 * 4; if (gx < 1) gx = 1;
+    int gx = (int)((per_cls + 255) / 256); if (gx > ffc_sm_count() * 4) gx = ffc_sm_count() * 4; if (gx < 1) gx = 1;
     pack_v5_kernel<<<dim3(gx, pl.ncls), 256, 0, st>>>(pp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { ffc_set_error("pack_v5 launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
@@ -402,7 +402,8 @@ int conv_v5_run_block(const float* x0, const float* w0, const float* w0b, int ci
     if (nsb < 2) nsb = 2;
     p.nsb = nsb;
     const size_t smem = (size_t)nsb * stage_b + 256;
-    static size_t configured = 0;
+    static FfcPerDevice configured_dev = {};
+    size_t& configured = *ffc_device_slot(configured_dev);
     if (smem > configured) {
         e = cudaFuncSetAttribute(conv_v5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_v5_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -420,8 +421,8 @@ int conv_v5_run_block(const float* x0, const float* w0, const float* w0b, int ci
             const int n = g.Ta * g.Tb * (pl.cps[0] + pl.cps[1]);
             if (n < min_chunks) min_chunks = n;
         }
-        if (slope == 1.f && ctas * 2 <= 148) {
-            ksplit = 148 / ctas;
+        if (slope == 1.f && ctas * 2 <= ffc_sm_count()) {
+            ksplit = ffc_sm_count() / ctas;
             if (ksplit > min_chunks / 8) ksplit = min_chunks / 8;
             if (ksplit > 16) ksplit = 16;
             if (ksplit < 1) ksplit = 1;

@@ -281,7 +281,8 @@ static int fu2_launch(const Fu2Params& p, ffc_stream_t st) {
     if (per_sm > 2048 / pl.nt) per_sm = 2048 / pl.nt;
     if (per_sm > Fu2Cfg<N, CP>::kMinBlocks) per_sm = Fu2Cfg<N, CP>::kMinBlocks;
     if (per_sm < 1) per_sm = 1;
-    const int grid = p.B < 148 * per_sm ? p.B : 148 * per_sm;
+    const int sms = ffc_sm_count();
+    const int grid = p.B < sms * per_sm ? p.B : sms * per_sm;
     if (p.training) {
         FFC_CHECK(ffc_memset_async(p.sums, 0, (size_t)4 * p.Cout * sizeof(double), st));
         if (!ffc_fu2_force_two_pass && p.B <= ffc_coop_capacity_blocks<Fu2Coop<N, CP>>(pl.nt, pl.smem))

@@ -392,7 +392,7 @@ static FuPlan fu_plan(int B, int Cin, int Cout) {
             if (per_sm > by_threads) per_sm = by_threads;
             if (per_sm > 8) per_sm = 8;
             if (per_sm < 1) per_sm = 1;
-            pl.grid = ntiles < 148 * per_sm ? ntiles : 148 * per_sm;
+            pl.grid = ntiles < ffc_sm_count() * per_sm ? ntiles : ffc_sm_count() * per_sm;
             return pl;
         }
     }

@@ -192,7 +192,7 @@ extern "C" int ffc_spectral_norm_fwd(const float* w_orig, float* u, float* v, fl
     p.t = (float*)(((uintptr_t)workspace + 15) & ~(uintptr_t)15); p.s = p.t + w;
     p.h = h; p.w = w; p.kk = kk; p.power_iteration = power_iteration ? 1 : 0; p.eps = eps;
     const int colblocks = ffc_cdiv(w, SN_THREADS);
-    int rsplit = ffc_cdiv(2 * 148, colblocks);
+    int rsplit = ffc_cdiv(2 * ffc_sm_count(), colblocks);
     if (rsplit > ffc_cdiv(h, 16)) rsplit = ffc_cdiv(h, 16);
     if (rsplit < 1) rsplit = 1;
     p.rows_per_split = ffc_cdiv(h, rsplit);
@@ -203,6 +203,6 @@ extern "C" int ffc_spectral_norm_fwd(const float* w_orig, float* u, float* v, fl
     }
     FFC_CHECK((ffc_launch<SnRowKernel>(ffc_cdiv(h, SnRowKernel::kRows), 1, 1, SN_THREADS, SnRowKernel::smem_bytes(), st, p)));
     long long items = ((long long)h * w + SN_THREADS - 1) / SN_THREADS;
-    if (items > 148 * 8) items = 148 * 8;
+    if (items > ffc_sm_count() * 8) items = ffc_sm_count() * 8;
     return ffc_launch<SnScaleKernel>((int)items, 1, 1, SN_THREADS, SnScaleKernel::smem_bytes(), st, p);
 }

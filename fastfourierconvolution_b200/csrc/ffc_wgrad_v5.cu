@@ -241,13 +241,14 @@ int wgrad_v5_run(const float* S, const float* L, float* dW, int B, int SC, int L
     const int mtiles = ffc_cdiv(LC * k * k, 128);
     const int Ktot = B * Hs * Ws, kchunks = ffc_cdiv(Ktot, WG5_BK);
     // split K so that the grid has ~2 CTAs per SM, at least 8 chunks per CTA
-    int ksplit = ffc_cdiv(2 * 148, mtiles * ntiles);
+    int ksplit = ffc_cdiv(2 * ffc_sm_count(), mtiles * ntiles);
     if (ksplit > kchunks / 8) ksplit = kchunks / 8;
     if (ksplit < 1) ksplit = 1;
     p.chunks_per_split = ffc_cdiv(kchunks, ksplit);
     ksplit = ffc_cdiv(kchunks, p.chunks_per_split);
     const size_t smem = (size_t)WG5_SB * 2 * p.nt_full * WG5_BK * 4 + 256;
-    static size_t configured = 0;
+    static FfcPerDevice configured_dev = {};
+    size_t& configured = *ffc_device_slot(configured_dev);
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(wgrad_v5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { ffc_set_error("cudaFuncSetAttribute(wgrad_v5, %zu B): %s", smem, cudaGetErrorString(e)); return FFC_ERR_CUDA; }

@@ -4,6 +4,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 from torch.nn.utils.spectral_norm import SpectralNorm as _SpectralNorm
+from torch.nn.utils.weight_norm import WeightNorm as _WeightNorm
 
 from .. import ops
 
@@ -23,7 +24,9 @@ def effective_weight(mod: nn.Module) -> torch.Tensor:
             w = ops.spectral_norm_weight(mod.weight_orig, mod.weight_u, mod.weight_v, mod.training, hook.eps, hook.dim)
             setattr(mod, "weight", w)                 # what the hook leaves behind for other readers of mod.weight
             return w
-        hook(mod, (None,))
+        if isinstance(hook, (_SpectralNorm, _WeightNorm)) and getattr(hook, "name", None) == "weight":
+            hook(mod, (None,))       # a non-standard spectral norm / weight norm: let the hook itself recompute mod.weight
+        # any other forward-pre-hook (user, profiler, framework) is not ours to fire: mod.forward is never called here
     return mod.weight
 
 

@@ -3,12 +3,17 @@
 Each Function is one primitive of the FFC hot path with a hand-written forward and backward; the
 nn.Modules in ``fastfourierconvolution_b200.layers`` compose them exactly where the reference
 composes ATen ops.  PyTorch is used for memory, streams and the autograd tape only.
+
+Every backward is ``once_differentiable``: the gradients are written by kernels into fresh tensors, so a double
+backward (``create_graph=True``: gradient penalties such as benchmark_models/sagan/trainer.py:136) raises instead of
+silently returning a cut graph.  The FFC hot path of the reference's own scripts (hinge losses) never needs it.
 """
 from __future__ import annotations
 
 from typing import Optional
 
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _C
 
@@ -69,6 +74,7 @@ class Conv2dFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dy):
         x0, w0, x1, w1 = ctx.saved_tensors
         return _conv_backward(ctx.cfg, x0, w0, x1, w1, dy, ctx.needs_input_grad)
@@ -153,6 +159,7 @@ class ConvBlockFn(torch.autograd.Function):
         return y0, y1
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dy0, dy1):
         x0, w00, w01, x1, w10 = ctx.saved_tensors
         stride, pad, transposed, k, cout0, cout1, has_b0, has_b1 = ctx.cfg
@@ -233,6 +240,7 @@ class ConvActFn(torch.autograd.Function):
         return a
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, da):
         x, w, a = ctx.saved_tensors
         act, slope = ctx.act
@@ -286,6 +294,7 @@ class SpectralNormFn(torch.autograd.Function):
         return w_eff
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g):
         w_orig, u_s, v_s, sigma = ctx.saved_tensors
         g = g.contiguous()
@@ -336,6 +345,7 @@ class BnActFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dy):
         x, gamma, beta, save_mean, save_invstd = ctx.saved_tensors
         norm, training, act, slope = ctx.cfg
@@ -389,6 +399,7 @@ class Rfft2Fn(torch.autograd.Function):
         return _rfft2(x.contiguous(), 0)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dspec):
         return _irfft2(dspec.contiguous(), None, 1)
 
@@ -403,6 +414,7 @@ class Irfft2Fn(torch.autograd.Function):
         return _irfft2(spec.contiguous(), _c(residual), 0)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dout):
         dout = dout.contiguous()
         dspec = _rfft2(dout, 1) if ctx.needs_input_grad[0] else None
@@ -437,6 +449,7 @@ class BnReluIrfft2Fn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dout):
         spec, gamma, beta, save_mean, save_invstd = ctx.saved_tensors
         training, has_res = ctx.cfg
@@ -502,6 +515,7 @@ class FusedFuFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dout):
         x, weight, gamma, beta, save_mean, save_invstd = ctx.saved_tensors
         training, has_res = ctx.cfg
@@ -576,6 +590,7 @@ class SeFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dy):
         x, w1, w2, mean, hidden, gate = ctx.saved_tensors
         dy = dy.contiguous()

@@ -37,6 +37,53 @@ Branch = Union[Tensor, int]
 
 
 # --------------------------------------------------------------------------------------
+# activation tape (for the parity tests' mask-flip analysis, SURVEY.md section 8(c) caveat 1)
+# --------------------------------------------------------------------------------------
+class ActTape:
+    """Records the pre-activation of every ReLU / LeakyReLU site of one oracle run, in call order, and lets a later run
+    use a prescribed 0/1 mask at chosen sites instead of ``x > 0``.
+
+    Two FP32-accurate evaluations of the same network round a pre-activation that is ~0 to different sides of the
+    kink now and then; the forward value does not notice, the gradient does (one flipped element of ~400k moved dX by
+    2e-2).  The tests use this tape to (1) list the elements close enough to the kink to flip and (2) obtain the exact
+    gradient change each such flip causes, so that the 1e-4 bound can be held on everything else.
+
+        with ActTape() as t:            # record
+            out = fgenerator(z, P, True)
+        with ActTape({3: mask}) as t2:  # replay with site 3's mask prescribed (bool tensor of the site's shape)
+            ...
+    """
+    current: "Optional[ActTape]" = None
+
+    def __init__(self, overrides=None):
+        self.overrides = dict(overrides or {})
+        self.pre = []                     # detached pre-activations, one per site
+
+    def __enter__(self):
+        assert ActTape.current is None, "ActTape is not re-entrant"
+        ActTape.current = self
+        return self
+
+    def __exit__(self, *exc):
+        ActTape.current = None
+        return False
+
+
+def _kinked(x: Tensor, slope: float) -> Tensor:
+    """ReLU (slope 0) / LeakyReLU(slope): every non-smooth activation of the oracle goes through here."""
+    t = ActTape.current
+    if t is None:
+        return F.relu(x) if slope == 0.0 else F.leaky_relu(x, slope)
+    idx = len(t.pre)
+    t.pre.append(x.detach())
+    mask = t.overrides.get(idx)
+    if mask is None:
+        mask = x.detach() > 0
+    m = mask.to(x.dtype)
+    return x * (m + slope * (1.0 - m)) if slope != 0.0 else x * m
+
+
+# --------------------------------------------------------------------------------------
 # configuration records
 # --------------------------------------------------------------------------------------
 @dataclass(frozen=True)
@@ -97,9 +144,9 @@ def activation(x: Tensor, act: str) -> Tensor:
     if act == "identity":
         return x
     if act == "relu":
-        return F.relu(x)
+        return _kinked(x, 0.0)
     if act == "leaky_relu":            # ffc_bn_act.py:66-67 -> LeakyReLU(0.1)
-        return F.leaky_relu(x, 0.1)
+        return _kinked(x, 0.1)
     if act == "gelu":
         return F.gelu(x)
     if act == "tanh":
@@ -151,7 +198,7 @@ def fourier_unit(x: Tensor, P: Params, pre: str, training: bool) -> Tensor:
     # :45  1x1 channel mix, no bias
     y = F.conv2d(s, P[pre + "conv_layer.weight"])
     # :49  BN (batch stats over b,h,wf in training) + ReLU
-    y = F.relu(batch_norm(y, P, pre + "bn.", training))
+    y = _kinked(batch_norm(y, P, pre + "bn.", training), 0.0)
     # :51-53  back to complex
     y = y.reshape(b, -1, 2, h, y.shape[-1])
     yc = torch.complex(y[:, :, 0].contiguous(), y[:, :, 1].contiguous())
@@ -165,7 +212,7 @@ def fourier_unit(x: Tensor, P: Params, pre: str, training: bool) -> Tensor:
 def se_layer(x: Tensor, P: Params, pre: str) -> Tensor:
     b, c = x.shape[:2]
     y = x.mean(dim=(2, 3))                                             # AdaptiveAvgPool2d(1)
-    y = F.relu(F.linear(y, P[pre + "fc.0.weight"]))
+    y = _kinked(F.linear(y, P[pre + "fc.0.weight"]), 0.0)
     y = torch.sigmoid(F.linear(y, P[pre + "fc.2.weight"]))
     return x * y.view(b, c, 1, 1)
 
@@ -181,7 +228,7 @@ def spectral_transform(x: Tensor, P: Params, pre: str, stride: int, upsample: bo
         x = F.avg_pool2d(x, kernel_size=2, stride=2)
     x = se_layer(x, P, pre + "se_block.")                             # :87
     w1 = _weight(P, pre + "conv1.", training, sn)
-    x = F.relu(batch_norm(F.conv2d(x, w1), P, pre + "bn1.", training))  # :89
+    x = _kinked(batch_norm(F.conv2d(x, w1), P, pre + "bn1.", training), 0.0)  # :89
     f = fourier_unit(x, P, pre + "fu.", training)                     # :91
     w2 = _weight(P, pre + "conv2.", training, sn)
     return F.conv2d(x + f, w2)                                         # :108 (LFU term commented out)
@@ -322,7 +369,7 @@ def sn_discriminator(x: Tensor, P: Params, training: bool, n_convs: int = 7, mg:
         pre = f"conv{i}."
         w = spectral_norm_weight(P, pre, training)
         k = w.shape[-1]
-        m = F.leaky_relu(F.conv2d(m, w, P[pre + "bias"], 1 if k == 3 else 2, 1), 0.1)
+        m = _kinked(F.conv2d(m, w, P[pre + "bias"], 1 if k == 3 else 2, 1), 0.1)
     w = spectral_norm_weight(P, "fc.", training)
     return F.linear(m.reshape(-1, mg * mg * 512), w, P["fc.bias"])
 

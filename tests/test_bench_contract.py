@@ -34,3 +34,16 @@ def test_reference_arm_runs_the_snffc_discriminator_workload():
     assert r.returncode == 0, r.stderr[-2000:]
     d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
     assert d["impl"] == "reference" and d["config"]["workload"].startswith("fgan64_snffc") and d["scaling"] == "weak"
+
+
+def test_reference_arm_runs_config0_at_the_workload_batch_by_default():
+    """configs[0] (bench.py --workload ffcgen_cfg1) and: without --cpu-batch the CPU arm runs the workload's own batch, so the
+    ``config`` object equals our arm's (the driver's same_config check)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "ffcgen_cfg1",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert d["config"] == bench.cfg1_config(128) and d["notes"]["cpu_step_batch"] == 128
+    assert bench.workload_config("fgan32", 256)["global_batch"] == 256
