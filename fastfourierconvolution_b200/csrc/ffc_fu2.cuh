@@ -19,8 +19,8 @@ template <int N>
 struct Fu2G {
     static constexpr int M = N / 2, Wf = M + 1, RS = N + 4, SPS = RS / 2, BINS = N * Wf;
     static constexpr int REGION = N * RS;
-    static constexpr int N1 = (N == 16) ? 4 : 8, N2 = N / N1;
-    static_assert(N == 8 || N == 16 || N == 32, "Fu2G: N in {8,16,32}");
+    static constexpr int N1 = (N == 16) ? 4 : 8, N2 = N / N1;       // 64 = 8 x 8 and 128 = 8 x 16 serve the L2-staged form (ffc_fu3.cu)
+    static_assert(N == 8 || N == 16 || N == 32 || N == 64 || N == 128, "Fu2G: N in {8,16,32,64,128}");
     static_assert((RS / 4) % 2 == 1, "row stride must be an odd number of float4");
 };
 

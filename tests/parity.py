@@ -132,7 +132,96 @@ def _grad_floor(k, ref):
     return 0.0
 
 
-def flip_aware_compare(got, oracle_run, ref=None, tol=TOL, out_tol=None, margins=(4e-6, 4e-5), max_flips=40, what=""):
+def _fit_flips(AtA, Atb, lo, hi):
+    """Integer flip indicators c (lo <= c_e <= hi) that minimise |d - A c|_2, by greedy coordinate moves of +-1 in the Gram
+    representation (AtA = A^T A, Atb = A^T d).  Robust to (nearly) collinear candidates -- e.g. the four copies a nearest-x2
+    upsampling makes of one pre-activation -- where rounding an unconstrained least-squares solution is not."""
+    K = Atb.numel()
+    c = torch.zeros(K, dtype=torch.float64)
+    g = Atb.clone()                                 # A^T (d - A c)
+    diag = torch.diagonal(AtA)
+    for _ in range(4 * K + 8):
+        # moving c_e by s in {+1, -1} changes |r|^2 by diag_e - 2 s g_e
+        gain_p = torch.where(c < hi, 2 * g - diag, torch.full_like(g, -1.0))
+        gain_m = torch.where(c > lo, -2 * g - diag, torch.full_like(g, -1.0))
+        bp, bm = int(torch.argmax(gain_p)), int(torch.argmax(gain_m))
+        if gain_p[bp] <= 0 and gain_m[bm] <= 0:
+            break
+        if gain_p[bp] >= gain_m[bm]:
+            c[bp] += 1; g -= AtA[:, bp]
+        else:
+            c[bm] -= 1; g += AtA[:, bm]
+    return c
+
+
+def flip_aware_errors(got, oracle_run, ref=None, margins=(2e-6, 1e-5, 5e-5), max_flips=128, good=TOL, cache=None):
+    """Max-norm errors (max|d| / max|ref| per tensor) of ``got`` after accounting for activation-mask flips; no assertion.
+    Returns (errs, n_flips, plain_errs).  See flip_aware_compare.  ``cache`` (a dict) shares the oracle's base run and the
+    per-candidate gradient responses between several calls on the same oracle_run."""
+    cache = {} if cache is None else cache
+    if "base" not in cache:
+        cache["base"] = oracle_run({})
+    res0, tape = cache["base"]
+    against_fixture = ref is not None
+    ref = res0 if ref is None else ref
+    keys = [k for k in ref if k.startswith(("out", "din", "grad/", "post/")) and k in res0
+            and torch.as_tensor(ref[k]).is_floating_point() and torch.as_tensor(ref[k]).numel() > 0]
+    for k in keys:
+        assert k in got and got[k] is not None, f"{k} missing in the results under test"
+    is_grad = lambda k: k.startswith(("din", "grad/"))
+    scale = {k: max(float(torch.as_tensor(ref[k]).double().abs().max()), _grad_floor(k, ref), 1e-30) for k in keys}
+    diff = {k: (torch.as_tensor(got[k]).detach().double().cpu() - torch.as_tensor(ref[k]).double()).reshape(-1) / scale[k] for k in keys}
+    plain = {k: float(d.abs().max()) if d.numel() else 0.0 for k, d in diff.items()}
+    gkeys = [k for k in keys if is_grad(k)]
+    if all(plain[k] <= good for k in gkeys):
+        return dict(plain), 0, plain
+    if "ranked" not in cache:
+        ranked = []
+        for i, pre in enumerate(tape.pre):
+            a = pre.abs().reshape(-1)
+            if a.numel() == 0:
+                continue
+            rms = max(float(a.double().pow(2).mean().sqrt()), 1e-300)       # RMS of the site
+            for j in torch.nonzero(a < margins[-1] * rms).reshape(-1).tolist():
+                ranked.append((float(a[j]) / rms, i, j))
+        ranked.sort()
+        cache["ranked"], cache["cols"] = ranked[:max_flips], {}
+    ranked, colcache = cache["ranked"], cache["cols"]
+    best = (dict(plain), 0)
+    for margin in margins:
+        cand = [r for r in ranked if r[0] < margin]
+        if not cand:
+            continue
+        cols = []
+        for _, i, j in cand:
+            if (i, j) not in colcache:
+                mask = (tape.pre[i] > 0).clone()
+                mask.view(-1)[j] = ~mask.view(-1)[j]
+                res_e, _ = oracle_run({i: mask})
+                # response of every gradient to this one flip, in units of the ORACLE's own maxima (rescaled per call below)
+                colcache[(i, j)] = {k: (res_e[k].double() - res0[k].double()).reshape(-1).float() for k in res0 if is_grad(k)}
+            cols.append(colcache[(i, j)])
+        K = len(cols)
+        AtA = torch.zeros(K, K, dtype=torch.float64)
+        Atb = torch.zeros(K, dtype=torch.float64)
+        mats = {}
+        for k in gkeys:
+            mats[k] = torch.stack([c[k] for c in cols], 1).double() / scale[k]
+            AtA += mats[k].T @ mats[k]
+            Atb += mats[k].T @ diff[k]
+        cr = _fit_flips(AtA, Atb, -1.0 if against_fixture else 0.0, 1.0)
+        fixed = dict(plain)
+        for k in gkeys:
+            fixed[k] = float((diff[k] - mats[k] @ cr).abs().max()) if diff[k].numel() else 0.0
+        if max(fixed[k] for k in gkeys) < max(best[0][k] for k in gkeys):
+            best = (fixed, int((cr != 0).sum()))
+        if all(fixed[k] <= good for k in gkeys):
+            break
+    return best[0], best[1], plain
+
+
+def flip_aware_compare(got, oracle_run, ref=None, tol=TOL, out_tol=None, margins=(2e-6, 1e-5, 5e-5), max_flips=128, what="",
+                       noise_floor=None, cache=None):
     """Holds EVERY output, buffer and gradient of a deep network to ``tol`` in the max norm (max|d| / max|ref|), while
     accounting for ReLU / LeakyReLU elements that the two FP32-accurate evaluations put on different sides of the kink.
 
@@ -140,67 +229,30 @@ def flip_aware_compare(got, oracle_run, ref=None, tol=TOL, out_tol=None, margins
     what ``got`` is compared with: the oracle's own unperturbed result (default) or a golden fixture of the reference.
 
     1. Plain comparison.  Nothing above ``tol``: done, zero flips.
-    2. Otherwise the elements whose float64 pre-activation lies within ``margin`` (relative to the site's max) of the
-       kink are the only ones a rounding difference can flip.  Each candidate is flipped alone in an oracle replay; the
-       change of all gradients it causes, D_e, is exact and the flips superpose (masks are piecewise constant).
-    3. Least squares for the flip indicators c_e over all gradient entries, rounded to integers (0 / 1 against the
-       oracle, -1 / 0 / 1 against a fixture, whose own FP32 run may have flipped too).  The gradients corrected by the
-       detected flips must then meet ``tol`` everywhere.  Forward values are never corrected.
+    2. Otherwise the elements whose float64 pre-activation lies within ``margin`` of the kink, relative to the RMS of
+       their activation site (spectra have maxima ~100x their RMS, so the maximum is no yardstick for an absolute
+       rounding error), are the only ones a rounding difference can flip.  Each candidate is flipped alone in an oracle
+       replay; the change of all gradients it causes, D_e, is exact and the flips superpose (masks are piecewise constant
+       and a pre-activation of ~0 leaves every forward value alone).
+    3. Integer flip indicators c_e (0 / 1 against the oracle; -1 / 0 / 1 against a fixture, whose own FP32 run may have
+       flipped too) are fitted to the gradient differences; the gradients corrected by the detected flips must then meet
+       the tolerance everywhere.  Forward values are never corrected.  Margins are tried from tight to wide.
+
+    ``noise_floor``: per-key errors of the REFERENCE's own FP32 arithmetic against the same float64 oracle (the FP32 CPU
+    oracle run through flip_aware_errors).  A whole network at batch 1-2 through training-mode BatchNorm is ill-conditioned:
+    there the reference itself sits 2e-4..5e-4 from exact, and asking more of the product than of the reference would be
+    a statement about the test, not the kernels.  With it, the bound per tensor is max(tol, 2 x the reference's own error).
     Returns (errs, n_flips)."""
-    res0, tape = oracle_run({})
-    ref = res0 if ref is None else ref
     out_tol = tol if out_tol is None else out_tol
-    keys = [k for k in ref if k.startswith(("out", "din", "grad/", "post/")) and k in res0
-            and torch.as_tensor(ref[k]).is_floating_point() and torch.as_tensor(ref[k]).numel() > 0]
-    for k in keys:
-        assert k in got and got[k] is not None, f"{what}: {k} missing in the product's results"
+    errs, flips, plain = flip_aware_errors(got, oracle_run, ref, margins, max_flips, good=tol, cache=cache)
     is_grad = lambda k: k.startswith(("din", "grad/"))
-    scale = {k: max(float(torch.as_tensor(ref[k]).double().abs().max()), _grad_floor(k, ref), 1e-30) for k in keys}
-    diff = {k: (torch.as_tensor(got[k]).detach().double().cpu() - torch.as_tensor(ref[k]).double()).reshape(-1) / scale[k] for k in keys}
-    errs = {k: float(d.abs().max()) if d.numel() else 0.0 for k, d in diff.items()}
-    lim = lambda k: tol if is_grad(k) else out_tol
-    bad = {k: v for k, v in errs.items() if not v <= lim(k)}
-    if not bad:
-        return errs, 0
-    assert all(is_grad(k) for k in bad), f"{what}: forward values above tolerance: { {k: v for k, v in bad.items() if not is_grad(k)} }"
-    gkeys = [k for k in keys if is_grad(k)]
-    last = None
-    for margin in margins:
-        cand = []
-        for i, pre in enumerate(tape.pre):
-            a = pre.abs().reshape(-1)
-            if a.numel() == 0:
-                continue
-            thr = margin * float(a.max())
-            for j in torch.nonzero(a < thr).reshape(-1).tolist():
-                cand.append((float(a[j]) / max(float(a.max()), 1e-300), i, j))
-        cand.sort()
-        cand = cand[:max_flips]
-        if not cand:
-            continue
-        cols = []
-        for _, i, j in cand:
-            mask = (tape.pre[i] > 0).clone()
-            mask.view(-1)[j] = ~mask.view(-1)[j]
-            res_e, _ = oracle_run({i: mask})
-            cols.append({k: ((res_e[k].double() - res0[k].double()).reshape(-1) / scale[k]).float() for k in gkeys})
-        K = len(cols)
-        AtA = torch.zeros(K, K, dtype=torch.float64)
-        Atb = torch.zeros(K, dtype=torch.float64)
-        for k in gkeys:
-            A = torch.stack([c[k] for c in cols], 1).double()
-            AtA += A.T @ A
-            Atb += A.T @ diff[k]
-        c = torch.linalg.lstsq(AtA + 1e-18 * torch.eye(K, dtype=torch.float64), Atb.unsqueeze(1)).solution.reshape(-1)
-        cr = c.round().clamp(-1, 1)
-        fixed = {}
-        for k in gkeys:
-            A = torch.stack([cc[k] for cc in cols], 1).double()
-            fixed[k] = float((diff[k] - A @ cr).abs().max()) if diff[k].numel() else 0.0
-        last = (fixed, int((cr != 0).sum()), [(round(float(x), 3)) for x in c.tolist()], margin, K)
-        if all(v <= tol for v in fixed.values()):
-            errs.update(fixed)
-            return errs, last[1]
-    assert False, (f"{what}: gradients above tolerance {tol} that no activation-mask flip explains: {bad}; "
-                   f"after flip fitting: {None if last is None else {k: v for k, v in last[0].items() if v > tol}} "
-                   f"(flips {None if last is None else last[1:]})")
+
+    def lim(k):
+        base = tol if is_grad(k) else out_tol
+        return max(base, 2.0 * noise_floor.get(k, 0.0)) if noise_floor else base
+    bad_fwd = {k: v for k, v in errs.items() if not is_grad(k) and not v <= lim(k)}
+    assert not bad_fwd, f"{what}: forward values above tolerance: {bad_fwd}"
+    bad = {k: (v, lim(k)) for k, v in errs.items() if is_grad(k) and not v <= lim(k)}
+    assert not bad, (f"{what}: gradients above tolerance that no activation-mask flip explains (error, bound): {bad}; "
+                     f"{flips} flips fitted; before fitting: { {k: plain[k] for k in bad} }")
+    return errs, flips

@@ -59,7 +59,7 @@ def test_detects_exactly_the_flipped_elements():
     fake = {k: (res0[k] if k.startswith("out") else v).float() for k, v in fake.items()}
     plain = {k: parity.relerr(fake[k], res0[k]) for k in res0 if k.startswith(("din", "grad/"))}
     assert max(plain.values()) > 1e-4, "the fabricated flips must matter, otherwise this test shows nothing"
-    errs, flips = parity.flip_aware_compare(fake, oracle_run, margins=(1.0e-2,), max_flips=12, what="fabricated flips")
+    errs, flips = parity.flip_aware_compare(fake, oracle_run, margins=(5.0e-2,), max_flips=12, what="fabricated flips")
     assert flips == 2 and max(errs.values()) < 1e-4, (flips, errs)
 
 
@@ -69,7 +69,7 @@ def test_rejects_an_error_that_is_not_a_flip():
     fake = {k: v.float().clone() for k, v in res0.items()}
     fake["grad/ffc.convl2l.weight"] *= 1.001               # a 1e-3 relative error in one gradient
     with pytest.raises(AssertionError, match="no activation-mask flip explains"):
-        parity.flip_aware_compare(fake, oracle_run, margins=(1e-3,), max_flips=8, what="scaled gradient")
+        parity.flip_aware_compare(fake, oracle_run, margins=(1e-2,), max_flips=8, what="scaled gradient")
 
 
 def test_clean_result_needs_no_flips():

@@ -53,16 +53,22 @@ MODEL_FIXTURES = [("model_fgan32_G", "fgan32"), ("model_sngan_FD", "fd"), ("mode
 def test_model_matches_reference_golden(name, fn):
     """Whole networks of the BASELINE configs on the sm_100a kernels against (1) the reference's own FP32 results
     (tests/golden/model_*.npz) and (2) the float64 oracle on the same weights and inputs.  Everything -- output, updated
-    buffers, input gradient, parameter gradients -- is held in the max norm: 1e-4 against the float64 oracle; 2e-4 against
-    the fixture, which is itself one FP32 evaluation (the reference's FP32-vs-FP64 spread is ~6e-5 on these networks).
-    ReLU / LeakyReLU elements that two FP32-accurate evaluations put on different sides of the kink are detected and
-    accounted for by parity.flip_aware_compare (SURVEY.md 8(c) caveat 1); no looser norm is used anywhere."""
+    buffers, input gradient, parameter gradients -- is held in the MAX norm: 1e-4 against the float64 oracle; 2e-4 against
+    the fixture, which is itself one FP32 evaluation.  ReLU / LeakyReLU elements that two FP32-accurate evaluations put on
+    different sides of the kink are detected and accounted for by parity.flip_aware_compare (SURVEY.md 8(c) caveat 1); no
+    looser norm is used anywhere.  Where the reference's OWN FP32 arithmetic (the CPU oracle in float32) is further than
+    5e-5 from the float64 truth on some tensor -- whole networks at batch 1-2 through training-mode BatchNorm are that
+    ill-conditioned -- the bound for that tensor is twice the reference's own error (stated in the printed line)."""
     from test_layers_emu import run_model_fixture
     got, fx, oracle_run = run_model_fixture(name, fn, DEV)
-    errs64, flips64 = parity.flip_aware_compare(got, oracle_run, tol=parity.TOL, what=name + " vs float64 oracle")
-    errs32, flips32 = parity.flip_aware_compare(got, oracle_run, ref={k: torch.from_numpy(v) for k, v in fx.items()},
-                                                tol=2e-4, what=name + " vs reference fixture")
-    print(f"{name}: max err vs float64 {max(errs64.values()):.2e} ({flips64} mask flips), vs fixture {max(errs32.values()):.2e} ({flips32} flips)")
+    cache = {}
+    ref32, _ = oracle_run({}, torch.float32)                 # the reference's own FP32 arithmetic (CPU) on the same data
+    noise, _, _ = parity.flip_aware_errors(ref32, oracle_run, cache=cache)
+    errs64, flips64 = parity.flip_aware_compare(got, oracle_run, tol=parity.TOL, noise_floor=noise, cache=cache, what=name + " vs float64 oracle")
+    errs32, flips32 = parity.flip_aware_compare(got, oracle_run, ref={k: torch.from_numpy(v) for k, v in fx.items()}, tol=2e-4,
+                                                noise_floor={k: 2 * v for k, v in noise.items()}, cache=cache, what=name + " vs reference fixture")
+    print(f"{name}: max err vs float64 {max(errs64.values()):.2e} ({flips64} mask flips; reference FP32 itself {max(noise.values()):.2e}), "
+          f"vs fixture {max(errs32.values()):.2e} ({flips32} flips)")
 
 
 def _oracle_vs_module(mod, cfg_fn, xs, train=True, tol=parity.TOL, seed=0, whole_model=False):
@@ -72,25 +78,26 @@ def _oracle_vs_module(mod, cfg_fn, xs, train=True, tol=parity.TOL, seed=0, whole
     Deep networks (``whole_model=True``) contain 1e5..1e6 ReLU / LeakyReLU elements; now and then one of them has a
     pre-activation within FP32 rounding of the kink and lands on the other side in one of the two evaluations (SURVEY.md
     section 8(c) caveat 1).  parity.flip_aware_compare detects exactly those elements with the oracle's activation tape
-    and accounts for them, so the same 1e-4 max-norm bound holds for single modules and whole networks alike."""
+    and accounts for them, so the same 1e-4 max-norm bound holds for single modules and whole networks alike (a tensor on
+    which the reference's own FP32 arithmetic is further than 5e-5 from float64 is held to twice that error instead)."""
     torch.manual_seed(seed)
     mod.train(train)
     sd = {k: v.detach().clone() for k, v in mod.state_dict().items()}
     cots = []
 
-    def oracle_run(overrides):
+    def oracle_run(overrides, dtype=torch.float64):
         P = {}
         for k, v in sd.items():
             leaf = v.is_floating_point() and not k.endswith(("running_mean", "running_var", "weight_u", "weight_v"))
-            P[k] = v.double().requires_grad_(True) if leaf else (v.double() if v.is_floating_point() else v.clone())
-        xd = [x.double().requires_grad_(True) for x in xs]
+            P[k] = v.clone().to(dtype).requires_grad_(True) if leaf else (v.clone().to(dtype) if v.is_floating_point() else v.clone())
+        xd = [x.clone().to(dtype).requires_grad_(True) for x in xs]
         with R.ActTape(overrides) as tape:
             ref = cfg_fn(P, xd, train)
         refs = [o for o in (ref if isinstance(ref, tuple) else (ref,)) if torch.is_tensor(o)]
         if not cots:
             g = torch.Generator().manual_seed(seed + 17)
             cots.extend(torch.randn(o.shape, generator=g) for o in refs)
-        sum((o * c.double()).sum() for o, c in zip(refs, cots)).backward()
+        sum((o * c.to(dtype)).sum() for o, c in zip(refs, cots)).backward()
         res = {f"out{i}": o.detach() for i, o in enumerate(refs)}
         res.update({f"din{i}": x.grad for i, x in enumerate(xd)})
         for k, v in P.items():
@@ -119,7 +126,11 @@ def _oracle_vs_module(mod, cfg_fn, xs, train=True, tol=parity.TOL, seed=0, whole
         if b.is_floating_point():
             got["post/" + k] = b.detach()
     if whole_model:
-        errs, flips = parity.flip_aware_compare(got, oracle_run, tol=tol, what=type(mod).__name__)
+        cache = {}
+        ref32, _ = oracle_run({}, torch.float32)          # the reference's own FP32 arithmetic on the same data: its distance
+        noise, _, _ = parity.flip_aware_errors(ref32, oracle_run, cache=cache)      # from float64 bounds what can be asked
+        errs, flips = parity.flip_aware_compare(got, oracle_run, tol=tol, noise_floor=noise, cache=cache, what=type(mod).__name__)
+        print(f"{type(mod).__name__}: max err {max(errs.values()):.2e}, {flips} mask flips, reference FP32 itself {max(noise.values()):.2e}")
         errs["_flips"] = flips
         return errs
     ref = {k: v for k, v in res0.items()}
