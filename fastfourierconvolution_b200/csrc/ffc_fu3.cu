@@ -17,6 +17,7 @@
 // the mix sees every plane as a flat list of NB = N * SPS complex "bins" (pads are computed and ignored; statistics skip
 // them).  Mix, BatchNorm and ReLU are pointwise in (u, v), so neither the permutation nor the pads are ever undone.
 #include "ffc_fu2.cuh"
+#include "ffc_fu3.cuh"
 
 template <int N> struct Fu3G {
     typedef Fu2G<N> G;
@@ -135,18 +136,6 @@ struct Fu3Irfft2 {
 // channel mix, plain FP32 form: the host emulation build's mix and the device cross-check of the tensor-core kernel
 // (ffc_fu3_mix.cu).  One thread per complex slot.
 // ------------------------------------------------------------------------------------------------------------------
-struct Fu3MixParams {
-    const float* s;          // (G, Cin, NB) complex
-    float* y;                // (G, Cout, NB) complex, or null (statistics only)
-    const float* w;          // [2*Cout][2*Cin] (conv_layer.weight)
-    const float* wp;         // packed tensor-core image of w (ffc_fu3_mix.cu) or null
-    const float* bn_a;       // [2*Cout] or null: apply relu(y * a + b) before storing
-    const float* bn_b;
-    double* sums;            // [4*Cout] or null: sum(y) | sum(y^2) over the REAL bins (pads skipped), channel-major
-    int G, Cin, Cout, NB, SPS;
-    float scale;             // forward transform scale folded into the mix (1/N)
-};
-
 struct Fu3MixSimt {
     typedef Fu3MixParams Params;
     static constexpr int kThreads = 256;
@@ -240,6 +229,9 @@ int fu3_mix_tc_run(const Fu3MixParams& p, ffc_stream_t st);
 #endif
 static int g_fu3_simt_mix = 0;
 extern "C" void ffc_debug_fu3_simt_mix(int on) { g_fu3_simt_mix = on; }
+// bytes of spectrum a chunk of images may occupy (default 24 MB: S [+ Y in eval mode] of a chunk stay resident in L2)
+static size_t g_fu3_chunk_bytes = (size_t)24 << 20;
+extern "C" void ffc_debug_fu3_chunk_bytes(size_t bytes) { g_fu3_chunk_bytes = bytes ? bytes : ((size_t)24 << 20); }
 
 static bool fu3_mix_supported(int Cin, int Cout) {
 #ifdef FFC_EMU
@@ -264,7 +256,7 @@ static Fu3Plan fu3_plan(int B, int Cin, int Cout, int N, int training) {
     pl.region = 2 * pl.NB;
     // images per chunk: the spectrum of a chunk (and, in eval mode, its mixed spectrum) stays in L2 between two kernels
     const size_t per_image = (size_t)(Cin + (training ? 0 : Cout)) * pl.region * 4;
-    size_t g = ((size_t)24 << 20) / (per_image ? per_image : 1);
+    size_t g = g_fu3_chunk_bytes / (per_image ? per_image : 1);
     if (g < 1) g = 1;
     if (g > (size_t)B) g = (size_t)B;
     pl.chunk = (int)g;

@@ -27,7 +27,9 @@ class FourierUnitSN(nn.Module):
                                     groups=groups, bias=False)
         self.bn = nn.BatchNorm2d(out_channels * 2)
         self.relu = nn.ReLU(inplace=True)
-        self.fused = True     # False forces the general (spectrum-through-L2) form; used by tests and benchmarks
+        # True: the single-kernel fused form where one image's spectrum fits a CTA, else the L2-staged form (csrc/ffc_fu3.cu);
+        # "staged" forces the L2-staged form, False the first-generation general form (tests and benchmarks)
+        self.fused = True
 
     def forward(self, x, y=None):
         return self._run(x, y, None)
@@ -46,11 +48,13 @@ class FourierUnitSN(nn.Module):
         bn = self.bn
         cin, cout = x.shape[1], weight.shape[0] // 2
         plain_bn = bn.affine and bn.track_running_stats and bn.momentum is not None
-        if plain_bn and self.fused and ops.fu_fused_supported(x.shape[0], cin, cout, h, w):
+        single = plain_bn and self.fused is True and ops.fu_fused_supported(x.shape[0], cin, cout, h, w)
+        staged = plain_bn and self.fused and not single and ops.fu_staged_supported(x.shape[0], cin, cout, h, w)
+        if single or staged:
             if bn.training:
                 bn.num_batches_tracked.add_(1)
             return ops.fourier_unit_fused(x, weight.view(2 * cout, 2 * cin), bn.weight, bn.bias, bn.running_mean,
-                                          bn.running_var, residual, bn.training, bn.eps, bn.momentum)
+                                          bn.running_var, residual, bn.training, bn.eps, bn.momentum, staged=bool(staged))
         spec = ops.rfft2(x)                                            # fourier_unity.py:38-42
         mixed = ops.conv2d(spec, weight)                               # :45
         if plain_bn:                                                   # :49 applied inside the load of :51-56

@@ -488,6 +488,11 @@ def fu_fused_supported(B, Cin, Cout, H, W) -> bool:
     return bool(_C.lib().ffc_fu_fused_supported(int(B), int(Cin), int(Cout), int(H), int(W)))
 
 
+def fu_staged_supported(B, Cin, Cout, H, W) -> bool:
+    """The L2-staged form (csrc/ffc_fu3.cu): 16..128 planes, channel counts whose packed mix weights fit shared memory."""
+    return bool(_C.lib().ffc_fu3_supported(int(B), int(Cin), int(Cout), int(H), int(W)))
+
+
 class FusedFuFn(torch.autograd.Function):
     """out = [residual +] irfft2(relu(bn(conv1x1(rfft2(x)))))   (fourier_unity.py:32-58 in one op).
 
@@ -497,7 +502,7 @@ class FusedFuFn(torch.autograd.Function):
     irfft2).  Nothing spectral is saved between forward and backward."""
 
     @staticmethod
-    def forward(ctx, x, weight, gamma, beta, running_mean, running_var, residual, training, eps, momentum):
+    def forward(ctx, x, weight, gamma, beta, running_mean, running_var, residual, training, eps, momentum, staged=False):
         _C.require_device(x, weight, gamma, beta, running_mean, running_var, residual)
         x, weight, residual = x.contiguous(), weight.contiguous(), _c(residual)
         B, Cin, H, W = x.shape
@@ -505,8 +510,14 @@ class FusedFuFn(torch.autograd.Function):
         out = torch.empty((B, Cout, H, W), device=x.device, dtype=torch.float32)
         save_mean = torch.empty(2 * Cout, device=x.device, dtype=torch.float32)
         save_invstd = torch.empty(2 * Cout, device=x.device, dtype=torch.float32)
-        ws = _C.workspace(4 * Cout * 8, x.device)
-        _C.check(_C.lib().ffc_fu_fwd(_C.ptr(x), _C.ptr(weight), _C.ptr(gamma), _C.ptr(beta),
+        L = _C.lib()
+        if staged:       # planes / channel counts beyond one CTA's shared memory: spectrum staged through L2 in chunks of images
+            ws = _C.workspace(L.ffc_fu3_workspace_bytes(B, Cin, Cout, H, W, int(training)), x.device)
+            fwd = L.ffc_fu3_fwd
+        else:
+            ws = _C.workspace(4 * Cout * 8, x.device)
+            fwd = L.ffc_fu_fwd
+        _C.check(fwd(_C.ptr(x), _C.ptr(weight), _C.ptr(gamma), _C.ptr(beta),
                                      _C.ptr(running_mean), _C.ptr(running_var), _C.ptr(save_mean), _C.ptr(save_invstd),
                                      _C.ptr(residual), _C.ptr(out), B, Cin, Cout, H, W, int(training), float(eps),
                                      float(momentum), _C.ptr(ws), ws.numel(), _C.current_stream(x.device)))
@@ -534,7 +545,7 @@ class FusedFuFn(torch.autograd.Function):
                                   _C.ptr(save_mean), _C.ptr(save_invstd), _C.ptr(dx), _C.ptr(dw), _C.ptr(dgamma), _C.ptr(dbeta),
                                   B, Cin, C2o // 2, H, W, int(training), _C.ptr(ws), ws.numel(), st))
             dres = dout if (has_res and ctx.needs_input_grad[6]) else None
-            return dx, dw, dgamma, dbeta, None, None, dres, None, None, None
+            return dx, dw, dgamma, dbeta, None, None, dres, None, None, None, None
         w4 = weight.view(C2o, C2i, 1, 1)
         spec = _rfft2(x, 0)                                            # recompute S
         y = torch.empty((B, C2o, H, Wf), device=x.device, dtype=torch.float32)
@@ -557,11 +568,11 @@ class FusedFuFn(torch.autograd.Function):
                                       B, C2i, H, Wf, H, Wf, 1, 1, 0, 1, st))     # dS = W^T dY
             dx = _irfft2(dspec, None, 1)                               # adjoint of rfft2
         dres = dout if (has_res and ctx.needs_input_grad[6]) else None
-        return dx, dw, dgamma, dbeta, None, None, dres, None, None, None
+        return dx, dw, dgamma, dbeta, None, None, dres, None, None, None, None
 
 
-def fourier_unit_fused(x, weight2d, gamma, beta, running_mean, running_var, residual, training, eps, momentum):
-    return FusedFuFn.apply(x, weight2d, gamma, beta, running_mean, running_var, residual, training, eps, momentum)
+def fourier_unit_fused(x, weight2d, gamma, beta, running_mean, running_var, residual, training, eps, momentum, staged=False):
+    return FusedFuFn.apply(x, weight2d, gamma, beta, running_mean, running_var, residual, training, eps, momentum, staged)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -85,6 +85,25 @@ int ffc_fu_fwd(const float* x, const float* w, const float* gamma, const float* 
                int B, int Cin, int Cout, int H, int W, int training, float eps, float momentum,
                void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- Fourier unit, L2-staged form (planes / channel counts beyond one CTA's shared memory) -------------
+ * ffc_fu3_fwd: the same contract as ffc_fu_fwd (replaces FourierUnitSN.forward, layers/ffc/fourier_unity.py:32-58) for
+ * H == W in {16,32,64,128} and any Cin / Cout whose packed mix weights fit shared memory (2*Cout <= 128 on the tensor-core
+ * path): three kernels per chunk of images -- plane rfft2 | tcgen05 channel mix with the BatchNorm statistics (training) or
+ * BatchNorm + ReLU (eval) in its epilogue | plane irfft2 (BatchNorm + ReLU applied on load in training mode) -- with the
+ * spectrum of a chunk staged in a caller-provided scratch that is sized to stay resident in the 126 MB L2 and reused
+ * by every chunk; in training mode the mixed spectrum of the whole batch makes one round trip (it waits for the batch
+ * statistics).  workspace >= ffc_fu3_workspace_bytes(B, Cin, Cout, H, W, training) bytes.
+ * ffc_debug_fu3_simt_mix(1) routes the channel mix through the plain FP32 kernel (cross-check of the tensor-core one). */
+int ffc_fu3_supported(int B, int Cin, int Cout, int H, int W);
+size_t ffc_fu3_workspace_bytes(int B, int Cin, int Cout, int H, int W, int training);
+int ffc_fu3_fwd(const float* x, const float* w, const float* gamma, const float* beta,
+                float* running_mean, float* running_var, float* save_mean, float* save_invstd,
+                const float* residual, float* out,
+                int B, int Cin, int Cout, int H, int W, int training, float eps, float momentum,
+                void* workspace, size_t workspace_bytes, void* stream);
+void ffc_debug_fu3_simt_mix(int on);
+void ffc_debug_fu3_chunk_bytes(size_t bytes);      /* spectrum bytes per chunk of images (0 = default 24 MB); tuning / tests */
+
 /* ffc_fu_bwd: the autograd backward of FourierUnitSN.forward (fourier_unity.py:32-58; derived from ATen's
  * fft_r2c / fft_c2r / batch_norm / relu / conv backward formulas) as ONE cooperative kernel, one image per CTA:
  * rfft2(x) and the adjoint-c2r transform of dout stay in shared memory, Y = W S is recomputed, ReLU mask and the two

@@ -139,22 +139,25 @@ def _oracle_vs_module(mod, cfg_fn, xs, train=True, tol=parity.TOL, seed=0, whole
 
 # FourierUnit shapes of the BASELINE configs and of the isolated sweep
 FU_SHAPES = [(8, 8, 32), (8, 16, 16), (8, 32, 8), (8, 8, 64), (4, 64, 16), (4, 32, 32), (2, 32, 64), (2, 32, 128),
-             (8, 128, 4), (4, 24, 16), (2, 96, 32), (2, 192, 16)]
+             (8, 128, 4), (4, 24, 16), (2, 96, 32), (2, 192, 16), (3, 64, 32), (5, 20, 64), (3, 48, 16)]
 
 
 @pytest.mark.parametrize("B,C,N", FU_SHAPES)
 @pytest.mark.parametrize("train", [True, False])
-@pytest.mark.parametrize("fused", [True, False, "two_pass"])
+@pytest.mark.parametrize("fused", [True, False, "two_pass", "staged", "staged_chunked"])
 def test_fourier_unit_config_shapes(B, C, N, train, fused):
     """fused=True: ffc_fu_fwd where the shape is supported (general form otherwise); fused=False forces
     the general rfft2 | mix | BN+ReLU | irfft2 form, so both code paths are checked on every shape."""
     torch.manual_seed(C * 1000 + N)
-    if fused and not ops.fu_fused_supported(B, C, C, N, N):
+    staged = isinstance(fused, str) and fused.startswith("staged")
+    if staged and not ops.fu_staged_supported(B, C, C, N, N):
+        pytest.skip("shape not covered by the L2-staged form (4x4 / 8x8 planes, 2*Cout > 128)")
+    if fused and not staged and not ops.fu_fused_supported(B, C, C, N, N):
         pytest.skip("shape not covered by the fused kernel (general form is tested by fused=False)")
     if fused == "two_pass" and not train:
         pytest.skip("eval mode is always a single pass")
     mod = ffc.FourierUnitSN(C, C)
-    mod.fused = bool(fused)
+    mod.fused = "staged" if staged else bool(fused)      # "staged": csrc/ffc_fu3.cu with the tcgen05 channel mix
     with torch.no_grad():
         mod.bn.running_mean.normal_(0, 0.1)
         mod.bn.running_var.uniform_(0.5, 1.5)
@@ -162,10 +165,13 @@ def test_fourier_unit_config_shapes(B, C, N, train, fused):
         mod.bn.bias.normal_(0, 0.1)
     x = torch.randn(B, C, N, N)
     _C.lib().ffc_debug_fu_two_pass(1 if fused == "two_pass" else 0)      # default: cooperative single pass when it fits
+    if fused == "staged_chunked":                                        # two images per chunk: several chunks, the last one ragged
+        _C.lib().ffc_debug_fu3_chunk_bytes(2 * C * N * (N + 4) * 4)
     try:
         _oracle_vs_module(mod, lambda P, xs, tr: R.fourier_unit(xs[0], P, "", tr), [x], train)
     finally:
         _C.lib().ffc_debug_fu_two_pass(0)
+        _C.lib().ffc_debug_fu3_chunk_bytes(0)
 
 
 def _bn_away_from_the_kink(mod):

@@ -277,3 +277,29 @@ def test_fourier_unit_sweep_shapes_general_form(B, C, N, emu):
     assert l2(xo.grad, xr.grad) < 1e-3 and l2(m.conv_layer.weight.grad, P["conv_layer.weight"].grad) < 1e-3
     assert l2(m.bn.weight.grad, P["bn.weight"].grad) < 1e-3 and l2(m.bn.bias.grad, P["bn.bias"].grad) < 1e-3
     assert parity.relerr(m.bn.running_var, P["bn.running_var"]) < 1e-5
+
+
+@pytest.mark.parametrize("B,C,N,chunk", [(3, 6, 64, 0), (5, 4, 32, 3 * 4 * 32 * 36 * 4), (2, 40, 16, 0), (1, 4, 128, 0)])
+@pytest.mark.parametrize("train", [True, False])
+def test_fourier_unit_l2_staged_form(B, C, N, chunk, train, emu):
+    """The L2-staged Fourier unit (csrc/ffc_fu3.cu: plane rfft2 | channel mix + BN statistics | BN+ReLU -> plane irfft2 over
+    chunks of images) in host emulation against the float64 oracle, forward with residual and running statistics; ``chunk``
+    bytes force several chunks (one of them ragged).  The emulation build mixes in plain FP32; the tensor-core mix is checked
+    on the GPU (tests/test_gpu_parity.py)."""
+    from fastfourierconvolution_b200 import _C
+    torch.manual_seed(C + N)
+    m = ffc.FourierUnitSN(C, C).train(train)
+    m.fused = "staged"
+    with torch.no_grad():
+        m.bn.weight.uniform_(0.5, 1.5); m.bn.bias.normal_(0, 0.2); m.bn.running_mean.normal_(0, 0.1); m.bn.running_var.uniform_(0.5, 1.5)
+    P = {k: (v.double().clone() if v.is_floating_point() else v.clone()) for k, v in m.state_dict().items()}
+    x, res = torch.randn(B, C, N, N), torch.randn(B, C, N, N)
+    _C.lib().ffc_debug_fu3_chunk_bytes(chunk)
+    try:
+        with torch.no_grad():
+            out = m._run(x, None, res)
+    finally:
+        _C.lib().ffc_debug_fu3_chunk_bytes(0)
+    ref = R.fourier_unit(x.double(), P, "", train) + res.double()
+    assert parity.relerr(out, ref) < 1e-6
+    assert parity.relerr(m.bn.running_mean, P["bn.running_mean"]) < 1e-5 and parity.relerr(m.bn.running_var, P["bn.running_var"]) < 1e-5

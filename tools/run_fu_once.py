@@ -1,5 +1,5 @@
 """Runs the FourierUnit forward a few times on one shape (for ncu captures).
-usage: python tools/run_fu_once.py B C N [train|eval] [general] [bwd]"""
+usage: python tools/run_fu_once.py B C N [train|eval] [general|staged] [bwd]"""
 import os
 import sys
 
@@ -11,7 +11,7 @@ import fastfourierconvolution_b200 as ffc
 B, C, N = (int(a) for a in sys.argv[1:4])
 mode = sys.argv[4] if len(sys.argv) > 4 else "eval"
 m = ffc.FourierUnitSN(C, C).to("cuda:0").train(mode == "train")
-m.fused = "general" not in sys.argv
+m.fused = False if "general" in sys.argv else ("staged" if "staged" in sys.argv else True)
 xs = [torch.randn(B, C, N, N, device="cuda:0") for _ in range(4)]
 if "bwd" in sys.argv:
     for i in range(4):
