@@ -199,10 +199,10 @@ FFC_DEVICE void fu2_load_rows(int tid, int nt, int nrows, const float* FFC_RESTR
     }
     for (; r < nrows; r += rstep, s4 += nt, d += rstep * G::RS) *reinterpret_cast<float4*>(d) = FFC_LDG(s4);
 }
-template <int N, bool RES>
+template <int N, bool RES, int LDU = 4>
 FFC_DEVICE void fu2_store_rows_impl(int tid, int nt, int nrows, const float* planes, const float* FFC_RESTRICT res, float* FFC_RESTRICT dst) {
     typedef Fu2G<N> G;
-    constexpr int Q = N / 4, LDU = 4;
+    constexpr int Q = N / 4;
     const int rstep = nt / Q;
     float4* d4 = reinterpret_cast<float4*>(dst) + tid;
     const float4* r4 = reinterpret_cast<const float4*>(res) + tid;

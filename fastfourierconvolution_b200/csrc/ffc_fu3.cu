@@ -18,6 +18,9 @@
 // them).  Mix, BatchNorm and ReLU are pointwise in (u, v), so neither the permutation nor the pads are ever undone.
 #include "ffc_fu2.cuh"
 #include "ffc_fu3.cuh"
+#ifndef FFC_EMU
+#include "ffc_umma.cuh"      // mbarrier + bulk-copy wrappers (the plane kernels move whole rows / planes with cp.async.bulk)
+#endif
 
 template <int N> struct Fu3G {
     typedef Fu2G<N> G;
@@ -45,29 +48,57 @@ struct Fu3Rfft2 {
     static constexpr int P = Fu3G<N>::P;
     static constexpr int kThreads = Fu3G<N>::kThreads;
     static constexpr int kMinBlocks = (N == 128) ? 3 : (N == 64 ? 4 : 4);
-    static size_t smem_bytes() { return ((size_t)P * G::REGION + 2 * N) * 4; }
+    static size_t smem_bytes() { return ((size_t)P * G::REGION + 2 * N) * 4 + 16; }
 
     static FFC_DEVICE void run(const Params& p, const BlockCtx& ctx, float* smem) {
         const int plane0 = ctx.bx * P;
         const int np = (p.nplanes - plane0) < P ? (p.nplanes - plane0) : P;
         float* planes = smem;
         float2* tw = reinterpret_cast<float2*>(smem + (size_t)P * G::REGION);
+#ifndef FFC_EMU
+        // Device: every thread owns one row (kThreads == P * N) and fetches it with ONE bulk copy (cp.async.bulk, N*4 bytes
+        // into the padded shared-memory row); all rows of the CTA are in flight at once and complete on one mbarrier, so the
+        // load costs one memory latency instead of one per batch of register-staged loads.
+        uint64_t* bar = reinterpret_cast<uint64_t*>(tw + N);
+        {
+            const int tid = (int)threadIdx.x;
+            if (tid == 0) { umma::mbar_init(bar, 1); umma::fence_barrier_init(); }
+            for (int k = tid; k < N; k += ctx.nt) tw[k] = c_tw128[k * (FFC_TW_N / N)];
+            __syncthreads();
+            if (tid == 0) umma::mbar_arrive_expect_tx(bar, (uint32_t)(np * N * N * 4));
+            for (int r = tid; r < np * N; r += ctx.nt)
+                umma::bulk_g2s(planes + (size_t)r * G::RS, p.x + ((size_t)plane0 * N + r) * N, (uint32_t)(N * 4), bar);
+            umma::mbar_wait(bar, 0);
+        }
+#else
         FFC_PHASE {
             for (int k = tid; k < N; k += ctx.nt) tw[k] = c_tw128[k * (FFC_TW_N / N)];
             fu2_load_rows<N>(tid, ctx.nt, np * N, p.x + (size_t)plane0 * N * N, planes);
         } FFC_SYNC;
+#endif
         FFC_PHASE {
             fu2_rows_fwd<N, ADJ>(tid, ctx.nt, np * N, planes);
             for (int r = tid; r < np * N; r += ctx.nt)           // the pad slot of every row (read by the mix, never used)
                 reinterpret_cast<float2*>(planes + (size_t)r * G::RS)[G::M + 1] = make_float2(0.f, 0.f);
         } FFC_SYNC;
         FU2_COLS_FWD(N, np, planes, tw);
+#ifndef FFC_EMU
+        // the scratch layout IS the shared-memory image: one bulk copy writes the CTA's planes back
+        umma::fence_proxy_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            umma::bulk_s2g(p.spec + (size_t)plane0 * G::REGION, planes, (uint32_t)(np * G::REGION * 4));
+            umma::bulk_commit_group();
+            umma::bulk_wait_group0();
+        }
+#else
         FFC_PHASE {
             const float4* s4 = reinterpret_cast<const float4*>(planes);
             float4* d4 = reinterpret_cast<float4*>(p.spec + (size_t)plane0 * G::REGION);
             const int total = np * (G::REGION / 4);
             for (int i = tid; i < total; i += ctx.nt) d4[i] = s4[i];
         } FFC_SYNC;
+#endif
     }
 };
 
@@ -88,46 +119,80 @@ struct Fu3Irfft2 {
     static constexpr int P = Fu3G<N>::P;
     static constexpr int kThreads = Fu3G<N>::kThreads;
     static constexpr int kMinBlocks = (N == 128) ? 3 : 4;
-    static size_t smem_bytes() { return ((size_t)P * G::REGION + 2 * N) * 4; }
+    static size_t smem_bytes() { return ((size_t)P * G::REGION + 2 * N + 4 * P) * 4 + 16; }
 
     static FFC_DEVICE void run(const Params& p, const BlockCtx& ctx, float* smem) {
         const int plane0 = ctx.bx * P;
         const int np = (p.nplanes - plane0) < P ? (p.nplanes - plane0) : P;
         float* planes = smem;
         float2* tw = reinterpret_cast<float2*>(smem + (size_t)P * G::REGION);
+        float2* bnp_a = tw + N;                 // per plane of this CTA: (a_re, a_im), (b_re, b_im)
+        float2* bnp_b = bnp_a + P;
+#ifndef FFC_EMU
+        // Device: the CTA's planes are contiguous in the scratch and the scratch layout IS the shared-memory image: ONE bulk
+        // copy brings them in (completion on an mbarrier); the residual rows are prefetched into L2 meanwhile.  BatchNorm +
+        // ReLU is applied by the first inverse column pass as it loads the spectrum from shared memory.
+        uint64_t* bar = reinterpret_cast<uint64_t*>(bnp_b + P);
+        {
+            const int tid = (int)threadIdx.x;
+            if (tid == 0) { umma::mbar_init(bar, 1); umma::fence_barrier_init(); }
+            __syncthreads();
+            if (tid == 0) {
+                umma::mbar_arrive_expect_tx(bar, (uint32_t)(np * G::REGION * 4));
+                umma::bulk_g2s(planes, p.spec + (size_t)plane0 * G::REGION, (uint32_t)(np * G::REGION * 4), bar);
+                if (p.residual) umma::bulk_prefetch_l2(p.residual + (size_t)plane0 * N * N, (uint32_t)(np * N * N * 4));
+            }
+            for (int k = tid; k < N; k += ctx.nt) tw[k] = c_tw128[k * (FFC_TW_N / N)];
+            if (p.bn_a && tid < np) {
+                const int o = (plane0 + tid) % p.cout;
+                bnp_a[tid] = make_float2(FFC_LDG(p.bn_a + 2 * o), FFC_LDG(p.bn_a + 2 * o + 1));
+                bnp_b[tid] = make_float2(FFC_LDG(p.bn_b + 2 * o), FFC_LDG(p.bn_b + 2 * o + 1));
+            }
+            umma::mbar_wait(bar, 0);
+            __syncthreads();
+        }
+        Fu2Bn bn; bn.a = bnp_a; bn.b = bnp_b;
+        if (p.bn_a) { FU2_COLS_INV(N, true, np, planes, tw, bn); }
+        else { FU2_COLS_INV(N, false, np, planes, tw, bn); }
+#else
         FFC_PHASE {
             for (int k = tid; k < N; k += ctx.nt) tw[k] = c_tw128[k * (FFC_TW_N / N)];
             const float4* s4 = reinterpret_cast<const float4*>(p.spec + (size_t)plane0 * G::REGION);
             float4* d4 = reinterpret_cast<float4*>(planes);
-            constexpr int PER = G::REGION / 4, LDU = 4;
+            constexpr int PER = G::REGION / 4;
             const int total = np * PER;
-            for (int i0 = tid; i0 < total; i0 += LDU * ctx.nt) {
-                float4 v[LDU];
-                FFC_UNROLL
-                for (int u = 0; u < LDU; ++u) { const int i = i0 + u * ctx.nt; if (i < total) v[u] = FFC_LDG(s4 + i); }
-                FFC_UNROLL
-                for (int u = 0; u < LDU; ++u) {
-                    const int i = i0 + u * ctx.nt;
-                    if (i < total) {
-                        float4 q = v[u];
-                        if (p.bn_a) {              // relu(y * a + b) on (re, im) pairs of output channel o: fourier_unity.py:49
-                            const int o = (plane0 + i / PER) % p.cout;
-                            const float ar = FFC_LDG(p.bn_a + 2 * o), ai = FFC_LDG(p.bn_a + 2 * o + 1);
-                            const float br = FFC_LDG(p.bn_b + 2 * o), bi = FFC_LDG(p.bn_b + 2 * o + 1);
-                            q.x = fmaf(q.x, ar, br); q.y = fmaf(q.y, ai, bi); q.z = fmaf(q.z, ar, br); q.w = fmaf(q.w, ai, bi);
-                            q.x = q.x > 0.f ? q.x : 0.f; q.y = q.y > 0.f ? q.y : 0.f; q.z = q.z > 0.f ? q.z : 0.f; q.w = q.w > 0.f ? q.w : 0.f;
-                        }
-                        d4[i] = q;
-                    }
+            for (int i = tid; i < total; i += ctx.nt) {
+                float4 q = s4[i];
+                if (p.bn_a) {              // relu(y * a + b) on (re, im) pairs of output channel o: fourier_unity.py:49
+                    const int o = (plane0 + i / PER) % p.cout;
+                    const float ar = p.bn_a[2 * o], ai = p.bn_a[2 * o + 1], br = p.bn_b[2 * o], bi = p.bn_b[2 * o + 1];
+                    q.x = fmaf(q.x, ar, br); q.y = fmaf(q.y, ai, bi); q.z = fmaf(q.z, ar, br); q.w = fmaf(q.w, ai, bi);
+                    q.x = q.x > 0.f ? q.x : 0.f; q.y = q.y > 0.f ? q.y : 0.f; q.z = q.z > 0.f ? q.z : 0.f; q.w = q.w > 0.f ? q.w : 0.f;
                 }
+                d4[i] = q;
             }
         } FFC_SYNC;
         Fu2Bn nobn; nobn.a = nullptr; nobn.b = nullptr;
         FU2_COLS_INV(N, false, np, planes, tw, nobn);
+#endif
         FFC_PHASE { fu2_rows_inv<N, ADJ>(tid, ctx.nt, np * N, planes, p.scale); } FFC_SYNC;
+#ifndef FFC_EMU
+        if (!p.residual) {
+            // no residual: every thread sends its finished row with one bulk copy (shared -> global, N*4 bytes)
+            umma::fence_proxy_async_smem();
+            __syncthreads();
+            const int tid = (int)threadIdx.x;
+            for (int r = tid; r < np * N; r += ctx.nt)
+                umma::bulk_s2g(p.out + ((size_t)plane0 * N + r) * N, planes + (size_t)r * G::RS, (uint32_t)(N * 4));
+            umma::bulk_commit_group();
+            umma::bulk_wait_group0();
+            return;
+        }
+#endif
         FFC_PHASE {
             const size_t g0 = (size_t)plane0 * N * N;
-            fu2_store_rows<N>(tid, ctx.nt, np * N, planes, p.residual ? p.residual + g0 : nullptr, p.out + g0);
+            if (p.residual) fu2_store_rows_impl<N, true, 8>(tid, ctx.nt, np * N, planes, p.residual + g0, p.out + g0);
+            else fu2_store_rows_impl<N, false, 8>(tid, ctx.nt, np * N, planes, nullptr, p.out + g0);
         } FFC_SYNC;
     }
 };

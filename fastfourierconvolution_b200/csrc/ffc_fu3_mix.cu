@@ -19,8 +19,9 @@
 //     is resident in shared memory for the life of the CTA: one cp.async.bulk per K chunk at start.
 //   * Epilogue per tile: tcgen05.ld 16 columns (= 8 complex output channels) at a time; either BN + ReLU with folded
 //     constants, or the per-channel sum / sum of squares over the real bins (pad slots masked) by a transposing warp
-//     butterfly (16 shuffles per 16 columns), accumulated in double per lane over all tiles of the warpgroup and
-//     flushed with one double atomic per lane and column group at the end; then one coalesced 8-byte store per channel.
+//     butterfly (16 shuffles per 16 columns), accumulated in double per lane over all tiles of the warpgroup, reduced over
+//     the CTA in shared memory and flushed with one double atomic per channel and CTA; then one coalesced 8-byte store
+//     per channel.
 #include "ffc_fu3.cuh"
 
 #ifndef FFC_EMU
@@ -238,14 +239,29 @@ __global__ void __launch_bounds__(NWG * 128, 1) fu3_mix_kernel(const Fu3MixParam
         }
         umma::fence_before_sync();       // the TMEM loads above are ordered before the next tile's MMAs (issued after a barrier)
     }
-    if (do_stats && !(lane & 1)) {
-        const int col = fm_col_of_lane(lane);
+    if (do_stats) {
+        // CTA-level reduction before the global atomics (148 CTAs x 16 warps hammering 4*Cout addresses serialise in L2):
+        // the weight tiles are dead now (every MMA of this CTA has completed), their shared memory holds the partials
+        __syncthreads();
+        double* red = reinterpret_cast<double*>(bsm);                  // [warps][NT][2]
+        const int nwarps = NWG * 4;
+        if (!(lane & 1)) {
+            const int col = fm_col_of_lane(lane);
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            const int n = 16 * g + col;
-            if (16 * g < NT && n < 2 * Cout) {
-                atomicAdd(p.sums + n, st_sum[g]);
-                atomicAdd(p.sums + 2 * Cout + n, st_sq[g]);
+            for (int g = 0; g < 8; ++g) {
+                if (16 * g < NT) {
+                    red[((size_t)warp * NT + 16 * g + col) * 2] = st_sum[g];
+                    red[((size_t)warp * NT + 16 * g + col) * 2 + 1] = st_sq[g];
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < 2 * NT; i += blockDim.x) {
+            const int n = i >> 1, which = i & 1;
+            if (n < 2 * Cout) {
+                double acc = 0.0;
+                for (int w = 0; w < nwarps; ++w) acc += red[((size_t)w * NT + n) * 2 + which];
+                atomicAdd(p.sums + (which ? 2 * Cout + n : n), acc);
             }
         }
     }
