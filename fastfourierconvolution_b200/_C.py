@@ -43,6 +43,7 @@ _SIGNATURES = {
     "ffc_irfft2_bn_relu": (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p] * 5),
     "ffc_spectral_norm_workspace_bytes": (c_size_t, [c_int, c_int]),
     "ffc_spectral_norm_fwd": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
+    "ffc_spectral_norm_bwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "ffc_se_fwd": (c_int, [c_void_p] * 7 + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
     "ffc_se_bwd": (c_int, [c_void_p] * 10 + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
     "ffc_fu_fwd": (c_int, [c_void_p] * 10 + [c_int] * 6 + [c_float, c_float, c_void_p, c_size_t, c_void_p]),
@@ -156,3 +157,21 @@ def workspace(nbytes: int, device) -> torch.Tensor:
         ws = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
+
+
+_side_streams = {}
+
+
+def side_streams(device, n: int = 2):
+    """Side streams of ``device`` for work that is independent of what follows on the current stream (weight gradient vs data
+    gradient of one convolution, spectral transform vs local convolutions of one FFC layer).  Always used fork / join:
+    ``side.wait_stream(cur)`` ... ``cur.wait_stream(side)``, so that a CUDA-graph capture of the caller records parallel
+    branches and eager execution overlaps the small kernels of a batch shard.  FFC_B200_SINGLE_STREAM=1 disables the forks."""
+    if os.environ.get("FFC_B200_SINGLE_STREAM") == "1":
+        return None
+    key = str(device)
+    st = _side_streams.get(key)
+    if st is None or len(st) < n:
+        st = [torch.cuda.Stream(device=device) for _ in range(n)]
+        _side_streams[key] = st
+    return st

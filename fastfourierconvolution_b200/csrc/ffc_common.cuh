@@ -225,6 +225,17 @@ static inline int ffc_memset_async(void* p, int v, size_t n, ffc_stream_t s) {
 #define FFC_CHECK(call) do { int _e = (call); if (_e != FFC_OK) return _e; } while (0)
 #define FFC_REQUIRE(cond, ...) do { if (!(cond)) { ffc_set_error(__VA_ARGS__); return FFC_ERR_BAD_ARG; } } while (0)
 
+// ------------------------------------------------------------------ 3xTF32 operand split
+// hi = x rounded to NEAREST TF32 (10 explicit mantissa bits), lo = x - hi (exact in FP32, |lo| <= 2^-11 |x|).  The tensor core
+// truncates its FP32 inputs to TF32: hi passes unchanged, lo loses <= 2^-10 |lo|.  Rounding instead of truncating the split
+// halves |lo| and with it every error term of a*b ~ a_hi*b_hi + a_lo*b_hi + a_hi*b_lo (measured on the fgan128 fixture:
+// tools/diag_fixture_accuracy.py).  The +0x1000 carries into the exponent correctly; inf / nan do not occur here.
+#ifndef FFC_EMU
+__device__ __forceinline__ float ffc_tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+#else
+static inline float ffc_tf32_hi(float x) { uint32_t u; memcpy(&u, &x, 4); u = (u + 0x1000u) & 0xffffe000u; float r; memcpy(&r, &u, 4); return r; }
+#endif
+
 // ------------------------------------------------------------------ small helpers
 FFC_HD int ffc_cdiv(int a, int b) { return (a + b - 1) / b; }
 FFC_HD int ffc_ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }

@@ -464,11 +464,10 @@ struct ConvFwdV3 {
 #ifdef FFC_EMU
         return make_float2(x, 0.f);
 #else
-        // hi = x truncated to TF32 (one LOP3), lo = x - hi (exact in FP32, one FADD).  The tensor core reads only the
-        // top 19 bits of lo, so a.b keeps ~21 significant bits per product.  (cvt.rna.tf32.f32 expands to a ~7
-        // instruction sequence on sm_100 -- ncu showed it dominating the issue slots -- and round-to-nearest of hi
-        // buys nothing once lo carries the remainder.)
-        const float hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+        // hi = x rounded to the nearest TF32 (IADD + LOP3, ffc_common.cuh), lo = x - hi (exact in FP32, one FADD).  The tensor
+        // core reads only the top 19 bits of lo, so a.b keeps ~22 significant bits per product.  (cvt.rna.tf32.f32 expands
+        // to a ~7 instruction sequence on sm_100 -- ncu showed it dominating the issue slots.)
+        const float hi = ffc_tf32_hi(x);
         return make_float2(hi, x - hi);
 #endif
     }

@@ -8,7 +8,7 @@
 //     already split into (hi, lo) TF32 halves and zero padded:  Wp[class][K_pad][N_pad] float2, K = (segment, tap,
 //     ci) tap-major.  A B tile is then BK contiguous rows: two 16-byte cp.async per thread, no index math.
 //   * The gathered activations stay raw FP32 in shared memory (4-byte cp.async with zero fill for padding and
-//     channel tails); hi is the raw word (the tensor core reads its top 19 bits), lo = x - trunc(x): 2 ALU ops.
+//     channel tails); hi = x rounded to the nearest TF32, lo = x - hi: 3 ALU ops.
 //   * 3-stage cp.async ring, one __syncthreads per K chunk, no staging registers.
 //   * The three products of a chunk are accumulated in a zeroed fragment and folded into the FP32 running sum
 //     with a round-to-nearest FADD (the tensor core truncates its addend).
@@ -91,7 +91,7 @@ struct PackWeightsKernel {
 #ifdef FFC_EMU
                 p.wp[p.cls_off[cls] + e] = make_float2(v, 0.f);
 #else
-                const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+                const float hi = ffc_tf32_hi(v);
                 p.wp[p.cls_off[cls] + e] = make_float2(hi, v - hi);
 #endif
             }
@@ -218,8 +218,8 @@ struct ConvFwdV4 {
                         FFC_UNROLL
                         for (int r = 0; r < 4; ++r) {
                             const float x = as[(k8 + t + (r >> 1) * 4) * AS + mw + 16 * mt + gq + (r & 1) * 8];
-                            const float hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
-                            ah[mt][r] = __float_as_uint(x);              // the tensor core reads the top 19 bits
+                            const float hi = ffc_tf32_hi(x);
+                            ah[mt][r] = __float_as_uint(hi);             // (rounded to nearest: not what the tensor core would truncate x to)
                             al[mt][r] = __float_as_uint(x - hi);
                         }
                     }

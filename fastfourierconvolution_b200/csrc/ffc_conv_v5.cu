@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) pack_v5_kernel(const PackV5Params p) {
                     else v = __ldg(w + ((size_t)cl * cin + ci) * KK + a * p.k + b);
                 }
             }
-            const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+            const float hi = ffc_tf32_hi(v);
             float* dst = p.wp + p.cls_off[cls] + tile_base + (long long)chunk_all * per_chunk
                        + (n / 8) * 256 + (kk / 4) * 32 + (n % 8) * 4 + (kk % 4);
             dst[0] = hi;
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(V5_GW * 128 + 64, V5_GW == 2 ? 2 : 1) conv_v5_
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const float xv = v[16 * h + j];
-                    const float xh = __uint_as_float(__float_as_uint(xv) & 0xffffe000u);
+                    const float xh = ffc_tf32_hi(xv);
                     hi[j] = __float_as_uint(xh);
                     lo[j] = __float_as_uint(xv - xh);
                 }

@@ -6,10 +6,9 @@
 // The plane-wise transforms want one H x W plane per CTA, the channel mix wants all 2C channels of a bin: for 32 channels
 // at 128 x 128 one image's spectrum is 2.1 MB, so the two tilings meet in L2 instead of shared memory.  The batch is
 // walked in CHUNKS of images whose spectrum (<= ~24 MB) stays resident in the 126 MB L2 between the kernel that writes it
-// and the kernel that reads it, and the scratch buffer is reused by every chunk, so S never reaches HBM; in training
-// mode the mixed spectrum Y of the whole batch has to wait for the batch statistics and makes one round trip.
-// HBM traffic: x once, out once (+ residual), Y once each way in training -- 2 (eval) / 4 (training) tensor passes where
-// the first-generation general form made 7-8.
+// and the kernel that reads it, and the scratch buffer is reused by every chunk; in training mode the mixed spectrum Y of
+// the whole batch has to wait for the batch statistics and makes one round trip.  Three kernels per chunk (+ statistics
+// finalisation), 4-6 tensor passes where the first-generation general form made 7-8 in five slower kernels.
 //
 // Scratch layout ("shared-memory image"): plane (b, c) is N rows of RS = N + 4 floats = SPS = N/2 + 2 complex slots, bins
 // v = 0..N/2 of spectrum row p followed by one zero pad slot, rows in the permuted u order of the two-level column
@@ -294,9 +293,13 @@ int fu3_mix_tc_run(const Fu3MixParams& p, ffc_stream_t st);
 #endif
 static int g_fu3_simt_mix = 0;
 extern "C" void ffc_debug_fu3_simt_mix(int on) { g_fu3_simt_mix = on; }
-// bytes of spectrum a chunk of images may occupy (default 24 MB: S [+ Y in eval mode] of a chunk stay resident in L2)
-static size_t g_fu3_chunk_bytes = (size_t)24 << 20;
-extern "C" void ffc_debug_fu3_chunk_bytes(size_t bytes) { g_fu3_chunk_bytes = bytes ? bytes : ((size_t)24 << 20); }
+// Bytes of spectrum a chunk of images may occupy.  Measured (profiles/r02c_fu3_chunk_sweep.txt, FourierUnitSN(32,32) @128x128,
+// batch 64): every kernel of a chunk must fill the 148 SMs for several waves (3 planes per SM and wave), so chunks below
+// ~50 MB cost more in partial waves and launches than L2 residency of S returns; 160 MB keeps the largest BASELINE unit in one
+// chunk and still bounds the scratch for larger batches.
+static const size_t kFu3ChunkDefault = (size_t)160 << 20;
+static size_t g_fu3_chunk_bytes = kFu3ChunkDefault;
+extern "C" void ffc_debug_fu3_chunk_bytes(size_t bytes) { g_fu3_chunk_bytes = bytes ? bytes : kFu3ChunkDefault; }
 
 static bool fu3_mix_supported(int Cin, int Cout) {
 #ifdef FFC_EMU

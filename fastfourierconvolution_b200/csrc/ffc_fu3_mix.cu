@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) fu3_pack_kernel(const float* __restrict__
         const int k = chunk * FM_BK + kk;
         float v = 0.f;
         if (n < 2 * Cout && k < 2 * Cin) v = __ldg(w + (size_t)n * 2 * Cin + k) * scale;
-        const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        const float hi = ffc_tf32_hi(v);
         float* dst = wp + (size_t)chunk * 2 * NT * FM_BK + (n / 8) * 256 + (kk / 4) * 32 + (n % 8) * 4 + (kk % 4);
         dst[0] = hi;
         dst[(size_t)NT * FM_BK] = v - hi;
@@ -168,8 +168,8 @@ __global__ void __launch_bounds__(NWG * 128, 1) fu3_mix_kernel(const Fu3MixParam
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float2 x = v[8 * h + j];
-                    const float xh = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
-                    const float yh = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+                    const float xh = ffc_tf32_hi(x.x);
+                    const float yh = ffc_tf32_hi(x.y);
                     hi[2 * j] = __float_as_uint(xh); hi[2 * j + 1] = __float_as_uint(yh);
                     lo[2 * j] = __float_as_uint(x.x - xh); lo[2 * j + 1] = __float_as_uint(x.y - yh);
                 }

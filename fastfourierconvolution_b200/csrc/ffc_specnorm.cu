@@ -206,3 +206,78 @@ extern "C" int ffc_spectral_norm_fwd(const float* w_orig, float* u, float* v, fl
     if (items > ffc_sm_count() * 8) items = ffc_sm_count() * 8;
     return ffc_launch<SnScaleKernel>((int)items, 1, 1, SN_THREADS, SnScaleKernel::smem_bytes(), st, p);
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// backward through weight = W / sigma, sigma = u^T W v (u, v constants of the forward's power iteration):
+//     dW = g / sigma - (sum(g * W) / sigma^2) * u v^T          (torch.nn.utils.spectral_norm's autograd, restated)
+// two kernels: the dot product (double atomics), then the element-wise combination.
+// ---------------------------------------------------------------------------------------------------------------------
+struct SnBwdParams {
+    const float* g; const float* W; const float* u; const float* v; const float* sigma;
+    float* dW; double* dot;
+    int h, w, kk;
+};
+struct SnDotKernel {
+    typedef SnBwdParams Params;
+    static constexpr int kThreads = SN_THREADS;
+    static size_t smem_bytes() { return (size_t)SN_THREADS * sizeof(double); }
+    static FFC_DEVICE void run(const Params& p, const BlockCtx& ctx, float* smem) {
+        double* red = reinterpret_cast<double*>(smem);
+        FFC_PHASE {
+            const long long n = (long long)p.h * p.w;
+            float a0 = 0.f, a1 = 0.f;
+            long long i = (long long)ctx.bx * kThreads + tid;
+            const long long step = (long long)ctx.gx * kThreads;
+            for (; i + step < n; i += 2 * step) {
+                a0 = fmaf(FFC_LDG(p.g + i), FFC_LDG(p.W + i), a0);
+                a1 = fmaf(FFC_LDG(p.g + i + step), FFC_LDG(p.W + i + step), a1);
+            }
+            if (i < n) a0 = fmaf(FFC_LDG(p.g + i), FFC_LDG(p.W + i), a0);
+            red[tid] = (double)a0 + (double)a1;
+        } FFC_SYNC;
+        for (int s = kThreads / 2; s > 0; s >>= 1) {
+            FFC_PHASE { if (tid < s) red[tid] += red[tid + s]; } FFC_SYNC;
+        }
+        FFC_PHASE { if (tid == 0) ffc_atomic_add(p.dot, red[0]); } FFC_SYNC;
+    }
+};
+struct SnBwdKernel {
+    typedef SnBwdParams Params;
+    static constexpr int kThreads = SN_THREADS;
+    static FFC_DEVICE void run(const Params& p, const BlockCtx& ctx, float*) {
+        FFC_PHASE {
+            const float sg = FFC_LDG(p.sigma);
+            const float inv = 1.0f / sg;
+            const float coef = (float)(p.dot[0] / ((double)sg * (double)sg));
+            const long long n = (long long)p.h * p.w;
+            for (long long e = (long long)ctx.bx * kThreads + tid; e < n; e += (long long)ctx.gx * kThreads) {
+                int i, j;                                   // storage index e -> element (i, j) of the matrix view
+                if (p.kk == 0) { i = (int)(e / p.w); j = (int)(e % p.w); }
+                else { const int r = (int)(e % p.kk); const long long q = e / p.kk; i = (int)(q % p.h); j = (int)(q / p.h) * p.kk + r; }
+                p.dW[e] = FFC_LDG(p.g + e) * inv - coef * FFC_LDG(p.u + i) * FFC_LDG(p.v + j);
+            }
+        } FFC_SYNC;
+    }
+};
+
+// g, w_orig, dw: the weight tensor's own storage order (same kk convention as the forward); u (h), v (w), sigma (1): what
+// ffc_spectral_norm_fwd saved.  workspace >= 8 bytes.
+extern "C" int ffc_spectral_norm_bwd(const float* g, const float* w_orig, const float* u, const float* v, const float* sigma,
+                                     float* dw, int h, int w, int kk, void* workspace, size_t workspace_bytes, void* stream) {
+    FFC_REQUIRE(g && w_orig && u && v && sigma && dw, "ffc_spectral_norm_bwd: null pointer");
+    FFC_REQUIRE(h > 0 && w > 0 && kk >= 0 && (kk == 0 || w % kk == 0), "ffc_spectral_norm_bwd: bad sizes");
+    FFC_REQUIRE(workspace && workspace_bytes >= 16, "ffc_spectral_norm_bwd: workspace too small");
+    ffc_stream_t st = (ffc_stream_t)stream;
+    SnBwdParams p;
+    p.g = g; p.W = w_orig; p.u = u; p.v = v; p.sigma = sigma; p.dW = dw; p.h = h; p.w = w; p.kk = kk;
+    p.dot = (double*)(((uintptr_t)workspace + 7) & ~(uintptr_t)7);
+    FFC_CHECK(ffc_memset_async(p.dot, 0, sizeof(double), st));
+    long long items = ((long long)h * w + 2 * SN_THREADS - 1) / (2 * SN_THREADS);
+    if (items > ffc_sm_count() * 4) items = ffc_sm_count() * 4;
+    if (items < 1) items = 1;
+    FFC_CHECK((ffc_launch<SnDotKernel>((int)items, 1, 1, SN_THREADS, SnDotKernel::smem_bytes(), st, p)));
+    long long items2 = ((long long)h * w + SN_THREADS - 1) / SN_THREADS;
+    if (items2 > ffc_sm_count() * 8) items2 = ffc_sm_count() * 8;
+    return ffc_launch<SnBwdKernel>((int)items2, 1, 1, SN_THREADS, 0, st, p);
+}

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(WG5_THREADS, 1) wgrad_v5_kernel(const WgradV5P
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const float xv = v[16 * h + j];
-                    const float xh = __uint_as_float(__float_as_uint(xv) & 0xffffe000u);
+                    const float xh = ffc_tf32_hi(xv);
                     hi[j] = __float_as_uint(xh);
                     lo[j] = __float_as_uint(xv - xh);
                 }
@@ -173,8 +173,8 @@ __global__ void __launch_bounds__(WG5_THREADS, 1) wgrad_v5_kernel(const WgradV5P
                 if (g < ngroups) {
                     const int n = 8 * (g >> 1) + n8, q = 4 * (g & 1) + qs;
                     float4 h;
-                    h.x = __uint_as_float(__float_as_uint(v[i].x) & 0xffffe000u); h.y = __uint_as_float(__float_as_uint(v[i].y) & 0xffffe000u);
-                    h.z = __uint_as_float(__float_as_uint(v[i].z) & 0xffffe000u); h.w = __uint_as_float(__float_as_uint(v[i].w) & 0xffffe000u);
+                    h.x = ffc_tf32_hi(v[i].x); h.y = ffc_tf32_hi(v[i].y);
+                    h.z = ffc_tf32_hi(v[i].z); h.w = ffc_tf32_hi(v[i].w);
                     const uint32_t off = (uint32_t)((n >> 3) * 1024 + q * 128 + (n & 7) * 16);
                     *reinterpret_cast<float4*>(st + off) = h;
                     *reinterpret_cast<float4*>(st + half_bytes + off) = make_float4(v[i].x - h.x, v[i].y - h.y, v[i].z - h.z, v[i].w - h.w);

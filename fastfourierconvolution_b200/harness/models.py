@@ -26,6 +26,17 @@ def weights_init(m):
         nn.init.constant_(m.bias.data, 0)
 
 
+def _sn_linear(fc, x):
+    """The spectral-norm Linear head of the discriminators (fgan_complete.py:157, 170): the hook's power iteration and
+    W / sigma run in the library's three spectral-norm kernels (the same ones the SN convolutions use) instead of the stock
+    hook's ~14 PyTorch launches; the matrix-vector product itself stays a library GEMV.  CPU tensors (the host oracle
+    side of a comparison) go through the module's own forward."""
+    if not x.is_cuda:
+        return fc(x)
+    from ..layers import _util
+    return F.linear(x, _util.effective_weight(fc), fc.bias)
+
+
 def hinge_loss_dis(fake, real):
     """fgan_complete.py:216-222."""
     return F.relu(1.0 - real).mean() + F.relu(1.0 + fake).mean()
@@ -121,7 +132,7 @@ class SNDiscriminator(nn.Module):
                 conv = getattr(self, f"conv{i}")
                 w = _util.effective_weight(conv)          # spectral_norm pre-forward hook: W / sigma, one power iteration
                 m = ops.conv2d_act(m, w, conv.bias, conv.stride[0], conv.padding[0], ops.ACT_LEAKY, self.act.negative_slope)
-            return self.fc(m.reshape(-1, self.mg * self.mg * 512))
+            return _sn_linear(self.fc, m.reshape(-1, self.mg * self.mg * 512))
         m = x.contiguous(memory_format=torch.channels_last) if self.channels_last else x
         for i in range(1, self.n_convs + 1):
             m = self.act(getattr(self, f"conv{i}")(m))
@@ -148,7 +159,7 @@ class FDiscriminator(nn.Module):
 
     def forward(self, x):
         m = self.resizer(self.main(x))
-        return self.fc(m.view(-1, self.mg * self.mg * 512))
+        return _sn_linear(self.fc, m.view(-1, self.mg * self.mg * 512))
 
 
 # stages of the SNFFC discriminator below: (in, out, kernel, ratio_gin, ratio_gout, stride, padding, norm)
@@ -185,7 +196,7 @@ class FDiscriminatorSN64(nn.Module):
 
     def forward(self, x):
         m = self.resizer(self.main(x))
-        return self.fc(m.view(-1, self.mg * self.mg * 512))
+        return _sn_linear(self.fc, m.view(-1, self.mg * self.mg * 512))
 
 
 class FFCGenerator(nn.Module):

@@ -88,12 +88,27 @@ class _FFCBase(nn.Module):
     def forward(self, x, y=None):
         x_l, x_g = x if type(x) is tuple else (x, 0)
         out_xl, out_xg = 0, 0
+        st = self.convg2g if type(self.convg2g) is not nn.Identity else None
+        fork = None
+        if st is not None and torch.is_tensor(x_g) and x_g.is_cuda and not isinstance(self.convl2l, nn.Identity):
+            # The spectral transform up to its last convolution (SE, conv1, BN+ReLU, Fourier unit: small kernels) does not
+            # depend on the local convolutions (one large launch): queue it on a side stream, join before conv2 adds the
+            # l2g output.  autograd runs each backward node on its forward stream, so the backward forks the same way, and a
+            # CUDA-graph capture of the step records the two chains as parallel branches.
+            fork = ops._Fork(x_g.device, 1)
+            with fork:
+                s = st._pre(x_g, y)
         blk = self._local_block(x_l, x_g)
+        if fork is not None:
+            ops._join(x_g.device)
         if blk is not None:
             out_xl, base = blk
-            if type(self.convg2g) is not nn.Identity:
-                return out_xl, self.convg2g._run(x_g, y, base)
+            if st is not None:
+                return out_xl, (st._post(s, base) if fork is not None else st._run(x_g, y, base))
             return out_xl, base
+        if fork is not None:
+            return self._local_sum([(self.convl2l, x_l), (self.convg2l, x_g)]) if self.ratio_gout != 1 else 0, \
+                self._local_sum([(self.convl2g, x_l)], addend_fn=lambda base: st._post(s, base))
         if self.ratio_gout != 1:
             out_xl = self._local_sum([(self.convl2l, x_l), (self.convg2l, x_g)])
         if self.ratio_gout != 0:

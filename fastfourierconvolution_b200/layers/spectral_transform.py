@@ -63,8 +63,14 @@ class SpectralTransform(nn.Module):
 
     def _run(self, x, y, addend):
         """conv2(x1 + fu(x1)) [+ addend], x1 = relu(bn1(conv1(se(resample(x)))))."""
+        return self._post(self._pre(x, y), addend)
+
+    def _pre(self, x, y):
+        """x1 + fu(x1): everything of the transform that does not depend on the local branches of the enclosing FFC."""
         xs = self.se_block._run(x, self._mode)                                       # :79, :87
         c1 = ops.conv2d(xs, _util.effective_weight(self.conv1))                       # :89
         x1 = _util.bn_act(c1, self.bn1, (ops.ACT_RELU, 0.0))
-        s = self.fu._run(x1, y, x1)                                                   # :91 + the add of :108
+        return self.fu._run(x1, y, x1)                                                # :91 + the add of :108
+
+    def _post(self, s, addend):
         return ops.conv2d(s, _util.effective_weight(self.conv2), addend=addend)       # :108

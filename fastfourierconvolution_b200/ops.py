@@ -80,35 +80,76 @@ class Conv2dFn(torch.autograd.Function):
         return _conv_backward(ctx.cfg, x0, w0, x1, w1, dy, ctx.needs_input_grad)
 
 
+class _Fork:
+    """``with _Fork(device, i):`` runs the block on side stream ``i`` after everything already queued on the current stream;
+    ``_join(device)`` makes the current stream wait for all forks.  Output tensors are allocated BEFORE the block (on the
+    current stream's pool).  No-op on CPU tensors (host emulation) and with FFC_B200_SINGLE_STREAM=1."""
+
+    def __init__(self, device, index=0):
+        self.ctx = None
+        if device.type == "cuda":
+            sides = _C.side_streams(device)
+            if sides is not None:
+                self.side = sides[index % len(sides)]
+                self.side.wait_stream(torch.cuda.current_stream(device))
+                self.ctx = torch.cuda.stream(self.side)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
+def _join(device):
+    if device.type == "cuda":
+        sides = _C.side_streams(device)
+        if sides is not None:
+            cur = torch.cuda.current_stream(device)
+            for s in sides:
+                cur.wait_stream(s)
+
+
 def _conv_backward(cfg, x0, w0, x1, w1, dy, needs):
-    """Gradients of Conv2dFn's ten inputs (None where not needed)."""
+    """Gradients of Conv2dFn's ten inputs (None where not needed).  The data gradients stay on the current stream; the weight
+    and bias gradients -- independent of them -- are queued on side streams (fork / join)."""
     stride, pad, transposed, k, cout, has_bias, has_addend = cfg
     dy = dy.contiguous()
     B, _, Ho, Wo = dy.shape
     L = _C.lib()
-    st = _C.current_stream(dy.device)
+    dev = dy.device
     grads = [None] * 10
-    for slot, (x, w) in enumerate(((x0, w0), (x1, w1))):
-        if x is None:
-            continue
-        cin, Hi, Wi = x.shape[1], x.shape[2], x.shape[3]
-        if needs[2 * slot]:
-            dx = torch.empty_like(x)
+    segs = [(slot, x, w) for slot, (x, w) in enumerate(((x0, w0), (x1, w1))) if x is not None]
+    dws = {slot: torch.empty_like(w) for slot, x, w in segs if needs[2 * slot + 1]}
+    dxs = {slot: torch.empty_like(x) for slot, x, w in segs if needs[2 * slot]}
+    db = torch.empty(cout, device=dev, dtype=torch.float32) if (has_bias and needs[4]) else None
+    if dws or db is not None:
+        with _Fork(dev, 0):
+            st = _C.current_stream(dev)
+            for slot, x, w in segs:
+                if slot not in dws:
+                    continue
+                cin, Hi, Wi = x.shape[1], x.shape[2], x.shape[3]
+                if transposed:   # S = x (cin, Hi), L = dy (cout, Ho) -> [cin][cout][k][k]
+                    _C.check(L.ffc_conv2d_wgrad(_C.ptr(x), _C.ptr(dy), _C.ptr(dws[slot]), B, cin, cout, Hi, Wi, Ho, Wo, k, stride, pad, st))
+                else:            # S = dy, L = x -> [cout][cin][k][k]
+                    _C.check(L.ffc_conv2d_wgrad(_C.ptr(dy), _C.ptr(x), _C.ptr(dws[slot]), B, cout, cin, Ho, Wo, Hi, Wi, k, stride, pad, st))
+                grads[2 * slot + 1] = dws[slot]
+            if db is not None:
+                ws = _C.workspace(2 * cout * 8, dev)
+                _C.check(L.ffc_bias_grad(_C.ptr(dy), _C.ptr(db), B, cout, Ho * Wo, _C.ptr(ws), ws.numel(), st))
+                grads[4] = db
+    for slot, x, w in segs:
+        if slot in dxs:
+            cin, Hi, Wi = x.shape[1], x.shape[2], x.shape[3]
             # data gradient = the opposite gather form over dy with the same weight tensor
-            _conv_launch(dy, w, cout, None, None, 0, None, None, dx, B, cin, Ho, Wo, Hi, Wi, k, stride, pad, not transposed)
-            grads[2 * slot] = dx
-        if needs[2 * slot + 1]:
-            dw = torch.empty_like(w)
-            if transposed:   # S = x (cin, Hi), L = dy (cout, Ho) -> [cin][cout][k][k]
-                _C.check(L.ffc_conv2d_wgrad(_C.ptr(x), _C.ptr(dy), _C.ptr(dw), B, cin, cout, Hi, Wi, Ho, Wo, k, stride, pad, st))
-            else:            # S = dy, L = x -> [cout][cin][k][k]
-                _C.check(L.ffc_conv2d_wgrad(_C.ptr(dy), _C.ptr(x), _C.ptr(dw), B, cout, cin, Ho, Wo, Hi, Wi, k, stride, pad, st))
-            grads[2 * slot + 1] = dw
-    if has_bias and needs[4]:
-        db = torch.empty(cout, device=dy.device, dtype=torch.float32)
-        ws = _C.workspace(2 * cout * 8, dy.device)
-        _C.check(L.ffc_bias_grad(_C.ptr(dy), _C.ptr(db), B, cout, Ho * Wo, _C.ptr(ws), ws.numel(), st))
-        grads[4] = db
+            _conv_launch(dy, w, cout, None, None, 0, None, None, dxs[slot], B, cin, Ho, Wo, Hi, Wi, k, stride, pad, not transposed)
+            grads[2 * slot] = dxs[slot]
+    _join(dev)
     if has_addend and needs[5]:
         grads[5] = dy
     return tuple(grads)
@@ -167,44 +208,54 @@ class ConvBlockFn(torch.autograd.Function):
         B, _, Ho, Wo = dy0.shape
         cin0, Hi, Wi = x0.shape[1], x0.shape[2], x0.shape[3]
         L = _C.lib()
-        st = _C.current_stream(dy0.device)
         need = ctx.needs_input_grad
         g = [None] * 11
 
-        def wgrad(x, dy, w, cin, cout):
-            dw = torch.empty_like(w)
+        dev = dy0.device
+
+        def wgrad(x, dy, dw, cin, cout, st):
             if transposed:
                 _C.check(L.ffc_conv2d_wgrad(_C.ptr(x), _C.ptr(dy), _C.ptr(dw), B, cin, cout, Hi, Wi, Ho, Wo, k, stride, pad, st))
             else:
                 _C.check(L.ffc_conv2d_wgrad(_C.ptr(dy), _C.ptr(x), _C.ptr(dw), B, cout, cin, Ho, Wo, Hi, Wi, k, stride, pad, st))
-            return dw
 
-        def bgrad(dy, cout):
-            db = torch.empty(cout, device=dy.device, dtype=torch.float32)
-            ws = _C.workspace(2 * cout * 8, dy.device)
+        def bgrad(dy, db, cout, st):
+            ws = _C.workspace(2 * cout * 8, dev)
             _C.check(L.ffc_bias_grad(_C.ptr(dy), _C.ptr(db), B, cout, Ho * Wo, _C.ptr(ws), ws.numel(), st))
-            return db
 
+        # outputs are allocated on the current stream; the weight / bias gradients and the second segment's data gradient are
+        # independent of dx0 and run on side streams (fork / join)
+        cin1 = x1.shape[1] if x1 is not None else 0
+        dw00 = torch.empty_like(w00) if need[1] else None
+        dw01 = torch.empty_like(w01) if need[2] else None
+        dx1 = torch.empty_like(x1) if (x1 is not None and need[3]) else None
+        dw10 = torch.empty_like(w10) if (x1 is not None and need[4]) else None
+        db0 = torch.empty(cout0, device=dev, dtype=torch.float32) if (has_b0 and need[5]) else None
+        db1 = torch.empty(cout1, device=dev, dtype=torch.float32) if (has_b1 and need[6]) else None
+        if dw00 is not None or dw01 is not None or dw10 is not None:
+            with _Fork(dev, 0):
+                st0 = _C.current_stream(dev)
+                if dw00 is not None:
+                    wgrad(x0, dy0, dw00, cin0, cout0, st0)
+                if dw01 is not None:
+                    wgrad(x0, dy1, dw01, cin0, cout1, st0)
+                if dw10 is not None:
+                    wgrad(x1, dy0, dw10, cin1, cout0, st0)
+        if dx1 is not None or db0 is not None or db1 is not None:
+            with _Fork(dev, 1):
+                st1 = _C.current_stream(dev)
+                if dx1 is not None:
+                    _conv_launch(dy0, w10, cout0, None, None, 0, None, None, dx1, B, cin1, Ho, Wo, Hi, Wi, k, stride, pad, not transposed)
+                if db0 is not None:
+                    bgrad(dy0, db0, cout0, st1)
+                if db1 is not None:
+                    bgrad(dy1, db1, cout1, st1)
         if need[0]:     # both output blocks flow back into x0: one two-segment launch of the opposite gather form
             dx0 = torch.empty_like(x0)
             _conv_launch(dy0, w00, cout0, dy1, w01, cout1, None, None, dx0, B, cin0, Ho, Wo, Hi, Wi, k, stride, pad, not transposed)
             g[0] = dx0
-        if need[1]:
-            g[1] = wgrad(x0, dy0, w00, cin0, cout0)
-        if need[2]:
-            g[2] = wgrad(x0, dy1, w01, cin0, cout1)
-        if x1 is not None:
-            cin1 = x1.shape[1]
-            if need[3]:
-                dx1 = torch.empty_like(x1)
-                _conv_launch(dy0, w10, cout0, None, None, 0, None, None, dx1, B, cin1, Ho, Wo, Hi, Wi, k, stride, pad, not transposed)
-                g[3] = dx1
-            if need[4]:
-                g[4] = wgrad(x1, dy0, w10, cin1, cout0)
-        if has_b0 and need[5]:
-            g[5] = bgrad(dy0, cout0)
-        if has_b1 and need[6]:
-            g[6] = bgrad(dy1, cout1)
+        _join(dev)
+        g[1], g[2], g[3], g[4], g[5], g[6] = dw00, dw01, dx1, dw10, db0, db1
         return tuple(g)
 
 
@@ -298,14 +349,13 @@ class SpectralNormFn(torch.autograd.Function):
     def backward(ctx, g):
         w_orig, u_s, v_s, sigma = ctx.saved_tensors
         g = g.contiguous()
-        coef = (g * w_orig).sum() / (sigma * sigma)                    # sum(g * W) / sigma^2, a one-element tensor
-        uv = torch.outer(u_s, v_s)                                     # d sigma / d W in the (out channels, rest) view
-        if ctx.dim == 1:
-            s = w_orig.shape
-            uv = uv.view(s[1], s[0], *s[2:]).transpose(0, 1)
-        else:
-            uv = uv.view_as(w_orig)
-        dw = g / sigma - coef * uv
+        h = w_orig.shape[ctx.dim]
+        wd = w_orig.numel() // h
+        kk = w_orig[0, 0].numel() if ctx.dim == 1 else 0
+        dw = torch.empty_like(w_orig)                   # dW = g / sigma - (sum(g * W) / sigma^2) u v^T in two kernels
+        ws = _C.workspace(64, w_orig.device)
+        _C.check(_C.lib().ffc_spectral_norm_bwd(_C.ptr(g), _C.ptr(w_orig), _C.ptr(u_s), _C.ptr(v_s), _C.ptr(sigma), _C.ptr(dw),
+                                                h, wd, kk, _C.ptr(ws), ws.numel(), _C.current_stream(w_orig.device)))
         return dw, None, None, None, None
 
 

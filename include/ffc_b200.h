@@ -102,7 +102,7 @@ int ffc_fu3_fwd(const float* x, const float* w, const float* gamma, const float*
                 int B, int Cin, int Cout, int H, int W, int training, float eps, float momentum,
                 void* workspace, size_t workspace_bytes, void* stream);
 void ffc_debug_fu3_simt_mix(int on);
-void ffc_debug_fu3_chunk_bytes(size_t bytes);      /* spectrum bytes per chunk of images (0 = default 24 MB); tuning / tests */
+void ffc_debug_fu3_chunk_bytes(size_t bytes);      /* spectrum bytes per chunk of images (0 = default 160 MB); tuning / tests */
 
 /* ffc_fu_bwd: the autograd backward of FourierUnitSN.forward (fourier_unity.py:32-58; derived from ATen's
  * fft_r2c / fft_c2r / batch_norm / relu / conv backward formulas) as ONE cooperative kernel, one image per CTA:
@@ -222,6 +222,11 @@ size_t ffc_spectral_norm_workspace_bytes(int h, int w);
 int ffc_spectral_norm_fwd(const float* w_orig, float* u, float* v, float* u_save, float* v_save,
                           float* w_eff, float* sigma, int h, int w, int kk, int power_iteration, float eps,
                           void* workspace, size_t workspace_bytes, void* stream);
+/* backward through weight = W / sigma (sigma = u^T W v with the u, v the forward saved):
+ *   dW = g / sigma - (sum(g * W) / sigma^2) * u v^T   -- torch.nn.utils.spectral_norm's autograd in two kernels.
+ * g / w_orig / dw in the weight's own storage order (kk as in the forward); workspace >= 16 bytes. */
+int ffc_spectral_norm_bwd(const float* g, const float* w_orig, const float* u, const float* v, const float* sigma,
+                          float* dw, int h, int w, int kk, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- SE gate + resampling ---------------------------------------------------------------------
  * y = r(x) * sigmoid(W2 relu(W1 mean_hw(r(x)))): SpectralTransform.downsample followed by SELayer
