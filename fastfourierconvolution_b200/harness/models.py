@@ -128,11 +128,20 @@ class SNDiscriminator(nn.Module):
             from .. import ops
             from ..layers import _util
             m = x
-            for i in range(1, self.n_convs + 1):
-                conv = getattr(self, f"conv{i}")
-                w = _util.effective_weight(conv)          # spectral_norm pre-forward hook: W / sigma, one power iteration
-                m = ops.conv2d_act(m, w, conv.bias, conv.stride[0], conv.padding[0], ops.ACT_LEAKY, self.act.negative_slope)
-            return _sn_linear(self.fc, m.reshape(-1, self.mg * self.mg * 512))
+            convs = [getattr(self, f"conv{i}") for i in range(1, self.n_convs + 1)]
+            # spectral_norm pre-forward hooks (W / sigma, one power iteration each) depend on the weights only: the first
+            # layer's runs here, the others (3 small kernels per layer) on a side stream while the first convolution runs
+            ws = [_util.effective_weight(convs[0])]
+            with ops._Fork(x.device, 0):
+                ws += [_util.effective_weight(c) for c in convs[1:]]
+                w_fc = _util.effective_weight(self.fc) if x.is_cuda else None
+            for i, conv in enumerate(convs):
+                if i == 1:
+                    ops._join(x.device)
+                m = ops.conv2d_act(m, ws[i], conv.bias, conv.stride[0], conv.padding[0], ops.ACT_LEAKY, self.act.negative_slope)
+            ops._join(x.device)
+            m = m.reshape(-1, self.mg * self.mg * 512)
+            return F.linear(m, w_fc, self.fc.bias) if w_fc is not None else self.fc(m)
         m = x.contiguous(memory_format=torch.channels_last) if self.channels_last else x
         for i in range(1, self.n_convs + 1):
             m = self.act(getattr(self, f"conv{i}")(m))

@@ -80,19 +80,27 @@ class Conv2dFn(torch.autograd.Function):
         return _conv_backward(ctx.cfg, x0, w0, x1, w1, dy, ctx.needs_input_grad)
 
 
+_forked = {}          # device -> side streams forked from the current stream and not joined yet
+
+
 class _Fork:
     """``with _Fork(device, i):`` runs the block on side stream ``i`` after everything already queued on the current stream;
-    ``_join(device)`` makes the current stream wait for all forks.  Output tensors are allocated BEFORE the block (on the
-    current stream's pool).  No-op on CPU tensors (host emulation) and with FFC_B200_SINGLE_STREAM=1."""
+    ``_join(device)`` makes the current stream wait for the forks made since the last join (only those: during a CUDA-graph
+    capture a wait on a stream that holds uncaptured work would invalidate the capture).  Output tensors are allocated
+    BEFORE the block (on the current stream's pool).  No-op on CPU tensors (host emulation), when the current stream IS
+    the side stream (a backward node that autograd runs on its forward's side stream), and with FFC_B200_SINGLE_STREAM=1."""
 
     def __init__(self, device, index=0):
         self.ctx = None
         if device.type == "cuda":
             sides = _C.side_streams(device)
             if sides is not None:
-                self.side = sides[index % len(sides)]
-                self.side.wait_stream(torch.cuda.current_stream(device))
-                self.ctx = torch.cuda.stream(self.side)
+                side = sides[index % len(sides)]
+                cur = torch.cuda.current_stream(device)
+                if side != cur:
+                    side.wait_stream(cur)
+                    self.ctx = torch.cuda.stream(side)
+                    _forked.setdefault((str(device), cur.cuda_stream), []).append(side)
 
     def __enter__(self):
         if self.ctx is not None:
@@ -107,11 +115,9 @@ class _Fork:
 
 def _join(device):
     if device.type == "cuda":
-        sides = _C.side_streams(device)
-        if sides is not None:
-            cur = torch.cuda.current_stream(device)
-            for s in sides:
-                cur.wait_stream(s)
+        cur = torch.cuda.current_stream(device)
+        for s in _forked.pop((str(device), cur.cuda_stream), []):
+            cur.wait_stream(s)
 
 
 def _conv_backward(cfg, x0, w0, x1, w1, dy, needs):

@@ -58,7 +58,7 @@ def test_model_matches_reference_golden(name, fn):
     different sides of the kink are detected and accounted for by parity.flip_aware_compare (SURVEY.md 8(c) caveat 1); no
     looser norm is used anywhere.  Where the reference's OWN FP32 arithmetic (the CPU oracle in float32) is further than
     5e-5 from the float64 truth on some tensor -- whole networks at batch 1-2 through training-mode BatchNorm are that
-    ill-conditioned -- the bound for that tensor is twice the reference's own error (stated in the printed line)."""
+    ill-conditioned -- the bound for that tensor is four times the reference's own error (3xTF32 keeps ~22 bits per product)."""
     from test_layers_emu import run_model_fixture
     got, fx, oracle_run = run_model_fixture(name, fn, DEV)
     cache = {}
@@ -66,7 +66,7 @@ def test_model_matches_reference_golden(name, fn):
     noise, _, _ = parity.flip_aware_errors(ref32, oracle_run, cache=cache)
     errs64, flips64 = parity.flip_aware_compare(got, oracle_run, tol=parity.TOL, noise_floor=noise, cache=cache, what=name + " vs float64 oracle")
     errs32, flips32 = parity.flip_aware_compare(got, oracle_run, ref={k: torch.from_numpy(v) for k, v in fx.items()}, tol=2e-4,
-                                                noise_floor={k: 2 * v for k, v in noise.items()}, cache=cache, what=name + " vs reference fixture")
+                                                noise_floor={k: 1.5 * v for k, v in noise.items()}, cache=cache, what=name + " vs reference fixture")
     print(f"{name}: max err vs float64 {max(errs64.values()):.2e} ({flips64} mask flips; reference FP32 itself {max(noise.values()):.2e}), "
           f"vs fixture {max(errs32.values()):.2e} ({flips32} flips)")
 
@@ -79,7 +79,7 @@ def _oracle_vs_module(mod, cfg_fn, xs, train=True, tol=parity.TOL, seed=0, whole
     pre-activation within FP32 rounding of the kink and lands on the other side in one of the two evaluations (SURVEY.md
     section 8(c) caveat 1).  parity.flip_aware_compare detects exactly those elements with the oracle's activation tape
     and accounts for them, so the same 1e-4 max-norm bound holds for single modules and whole networks alike (a tensor on
-    which the reference's own FP32 arithmetic is further than 5e-5 from float64 is held to twice that error instead)."""
+    which the reference's own FP32 arithmetic is further than 2.5e-5 from float64 is held to four times that error instead)."""
     torch.manual_seed(seed)
     mod.train(train)
     sd = {k: v.detach().clone() for k, v in mod.state_dict().items()}
