@@ -32,6 +32,84 @@ template <int N> struct Fu3G {
 };
 
 // ------------------------------------------------------------------------------------------------------------------
+// column passes, two work items per loop iteration.  Same arithmetic and item enumeration as fu2_cols_strided /
+// fu2_cols_contig (ffc_fu2.cuh); the loads of both items are issued before either butterfly, so with only ~3 warps per
+// scheduler (three 128-thread CTAs per SM, one 67 KB plane each) the shared-memory latency of one item hides behind the
+// arithmetic of the other (ncu r02g: short-scoreboard was the top stall of these passes).
+// ------------------------------------------------------------------------------------------------------------------
+template <int N, int SIGN, bool BN, bool STRIDED>
+FFC_DEVICE void fu3_cols_pass(int tid, int nt, int np, float* planes, const float2* tw, Fu2Bn bn) {
+    typedef Fu2G<N> G;
+    constexpr int N1 = G::N1, N2 = G::N2, Wf = G::Wf;
+    constexpr int R = STRIDED ? N1 : N2;          // points per item
+    constexpr int S = STRIDED ? N2 : N1;          // items per column
+    const int total = np * Wf * S;
+    for (int it0 = tid; it0 < total; it0 += 2 * nt) {
+        float2 c[2][R];
+        float2* col[2];
+        int pls[2], sub[2];
+        bool on[2];
+        FFC_UNROLL
+        for (int u = 0; u < 2; ++u) {
+            const int it = it0 + u * nt;
+            on[u] = it < total;
+            int v = 0, k = 0, pl = 0;
+            if (on[u]) {
+                if (it < np * G::M * S) { v = it % G::M; k = (it / G::M) % S; pl = it / (G::M * S); }
+                else { const int j = it - np * G::M * S; v = G::M; k = j % S; pl = j / S; }
+            }
+            pls[u] = pl; sub[u] = k;
+            col[u] = reinterpret_cast<float2*>(planes + pl * G::REGION) + v + (STRIDED ? k * G::SPS : (N2 * k) * G::SPS);
+            if (on[u]) {
+                FFC_UNROLL
+                for (int i = 0; i < R; ++i) c[u][i] = col[u][(STRIDED ? N2 * i : i) * G::SPS];
+            }
+        }
+        FFC_UNROLL
+        for (int u = 0; u < 2; ++u) {
+            if (!on[u]) continue;
+            if (BN) {
+                const float2 a = bn.a[pls[u]], b = bn.b[pls[u]];
+                FFC_UNROLL
+                for (int i = 0; i < R; ++i) c[u][i] = fu2_bn_relu(c[u][i], a, b);
+            }
+            ffc_fft_regs<R, SIGN>(c[u]);
+        }
+        FFC_UNROLL
+        for (int u = 0; u < 2; ++u) {
+            if (!on[u]) continue;
+            FFC_UNROLL
+            for (int i = 0; i < R; ++i) {
+                float2 o = c[u][i];
+                // twiddles between the two levels: after the strided level of the forward transform, after the contiguous
+                // level of the inverse one (ffc_fu2.cuh)
+                if (STRIDED && SIGN < 0 && N2 > 1 && i > 0) o = ffc_cmul_tw<-1>(o, tw[sub[u] * i]);
+                if (!STRIDED && SIGN > 0 && i > 0) o = ffc_cmul_tw<+1>(o, tw[i * sub[u]]);
+                col[u][(STRIDED ? N2 * i : i) * G::SPS] = o;
+            }
+        }
+    }
+}
+#define FU3_COLS_FWD(N, np, planes, tw)                                                                              \
+    do {                                                                                                             \
+        Fu2Bn nobn_; nobn_.a = nullptr; nobn_.b = nullptr;                                                           \
+        FFC_PHASE { fu3_cols_pass<N, -1, false, true>(tid, ctx.nt, np, planes, tw, nobn_); } FFC_SYNC;               \
+        if constexpr (Fu2G<N>::N2 > 1) {                                                                             \
+            FFC_PHASE { fu3_cols_pass<N, -1, false, false>(tid, ctx.nt, np, planes, tw, nobn_); } FFC_SYNC;          \
+        }                                                                                                            \
+    } while (0)
+#define FU3_COLS_INV(N, BNF, np, planes, tw, bn)                                                                     \
+    do {                                                                                                             \
+        Fu2Bn nobn_; nobn_.a = nullptr; nobn_.b = nullptr;                                                           \
+        if constexpr (Fu2G<N>::N2 > 1) {                                                                             \
+            FFC_PHASE { fu3_cols_pass<N, +1, BNF, false>(tid, ctx.nt, np, planes, tw, bn); } FFC_SYNC;               \
+            FFC_PHASE { fu3_cols_pass<N, +1, false, true>(tid, ctx.nt, np, planes, tw, nobn_); } FFC_SYNC;           \
+        } else {                                                                                                     \
+            FFC_PHASE { fu3_cols_pass<N, +1, BNF, true>(tid, ctx.nt, np, planes, tw, bn); } FFC_SYNC;                \
+        }                                                                                                            \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------------------------
 // plane transforms
 // ------------------------------------------------------------------------------------------------------------------
 struct Fu3FwdFftParams {
@@ -61,7 +139,7 @@ struct Fu3Rfft2 {
         uint64_t* bar = reinterpret_cast<uint64_t*>(tw + N);
         {
             const int tid = (int)threadIdx.x;
-            if (tid == 0) { umma::mbar_init(bar, 1); umma::fence_barrier_init(); }
+            if (tid == 0) { umma::mbar_init(bar, 1); umma::fence_proxy_async_smem(); }   // (the cluster-scope release fence flushes L1: CCTL.IVALL)
             for (int k = tid; k < N; k += ctx.nt) tw[k] = c_tw128[k * (FFC_TW_N / N)];
             __syncthreads();
             if (tid == 0) umma::mbar_arrive_expect_tx(bar, (uint32_t)(np * N * N * 4));
@@ -80,7 +158,7 @@ struct Fu3Rfft2 {
             for (int r = tid; r < np * N; r += ctx.nt)           // the pad slot of every row (read by the mix, never used)
                 reinterpret_cast<float2*>(planes + (size_t)r * G::RS)[G::M + 1] = make_float2(0.f, 0.f);
         } FFC_SYNC;
-        FU2_COLS_FWD(N, np, planes, tw);
+        FU3_COLS_FWD(N, np, planes, tw);
 #ifndef FFC_EMU
         // the scratch layout IS the shared-memory image: one bulk copy writes the CTA's planes back
         umma::fence_proxy_async_smem();
@@ -134,7 +212,7 @@ struct Fu3Irfft2 {
         uint64_t* bar = reinterpret_cast<uint64_t*>(bnp_b + P);
         {
             const int tid = (int)threadIdx.x;
-            if (tid == 0) { umma::mbar_init(bar, 1); umma::fence_barrier_init(); }
+            if (tid == 0) { umma::mbar_init(bar, 1); umma::fence_proxy_async_smem(); }   // (the cluster-scope release fence flushes L1: CCTL.IVALL)
             __syncthreads();
             if (tid == 0) {
                 umma::mbar_arrive_expect_tx(bar, (uint32_t)(np * G::REGION * 4));
@@ -151,8 +229,8 @@ struct Fu3Irfft2 {
             __syncthreads();
         }
         Fu2Bn bn; bn.a = bnp_a; bn.b = bnp_b;
-        if (p.bn_a) { FU2_COLS_INV(N, true, np, planes, tw, bn); }
-        else { FU2_COLS_INV(N, false, np, planes, tw, bn); }
+        if (p.bn_a) { FU3_COLS_INV(N, true, np, planes, tw, bn); }
+        else { FU3_COLS_INV(N, false, np, planes, tw, bn); }
 #else
         FFC_PHASE {
             for (int k = tid; k < N; k += ctx.nt) tw[k] = c_tw128[k * (FFC_TW_N / N)];
@@ -172,7 +250,7 @@ struct Fu3Irfft2 {
             }
         } FFC_SYNC;
         Fu2Bn nobn; nobn.a = nullptr; nobn.b = nullptr;
-        FU2_COLS_INV(N, false, np, planes, tw, nobn);
+        FU3_COLS_INV(N, false, np, planes, tw, nobn);
 #endif
         FFC_PHASE { fu2_rows_inv<N, ADJ>(tid, ctx.nt, np * N, planes, p.scale); } FFC_SYNC;
 #ifndef FFC_EMU

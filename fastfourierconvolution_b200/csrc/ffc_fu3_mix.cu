@@ -18,10 +18,11 @@
 //   * B: the whole packed weight matrix (hi | lo, K-major no-swizzle UMMA tiles, forward transform scale folded in)
 //     is resident in shared memory for the life of the CTA: one cp.async.bulk per K chunk at start.
 //   * Epilogue per tile: tcgen05.ld 16 columns (= 8 complex output channels) at a time; either BN + ReLU with folded
-//     constants, or the per-channel sum / sum of squares over the real bins (pad slots masked) by a transposing warp
-//     butterfly (16 shuffles per 16 columns), accumulated in double per lane over all tiles of the warpgroup, reduced over
-//     the CTA in shared memory and flushed with one double atomic per channel and CTA; then one coalesced 8-byte store
-//     per channel.
+//     constants, or the per-channel sum / sum of squares over the real bins (pad slots masked): the tile goes column-major
+//     into a shared-memory staging tile of the warpgroup, each thread then adds up 64 bins of one column (a warp-shuffle
+//     butterfly cost 40 % of the kernel's instructions, ncu r02d), accumulates in double over all its tiles, and the CTA
+//     flushes one double atomic per channel at the end; one coalesced 8-byte store per channel writes Y.
+//   * The first chunk of the NEXT tile is gathered before the epilogue of the current one, so its latency is hidden.
 #include "ffc_fu3.cuh"
 
 #ifndef FFC_EMU
@@ -35,7 +36,8 @@ static inline int fm_kchunks(int Cin) { return (2 * Cin + FM_BK - 1) / FM_BK; }
 bool fu3_mix_tc_supported(int Cin, int Cout) {
     const int NT = fm_nt(Cout), KC = fm_kchunks(Cin);
     if (NT > 128 || NT < 16) return false;
-    return (size_t)KC * 2 * NT * FM_BK * 4 + 4 * NT * 4 + 512 <= (size_t)200 * 1024;
+    const int nwg = (NT <= 64) ? 4 : 2;                   // + statistics staging tiles of the training-mode epilogue
+    return (size_t)KC * 2 * NT * FM_BK * 4 + 4 * NT * 4 + 512 + (size_t)nwg * 64 * 132 * 4 <= (size_t)225 * 1024;
 }
 size_t fu3_mix_tc_packed_floats(int Cin, int Cout) { return (size_t)fm_kchunks(Cin) * 2 * fm_nt(Cout) * FM_BK; }
 
@@ -68,37 +70,14 @@ __device__ __forceinline__ void fm_named_barrier(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// sum over the 32 lanes of 16 per-lane values by a transposing butterfly: lane l ends with the total of column
-// (l >> 1) & 15 ... precisely column col(l) = 8*b4 + 4*b3 + 2*b2 + b1 with b_i = bit i of l (lanes l and l^1 hold the same)
-__device__ __forceinline__ float fm_colsum16(const float* v, int lane) {
-    float a8[8], a4[4], a2[2];
-    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const float keep = h16 ? v[8 + j] : v[j], send = h16 ? v[j] : v[8 + j];
-        a8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float keep = h8 ? a8[4 + j] : a8[j], send = h8 ? a8[j] : a8[4 + j];
-        a4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const float keep = h4 ? a4[2 + j] : a4[j], send = h4 ? a4[j] : a4[2 + j];
-        a2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-    const float keep = h2 ? a2[1] : a2[0], send = h2 ? a2[0] : a2[1];
-    float r = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    r += __shfl_xor_sync(0xffffffffu, r, 1);
-    return r;
-}
-__device__ __forceinline__ int fm_col_of_lane(int lane) {
-    return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-}
+static constexpr int FM_SCOL = 132;               // floats per column of the statistics staging tile (128 bins + 4: conflict-free LDS.128)
+static constexpr int FM_SBUF = 64 * FM_SCOL;      // floats per warpgroup
 
-template <int NWG>
+// N = plane size: NB (complex slots per plane) and SPS (slots per spectrum row) are compile-time, so the per-channel
+// address offsets of the gather and of the stores are immediates and the bin -> (image, slot) split is a constant division
+template <int NWG, int N>
 __global__ void __launch_bounds__(NWG * 128, 1) fu3_mix_kernel(const Fu3MixParams p, const int NT, const int KC, const long long Mtot, const int ntiles) {
+    constexpr int SPS = N / 2 + 2, NB = N * SPS;
     extern __shared__ __align__(128) unsigned char fm_smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = warp >> 2;
     const uint32_t chunk_bytes = (uint32_t)(2 * NT * FM_BK * 4);
@@ -110,6 +89,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) fu3_mix_kernel(const Fu3MixParam
     uint64_t* a_free = bars + 1;             // [NWG]
     uint64_t* acc_done = a_free + NWG;       // [NWG]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + NWG);
+    float* sbuf = reinterpret_cast<float*>(bars + 16) + (size_t)wg * FM_SBUF;           // statistics staging tile of this warpgroup
 
     if (tid == 0) {
         umma::mbar_init(w_full, 1);
@@ -135,31 +115,40 @@ __global__ void __launch_bounds__(NWG * 128, 1) fu3_mix_kernel(const Fu3MixParam
     const uint32_t idesc = umma::idesc_tf32(128, NT);
     const uint32_t b0 = umma::smem_u32(bsm);
     const bool issuer = (warp & 3) == 0;                             // first warp of the warpgroup issues its MMAs
-    const int NB = p.NB, Cin = p.Cin, Cout = p.Cout;
+    const int Cin = p.Cin, Cout = p.Cout;
     const float2* S = reinterpret_cast<const float2*>(p.s);
     float2* Y = reinterpret_cast<float2*>(p.y);
     const bool do_bn = p.bn_a != nullptr, do_stats = p.sums != nullptr;
+    const int stride = gridDim.x * NWG;
 
-    // per-lane statistics accumulators: column group g (16 columns) -> (sum, sum of squares) of column 16 g + col(lane)
-    double st_sum[8], st_sq[8];
+    // statistics: this thread sums column (64 * half + (row & 63)) over bins [64 * (row >> 6), +64) of every tile
+    double st_sum[2] = {0.0, 0.0}, st_sq[2] = {0.0, 0.0};
+
+    auto locate = [&](int tile, bool& ok, int& b, int& r) {
+        const long long m = (long long)tile * 128 + row;
+        ok = tile < ntiles && m < Mtot;
+        b = ok ? (int)(m / NB) : 0;
+        r = ok ? (int)(m % NB) : 0;
+    };
+    // 16 complex channels of one bin: coalesced 8-byte loads, immediate offsets j * NB
+    auto gather = [&](float2 (&v)[16], const float2* sp, bool ok, int c) {
+        const float2* q = sp + (size_t)c * 16 * NB;
+        const int left = Cin - c * 16;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) { st_sum[g] = 0.0; st_sq[g] = 0.0; }
+        for (int j = 0; j < 16; ++j) v[j] = (ok && j < left) ? __ldg(q + (size_t)j * NB) : make_float2(0.f, 0.f);
+    };
 
     uint32_t q = 0;             // chunks this warpgroup has handed to the tensor core so far (a_free phase counter)
     uint32_t t_done = 0;        // tiles finished (acc_done phase counter)
     bool weights_ready = false;
-    for (int tile = blockIdx.x * NWG + wg; tile < ntiles; tile += gridDim.x * NWG) {
-        const long long m = (long long)tile * 128 + row;
-        const bool ok = m < Mtot;
-        const int b = ok ? (int)(m / NB) : 0, r = ok ? (int)(m % NB) : 0;
+    int tile = blockIdx.x * NWG + wg;
+    bool ok; int b, r;
+    locate(tile, ok, b, r);
+    float2 v[16];
+    gather(v, S + (size_t)b * Cin * NB + r, ok, 0);
+    while (tile < ntiles) {
         const float2* sp = S + (size_t)b * Cin * NB + r;
         for (int c = 0; c < KC; ++c) {
-            float2 v[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int ch = c * 16 + j;
-                v[j] = (ok && ch < Cin) ? __ldg(sp + (size_t)ch * NB) : make_float2(0.f, 0.f);
-            }
             if (q > 0) umma::mbar_wait(&a_free[wg], (q - 1) & 1u);          // the MMAs that read the A stage are done
             umma::fence_after_sync();
 #pragma unroll
@@ -198,61 +187,84 @@ __global__ void __launch_bounds__(NWG * 128, 1) fu3_mix_kernel(const Fu3MixParam
                 __syncwarp();
             }
             ++q;
+            if (c + 1 < KC) gather(v, sp, ok, c + 1);          // in flight while the tensor core works on chunk c
         }
+        // ---------------- the next tile's first chunk is fetched now: its latency hides behind this tile's epilogue
+        const int ntile = tile + stride;
+        bool nok; int nb_, nr;
+        locate(ntile, nok, nb_, nr);
+        gather(v, S + (size_t)nb_ * Cin * NB + nr, nok, 0);
         // ---------------- epilogue of this tile
         umma::mbar_wait(&acc_done[wg], t_done & 1u);
         ++t_done;
         umma::fence_after_sync();
-        const bool real_bin = ok && (r % p.SPS) != p.SPS - 1;
+        const bool real_bin = ok && (r % SPS) != SPS - 1;
         float2* yp = Y ? Y + (size_t)b * Cout * NB + r : nullptr;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {                 // column groups of 16 (fully unrolled: the statistics stay in registers)
-            const int n0 = 16 * g;
-            if (n0 >= NT) break;
-            uint32_t rr[16];
-            umma::tmem_ld16(lane_base + d_col + (uint32_t)n0, rr);
-            umma::wait_ld();
-            float f[16];
+        for (int half = 0; half < 2; ++half) {                  // 64 output columns (32 complex channels) per pass
+            if (64 * half >= NT) break;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(rr[j]);
+            for (int gg = 0; gg < 4; ++gg) {
+                const int n0 = 64 * half + 16 * gg;
+                if (n0 >= NT) break;
+                uint32_t rr[16];
+                umma::tmem_ld16(lane_base + d_col + (uint32_t)n0, rr);
+                umma::wait_ld();
+                float f[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(rr[j]);
+                if (do_stats) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) sbuf[(16 * gg + j) * FM_SCOL + row] = real_bin ? f[j] : 0.f;
+                }
+                if (do_bn) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float z = fmaf(f[j], bn_a[n0 + j], bn_b[n0 + j]);
+                        f[j] = z > 0.f ? z : 0.f;
+                    }
+                }
+                if (yp && ok) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int o = (n0 >> 1) + j;
+                        if (o < Cout) yp[(size_t)o * NB] = make_float2(f[2 * j], f[2 * j + 1]);
+                    }
+                }
+            }
             if (do_stats) {
-                float sq[16], sv[16];
+                // transposed reduction through shared memory: the tile's 64 columns x 128 bins were written bin-major per
+                // column; now each thread adds up 64 bins of one column (16 conflict-free 16-byte loads)
+                fm_named_barrier(1 + wg, 128);
+                const float4* src = reinterpret_cast<const float4*>(sbuf + (row & 63) * FM_SCOL + (row >> 6) * 64);
+                float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { sv[j] = real_bin ? f[j] : 0.f; sq[j] = sv[j] * sv[j]; }
-                st_sum[g] += (double)fm_colsum16(sv, lane);
-                st_sq[g] += (double)fm_colsum16(sq, lane);
-            }
-            if (do_bn) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float z = fmaf(f[j], bn_a[n0 + j], bn_b[n0 + j]);
-                    f[j] = z > 0.f ? z : 0.f;
+                for (int i = 0; i < 16; i += 2) {
+                    const float4 a = src[i], c4 = src[i + 1];
+                    s0 += (a.x + a.y) + (a.z + a.w); s1 += (c4.x + c4.y) + (c4.z + c4.w);
+                    q0 = fmaf(a.x, a.x, q0); q0 = fmaf(a.y, a.y, q0); q0 = fmaf(a.z, a.z, q0); q0 = fmaf(a.w, a.w, q0);
+                    q1 = fmaf(c4.x, c4.x, q1); q1 = fmaf(c4.y, c4.y, q1); q1 = fmaf(c4.z, c4.z, q1); q1 = fmaf(c4.w, c4.w, q1);
                 }
-            }
-            if (yp && ok) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int o = (n0 >> 1) + j;
-                    if (o < Cout) yp[(size_t)o * NB] = make_float2(f[2 * j], f[2 * j + 1]);
-                }
+                st_sum[half] += (double)(s0 + s1);
+                st_sq[half] += (double)(q0 + q1);
+                fm_named_barrier(1 + wg, 128);                   // the staging tile may be overwritten
             }
         }
         umma::fence_before_sync();       // the TMEM loads above are ordered before the next tile's MMAs (issued after a barrier)
+        tile = ntile; ok = nok; b = nb_; r = nr;
     }
     if (do_stats) {
-        // CTA-level reduction before the global atomics (148 CTAs x 16 warps hammering 4*Cout addresses serialise in L2):
-        // the weight tiles are dead now (every MMA of this CTA has completed), their shared memory holds the partials
+        // CTA-level reduction before the global atomics: the weight tiles are dead now (every MMA of this CTA has completed),
+        // their shared memory holds the partials [warpgroup][bin half][column][sum | sum of squares]
         __syncthreads();
-        double* red = reinterpret_cast<double*>(bsm);                  // [warps][NT][2]
-        const int nwarps = NWG * 4;
-        if (!(lane & 1)) {
-            const int col = fm_col_of_lane(lane);
+        double* red = reinterpret_cast<double*>(bsm);
+        const int part = wg * 2 + (row >> 6);
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                if (16 * g < NT) {
-                    red[((size_t)warp * NT + 16 * g + col) * 2] = st_sum[g];
-                    red[((size_t)warp * NT + 16 * g + col) * 2 + 1] = st_sq[g];
-                }
+        for (int half = 0; half < 2; ++half) {
+            const int n = 64 * half + (row & 63);
+            if (n < NT) {
+                red[((size_t)part * NT + n) * 2] = st_sum[half];
+                red[((size_t)part * NT + n) * 2 + 1] = st_sq[half];
             }
         }
         __syncthreads();
@@ -260,7 +272,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) fu3_mix_kernel(const Fu3MixParam
             const int n = i >> 1, which = i & 1;
             if (n < 2 * Cout) {
                 double acc = 0.0;
-                for (int w = 0; w < nwarps; ++w) acc += red[((size_t)w * NT + n) * 2 + which];
+                for (int w = 0; w < 2 * NWG; ++w) acc += red[((size_t)w * NT + n) * 2 + which];
                 atomicAdd(p.sums + (which ? 2 * Cout + n : n), acc);
             }
         }
@@ -270,28 +282,44 @@ __global__ void __launch_bounds__(NWG * 128, 1) fu3_mix_kernel(const Fu3MixParam
     if (warp == 0) umma::tmem_dealloc(tbase, 512);
 }
 
-int fu3_mix_tc_run(const Fu3MixParams& p, ffc_stream_t st) {
-    const int NT = fm_nt(p.Cout), KC = fm_kchunks(p.Cin);
-    const long long Mtot = (long long)p.G * p.NB;
-    const int ntiles = (int)((Mtot + 127) / 128);
-    const size_t smem = (size_t)KC * 2 * NT * FM_BK * 4 + 2 * NT * 4 + 16 * 8 + 64;
-    const int nwg = (NT <= 64) ? 4 : 2;
-    int grid = (ntiles + nwg - 1) / nwg;
-    if (grid > ffc_sm_count()) grid = ffc_sm_count();
-    if (grid < 1) grid = 1;
+template <int NWG, int N>
+static int fu3_mix_launch(const Fu3MixParams& p, int NT, int KC, long long Mtot, int ntiles, int grid, size_t smem, ffc_stream_t st) {
     static FfcPerDevice configured_dev = {};
     size_t& configured = *ffc_device_slot(configured_dev);
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(fu3_mix_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fu3_mix_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(fu3_mix_kernel<NWG, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { ffc_set_error("cudaFuncSetAttribute(fu3_mix, %zu B): %s", smem, cudaGetErrorString(e)); return FFC_ERR_CUDA; }
         configured = smem;
     }
-    if (nwg == 4) fu3_mix_kernel<4><<<grid, 512, smem, st>>>(p, NT, KC, Mtot, ntiles);
-    else fu3_mix_kernel<2><<<grid, 256, smem, st>>>(p, NT, KC, Mtot, ntiles);
+    fu3_mix_kernel<NWG, N><<<grid, NWG * 128, smem, st>>>(p, NT, KC, Mtot, ntiles);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { ffc_set_error("fu3_mix launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
     ffc_count_launch();
     return FFC_OK;
+}
+
+template <int N>
+static int fu3_mix_run_n(const Fu3MixParams& p, ffc_stream_t st) {
+    const int NT = fm_nt(p.Cout), KC = fm_kchunks(p.Cin);
+    const long long Mtot = (long long)p.G * p.NB;
+    const int ntiles = (int)((Mtot + 127) / 128);
+    const int nwg = (NT <= 64) ? 4 : 2;
+    // weights | BN constants | barriers (16 x 8 bytes) | statistics staging tiles (training mode)
+    const size_t smem = (size_t)KC * 2 * NT * FM_BK * 4 + 2 * NT * 4 + 16 * 8 + (p.sums ? (size_t)nwg * FM_SBUF * 4 : 0) + 64;
+    int grid = (ntiles + nwg - 1) / nwg;
+    if (grid > ffc_sm_count()) grid = ffc_sm_count();
+    if (grid < 1) grid = 1;
+    if (nwg == 4) return fu3_mix_launch<4, N>(p, NT, KC, Mtot, ntiles, grid, smem, st);
+    return fu3_mix_launch<2, N>(p, NT, KC, Mtot, ntiles, grid, smem, st);
+}
+
+int fu3_mix_tc_run(const Fu3MixParams& p, ffc_stream_t st) {
+    switch (p.SPS) {                          // SPS = N / 2 + 2
+        case 10: return fu3_mix_run_n<16>(p, st);
+        case 18: return fu3_mix_run_n<32>(p, st);
+        case 34: return fu3_mix_run_n<64>(p, st);
+        case 66: return fu3_mix_run_n<128>(p, st);
+        default: ffc_set_error("fu3_mix: unsupported plane (SPS = %d)", p.SPS); return FFC_ERR_BAD_ARG;
+    }
 }
 #endif  // !FFC_EMU
