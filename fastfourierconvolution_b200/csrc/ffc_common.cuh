@@ -112,6 +112,7 @@ static int ffc_launch_coop(int gx, int nt, size_t smem_bytes, ffc_stream_t, cons
     return FFC_OK;
 }
 template <class K> static int ffc_coop_capacity_blocks(int, size_t) { return 1 << 30; }
+template <class K> static int ffc_resident_blocks(int, size_t) { return 1 << 30; }
 static inline int ffc_sm_count() { return 148; }
 static inline int ffc_memset_async(void* p, int v, size_t n, ffc_stream_t) { memset(p, v, n); return FFC_OK; }
 #else
@@ -177,6 +178,15 @@ static int ffc_launch(int gx, int gy, int gz, int nt, size_t smem_bytes, ffc_str
     if (e != cudaSuccess) { ffc_set_error("kernel launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
     ffc_count_launch();
     return FFC_OK;
+}
+// resident CTAs of ffc_kernel<K> on the whole device for this launch shape (persistent kernels size their grid with it)
+template <class K>
+static int ffc_resident_blocks(int nt, size_t smem_bytes) {
+    if (smem_bytes > 48 * 1024) cudaFuncSetAttribute(ffc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (smem_bytes > 16 * 1024) cudaFuncSetAttribute(ffc_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ffc_kernel<K>, nt, smem_bytes) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return per_sm * ffc_sm_count();
 }
 // ---- cooperative two-part kernels: part0, grid-wide barrier, part1 (all CTAs co-resident)
 #include <cooperative_groups.h>
