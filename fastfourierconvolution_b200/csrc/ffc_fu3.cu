@@ -127,76 +127,54 @@ struct Fu3Rfft2 {
     static constexpr int kMinBlocks = (N == 128) ? 3 : (N == 64 ? 4 : 4);
     static size_t smem_bytes() { return ((size_t)P * G::REGION + 2 * N) * 4 + 16; }
 
-    // PERSISTENT: the grid is min(plane groups, resident CTAs); a CTA walks plane groups blk = bx, bx + gx, ...
     static FFC_DEVICE void run(const Params& p, const BlockCtx& ctx, float* smem) {
+        const int plane0 = ctx.bx * P;
+        const int np = (p.nplanes - plane0) < P ? (p.nplanes - plane0) : P;
         float* planes = smem;
         float2* tw = reinterpret_cast<float2*>(smem + (size_t)P * G::REGION);
-        const int nblocks = (p.nplanes + P - 1) / P;
 #ifndef FFC_EMU
         // Device: every thread owns one row (kThreads == P * N) and fetches it with ONE bulk copy (cp.async.bulk, N*4 bytes
-        // into the padded shared-memory row); all rows of the CTA are in flight at once and complete on one mbarrier.  The
-        // planes of the NEXT group are prefetched into L2 at the same time, so in steady state the load waits for L2 only.
+        // into the padded shared-memory row); all rows of the CTA are in flight at once and complete on one mbarrier, so the
+        // load costs one memory latency instead of one per batch of register-staged loads.
         uint64_t* bar = reinterpret_cast<uint64_t*>(tw + N);
-        uint32_t phase = 0;
         {
             const int tid = (int)threadIdx.x;
             if (tid == 0) { umma::mbar_init(bar, 1); umma::fence_proxy_async_smem(); }   // (the cluster-scope release fence flushes L1: CCTL.IVALL)
             for (int k = tid; k < N; k += ctx.nt) tw[k] = c_tw128[k * (FFC_TW_N / N)];
             __syncthreads();
+            if (tid == 0) umma::mbar_arrive_expect_tx(bar, (uint32_t)(np * N * N * 4));
+            for (int r = tid; r < np * N; r += ctx.nt)
+                umma::bulk_g2s(planes + (size_t)r * G::RS, p.x + ((size_t)plane0 * N + r) * N, (uint32_t)(N * 4), bar);
+            umma::mbar_wait(bar, 0);
         }
 #else
-        FFC_PHASE { for (int k = tid; k < N; k += ctx.nt) tw[k] = c_tw128[k * (FFC_TW_N / N)]; } FFC_SYNC;
+        FFC_PHASE {
+            for (int k = tid; k < N; k += ctx.nt) tw[k] = c_tw128[k * (FFC_TW_N / N)];
+            fu2_load_rows<N>(tid, ctx.nt, np * N, p.x + (size_t)plane0 * N * N, planes);
+        } FFC_SYNC;
 #endif
-        for (int blk = ctx.bx; blk < nblocks; blk += ctx.gx) {
-            const int plane0 = blk * P;
-            const int np = (p.nplanes - plane0) < P ? (p.nplanes - plane0) : P;
+        FFC_PHASE {
+            fu2_rows_fwd<N, ADJ>(tid, ctx.nt, np * N, planes);
+            for (int r = tid; r < np * N; r += ctx.nt)           // the pad slot of every row (read by the mix, never used)
+                reinterpret_cast<float2*>(planes + (size_t)r * G::RS)[G::M + 1] = make_float2(0.f, 0.f);
+        } FFC_SYNC;
+        FU3_COLS_FWD(N, np, planes, tw);
 #ifndef FFC_EMU
-            {
-                const int tid = (int)threadIdx.x;
-                if (tid == 0) {
-                    umma::mbar_arrive_expect_tx(bar, (uint32_t)(np * N * N * 4));
-                    const int nxt = (blk + ctx.gx) * P;
-                    if (nxt < p.nplanes) {
-                        const int nn = (p.nplanes - nxt) < P ? (p.nplanes - nxt) : P;
-                        umma::bulk_prefetch_l2(p.x + (size_t)nxt * N * N, (uint32_t)(nn * N * N * 4));
-                    }
-                }
-                for (int r = tid; r < np * N; r += ctx.nt)
-                    umma::bulk_g2s(planes + (size_t)r * G::RS, p.x + ((size_t)plane0 * N + r) * N, (uint32_t)(N * 4), bar);
-                umma::mbar_wait(bar, phase);
-                phase ^= 1u;
-            }
-#else
-            FFC_PHASE { fu2_load_rows<N>(tid, ctx.nt, np * N, p.x + (size_t)plane0 * N * N, planes); } FFC_SYNC;
-#endif
-            FFC_PHASE {
-                fu2_rows_fwd<N, ADJ>(tid, ctx.nt, np * N, planes);
-                for (int r = tid; r < np * N; r += ctx.nt)           // the pad slot of every row (read by the mix, never used)
-                    reinterpret_cast<float2*>(planes + (size_t)r * G::RS)[G::M + 1] = make_float2(0.f, 0.f);
-            } FFC_SYNC;
-            FU3_COLS_FWD(N, np, planes, tw);
-#ifndef FFC_EMU
-            // the scratch layout IS the shared-memory image: one bulk copy writes the CTA's planes back; the next group's
-            // loads may overwrite shared memory as soon as the copy has READ it
-            umma::fence_proxy_async_smem();
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                umma::bulk_s2g(p.spec + (size_t)plane0 * G::REGION, planes, (uint32_t)(np * G::REGION * 4));
-                umma::bulk_commit_group();
-                umma::bulk_wait_group_read0();
-            }
-            __syncthreads();
-#else
-            FFC_PHASE {
-                const float4* s4 = reinterpret_cast<const float4*>(planes);
-                float4* d4 = reinterpret_cast<float4*>(p.spec + (size_t)plane0 * G::REGION);
-                const int total = np * (G::REGION / 4);
-                for (int i = tid; i < total; i += ctx.nt) d4[i] = s4[i];
-            } FFC_SYNC;
-#endif
+        // the scratch layout IS the shared-memory image: one bulk copy writes the CTA's planes back
+        umma::fence_proxy_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            umma::bulk_s2g(p.spec + (size_t)plane0 * G::REGION, planes, (uint32_t)(np * G::REGION * 4));
+            umma::bulk_commit_group();
+            umma::bulk_wait_group0();
         }
-#ifndef FFC_EMU
-        if (threadIdx.x == 0) umma::bulk_wait_group0();          // every bulk store of this CTA has completed
+#else
+        FFC_PHASE {
+            const float4* s4 = reinterpret_cast<const float4*>(planes);
+            float4* d4 = reinterpret_cast<float4*>(p.spec + (size_t)plane0 * G::REGION);
+            const int total = np * (G::REGION / 4);
+            for (int i = tid; i < total; i += ctx.nt) d4[i] = s4[i];
+        } FFC_SYNC;
 #endif
     }
 };
@@ -220,100 +198,79 @@ struct Fu3Irfft2 {
     static constexpr int kMinBlocks = (N == 128) ? 3 : 4;
     static size_t smem_bytes() { return ((size_t)P * G::REGION + 2 * N + 4 * P) * 4 + 16; }
 
-    // PERSISTENT, like Fu3Rfft2
     static FFC_DEVICE void run(const Params& p, const BlockCtx& ctx, float* smem) {
+        const int plane0 = ctx.bx * P;
+        const int np = (p.nplanes - plane0) < P ? (p.nplanes - plane0) : P;
         float* planes = smem;
         float2* tw = reinterpret_cast<float2*>(smem + (size_t)P * G::REGION);
         float2* bnp_a = tw + N;                 // per plane of this CTA: (a_re, a_im), (b_re, b_im)
         float2* bnp_b = bnp_a + P;
-        const int nblocks = (p.nplanes + P - 1) / P;
 #ifndef FFC_EMU
         // Device: the CTA's planes are contiguous in the scratch and the scratch layout IS the shared-memory image: ONE bulk
-        // copy brings them in (completion on an mbarrier); the next group's planes and residual rows are prefetched into L2
-        // meanwhile.  BatchNorm + ReLU is applied by the first inverse column pass as it loads the spectrum from shared memory.
+        // copy brings them in (completion on an mbarrier); the residual rows are prefetched into L2 meanwhile.  BatchNorm +
+        // ReLU is applied by the first inverse column pass as it loads the spectrum from shared memory.
         uint64_t* bar = reinterpret_cast<uint64_t*>(bnp_b + P);
-        uint32_t phase = 0;
         {
             const int tid = (int)threadIdx.x;
-            if (tid == 0) { umma::mbar_init(bar, 1); umma::fence_proxy_async_smem(); }
+            if (tid == 0) { umma::mbar_init(bar, 1); umma::fence_proxy_async_smem(); }   // (the cluster-scope release fence flushes L1: CCTL.IVALL)
+            __syncthreads();
+            if (tid == 0) {
+                umma::mbar_arrive_expect_tx(bar, (uint32_t)(np * G::REGION * 4));
+                umma::bulk_g2s(planes, p.spec + (size_t)plane0 * G::REGION, (uint32_t)(np * G::REGION * 4), bar);
+                if (p.residual) umma::bulk_prefetch_l2(p.residual + (size_t)plane0 * N * N, (uint32_t)(np * N * N * 4));
+            }
             for (int k = tid; k < N; k += ctx.nt) tw[k] = c_tw128[k * (FFC_TW_N / N)];
+            if (p.bn_a && tid < np) {
+                const int o = (plane0 + tid) % p.cout;
+                bnp_a[tid] = make_float2(FFC_LDG(p.bn_a + 2 * o), FFC_LDG(p.bn_a + 2 * o + 1));
+                bnp_b[tid] = make_float2(FFC_LDG(p.bn_b + 2 * o), FFC_LDG(p.bn_b + 2 * o + 1));
+            }
+            umma::mbar_wait(bar, 0);
             __syncthreads();
         }
+        Fu2Bn bn; bn.a = bnp_a; bn.b = bnp_b;
+        if (p.bn_a) { FU3_COLS_INV(N, true, np, planes, tw, bn); }
+        else { FU3_COLS_INV(N, false, np, planes, tw, bn); }
 #else
-        FFC_PHASE { for (int k = tid; k < N; k += ctx.nt) tw[k] = c_tw128[k * (FFC_TW_N / N)]; } FFC_SYNC;
-#endif
-        for (int blk = ctx.bx; blk < nblocks; blk += ctx.gx) {
-            const int plane0 = blk * P;
-            const int np = (p.nplanes - plane0) < P ? (p.nplanes - plane0) : P;
-#ifndef FFC_EMU
-            {
-                const int tid = (int)threadIdx.x;
-                if (tid == 0) {
-                    umma::mbar_arrive_expect_tx(bar, (uint32_t)(np * G::REGION * 4));
-                    umma::bulk_g2s(planes, p.spec + (size_t)plane0 * G::REGION, (uint32_t)(np * G::REGION * 4), bar);
-                    if (p.residual) umma::bulk_prefetch_l2(p.residual + (size_t)plane0 * N * N, (uint32_t)(np * N * N * 4));
-                    const int nxt = (blk + ctx.gx) * P;
-                    if (nxt < p.nplanes) {
-                        const int nn = (p.nplanes - nxt) < P ? (p.nplanes - nxt) : P;
-                        umma::bulk_prefetch_l2(p.spec + (size_t)nxt * G::REGION, (uint32_t)(nn * G::REGION * 4));
-                    }
+        FFC_PHASE {
+            for (int k = tid; k < N; k += ctx.nt) tw[k] = c_tw128[k * (FFC_TW_N / N)];
+            const float4* s4 = reinterpret_cast<const float4*>(p.spec + (size_t)plane0 * G::REGION);
+            float4* d4 = reinterpret_cast<float4*>(planes);
+            constexpr int PER = G::REGION / 4;
+            const int total = np * PER;
+            for (int i = tid; i < total; i += ctx.nt) {
+                float4 q = s4[i];
+                if (p.bn_a) {              // relu(y * a + b) on (re, im) pairs of output channel o: fourier_unity.py:49
+                    const int o = (plane0 + i / PER) % p.cout;
+                    const float ar = p.bn_a[2 * o], ai = p.bn_a[2 * o + 1], br = p.bn_b[2 * o], bi = p.bn_b[2 * o + 1];
+                    q.x = fmaf(q.x, ar, br); q.y = fmaf(q.y, ai, bi); q.z = fmaf(q.z, ar, br); q.w = fmaf(q.w, ai, bi);
+                    q.x = q.x > 0.f ? q.x : 0.f; q.y = q.y > 0.f ? q.y : 0.f; q.z = q.z > 0.f ? q.z : 0.f; q.w = q.w > 0.f ? q.w : 0.f;
                 }
-                if (p.bn_a && tid < np) {
-                    const int o = (plane0 + tid) % p.cout;
-                    bnp_a[tid] = make_float2(FFC_LDG(p.bn_a + 2 * o), FFC_LDG(p.bn_a + 2 * o + 1));
-                    bnp_b[tid] = make_float2(FFC_LDG(p.bn_b + 2 * o), FFC_LDG(p.bn_b + 2 * o + 1));
-                }
-                umma::mbar_wait(bar, phase);
-                phase ^= 1u;
-                __syncthreads();
+                d4[i] = q;
             }
-            Fu2Bn bn; bn.a = bnp_a; bn.b = bnp_b;
-            if (p.bn_a) { FU3_COLS_INV(N, true, np, planes, tw, bn); }
-            else { FU3_COLS_INV(N, false, np, planes, tw, bn); }
-#else
-            FFC_PHASE {
-                const float4* s4 = reinterpret_cast<const float4*>(p.spec + (size_t)plane0 * G::REGION);
-                float4* d4 = reinterpret_cast<float4*>(planes);
-                constexpr int PER = G::REGION / 4;
-                const int total = np * PER;
-                for (int i = tid; i < total; i += ctx.nt) {
-                    float4 q = s4[i];
-                    if (p.bn_a) {              // relu(y * a + b) on (re, im) pairs of output channel o: fourier_unity.py:49
-                        const int o = (plane0 + i / PER) % p.cout;
-                        const float ar = p.bn_a[2 * o], ai = p.bn_a[2 * o + 1], br = p.bn_b[2 * o], bi = p.bn_b[2 * o + 1];
-                        q.x = fmaf(q.x, ar, br); q.y = fmaf(q.y, ai, bi); q.z = fmaf(q.z, ar, br); q.w = fmaf(q.w, ai, bi);
-                        q.x = q.x > 0.f ? q.x : 0.f; q.y = q.y > 0.f ? q.y : 0.f; q.z = q.z > 0.f ? q.z : 0.f; q.w = q.w > 0.f ? q.w : 0.f;
-                    }
-                    d4[i] = q;
-                }
-            } FFC_SYNC;
-            Fu2Bn nobn; nobn.a = nullptr; nobn.b = nullptr;
-            FU3_COLS_INV(N, false, np, planes, tw, nobn);
+        } FFC_SYNC;
+        Fu2Bn nobn; nobn.a = nullptr; nobn.b = nullptr;
+        FU3_COLS_INV(N, false, np, planes, tw, nobn);
 #endif
-            FFC_PHASE { fu2_rows_inv<N, ADJ>(tid, ctx.nt, np * N, planes, p.scale); } FFC_SYNC;
+        FFC_PHASE { fu2_rows_inv<N, ADJ>(tid, ctx.nt, np * N, planes, p.scale); } FFC_SYNC;
 #ifndef FFC_EMU
-            if (!p.residual) {
-                // no residual: every thread sends its finished row with one bulk copy (shared -> global, N*4 bytes)
-                umma::fence_proxy_async_smem();
-                __syncthreads();
-                const int tid = (int)threadIdx.x;
-                for (int r = tid; r < np * N; r += ctx.nt)
-                    umma::bulk_s2g(p.out + ((size_t)plane0 * N + r) * N, planes + (size_t)r * G::RS, (uint32_t)(N * 4));
-                umma::bulk_commit_group();
-                umma::bulk_wait_group_read0();
-                __syncthreads();
-                continue;
-            }
-#endif
-            FFC_PHASE {
-                const size_t g0 = (size_t)plane0 * N * N;
-                if (p.residual) fu2_store_rows_impl<N, true, 8>(tid, ctx.nt, np * N, planes, p.residual + g0, p.out + g0);
-                else fu2_store_rows_impl<N, false, 8>(tid, ctx.nt, np * N, planes, nullptr, p.out + g0);
-            } FFC_SYNC;
+        if (!p.residual) {
+            // no residual: every thread sends its finished row with one bulk copy (shared -> global, N*4 bytes)
+            umma::fence_proxy_async_smem();
+            __syncthreads();
+            const int tid = (int)threadIdx.x;
+            for (int r = tid; r < np * N; r += ctx.nt)
+                umma::bulk_s2g(p.out + ((size_t)plane0 * N + r) * N, planes + (size_t)r * G::RS, (uint32_t)(N * 4));
+            umma::bulk_commit_group();
+            umma::bulk_wait_group0();
+            return;
         }
-#ifndef FFC_EMU
-        umma::bulk_wait_group0();                                 // every bulk store of this thread has completed
 #endif
+        FFC_PHASE {
+            const size_t g0 = (size_t)plane0 * N * N;
+            if (p.residual) fu2_store_rows_impl<N, true, 8>(tid, ctx.nt, np * N, planes, p.residual + g0, p.out + g0);
+            else fu2_store_rows_impl<N, false, 8>(tid, ctx.nt, np * N, planes, nullptr, p.out + g0);
+        } FFC_SYNC;
     }
 };
 
@@ -474,15 +431,6 @@ extern "C" size_t ffc_fu3_workspace_bytes(int B, int Cin, int Cout, int H, int W
     return fu3_plan(B, Cin, Cout, H, training).total;
 }
 
-// plane kernels are persistent on the device: grid = min(plane groups, CTAs resident at once)
-template <class K>
-static int fu3_launch_planes(int nplanes, int P, int nt, ffc_stream_t st, const typename K::Params& prm) {
-    const int nblocks = ffc_cdiv(nplanes, P);
-    int grid = ffc_resident_blocks<K>(nt, K::smem_bytes());
-    if (grid > nblocks) grid = nblocks;
-    return ffc_launch<K>(grid, 1, 1, nt, K::smem_bytes(), st, prm);
-}
-
 template <int N>
 static int fu3_run(const float* x, const float* w, const float* gamma, const float* beta, float* running_mean, float* running_var,
                    float* save_mean, float* save_invstd, const float* residual, float* out, int B, int Cin, int Cout,
@@ -510,7 +458,7 @@ static int fu3_run(const float* x, const float* w, const float* gamma, const flo
     for (int b0 = 0; b0 < B; b0 += pl.chunk) {
         const int g = (B - b0) < pl.chunk ? (B - b0) : pl.chunk;
         Fu3FwdFftParams ap; ap.x = x + (size_t)b0 * Cin * N * N; ap.spec = S; ap.nplanes = g * Cin;
-        FFC_CHECK((fu3_launch_planes<Fu3Rfft2<N, false>>(ap.nplanes, G3::P, G3::kThreads, st, ap)));
+        FFC_CHECK((ffc_launch<Fu3Rfft2<N, false>>(ffc_cdiv(ap.nplanes, G3::P), 1, 1, G3::kThreads, Fu3Rfft2<N, false>::smem_bytes(), st, ap)));
         Fu3MixParams mp;
         mp.s = S; mp.y = training ? Y + (size_t)b0 * Cout * pl.region : Y; mp.w = w; mp.wp = tc ? wp : nullptr;
         mp.bn_a = training ? nullptr : bn_a; mp.bn_b = training ? nullptr : bn_b; mp.sums = training ? sums : nullptr;
@@ -528,14 +476,14 @@ static int fu3_run(const float* x, const float* w, const float* gamma, const flo
             Fu3InvFftParams ip; ip.spec = Y; ip.bn_a = nullptr; ip.bn_b = nullptr;
             ip.residual = residual ? residual + (size_t)b0 * Cout * N * N : nullptr; ip.out = out + (size_t)b0 * Cout * N * N;
             ip.nplanes = g * Cout; ip.cout = Cout; ip.scale = 1.0f;
-            FFC_CHECK((fu3_launch_planes<Fu3Irfft2<N, false>>(ip.nplanes, G3::P, G3::kThreads, st, ip)));
+            FFC_CHECK((ffc_launch<Fu3Irfft2<N, false>>(ffc_cdiv(ip.nplanes, G3::P), 1, 1, G3::kThreads, Fu3Irfft2<N, false>::smem_bytes(), st, ip)));
         }
     }
     if (training) {
         FFC_CHECK((ffc_launch<Fu3Finalize>(1, 1, 1, 256, 0, st, fp)));
         Fu3InvFftParams ip; ip.spec = Y; ip.bn_a = bn_a; ip.bn_b = bn_b; ip.residual = residual; ip.out = out;
         ip.nplanes = B * Cout; ip.cout = Cout; ip.scale = 1.0f;
-        FFC_CHECK((fu3_launch_planes<Fu3Irfft2<N, false>>(ip.nplanes, G3::P, G3::kThreads, st, ip)));
+        FFC_CHECK((ffc_launch<Fu3Irfft2<N, false>>(ffc_cdiv(ip.nplanes, G3::P), 1, 1, G3::kThreads, Fu3Irfft2<N, false>::smem_bytes(), st, ip)));
     }
     return FFC_OK;
 }
