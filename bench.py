@@ -251,21 +251,31 @@ def time_fourier_unit_shape(C, N, B, dev):
 
 
 def time_generation(G, z, steps, dev, world):
-    """Pure generation (G.eval() forward, uint8 images out for the fgan generators): batch shards, no collective.  Eager launches
-    (the fgan64 / fgan128 eval epilogue reads min / max on the host, fgan64_complete.py:150-153), CUDA events, max over ranks."""
+    """Pure generation (G.eval() forward, uint8 images out for the fgan generators): batch shards, no collective.  The forward
+    is captured once into a CUDA graph and replayed (like the training step); CUDA events, max over ranks."""
     import torch.distributed as dist
     was_training = G.training
     G.eval()
     with torch.no_grad():
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                G(z)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = G(z)
         for _ in range(3):
-            G(z)
+            graph.replay()
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier(); torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
-            out = G(z)
+            graph.replay()
         e1.record()
         torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1) / steps
@@ -276,7 +286,8 @@ def time_generation(G, z, steps, dev, world):
     G.train(was_training)
     return {"value": z.shape[0] * world / ms * 1000.0, "unit": "images/s", "ms_per_batch": ms, "per_gpu_batch": z.shape[0],
             "out_dtype": str(out.dtype).replace("torch.", ""), "collectives": 0,
-            "what": "G.eval() forward on resident latents, batch sharded over the ranks (fgan_complete.py:413-427 path)"}
+            "what": "G.eval() forward on resident latents (one CUDA-graph replay per batch), batch sharded over the ranks "
+                    "(fgan_complete.py:413-427 path)"}
 
 
 # ---------------------------------------------------------------------------------------------

@@ -93,8 +93,8 @@ class FGenerator(nn.Module):
         if not self.training:                    # uint8 images for the metric code (fgan_complete.py:136-138)
             if self._clamp == "unit":
                 fake = 255 * (fake.clamp(-1, 1) * 0.5 + 0.5)
-            else:                                # fgan64_complete.py:150-153: clamp to own min/max
-                fake = 255 * (fake.clamp(float(fake.min()), float(fake.max())) * 0.5 + 0.5)
+            else:                                # fgan64_complete.py:150-153: clamp to own min/max (bounds stay on the device:
+                fake = 255 * (torch.clamp(fake, fake.min(), fake.max()) * 0.5 + 0.5)     # no host sync, CUDA-graph capturable)
             fake = fake.to(torch.uint8)
         return fake
 

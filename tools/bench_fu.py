@@ -91,40 +91,65 @@ def timeit_fwd_bwd(fn, xs, iters=5):
     return e0.elapsed_time(e1) / (iters * len(xs))
 
 
+def ref_spectral_transform(x, P, training):
+    """The reference's SpectralTransform.forward (layers/ffc/spectral_transform.py:77-110, stride 1) on PyTorch's GPU kernels."""
+    b, c = x.shape[:2]
+    g = torch.sigmoid(F.linear(F.relu(F.linear(x.mean(dim=(2, 3)), P["se_block.fc.0.weight"])), P["se_block.fc.2.weight"]))
+    x = x * g.view(b, c, 1, 1)
+    x = F.relu(F.batch_norm(F.conv2d(x, P["conv1.weight"]), P["bn1.running_mean"], P["bn1.running_var"], P["bn1.weight"], P["bn1.bias"],
+                            training, 0.1, 1e-5))
+    f = ref_fourier_unit(x, {k[3:]: v for k, v in P.items() if k.startswith("fu.")}, training)
+    return F.conv2d(x + f, P["conv2.weight"])
+
+
 def sweep_config5(out_path):
-    """BASELINE.json configs[4]: FourierUnitSN(Cf, Cf), Cf = int(C * r) // 2 for C in {64, 256, 512}, r in {.25, .5, .75},
-    H = W in {16, 32, 64, 128}, batch 32, training mode, forward and forward + backward, against the reference's op
-    sequence on the same GPU (cuFFT + cuDNN, TF32 off).  Algorithmic bytes: 8*B*C*H*W forward, 20*B*C*H*W fwd + bwd."""
-    import copy
+    """BASELINE.json configs[4]: FourierUnitSN(Cf, Cf) and SpectralTransform(Cg, Cg, stride 1), Cg = int(C * r), Cf = Cg // 2 for
+    C in {64, 256, 512}, r in {.25, .5, .75}, H = W in {16, 32, 64, 128}, batch 32 and 128, training and eval mode, forward
+    and forward + backward, against the reference's op sequence on the same GPU (cuFFT + cuDNN, TF32 off).
+    Algorithmic bytes: FU 8*B*C*H*W forward, 20*B*C*H*W fwd + bwd; ST 8*B*Cg*H*W forward, 20*B*Cg*H*W fwd + bwd."""
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    B = 32
     cfs = sorted({int(C * r) // 2 for C in (64, 256, 512) for r in (0.25, 0.5, 0.75)})
     with open(out_path, "w") as f:
         for Cf in cfs:
             for N in (16, 32, 64, 128):
-                torch.manual_seed(0)
-                m = ffc.FourierUnitSN(Cf, Cf).to(DEV).train()
-                nbytes = 4 * B * Cf * N * N
-                nbuf = min(max(2, int(200e6 // nbytes) + 1), 8)
-                xs = [torch.randn(B, Cf, N, N, device=DEV, requires_grad=True) for _ in range(nbuf)]
-                P = {k: v.detach().clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in m.state_dict().items()}
-                ref = lambda x: ref_fourier_unit(x, P, True)
-                row = {"B": B, "C": Cf, "N": N, "fused": bool(ops.fu_fused_supported(B, Cf, Cf, N, N))}
-                with torch.no_grad():
-                    row["ours_fwd_us"] = 1000 * timeit(m, xs, iters=5)
-                    row["torch_fwd_us"] = 1000 * timeit(ref, xs, iters=5)
-                row["ours_fwd_bwd_us"] = 1000 * timeit_fwd_bwd(m, xs)
-                row["torch_fwd_bwd_us"] = 1000 * timeit_fwd_bwd(ref, xs)
-                row["fwd_frac_hbm"] = 2.0 * nbytes / row["ours_fwd_us"] / 1e3 / PEAK
-                row["fwd_bwd_frac_hbm"] = 5.0 * nbytes / row["ours_fwd_bwd_us"] / 1e3 / PEAK
-                row["speedup_fwd"] = row["torch_fwd_us"] / row["ours_fwd_us"]
-                row["speedup_fwd_bwd"] = row["torch_fwd_bwd_us"] / row["ours_fwd_bwd_us"]
-                line = json.dumps({k: (round(v, 3) if isinstance(v, float) else v) for k, v in row.items()})
-                print(line, flush=True)
-                f.write(line + "\n")
-                del xs, m, P
-                torch.cuda.empty_cache()
+                for B in (32, 128):
+                    for kind in ("fu", "st"):
+                        C = Cf if kind == "fu" else 2 * Cf
+                        nbytes = 4 * B * C * N * N
+                        if nbytes > 1.7e9 or (B == 128 and nbytes > 0.9e9):
+                            continue
+                        torch.manual_seed(0)
+                        m = (ffc.FourierUnitSN(C, C) if kind == "fu" else ffc.SpectralTransform(C, C, 1, 1, True, False)).to(DEV)
+                        nbuf = min(max(2, int(200e6 // nbytes) + 1), 6)
+                        xs = [torch.randn(B, C, N, N, device=DEV, requires_grad=True) for _ in range(nbuf)]
+                        P = {k: v.detach().clone().requires_grad_(v.is_floating_point() and "running" not in k and "lfu" not in k)
+                             for k, v in m.state_dict().items()}
+                        reff = ref_fourier_unit if kind == "fu" else ref_spectral_transform
+                        fu_c = C if kind == "fu" else C // 2
+                        path = ("single-kernel" if ops.fu_fused_supported(B, fu_c, fu_c, N, N) else
+                                "L2-staged" if ops.fu_staged_supported(B, fu_c, fu_c, N, N) else "general")
+                        row = {"module": "FourierUnitSN" if kind == "fu" else "SpectralTransform", "B": B, "C": C, "N": N, "fu_path": path}
+                        with torch.no_grad():
+                            for mode in ("train", "eval"):
+                                m.train(mode == "train")
+                                row[f"ours_fwd_{mode}_us"] = 1000 * timeit(m, xs, iters=3)
+                                row[f"torch_fwd_{mode}_us"] = 1000 * timeit(lambda x: reff(x, P, mode == "train"), xs, iters=3)
+                        m.train()
+                        row["ours_fwd_bwd_us"] = 1000 * timeit_fwd_bwd(m, xs, iters=3)
+                        row["torch_fwd_bwd_us"] = 1000 * timeit_fwd_bwd(lambda x: reff(x, P, True), xs, iters=3)
+                        row["fwd_train_frac_hbm"] = 2.0 * nbytes / row["ours_fwd_train_us"] / 1e3 / PEAK
+                        row["fwd_eval_frac_hbm"] = 2.0 * nbytes / row["ours_fwd_eval_us"] / 1e3 / PEAK
+                        row["fwd_bwd_frac_hbm"] = 5.0 * nbytes / row["ours_fwd_bwd_us"] / 1e3 / PEAK
+                        row["speedup_fwd_train"] = row["torch_fwd_train_us"] / row["ours_fwd_train_us"]
+                        row["speedup_fwd_eval"] = row["torch_fwd_eval_us"] / row["ours_fwd_eval_us"]
+                        row["speedup_fwd_bwd"] = row["torch_fwd_bwd_us"] / row["ours_fwd_bwd_us"]
+                        line = json.dumps({k: (round(v, 3) if isinstance(v, float) else v) for k, v in row.items()})
+                        print(line, flush=True)
+                        f.write(line + "\n")
+                        f.flush()
+                        del xs, m, P
+                        torch.cuda.empty_cache()
 
 
 def main():
