@@ -55,6 +55,9 @@ _SIGNATURES = {
     "ffc_debug_fu3_chunk_bytes": (None, [c_size_t]),
     "ffc_fu_bwd": (c_int, [c_void_p] * 11 + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
     "ffc_fu_bwd_supported": (c_int, [c_int] * 5),
+    "ffc_noise_add_fwd": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),
+    "ffc_noise_add_bwd_w": (c_int, [c_void_p] * 3 + [c_int] * 3 + [c_void_p]),
+    "ffc_to_uint8": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_float, c_float, c_void_p]),
     "ffc_debug_conv_reference": (None, [c_int]),
     "ffc_debug_fu_two_pass": (None, [c_int]),
 }

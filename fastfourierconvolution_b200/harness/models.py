@@ -83,7 +83,12 @@ class FGenerator(nn.Module):
                                                       uses_sn=(variant != "fgan32")))
 
     def forward(self, z):
-        fake = self.noise_to_feature(z)
+        from .. import ops
+        lin = self.noise_to_feature[0]
+        if z.is_cuda:    # the Linear stem (fgan_complete.py:92-95, 117-119) is a 1x1 convolution of a 1x1 plane: same tcgen05 kernels
+            fake = ops.conv2d(z.reshape(z.size(0), -1, 1, 1), lin.weight.view(lin.out_features, lin.in_features, 1, 1), bias=lin.bias)
+        else:
+            fake = self.noise_to_feature(z)
         fake = fake.reshape(fake.size(0), -1, self.mg, self.mg)
         for n in self._stages:
             fake = getattr(self, f"conv{n}")(fake)
@@ -91,11 +96,8 @@ class FGenerator(nn.Module):
                 fake = getattr(self, f"lcl_noise{n}")(fake[0]), getattr(self, f"glb_noise{n}")(fake[1])
         fake = self.resizer(getattr(self, f"conv{self._last}")(fake))
         if not self.training:                    # uint8 images for the metric code (fgan_complete.py:136-138)
-            if self._clamp == "unit":
-                fake = 255 * (fake.clamp(-1, 1) * 0.5 + 0.5)
-            else:                                # fgan64_complete.py:150-153: clamp to own min/max (bounds stay on the device:
-                fake = 255 * (torch.clamp(fake, fake.min(), fake.max()) * 0.5 + 0.5)     # no host sync, CUDA-graph capturable)
-            fake = fake.to(torch.uint8)
+            # fgan64_complete.py:150-153 clamps to the tensor's own min / max, which is the identity
+            fake = ops.to_uint8(fake, -1.0, 1.0) if self._clamp == "unit" else ops.to_uint8(fake, 1.0, -1.0)
         return fake
 
 

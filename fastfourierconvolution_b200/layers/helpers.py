@@ -1,6 +1,6 @@
 """The small glue modules the reference's models pick up through ``from layers import *``
 (layers/resizer.py, layers/noise_injection.py, layers/print_layer.py, layers/gaussian_noise.py).
-They sit around the hot path and stay plain PyTorch."""
+NoiseInjection runs on the library's own kernel; the others are shape plumbing."""
 from __future__ import annotations
 
 import torch
@@ -52,7 +52,8 @@ class NoiseInjection(nn.Module):
         if noise is None:
             b, _, h, w = x.shape
             noise = x.new_empty(b, 1, h, w).normal_()
-        return torch.addcmul(x, self.weight, noise)          # x + weight * noise in one pass over the activation
+        from .. import ops
+        return ops.noise_add(x, self.weight, noise)           # x + weight * noise: one kernel (csrc/ffc_glue.cu)
 
 
 class GaussianNoise(nn.Module):

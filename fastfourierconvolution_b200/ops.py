@@ -676,3 +676,50 @@ class SeFn(torch.autograd.Function):
 
 def se_resample(x, w1, w2, mode=RESAMPLE_NONE):
     return SeFn.apply(x, w1, w2, mode)
+
+
+# ---------------------------------------------------------------------------------------------
+# glue of the generators: NoiseInjection, uint8 image epilogue
+# ---------------------------------------------------------------------------------------------
+class NoiseAddFn(torch.autograd.Function):
+    """x + weight * noise with one noise plane per image (layers/noise_injection.py:20-32) in one kernel; the weight gradient
+    sum(dy * noise) in one more (the activation gradient is dy itself)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, noise):
+        _C.require_device(x, weight, noise)
+        x, noise = x.contiguous(), noise.contiguous()
+        B, C = x.shape[0], x.shape[1]
+        HW = x.numel() // max(B * C, 1)
+        if weight.numel() != C or noise.numel() != B * HW:
+            raise ValueError("noise_add: weight must have one entry per channel and noise one plane per image")
+        out = torch.empty_like(x)
+        _C.check(_C.lib().ffc_noise_add_fwd(_C.ptr(x), _C.ptr(weight.contiguous()), _C.ptr(noise), _C.ptr(out), B, C, HW, _C.current_stream(x.device)))
+        ctx.save_for_backward(noise)
+        ctx.shape = (B, C, HW, tuple(weight.shape))
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        (noise,) = ctx.saved_tensors
+        B, C, HW, wshape = ctx.shape
+        dw = None
+        if ctx.needs_input_grad[1]:
+            dy = dy.contiguous()
+            dw = torch.empty(wshape, device=dy.device, dtype=torch.float32)
+            _C.check(_C.lib().ffc_noise_add_bwd_w(_C.ptr(dy), _C.ptr(noise), _C.ptr(dw), B, C, HW, _C.current_stream(dy.device)))
+        return (dy if ctx.needs_input_grad[0] else None), dw, None
+
+
+def noise_add(x, weight, noise):
+    return NoiseAddFn.apply(x, weight, noise)
+
+
+def to_uint8(x, lo=-1.0, hi=1.0):
+    """uint8(255 * (clamp(x, lo, hi) * 0.5 + 0.5)) in one kernel (fgan_complete.py:136-138); lo > hi: no clamp."""
+    _C.require_device(x)
+    x = x.contiguous()
+    out = torch.empty(x.shape, device=x.device, dtype=torch.uint8)
+    _C.check(_C.lib().ffc_to_uint8(_C.ptr(x), _C.ptr(out), x.numel(), float(lo), float(hi), _C.current_stream(x.device)))
+    return out

@@ -101,6 +101,16 @@ int ffc_fu3_fwd(const float* x, const float* w, const float* gamma, const float*
                 const float* residual, float* out,
                 int B, int Cin, int Cout, int H, int W, int training, float eps, float momentum,
                 void* workspace, size_t workspace_bytes, void* stream);
+/* ---- Glue between the FFC layers of the reference's generators, one bandwidth-bound kernel each ----
+ * ffc_noise_add_fwd: NoiseInjection.forward (layers/noise_injection.py:20-32; called on both branches after every
+ *   upsampling stage, fgan_complete.py:122-131): out = x + weight[c] * noise[b, 0, h, w]; x / out (B, C, HW), noise (B, HW).
+ * ffc_noise_add_bwd_w: its weight gradient dweight[c] = sum_{b,hw} dy * noise (dx = dy passes through unchanged).
+ * ffc_to_uint8: the eval-mode image epilogue (fgan_complete.py:136-138): out = uint8(255 * (clamp(x, lo, hi) * 0.5 + 0.5));
+ *   lo > hi disables the clamp (fgan64_complete.py:150-153 clamps to the tensor's own min / max, an identity). */
+int ffc_noise_add_fwd(const float* x, const float* w, const float* noise, float* out, int B, int C, int HW, void* stream);
+int ffc_noise_add_bwd_w(const float* dy, const float* noise, float* dw, int B, int C, int HW, void* stream);
+int ffc_to_uint8(const float* x, unsigned char* out, long long n, float lo, float hi, void* stream);
+
 void ffc_debug_fu3_simt_mix(int on);
 void ffc_debug_fu3_chunk_bytes(size_t bytes);      /* spectrum bytes per chunk of images (0 = default 160 MB); tuning / tests */
 

@@ -428,3 +428,49 @@ def test_fused_fourier_unit_backward(lib, case):
     assert parity.relerr(dx, dx_r) < 5e-6
     assert parity.relerr(dw, dw_r) < 5e-6
     assert parity.relerr(dg, dg_r) < 5e-6 and parity.relerr(db, db_r) < 5e-6
+
+
+# ---- glue kernels (csrc/ffc_glue.cu) and the spectral-norm backward -------------------------------------------------
+@pytest.mark.parametrize("B,C,H", [(3, 5, 8), (2, 48, 7), (4, 16, 32)])
+def test_noise_add_and_its_weight_gradient(lib, B, C, H):
+    """NoiseInjection (layers/noise_injection.py:20-32): x + weight * noise, and dweight = sum(dy * noise)."""
+    torch.manual_seed(B * C)
+    x, noise, w = torch.randn(B, C, H, H), torch.randn(B, 1, H, H), torch.randn(1, C, 1, 1)
+    out, dw = torch.zeros_like(x), torch.full((C,), 7.0)
+    call(lib, "ffc_noise_add_fwd", x, w, noise, out, B, C, H * H, None)
+    assert torch.equal(out, torch.addcmul(x, w, noise)) or (out - torch.addcmul(x, w, noise)).abs().max() < 1e-6
+    dy = torch.randn(B, C, H, H)
+    call(lib, "ffc_noise_add_bwd_w", dy, noise, dw, B, C, H * H, None)
+    ref = (dy.double() * noise.double()).sum((0, 2, 3))
+    assert parity.relerr(dw, ref) < 1e-6
+
+
+@pytest.mark.parametrize("lo,hi", [(-1.0, 1.0), (1.0, -1.0)])
+def test_to_uint8_matches_the_reference_epilogue(lib, lo, hi):
+    """fgan_complete.py:136-138: (255 * (clamp(x, -1, 1) * 0.5 + 0.5)).to(uint8); lo > hi: no clamp (fgan64's own-range clamp)."""
+    torch.manual_seed(0)
+    x = torch.tanh(torch.randn(3, 3, 9, 9) * 2) if lo > hi else torch.randn(3, 3, 9, 9) * 1.5
+    out = torch.zeros(x.shape, dtype=torch.uint8)
+    call(lib, "ffc_to_uint8", x, out, ctypes.c_longlong(x.numel()), ctypes.c_float(lo), ctypes.c_float(hi), None)
+    ref = (255 * ((x.clamp(-1, 1) if lo < hi else x) * 0.5 + 0.5)).to(torch.uint8)
+    assert (out.int() - ref.int()).abs().max() <= 1 and (out != ref).float().mean() < 0.01      # FMA contraction may move a value across an integer
+
+
+@pytest.mark.parametrize("h,w,kk", [(24, 70, 0), (16, 9 * 8, 9)])
+def test_spectral_norm_backward(lib, h, w, kk):
+    """dW = g / sigma - (sum(g * W) / sigma^2) u v^T in the weight's own storage order (kk > 0: ConvTranspose2d layout)."""
+    torch.manual_seed(h + w)
+    Wm = torch.randn(h, w)                       # matrix view
+    u, v = F.normalize(torch.randn(h), dim=0), F.normalize(torch.randn(w), dim=0)
+    sigma = torch.dot(u, Wm @ v).reshape(1)
+    gm = torch.randn(h, w)
+    ref = gm.double() / sigma.double() - (gm.double() * Wm.double()).sum() / sigma.double() ** 2 * torch.outer(u.double(), v.double())
+    if kk:                                       # storage (w / kk, h, kk) <-> matrix (h, w)
+        store = lambda m: m.reshape(h, w // kk, kk).permute(1, 0, 2).contiguous()
+        Ws, gs, refs = store(Wm), store(gm), store(ref)
+    else:
+        Ws, gs, refs = Wm, gm, ref
+    dw = torch.zeros_like(Ws)
+    ws = torch.zeros(16)
+    call(lib, "ffc_spectral_norm_bwd", gs, Ws, u, v, sigma, dw, h, w, kk, ws, ctypes.c_size_t(64), None)
+    assert parity.relerr(dw, refs) < 1e-5
