@@ -49,6 +49,9 @@ _SIGNATURES = {
     "ffc_fu_fwd": (c_int, [c_void_p] * 10 + [c_int] * 6 + [c_float, c_float, c_void_p, c_size_t, c_void_p]),
     "ffc_fu_fused_supported": (c_int, [c_int] * 5),
     "ffc_fu3_fwd": (c_int, [c_void_p] * 10 + [c_int] * 6 + [c_float, c_float, c_void_p, c_size_t, c_void_p]),
+    "ffc_fu3_fwd_keep": (c_int, [c_void_p] * 12 + [c_int] * 6 + [c_float, c_float, c_void_p, c_size_t, c_void_p]),
+    "ffc_fu3_bwd": (c_int, [c_void_p] * 12 + [c_int] * 6 + [c_void_p, c_size_t, c_void_p]),
+    "ffc_fu3_bwd_workspace_bytes": (c_size_t, [c_int] * 5),
     "ffc_fu3_supported": (c_int, [c_int] * 5),
     "ffc_fu3_workspace_bytes": (c_size_t, [c_int] * 6),
     "ffc_debug_fu3_simt_mix": (None, [c_int]),

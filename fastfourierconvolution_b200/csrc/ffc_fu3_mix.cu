@@ -42,13 +42,14 @@ bool fu3_mix_tc_supported(int Cin, int Cout) {
 size_t fu3_mix_tc_packed_floats(int Cin, int Cout) { return (size_t)fm_kchunks(Cin) * 2 * fm_nt(Cout) * FM_BK; }
 
 // wp[chunk][hi | lo][n/8][kk/4][n%8][kk%4]  (the shared-memory image of a K-major no-swizzle UMMA B tile, per chunk)
-__global__ void __launch_bounds__(256) fu3_pack_kernel(const float* __restrict__ w, float* __restrict__ wp, int Cin, int Cout, int NT, int KC, float scale) {
+// transposed: w is [2*Cin][2*Cout] (the forward's weight seen from the backward mix dS = dY W: contraction over its rows)
+__global__ void __launch_bounds__(256) fu3_pack_kernel(const float* __restrict__ w, float* __restrict__ wp, int Cin, int Cout, int NT, int KC, float scale, int transposed) {
     const int total = KC * NT * FM_BK;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         const int kk = e % FM_BK, n = (e / FM_BK) % NT, chunk = e / (FM_BK * NT);
         const int k = chunk * FM_BK + kk;
         float v = 0.f;
-        if (n < 2 * Cout && k < 2 * Cin) v = __ldg(w + (size_t)n * 2 * Cin + k) * scale;
+        if (n < 2 * Cout && k < 2 * Cin) v = __ldg(transposed ? w + (size_t)k * 2 * Cout + n : w + (size_t)n * 2 * Cin + k) * scale;
         const float hi = ffc_tf32_hi(v);
         float* dst = wp + (size_t)chunk * 2 * NT * FM_BK + (n / 8) * 256 + (kk / 4) * 32 + (n % 8) * 4 + (kk % 4);
         dst[0] = hi;
@@ -56,10 +57,10 @@ __global__ void __launch_bounds__(256) fu3_pack_kernel(const float* __restrict__
     }
 }
 
-int fu3_mix_tc_pack(const float* w, float* wp, int Cin, int Cout, float scale, ffc_stream_t st) {
+int fu3_mix_tc_pack(const float* w, float* wp, int Cin, int Cout, float scale, int transposed, ffc_stream_t st) {
     const int NT = fm_nt(Cout), KC = fm_kchunks(Cin);
     int gx = (KC * NT * FM_BK + 255) / 256; if (gx > 64) gx = 64;
-    fu3_pack_kernel<<<gx, 256, 0, st>>>(w, wp, Cin, Cout, NT, KC, scale);
+    fu3_pack_kernel<<<gx, 256, 0, st>>>(w, wp, Cin, Cout, NT, KC, scale, transposed);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { ffc_set_error("fu3_pack launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
     ffc_count_launch();

@@ -567,7 +567,22 @@ class FusedFuFn(torch.autograd.Function):
         save_mean = torch.empty(2 * Cout, device=x.device, dtype=torch.float32)
         save_invstd = torch.empty(2 * Cout, device=x.device, dtype=torch.float32)
         L = _C.lib()
-        if staged:       # planes / channel counts beyond one CTA's shared memory: spectrum staged through L2 in chunks of images
+        st = _C.current_stream(x.device)
+        keep = staged and any(ctx.needs_input_grad[:4])
+        if keep:
+            # planes / channel counts beyond one CTA's shared memory, with a backward to follow: both spectra are kept in
+            # the library's plane layout, so the backward (ffc_fu3_bwd) recomputes nothing
+            s_keep = torch.empty((B, Cin, H, W + 4), device=x.device, dtype=torch.float32)
+            y_keep = torch.empty((B, Cout, H, W + 4), device=x.device, dtype=torch.float32)
+            ws = _C.workspace(L.ffc_fu3_workspace_bytes(B, Cin, Cout, H, W, int(training)), x.device)
+            _C.check(L.ffc_fu3_fwd_keep(_C.ptr(x), _C.ptr(weight), _C.ptr(gamma), _C.ptr(beta),
+                                        _C.ptr(running_mean), _C.ptr(running_var), _C.ptr(save_mean), _C.ptr(save_invstd),
+                                        _C.ptr(residual), _C.ptr(out), _C.ptr(s_keep), _C.ptr(y_keep), B, Cin, Cout, H, W,
+                                        int(training), float(eps), float(momentum), _C.ptr(ws), ws.numel(), st))
+            ctx.save_for_backward(x, weight, gamma, beta, save_mean, save_invstd, s_keep, y_keep)
+            ctx.cfg = (bool(training), residual is not None)
+            return out
+        if staged:       # spectrum staged through L2 in chunks of images
             ws = _C.workspace(L.ffc_fu3_workspace_bytes(B, Cin, Cout, H, W, int(training)), x.device)
             fwd = L.ffc_fu3_fwd
         else:
@@ -576,7 +591,7 @@ class FusedFuFn(torch.autograd.Function):
         _C.check(fwd(_C.ptr(x), _C.ptr(weight), _C.ptr(gamma), _C.ptr(beta),
                                      _C.ptr(running_mean), _C.ptr(running_var), _C.ptr(save_mean), _C.ptr(save_invstd),
                                      _C.ptr(residual), _C.ptr(out), B, Cin, Cout, H, W, int(training), float(eps),
-                                     float(momentum), _C.ptr(ws), ws.numel(), _C.current_stream(x.device)))
+                                     float(momentum), _C.ptr(ws), ws.numel(), st))
         ctx.save_for_backward(x, weight, gamma, beta, save_mean, save_invstd)
         ctx.cfg = (bool(training), residual is not None)
         return out
@@ -584,7 +599,7 @@ class FusedFuFn(torch.autograd.Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, dout):
-        x, weight, gamma, beta, save_mean, save_invstd = ctx.saved_tensors
+        x, weight, gamma, beta, save_mean, save_invstd = ctx.saved_tensors[:6]
         training, has_res = ctx.cfg
         dout = dout.contiguous()
         B, Cin, H, W = x.shape
@@ -592,6 +607,18 @@ class FusedFuFn(torch.autograd.Function):
         Wf = W // 2 + 1
         L = _C.lib()
         st = _C.current_stream(x.device)
+        if len(ctx.saved_tensors) == 8 and FUSED_FU_BACKWARD:
+            # L2-staged form: adjoint transform + ReLU mask + BN sums | constants | dY + dW | dS (tensor cores) | adjoint transform
+            s_keep, y_keep = ctx.saved_tensors[6:]
+            dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+            dw = torch.empty_like(weight)
+            dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(beta)
+            ws = _C.workspace(L.ffc_fu3_bwd_workspace_bytes(B, Cin, C2o // 2, H, W), x.device)
+            _C.check(L.ffc_fu3_bwd(_C.ptr(dout), _C.ptr(s_keep), _C.ptr(y_keep), _C.ptr(weight), _C.ptr(gamma), _C.ptr(beta),
+                                   _C.ptr(save_mean), _C.ptr(save_invstd), _C.ptr(dx), _C.ptr(dw), _C.ptr(dgamma), _C.ptr(dbeta),
+                                   B, Cin, C2o // 2, H, W, int(training), _C.ptr(ws), ws.numel(), st))
+            dres = dout if (has_res and ctx.needs_input_grad[6]) else None
+            return dx, dw, dgamma, dbeta, None, None, dres, None, None, None, None
         if FUSED_FU_BACKWARD and L.ffc_fu_bwd_supported(B, Cin, C2o // 2, H, W):
             # one cooperative kernel: both spectra stay in shared memory (csrc/ffc_fu2_bwd.cu)
             dx, dw = torch.empty_like(x), torch.empty_like(weight)

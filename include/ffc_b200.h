@@ -101,6 +101,20 @@ int ffc_fu3_fwd(const float* x, const float* w, const float* gamma, const float*
                 const float* residual, float* out,
                 int B, int Cin, int Cout, int H, int W, int training, float eps, float momentum,
                 void* workspace, size_t workspace_bytes, void* stream);
+/* ffc_fu3_fwd_keep / ffc_fu3_bwd: FourierUnitSN forward that keeps its two spectra, and the backward that autograd derives for
+ * layers/ffc/fourier_unity.py:32-58 (cuFFT c2r/r2c adjoints, cudnn BatchNorm backward, ReLU mask, 1x1 conv dgrad / wgrad) as
+ * five kernels that recompute nothing.  s_keep (B, Cin, H, W + 4) and y_keep (B, Cout, H, W + 4) floats are opaque (the
+ * library's plane layout).  dx may be null; the gradient with respect to the residual is dout itself.
+ * workspace >= ffc_fu3_bwd_workspace_bytes(B, Cin, Cout, H, W). */
+int ffc_fu3_fwd_keep(const float* x, const float* w, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, float* save_mean, float* save_invstd,
+                     const float* residual, float* out, float* s_keep, float* y_keep,
+                     int B, int Cin, int Cout, int H, int W, int training, float eps, float momentum,
+                     void* workspace, size_t workspace_bytes, void* stream);
+size_t ffc_fu3_bwd_workspace_bytes(int B, int Cin, int Cout, int H, int W);
+int ffc_fu3_bwd(const float* dout, const float* s_keep, const float* y_keep, const float* w, const float* gamma, const float* beta,
+                const float* save_mean, const float* save_invstd, float* dx, float* dw, float* dgamma, float* dbeta,
+                int B, int Cin, int Cout, int H, int W, int training, void* workspace, size_t workspace_bytes, void* stream);
 /* ---- Glue between the FFC layers of the reference's generators, one bandwidth-bound kernel each ----
  * ffc_noise_add_fwd: NoiseInjection.forward (layers/noise_injection.py:20-32; called on both branches after every
  *   upsampling stage, fgan_complete.py:122-131): out = x + weight[c] * noise[b, 0, h, w]; x / out (B, C, HW), noise (B, HW).

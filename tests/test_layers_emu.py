@@ -303,3 +303,35 @@ def test_fourier_unit_l2_staged_form(B, C, N, chunk, train, emu):
     ref = R.fourier_unit(x.double(), P, "", train) + res.double()
     assert parity.relerr(out, ref) < 1e-6
     assert parity.relerr(m.bn.running_mean, P["bn.running_mean"]) < 1e-5 and parity.relerr(m.bn.running_var, P["bn.running_var"]) < 1e-5
+
+
+@pytest.mark.parametrize("B,C,Co,N", [(3, 6, 6, 64), (5, 4, 7, 32), (2, 40, 36, 16), (1, 3, 4, 128)])
+@pytest.mark.parametrize("train", [True, False])
+def test_fourier_unit_l2_staged_backward(B, C, Co, N, train, emu):
+    """Backward of the L2-staged Fourier unit (ffc_fu3_fwd_keep + ffc_fu3_bwd: adjoint transform with the ReLU mask and the
+    BatchNorm-backward sums | constants | dY + dW | dS = dY W | adjoint transform) in host emulation against the float64
+    oracle: dx, dW, dgamma, dbeta and the residual's gradient; channel counts that are not multiples of the 32-channel
+    tile and Cin != Cout included.  Relative L2 norm for the gradients (a ReLU element on the other side of its kink moves
+    the max norm, SURVEY.md 8(c) caveat 1)."""
+    torch.manual_seed(C + N + Co)
+    m = ffc.FourierUnitSN(C, Co).train(train)
+    m.fused = "staged"
+    with torch.no_grad():
+        m.bn.weight.uniform_(0.5, 1.5); m.bn.bias.normal_(0, 0.2); m.bn.running_mean.normal_(0, 0.1); m.bn.running_var.uniform_(0.5, 1.5)
+    P = {k: (v.double().clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else
+             (v.double().clone() if v.is_floating_point() else v.clone())) for k, v in m.state_dict().items()}
+    x, res = torch.randn(B, C, N, N), torch.randn(B, Co, N, N)
+    xr, rr = x.double().requires_grad_(True), res.double().requires_grad_(True)
+    ref = R.fourier_unit(xr, P, "", train) + rr
+    cot = torch.randn(ref.shape, dtype=torch.float64)
+    (ref * cot).sum().backward()
+    xo, ro = x.clone().requires_grad_(True), res.clone().requires_grad_(True)
+    out = m._run(xo, None, ro)
+    (out * cot.float()).sum().backward()
+
+    def l2(a, b):
+        return ((a.detach().double() - b.detach().double()).norm() / b.detach().double().norm()).item()
+    assert parity.relerr(out, ref.detach()) < 1e-5
+    assert l2(xo.grad, xr.grad) < 1e-3 and l2(m.conv_layer.weight.grad, P["conv_layer.weight"].grad) < 1e-3
+    assert l2(m.bn.weight.grad, P["bn.weight"].grad) < 1e-3 and l2(m.bn.bias.grad, P["bn.bias"].grad) < 1e-3
+    assert torch.equal(ro.grad, cot.float())
