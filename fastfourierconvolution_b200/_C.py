@@ -60,6 +60,11 @@ _SIGNATURES = {
     "ffc_fu_bwd_supported": (c_int, [c_int] * 5),
     "ffc_noise_add_fwd": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),
     "ffc_noise_add_bwd_w": (c_int, [c_void_p] * 3 + [c_int] * 3 + [c_void_p]),
+    "ffc_gemm_f32": (c_int, [c_void_p] * 4 + [c_int] * 3 + [ctypes.c_longlong] * 6 + [c_void_p]),
+    "ffc_colsum_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "ffc_adam_step": (c_int, [c_void_p] * 4 + [ctypes.c_longlong, c_void_p, c_void_p] + [c_float] * 5 + [c_int, c_void_p]),
+    "ffc_adam_step_table": (c_int, [c_void_p] * 8 + [c_int, c_int, c_void_p, c_void_p] + [c_float] * 5 + [c_int, c_void_p]),
+    "ffc_gather_table": (c_int, [c_void_p] * 6 + [c_int, c_void_p]),
     "ffc_to_uint8": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_float, c_float, c_void_p]),
     "ffc_debug_conv_reference": (None, [c_int]),
     "ffc_debug_fu_two_pass": (None, [c_int]),

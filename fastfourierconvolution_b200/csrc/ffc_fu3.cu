@@ -131,7 +131,7 @@ struct Fu3Rfft2 {
     typedef Fu2G<N> G;
     static constexpr int P = Fu3G<N>::P;
     static constexpr int kThreads = Fu3G<N>::kThreads;
-    static constexpr int kMinBlocks = (N == 128) ? 3 : (N == 64 ? 4 : 4);
+    static constexpr int kMinBlocks = (N == 128) ? 3 : (N == 64 ? 5 : 4);
     static constexpr int kS2 = (N / 4 < 8) ? N / 4 : 8;      // MASK: second-level fan-in of the per-plane reduction
     static size_t smem_bytes() { return ((size_t)P * G::REGION + 2 * N) * 4 + 16 + (MASK ? (size_t)(kThreads * 4 + P * 4 * kS2) * 4 : 0); }
 
@@ -236,7 +236,7 @@ struct Fu3Rfft2 {
         if (threadIdx.x == 0) {
             umma::bulk_s2g(p.spec + (size_t)plane0 * G::REGION, planes, (uint32_t)(np * G::REGION * 4));
             umma::bulk_commit_group();
-            umma::bulk_wait_group0();
+            umma::bulk_wait_group_read0();      // the shared-memory source has been read: the CTA may retire while the writes drain
         }
 #else
         FFC_PHASE {
@@ -265,7 +265,7 @@ struct Fu3Irfft2 {
     typedef Fu2G<N> G;
     static constexpr int P = Fu3G<N>::P;
     static constexpr int kThreads = Fu3G<N>::kThreads;
-    static constexpr int kMinBlocks = (N == 128) ? 3 : 4;
+    static constexpr int kMinBlocks = (N == 128) ? 3 : (N == 64 ? 5 : 4);
     static size_t smem_bytes() { return ((size_t)P * G::REGION + 2 * N + 4 * P) * 4 + 16; }
 
     static FFC_DEVICE void run(const Params& p, const BlockCtx& ctx, float* smem) {
@@ -332,7 +332,7 @@ struct Fu3Irfft2 {
             for (int r = tid; r < np * N; r += ctx.nt)
                 umma::bulk_s2g(p.out + ((size_t)plane0 * N + r) * N, planes + (size_t)r * G::RS, (uint32_t)(N * 4));
             umma::bulk_commit_group();
-            umma::bulk_wait_group0();
+            umma::bulk_wait_group_read0();      // the shared-memory source has been read: the CTA may retire while the writes drain
             return;
         }
 #endif
@@ -438,6 +438,9 @@ bool fu3_mix_tc_supported(int Cin, int Cout);
 size_t fu3_mix_tc_packed_floats(int Cin, int Cout);
 int fu3_mix_tc_pack(const float* w, float* wp, int Cin, int Cout, float scale, int transposed, ffc_stream_t st);
 int fu3_mix_tc_run(const Fu3MixParams& p, ffc_stream_t st);
+bool fu3_wgrad_tc_supported(int Cin, int Cout);
+size_t fu3_wgrad_tc_part_floats(int Cin);
+int fu3_wgrad_tc_run(const Fu3BwdWgradParams& p, ffc_stream_t st);
 #endif
 static int g_fu3_simt_mix = 0;
 extern "C" void ffc_debug_fu3_simt_mix(int on) { g_fu3_simt_mix = on; }
@@ -673,16 +676,6 @@ struct Fu3BwdFinalize {
 // dY and the weight gradient.  CTA tile: 64 rows n = 2*o + (re | im) of dY by 64 columns k = 2*c + (re | im) of S, over
 // chunks of 64 bins staged bin-major in shared memory; thread = 4 x 4 outputs (two 16-byte loads per 16 FMAs); persistent
 // over the chunks, one float atomic per output and CTA at the end.  The k-block 0 CTAs also write dY.
-struct Fu3BwdWgradParams {
-    const float* g;        // (B, Cout, NB) complex
-    const float* y;        // (B, Cout, NB)
-    const float* s;        // (B, Cin, NB)
-    float* dy;             // (B, Cout, NB)
-    const float* coef; const float* c1; const float* c2; const float* mean; const float* invstd;     // [2*Cout]
-    float* dw;             // [2*Cout][2*Cin], zeroed by the host wrapper
-    int B, Cin, Cout, NB;
-    float scale;
-};
 struct Fu3WgAcc { float v[16]; };
 struct Fu3BwdWgrad {
     typedef Fu3BwdWgradParams Params;
@@ -698,6 +691,7 @@ struct Fu3BwdWgrad {
         FFC_TLS(Fu3WgAcc, acc);
         FFC_PHASE {
             FFC_TLS_REF(Fu3WgAcc, acc);
+            (void)tid;
             FFC_UNROLL
             for (int i = 0; i < 16; ++i) acc.v[i] = 0.f;
         } FFC_SYNC;
@@ -757,7 +751,7 @@ struct Fu3BwdWgrad {
 
 struct Fu3BwdPlan {
     int NB, region;
-    size_t off_sums, off_consts, off_wp, off_g, off_dy, off_ds, total;
+    size_t off_sums, off_consts, off_wp, off_part, off_g, off_dy, off_ds, total;
 };
 static Fu3BwdPlan fu3_bwd_plan(int B, int Cin, int Cout, int N) {
     Fu3BwdPlan pl;
@@ -773,6 +767,10 @@ static Fu3BwdPlan fu3_bwd_plan(int B, int Cin, int Cout, int N) {
     if (packed > wbytes) wbytes = packed;
 #endif
     off = fu3_align(off + wbytes);
+    pl.off_part = off;
+#ifndef FFC_EMU
+    if (fu3_wgrad_tc_supported(Cin, Cout)) off = fu3_align(off + fu3_wgrad_tc_part_floats(Cin) * sizeof(float));
+#endif
     pl.off_g = off; off = fu3_align(off + (size_t)B * Cout * pl.region * 4);
     pl.off_dy = off; off = fu3_align(off + (size_t)B * Cout * pl.region * 4);
     pl.off_ds = off; off = fu3_align(off + (size_t)B * Cin * pl.region * 4);
@@ -822,7 +820,11 @@ static int fu3_bwd_run(const float* dout, const float* s_keep, const float* y_ke
     FFC_CHECK((ffc_launch<Fu3BwdFinalize>(1, 1, 1, 256, 0, st, fp)));
     Fu3BwdWgradParams wg;
     wg.g = Gs; wg.y = y_keep; wg.s = s_keep; wg.dy = dY; wg.coef = coef; wg.c1 = c1; wg.c2 = c2; wg.mean = save_mean; wg.invstd = save_invstd;
-    wg.dw = dw; wg.B = B; wg.Cin = Cin; wg.Cout = Cout; wg.NB = pl.NB; wg.scale = scale;
+    wg.dw = dw; wg.part = reinterpret_cast<float*>(ws + pl.off_part); wg.B = B; wg.Cin = Cin; wg.Cout = Cout; wg.NB = pl.NB; wg.scale = scale;
+#ifndef FFC_EMU
+    if (!g_fu3_simt_mix && fu3_wgrad_tc_supported(Cin, Cout)) { FFC_CHECK(fu3_wgrad_tc_run(wg, st)); }
+    else
+#endif
     {
         const int gy = ffc_cdiv(Cout, 32), gz = ffc_cdiv(Cin, 32);
         const long long nchunks = ((long long)B * pl.NB + Fu3BwdWgrad::KB - 1) / Fu3BwdWgrad::KB;

@@ -13,3 +13,16 @@ struct Fu3MixParams {
     int G, Cin, Cout, NB, SPS;
     float scale;             // forward transform scale folded into the mix (1/N)
 };
+
+// dY = coef * (g - c1 - xhat * c2) and dW = scale * dY^T S (backward of the mix + BatchNorm; ffc_fu3.cu FP32 form, ffc_fu3_mix.cu tensor cores)
+struct Fu3BwdWgradParams {
+    const float* g;        // (B, Cout, NB) complex
+    const float* y;        // (B, Cout, NB)
+    const float* s;        // (B, Cin, NB)
+    float* dy;             // (B, Cout, NB)
+    const float* coef; const float* c1; const float* c2; const float* mean; const float* invstd;     // [2*Cout]
+    float* dw;             // [2*Cout][2*Cin], zeroed by the host wrapper
+    float* part;           // tensor-core form: per-CTA partial tiles [CTA][128][NT] (workspace)
+    int B, Cin, Cout, NB;
+    float scale;
+};

@@ -30,37 +30,65 @@
 
 static constexpr int FM_BK = 32;                 // K per chunk (16 complex channels)
 
-static inline int fm_nt(int Cout) { return (2 * Cout + 15) / 16 * 16; }
 static inline int fm_kchunks(int Cin) { return (2 * Cin + FM_BK - 1) / FM_BK; }
 
-bool fu3_mix_tc_supported(int Cin, int Cout) {
-    const int NT = fm_nt(Cout), KC = fm_kchunks(Cin);
-    if (NT > 128 || NT < 16) return false;
-    const int nwg = (NT <= 64) ? 4 : 2;                   // + statistics staging tiles of the training-mode epilogue
-    return (size_t)KC * 2 * NT * FM_BK * 4 + 4 * NT * 4 + 512 + (size_t)nwg * 64 * 132 * 4 <= (size_t)225 * 1024;
-}
-size_t fu3_mix_tc_packed_floats(int Cin, int Cout) { return (size_t)fm_kchunks(Cin) * 2 * fm_nt(Cout) * FM_BK; }
+static constexpr int FM_SCOL = 132;               // floats per column of the statistics staging tile (128 bins + 4: conflict-free LDS.128)
+static constexpr int FM_SBUF = 64 * FM_SCOL;      // floats per warpgroup
 
-// wp[chunk][hi | lo][n/8][kk/4][n%8][kk%4]  (the shared-memory image of a K-major no-swizzle UMMA B tile, per chunk)
+// Tiling of the 2*Cout output columns.  Up to 128 columns the whole packed weight matrix (hi | lo) is resident in one CTA's
+// shared memory (one column tile).  Wider mixes (more than 64 output channels: the sweep's 96 / 128 / 192) are cut into column
+// tiles of NT <= 64 that fit beside the statistics staging tiles; gridDim.y walks the tiles and every tile re-reads the
+// spectrum (these shapes are tensor-bound: 2*Cin MACs x 3 per output value).
+struct FmPlan { int NT, ntiles, nwg; size_t smem_weights; bool ok; };
+static FmPlan fm_plan(int Cin, int Cout) {
+    FmPlan pl; pl.ok = false; pl.NT = 0; pl.ntiles = 0; pl.nwg = 0; pl.smem_weights = 0;
+    if (Cin < 1 || Cout < 1) return pl;
+    const int KC = fm_kchunks(Cin), full = (2 * Cout + 15) / 16 * 16;
+    const size_t budget = (size_t)224 * 1024, fixed = 2 * 128 * 4 + 16 * 8 + 64;
+    const int widths[] = {full <= 128 ? full : 0, 64, 48, 32, 16};
+    for (int wi = 0; wi < 5; ++wi) {
+        const int NT = widths[wi];
+        if (NT < 16 || NT > full) continue;
+        const size_t wbytes = (size_t)KC * 2 * NT * FM_BK * 4;
+        const int nwgs[] = {NT <= 64 ? 4 : 2, 2, 1};
+        for (int gi = 0; gi < 3; ++gi) {
+            const int nwg = nwgs[gi];
+            if (nwg * (64 + NT) > 512) continue;
+            if (wbytes + fixed + (size_t)nwg * FM_SBUF * 4 > budget) continue;
+            pl.NT = NT; pl.ntiles = (2 * Cout + NT - 1) / NT; pl.nwg = nwg; pl.smem_weights = wbytes; pl.ok = true;
+            return pl;
+        }
+    }
+    return pl;
+}
+
+bool fu3_mix_tc_supported(int Cin, int Cout) { return fm_plan(Cin, Cout).ok; }
+size_t fu3_mix_tc_packed_floats(int Cin, int Cout) {
+    const FmPlan pl = fm_plan(Cin, Cout);
+    return pl.ok ? (size_t)pl.ntiles * fm_kchunks(Cin) * 2 * pl.NT * FM_BK : 0;
+}
+
+// wp[tile][chunk][hi | lo][n/8][kk/4][n%8][kk%4]  (the shared-memory image of a K-major no-swizzle UMMA B tile, per chunk)
 // transposed: w is [2*Cin][2*Cout] (the forward's weight seen from the backward mix dS = dY W: contraction over its rows)
-__global__ void __launch_bounds__(256) fu3_pack_kernel(const float* __restrict__ w, float* __restrict__ wp, int Cin, int Cout, int NT, int KC, float scale, int transposed) {
-    const int total = KC * NT * FM_BK;
+__global__ void __launch_bounds__(256) fu3_pack_kernel(const float* __restrict__ w, float* __restrict__ wp, int Cin, int Cout, int NT, int KC, int ntiles, float scale, int transposed) {
+    const int total = ntiles * KC * NT * FM_BK;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-        const int kk = e % FM_BK, n = (e / FM_BK) % NT, chunk = e / (FM_BK * NT);
-        const int k = chunk * FM_BK + kk;
+        const int kk = e % FM_BK, nl = (e / FM_BK) % NT, chunk = (e / (FM_BK * NT)) % KC, tile = e / (FM_BK * NT * KC);
+        const int k = chunk * FM_BK + kk, n = tile * NT + nl;
         float v = 0.f;
         if (n < 2 * Cout && k < 2 * Cin) v = __ldg(transposed ? w + (size_t)k * 2 * Cout + n : w + (size_t)n * 2 * Cin + k) * scale;
         const float hi = ffc_tf32_hi(v);
-        float* dst = wp + (size_t)chunk * 2 * NT * FM_BK + (n / 8) * 256 + (kk / 4) * 32 + (n % 8) * 4 + (kk % 4);
+        float* dst = wp + ((size_t)tile * KC + chunk) * 2 * NT * FM_BK + (nl / 8) * 256 + (kk / 4) * 32 + (nl % 8) * 4 + (kk % 4);
         dst[0] = hi;
         dst[(size_t)NT * FM_BK] = v - hi;
     }
 }
 
 int fu3_mix_tc_pack(const float* w, float* wp, int Cin, int Cout, float scale, int transposed, ffc_stream_t st) {
-    const int NT = fm_nt(Cout), KC = fm_kchunks(Cin);
-    int gx = (KC * NT * FM_BK + 255) / 256; if (gx > 64) gx = 64;
-    fu3_pack_kernel<<<gx, 256, 0, st>>>(w, wp, Cin, Cout, NT, KC, scale, transposed);
+    const FmPlan pl = fm_plan(Cin, Cout);
+    const int KC = fm_kchunks(Cin);
+    int gx = (pl.ntiles * KC * pl.NT * FM_BK + 255) / 256; if (gx > 296) gx = 296;
+    fu3_pack_kernel<<<gx, 256, 0, st>>>(w, wp, Cin, Cout, pl.NT, KC, pl.ntiles, scale, transposed);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { ffc_set_error("fu3_pack launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
     ffc_count_launch();
@@ -70,9 +98,6 @@ int fu3_mix_tc_pack(const float* w, float* wp, int Cin, int Cout, float scale, i
 __device__ __forceinline__ void fm_named_barrier(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-
-static constexpr int FM_SCOL = 132;               // floats per column of the statistics staging tile (128 bins + 4: conflict-free LDS.128)
-static constexpr int FM_SBUF = 64 * FM_SCOL;      // floats per warpgroup
 
 // N = plane size: NB (complex slots per plane) and SPS (slots per spectrum row) are compile-time, so the per-channel
 // address offsets of the gather and of the stores are immediates and the bin -> (image, slot) split is a constant division
@@ -98,11 +123,12 @@ __global__ void __launch_bounds__(NWG * 128, 1) fu3_mix_kernel(const Fu3MixParam
         umma::fence_barrier_init();
         umma::mbar_arrive_expect_tx(w_full, (uint32_t)KC * chunk_bytes);
         for (int c = 0; c < KC; ++c)
-            umma::bulk_g2s(bsm + (size_t)c * chunk_bytes, p.wp + (size_t)c * 2 * NT * FM_BK, chunk_bytes, w_full);
+            umma::bulk_g2s(bsm + (size_t)c * chunk_bytes, p.wp + ((size_t)blockIdx.y * KC + c) * 2 * NT * FM_BK, chunk_bytes, w_full);
     }
     for (int i = tid; i < NT; i += blockDim.x) {
-        bn_a[i] = (p.bn_a && i < 2 * p.Cout) ? __ldg(p.bn_a + i) : 0.f;
-        bn_b[i] = (p.bn_b && i < 2 * p.Cout) ? __ldg(p.bn_b + i) : 0.f;
+        const int n = (int)blockIdx.y * NT + i;            // column tile blockIdx.y covers output columns [nbase, nbase + NT)
+        bn_a[i] = (p.bn_a && n < 2 * p.Cout) ? __ldg(p.bn_a + n) : 0.f;
+        bn_b[i] = (p.bn_b && n < 2 * p.Cout) ? __ldg(p.bn_b + n) : 0.f;
     }
     if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
     umma::fence_before_sync();
@@ -116,7 +142,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) fu3_mix_kernel(const Fu3MixParam
     const uint32_t idesc = umma::idesc_tf32(128, NT);
     const uint32_t b0 = umma::smem_u32(bsm);
     const bool issuer = (warp & 3) == 0;                             // first warp of the warpgroup issues its MMAs
-    const int Cin = p.Cin, Cout = p.Cout;
+    const int Cin = p.Cin, Cout = p.Cout, nbase = (int)blockIdx.y * NT;
     const float2* S = reinterpret_cast<const float2*>(p.s);
     float2* Y = reinterpret_cast<float2*>(p.y);
     const bool do_bn = p.bn_a != nullptr, do_stats = p.sums != nullptr;
@@ -228,7 +254,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) fu3_mix_kernel(const Fu3MixParam
                 if (yp && ok) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const int o = (n0 >> 1) + j;
+                        const int o = ((nbase + n0) >> 1) + j;
                         if (o < Cout) yp[(size_t)o * NB] = make_float2(f[2 * j], f[2 * j + 1]);
                     }
                 }
@@ -271,10 +297,10 @@ __global__ void __launch_bounds__(NWG * 128, 1) fu3_mix_kernel(const Fu3MixParam
         __syncthreads();
         for (int i = tid; i < 2 * NT; i += blockDim.x) {
             const int n = i >> 1, which = i & 1;
-            if (n < 2 * Cout) {
+            if (nbase + n < 2 * Cout) {
                 double acc = 0.0;
                 for (int w = 0; w < 2 * NWG; ++w) acc += red[((size_t)w * NT + n) * 2 + which];
-                atomicAdd(p.sums + (which ? 2 * Cout + n : n), acc);
+                atomicAdd(p.sums + (which ? 2 * Cout + nbase + n : nbase + n), acc);
             }
         }
     }
@@ -284,7 +310,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) fu3_mix_kernel(const Fu3MixParam
 }
 
 template <int NWG, int N>
-static int fu3_mix_launch(const Fu3MixParams& p, int NT, int KC, long long Mtot, int ntiles, int grid, size_t smem, ffc_stream_t st) {
+static int fu3_mix_launch(const Fu3MixParams& p, int NT, int KC, long long Mtot, int ntiles, int grid, int ncoltiles, size_t smem, ffc_stream_t st) {
     static FfcPerDevice configured_dev = {};
     size_t& configured = *ffc_device_slot(configured_dev);
     if (smem > configured) {
@@ -292,7 +318,7 @@ static int fu3_mix_launch(const Fu3MixParams& p, int NT, int KC, long long Mtot,
         if (e != cudaSuccess) { ffc_set_error("cudaFuncSetAttribute(fu3_mix, %zu B): %s", smem, cudaGetErrorString(e)); return FFC_ERR_CUDA; }
         configured = smem;
     }
-    fu3_mix_kernel<NWG, N><<<grid, NWG * 128, smem, st>>>(p, NT, KC, Mtot, ntiles);
+    fu3_mix_kernel<NWG, N><<<dim3(grid, ncoltiles), NWG * 128, smem, st>>>(p, NT, KC, Mtot, ntiles);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { ffc_set_error("fu3_mix launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
     ffc_count_launch();
@@ -301,17 +327,21 @@ static int fu3_mix_launch(const Fu3MixParams& p, int NT, int KC, long long Mtot,
 
 template <int N>
 static int fu3_mix_run_n(const Fu3MixParams& p, ffc_stream_t st) {
-    const int NT = fm_nt(p.Cout), KC = fm_kchunks(p.Cin);
+    const FmPlan pl = fm_plan(p.Cin, p.Cout);
+    if (!pl.ok) { ffc_set_error("fu3_mix: %d -> %d channels do not fit the tensor-core mix", p.Cin, p.Cout); return FFC_ERR_BAD_ARG; }
+    const int NT = pl.NT, KC = fm_kchunks(p.Cin), nwg = pl.nwg;
     const long long Mtot = (long long)p.G * p.NB;
     const int ntiles = (int)((Mtot + 127) / 128);
-    const int nwg = (NT <= 64) ? 4 : 2;
     // weights | BN constants | barriers (16 x 8 bytes) | statistics staging tiles (training mode)
     const size_t smem = (size_t)KC * 2 * NT * FM_BK * 4 + 2 * NT * 4 + 16 * 8 + (p.sums ? (size_t)nwg * FM_SBUF * 4 : 0) + 64;
     int grid = (ntiles + nwg - 1) / nwg;
-    if (grid > ffc_sm_count()) grid = ffc_sm_count();
+    int per_col = ffc_sm_count() / pl.ntiles;                  // persistent CTAs per column tile
+    if (per_col < 1) per_col = 1;
+    if (grid > per_col) grid = per_col;
     if (grid < 1) grid = 1;
-    if (nwg == 4) return fu3_mix_launch<4, N>(p, NT, KC, Mtot, ntiles, grid, smem, st);
-    return fu3_mix_launch<2, N>(p, NT, KC, Mtot, ntiles, grid, smem, st);
+    if (nwg == 4) return fu3_mix_launch<4, N>(p, NT, KC, Mtot, ntiles, grid, pl.ntiles, smem, st);
+    if (nwg == 2) return fu3_mix_launch<2, N>(p, NT, KC, Mtot, ntiles, grid, pl.ntiles, smem, st);
+    return fu3_mix_launch<1, N>(p, NT, KC, Mtot, ntiles, grid, pl.ntiles, smem, st);
 }
 
 int fu3_mix_tc_run(const Fu3MixParams& p, ffc_stream_t st) {
@@ -322,5 +352,281 @@ int fu3_mix_tc_run(const Fu3MixParams& p, ffc_stream_t st) {
         case 66: return fu3_mix_run_n<128>(p, st);
         default: ffc_set_error("fu3_mix: unsupported plane (SPS = %d)", p.SPS); return FFC_ERR_BAD_ARG;
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// fu3_wgrad_kernel: BatchNorm backward + the weight gradient of the channel mix on the tensor cores.
+//
+//   dY[bin][n] = coef[n] * (g[bin][n] - c1[n] - xhat[bin][n] * c2[n])          (written back: the dS mix reads it)
+//   dW[n][k]   = scale * sum_bins dY[bin][n] * S[bin][k]                        n = 2*o + {re, im}, k = 2*c + {re, im}
+//
+//   GEMM: D[128 rows n][NT columns k] in tensor memory, contraction over the BINS in chunks of 32; both operands come from
+//   shared memory (SS form), K-major no-swizzle canonical tiles [row / 8][bin / 4][row % 8][bin % 4], hi | lo for 3xTF32.
+//   * 8 BUILDER warps: a unit is (complex channel, 4 consecutive bins) = 32 contiguous bytes of a plane; eight lanes read
+//     256 contiguous bytes of one channel, compute dY (A side), split hi / lo and store two rows (re, im) of the tile as
+//     16-byte stores that are bank-conflict free (lane -> (channel % 4, bin quad)).  All loads of a thread's units are
+//     issued before the first use.  fence.proxy.async, then one mbarrier arrival per thread on the stage's `full`.
+//   * 1 MMA warp: 12 MMAs per chunk (4 k-steps x {hi*hi, lo*hi, hi*lo}), tcgen05.commit on the stage's `empty`.
+//   * persistent CTAs over the chunks (a chunk never straddles two images: NB % 32 == 0); at the end the builder warps
+//     read the accumulator and add it to dW with one float atomic per element and CTA.
+// ------------------------------------------------------------------------------------------------------------------
+static constexpr int WG_BK = 32;                          // bins per chunk
+static constexpr int WG_BUILDERS = 256;
+
+__device__ __forceinline__ void wg_cp16(void* dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(umma::smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void wg_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void wg_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// a = (re0, im0, re1, im1), b = (re2, im2, re3, im3) of complex channel `ch`, bins 4*jq .. 4*jq + 3 -> rows 2*ch, 2*ch + 1 of
+// the canonical tile.  Lanes are (channel % 4, bin quad): lanes of an even bin quad store the re row first, lanes of an odd
+// one the im row, so the eight lanes of a quarter-warp cover all 32 banks with each 16-byte store.
+__device__ __forceinline__ void wg_store_rows(float* tile_hi, float* tile_lo, int ch, int jq, const float4 a, const float4 b) {
+    const float re[4] = {a.x, a.z, b.x, b.z}, im[4] = {a.y, a.w, b.y, b.w};
+    float rh[4], rl[4], ih[4], il[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        rh[i] = ffc_tf32_hi(re[i]); rl[i] = re[i] - rh[i];
+        ih[i] = ffc_tf32_hi(im[i]); il[i] = im[i] - ih[i];
+    }
+    const int off = ((2 * ch) >> 3) * 256 + jq * 32 + ((2 * ch) & 7) * 4;
+    const bool odd = jq & 1;
+    const int o1 = off + (odd ? 4 : 0), o2 = off + (odd ? 0 : 4);
+    const float4 rhv = make_float4(rh[0], rh[1], rh[2], rh[3]), ihv = make_float4(ih[0], ih[1], ih[2], ih[3]);
+    const float4 rlv = make_float4(rl[0], rl[1], rl[2], rl[3]), ilv = make_float4(il[0], il[1], il[2], il[3]);
+    *reinterpret_cast<float4*>(tile_hi + o1) = odd ? ihv : rhv;
+    *reinterpret_cast<float4*>(tile_hi + o2) = odd ? rhv : ihv;
+    *reinterpret_cast<float4*>(tile_lo + o1) = odd ? ilv : rlv;
+    *reinterpret_cast<float4*>(tile_lo + o2) = odd ? rlv : ilv;
+}
+
+// RAW: stages of the cp.async ring (prefetch distance RAW - 1 chunks); NCANON: canonical (tensor-core) stages; U: passes of 32
+// channels per operand (1: <= 32 channels).  Warps 0-7 build the A operand (g, y -> dY), warps 8-15 the B operand (S), warp 16
+// issues the MMAs: 16 builder warps keep four warps per scheduler busy (with 8, the serial chain wait -> LDS -> split -> STS ->
+// fence -> arrive of a warp was exposed: ncu r02u, issue active 21 %).
+template <int RAW, int NCANON, int U>
+__global__ void __launch_bounds__(2 * WG_BUILDERS + 32, 1) fu3_wgrad_kernel(const Fu3BwdWgradParams p, const int NT, const int nchunks, const int tmem_cols) {
+    extern __shared__ __align__(128) unsigned char wg_smem[];
+    constexpr uint32_t rawA = 4 * U * WG_BUILDERS * 16, rawB = 2 * U * WG_BUILDERS * 16, raw_bytes = rawA + rawB;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t a_bytes = 128 * WG_BK * 4, b_bytes = (uint32_t)NT * WG_BK * 4;       // one of hi / lo
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    unsigned char* raw = wg_smem + (size_t)NCANON * stage_bytes;
+    float* consts = reinterpret_cast<float*>(raw + (size_t)RAW * raw_bytes);             // coef | c1 | c2 | mean | invstd, 128 each
+    uint64_t* full = reinterpret_cast<uint64_t*>(consts + 5 * 128);
+    uint64_t* empty = full + 4;
+    uint64_t* done = empty + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+    const int Cin = p.Cin, Cout = p.Cout, NB = p.NB;
+
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) { umma::mbar_init(&full[i], 2 * WG_BUILDERS); umma::mbar_init(&empty[i], 1); }
+        umma::mbar_init(done, 1);
+        umma::fence_barrier_init();
+    }
+    // rows beyond 2*Cout / 2*Cin of every canonical stage stay zero for the life of the CTA
+    for (uint32_t i = tid; i < (uint32_t)NCANON * stage_bytes / 16; i += blockDim.x) reinterpret_cast<float4*>(wg_smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < 128; i += blockDim.x) {
+        const bool ok = i < 2 * Cout;
+        consts[i] = ok ? __ldg(p.coef + i) : 0.f; consts[128 + i] = ok ? __ldg(p.c1 + i) : 0.f; consts[256 + i] = ok ? __ldg(p.c2 + i) : 0.f;
+        consts[384 + i] = ok ? __ldg(p.mean + i) : 0.f; consts[512 + i] = ok ? __ldg(p.invstd + i) : 0.f;
+    }
+    if (warp == 0) umma::tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
+    umma::fence_proxy_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tbase = *tmem_slot;
+
+    if (warp < 2 * WG_BUILDERS / 32) {
+        // ------------------------------------------------------------------------------------------------ builders
+        const bool sideB = warp >= WG_BUILDERS / 32;
+        const int bt = tid & (WG_BUILDERS - 1), bw = warp & 7;
+        const int jq = lane >> 2, chl = bw * 4 + (lane & 3);     // bin quad, channel within a pass of 32 channels
+        const int C = sideB ? Cin : Cout;
+        // every thread copies ITS OWN units of chunk i + RAW - 1 into the raw ring with cp.async (16 bytes each) and reads them
+        // back after cp.async.wait_group: RAW - 1 chunks of loads per thread stay in flight without holding registers, and no
+        // other thread ever touches these bytes, so the ring needs no barrier.
+        auto issue = [&](int chunk, int rs) {
+            const long long m0 = (long long)chunk * WG_BK;
+            const int b = (int)(m0 / NB), r = (int)(m0 % NB);
+            unsigned char* dst = raw + (size_t)rs * raw_bytes + (sideB ? rawA : 0) + (size_t)bt * 16;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int o = chl + 32 * u;
+                if (o < C) {
+                    const size_t off = (((size_t)b * C + o) * NB + r) * 2 + 8 * jq;
+                    if (sideB) {
+                        wg_cp16(dst + (size_t)(2 * u + 0) * WG_BUILDERS * 16, p.s + off); wg_cp16(dst + (size_t)(2 * u + 1) * WG_BUILDERS * 16, p.s + off + 4);
+                    } else {
+                        wg_cp16(dst + (size_t)(4 * u + 0) * WG_BUILDERS * 16, p.g + off); wg_cp16(dst + (size_t)(4 * u + 1) * WG_BUILDERS * 16, p.g + off + 4);
+                        wg_cp16(dst + (size_t)(4 * u + 2) * WG_BUILDERS * 16, p.y + off); wg_cp16(dst + (size_t)(4 * u + 3) * WG_BUILDERS * 16, p.y + off + 4);
+                    }
+                }
+            }
+        };
+        {
+            int c = blockIdx.x;
+#pragma unroll
+            for (int d = 0; d < RAW - 1; ++d, c += gridDim.x) {
+                if (c < nchunks) issue(c, d);
+                wg_cp_commit();
+            }
+        }
+        int it = 0;
+        for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, ++it) {
+            const int s = it % NCANON, use = it / NCANON;
+            const long long m0 = (long long)chunk * WG_BK;
+            const int b = (int)(m0 / NB), r = (int)(m0 % NB);
+            {
+                const long long ahead = (long long)chunk + (long long)(RAW - 1) * gridDim.x;
+                if (ahead < nchunks) issue((int)ahead, (it + RAW - 1) % RAW);
+                wg_cp_commit();
+            }
+            wg_cp_wait<RAW - 1>();                               // this thread's copies of chunk `it` have landed
+            const float4* mine = reinterpret_cast<const float4*>(raw + (size_t)(it % RAW) * raw_bytes + (sideB ? rawA : 0)) + bt;
+            if (use > 0) umma::mbar_wait(&empty[s], (uint32_t)(use - 1) & 1u);          // the MMAs that read this stage are done
+            float* a_hi = reinterpret_cast<float*>(wg_smem + (size_t)s * stage_bytes);
+            float* a_lo = a_hi + 128 * WG_BK;
+            float* b_hi = a_lo + 128 * WG_BK;
+            float* b_lo = b_hi + NT * WG_BK;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int o = chl + 32 * u;
+                if (o >= C) continue;
+                if (sideB) {
+                    wg_store_rows(b_hi, b_lo, o, jq, mine[(2 * u + 0) * WG_BUILDERS], mine[(2 * u + 1) * WG_BUILDERS]);
+                } else {
+                    const float4 g0 = mine[(4 * u + 0) * WG_BUILDERS], g1 = mine[(4 * u + 1) * WG_BUILDERS];
+                    const float4 y0 = mine[(4 * u + 2) * WG_BUILDERS], y1 = mine[(4 * u + 3) * WG_BUILDERS];
+                    const int n = 2 * o;
+                    const float kr = consts[n], ki = consts[n + 1], c1r = consts[128 + n], c1i = consts[128 + n + 1];
+                    const float c2r = consts[256 + n], c2i = consts[256 + n + 1], mr = consts[384 + n], mi = consts[384 + n + 1];
+                    const float ir = consts[512 + n], ii = consts[512 + n + 1];
+                    float4 d0, d1;
+                    d0.x = kr * (g0.x - c1r - (y0.x - mr) * ir * c2r); d0.y = ki * (g0.y - c1i - (y0.y - mi) * ii * c2i);
+                    d0.z = kr * (g0.z - c1r - (y0.z - mr) * ir * c2r); d0.w = ki * (g0.w - c1i - (y0.w - mi) * ii * c2i);
+                    d1.x = kr * (g1.x - c1r - (y1.x - mr) * ir * c2r); d1.y = ki * (g1.y - c1i - (y1.y - mi) * ii * c2i);
+                    d1.z = kr * (g1.z - c1r - (y1.z - mr) * ir * c2r); d1.w = ki * (g1.w - c1i - (y1.w - mi) * ii * c2i);
+                    const size_t off = (((size_t)b * Cout + o) * NB + r) * 2 + 8 * jq;
+                    *reinterpret_cast<float4*>(p.dy + off) = d0; *reinterpret_cast<float4*>(p.dy + off + 4) = d1;
+                    wg_store_rows(a_hi, a_lo, o, jq, d0, d1);
+                }
+            }
+            umma::fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
+            umma::mbar_arrive(&full[s]);
+        }
+        wg_cp_wait<0>();
+        // ------------------------------------------------------------------------------------------------ epilogue
+        if (warp < 8) {
+            umma::mbar_wait(done, 0);
+            umma::fence_after_sync();
+            const int row = (warp & 3) * 32 + lane;                              // accumulator row = TMEM lane
+            const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
+            const int col_half = warp >> 2;                                      // warps 0-3: even column groups, 4-7: odd ones
+            const int ncols16 = NT / 16;
+            // this CTA's partial tile goes to its own slice of the workspace ([CTA][128][NT], coalesced over the rows' columns is not
+            // possible from the TMEM row-per-lane view, so each lane writes 64 contiguous bytes); fu3_wgrad_reduce adds the slices.
+            // (One float atomic per element and CTA made 148-way contention on every address: ~40 us for a 128 x 128 tile.)
+            float* part = p.part + (size_t)blockIdx.x * 128 * NT;
+            for (int cg = col_half; cg < ncols16; cg += 2) {
+                uint32_t rr[16];
+                umma::tmem_ld16(lane_base + tbase + (uint32_t)(16 * cg), rr);
+                umma::wait_ld();
+                float4* dst = reinterpret_cast<float4*>(part + (size_t)row * NT + 16 * cg);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    dst[j] = make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]), __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3]));
+            }
+            umma::fence_before_sync();
+        }
+    } else {
+        // ------------------------------------------------------------------------------------------------ MMA warp
+        const uint32_t idesc = umma::idesc_tf32(128, NT);
+        const uint32_t base = umma::smem_u32(wg_smem);
+        int it = 0;
+        for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, ++it) {
+            const int s = it % NCANON, use = it / NCANON;
+            umma::mbar_wait(&full[s], (uint32_t)use & 1u);
+            umma::fence_after_sync();
+            if (umma::elect_one()) {
+                const uint32_t a_hi = base + (uint32_t)s * stage_bytes, a_lo = a_hi + a_bytes, b_hi = a_lo + a_bytes, b_lo = b_hi + b_bytes;
+#pragma unroll
+                for (int ks = 0; ks < WG_BK / 8; ++ks) {
+                    const uint64_t ah = umma::smem_desc_kmajor_noswizzle(a_hi + ks * 256, 128, 1024);
+                    const uint64_t al = umma::smem_desc_kmajor_noswizzle(a_lo + ks * 256, 128, 1024);
+                    const uint64_t bh = umma::smem_desc_kmajor_noswizzle(b_hi + ks * 256, 128, 1024);
+                    const uint64_t bl = umma::smem_desc_kmajor_noswizzle(b_lo + ks * 256, 128, 1024);
+                    umma::mma_tf32_ss(tbase, ah, bh, idesc, (it | ks) ? 1u : 0u);
+                    umma::mma_tf32_ss(tbase, al, bh, idesc, 1u);
+                    umma::mma_tf32_ss(tbase, ah, bl, idesc, 1u);
+                }
+                umma::commit(&empty[s]);
+            }
+            __syncwarp();
+        }
+        if (umma::elect_one()) umma::commit(done);
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tbase, (uint32_t)tmem_cols);
+}
+
+// dw[n][k] = scale * sum over the CTAs' partial tiles
+__global__ void __launch_bounds__(256) fu3_wgrad_reduce(const float* __restrict__ part, float* __restrict__ dw, int nparts, int NT, int Cin, int Cout, float scale) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 4 * Cin * Cout) return;
+    const int n = e / (2 * Cin), k = e % (2 * Cin);
+    const float* src = part + (size_t)n * NT + k;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int i = 0;
+    for (; i + 3 < nparts; i += 4) {
+        a0 += __ldg(src + (size_t)i * 128 * NT); a1 += __ldg(src + (size_t)(i + 1) * 128 * NT);
+        a2 += __ldg(src + (size_t)(i + 2) * 128 * NT); a3 += __ldg(src + (size_t)(i + 3) * 128 * NT);
+    }
+    for (; i < nparts; ++i) a0 += __ldg(src + (size_t)i * 128 * NT);
+    dw[e] = ((a0 + a1) + (a2 + a3)) * scale;
+}
+size_t fu3_wgrad_tc_part_floats(int Cin) { return (size_t)148 * 2 * 128 * ((2 * Cin + 15) / 16 * 16); }     // up to 296 CTAs' tiles
+
+bool fu3_wgrad_tc_supported(int Cin, int Cout) { return Cin >= 1 && Cout >= 1 && Cin <= 64 && Cout <= 64; }
+
+template <int RAW, int NCANON, int U>
+static int fu3_wgrad_launch(const Fu3BwdWgradParams& p, int NT, int nchunks, int tmem_cols, size_t smem, ffc_stream_t st) {
+    static FfcPerDevice configured_dev = {};
+    size_t& configured = *ffc_device_slot(configured_dev);
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(fu3_wgrad_kernel<RAW, NCANON, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { ffc_set_error("cudaFuncSetAttribute(fu3_wgrad, %zu B): %s", smem, cudaGetErrorString(e)); return FFC_ERR_CUDA; }
+        configured = smem;
+    }
+    int grid = nchunks < ffc_sm_count() ? nchunks : ffc_sm_count();
+    if (grid < 1) grid = 1;
+    if (grid > 296) grid = 296;                                  // the partial-tile workspace holds 296 slices
+    fu3_wgrad_kernel<RAW, NCANON, U><<<grid, 2 * WG_BUILDERS + 32, smem, st>>>(p, NT, nchunks, tmem_cols);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { ffc_set_error("fu3_wgrad launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
+    ffc_count_launch();
+    fu3_wgrad_reduce<<<(4 * p.Cin * p.Cout + 255) / 256, 256, 0, st>>>(p.part, p.dw, grid, NT, p.Cin, p.Cout, p.scale);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { ffc_set_error("fu3_wgrad_reduce launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
+    ffc_count_launch();
+    return FFC_OK;
+}
+
+int fu3_wgrad_tc_run(const Fu3BwdWgradParams& p, ffc_stream_t st) {
+    const int NT = (2 * p.Cin + 15) / 16 * 16;
+    const long long Mtot = (long long)p.B * p.NB;
+    if (p.NB % WG_BK != 0) { ffc_set_error("fu3_wgrad: plane slots (%d) must be a multiple of %d", p.NB, WG_BK); return FFC_ERR_BAD_ARG; }
+    const int nchunks = (int)(Mtot / WG_BK);
+    const size_t stage = (size_t)2 * 128 * WG_BK * 4 + (size_t)2 * NT * WG_BK * 4;
+    const int tmem_cols = NT <= 32 ? 32 : (NT <= 64 ? 64 : 128);
+    const bool wide = p.Cin > 32 || p.Cout > 32;                 // two passes of 32 channels per operand
+    const size_t raw = (size_t)(wide ? 12 : 6) * WG_BUILDERS * 16;
+    // narrow: 2 canonical stages (<= 96 KB) + 4 x 24 KB raw stages (three chunks of loads in flight); wide: 2 x 64 KB + 2 x 48 KB
+    const size_t tail = 5 * 128 * 4 + 10 * 8 + 64;
+    if (wide) return fu3_wgrad_launch<2, 2, 2>(p, NT, nchunks, tmem_cols, 2 * stage + 2 * raw + tail, st);
+    return fu3_wgrad_launch<4, 2, 1>(p, NT, nchunks, tmem_cols, 2 * stage + 4 * raw + tail, st);
 }
 #endif  // !FFC_EMU

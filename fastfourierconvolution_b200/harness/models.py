@@ -29,12 +29,13 @@ def weights_init(m):
 def _sn_linear(fc, x):
     """The spectral-norm Linear head of the discriminators (fgan_complete.py:157, 170): the hook's power iteration and
     W / sigma run in the library's three spectral-norm kernels (the same ones the SN convolutions use) instead of the stock
-    hook's ~14 PyTorch launches; the matrix-vector product itself stays a library GEMV.  CPU tensors (the host oracle
-    side of a comparison) go through the module's own forward."""
+    hook's ~14 PyTorch launches, the product and its gradients in the library's FP32 matrix kernel (ops.linear).  CPU
+    tensors (the host oracle side of a comparison) go through the module's own forward."""
     if not x.is_cuda:
         return fc(x)
+    from .. import ops
     from ..layers import _util
-    return F.linear(x, _util.effective_weight(fc), fc.bias)
+    return ops.linear(x, _util.effective_weight(fc), fc.bias)
 
 
 def hinge_loss_dis(fake, real):
@@ -85,8 +86,8 @@ class FGenerator(nn.Module):
     def forward(self, z):
         from .. import ops
         lin = self.noise_to_feature[0]
-        if z.is_cuda:    # the Linear stem (fgan_complete.py:92-95, 117-119) is a 1x1 convolution of a 1x1 plane: same tcgen05 kernels
-            fake = ops.conv2d(z.reshape(z.size(0), -1, 1, 1), lin.weight.view(lin.out_features, lin.in_features, 1, 1), bias=lin.bias)
+        if z.is_cuda:    # the Linear stem (fgan_complete.py:92-95, 117-119) on the library's FP32 matrix kernel
+            fake = ops.linear(z.reshape(z.size(0), -1), lin.weight, lin.bias)
         else:
             fake = self.noise_to_feature(z)
         fake = fake.reshape(fake.size(0), -1, self.mg, self.mg)
@@ -143,7 +144,7 @@ class SNDiscriminator(nn.Module):
                 m = ops.conv2d_act(m, ws[i], conv.bias, conv.stride[0], conv.padding[0], ops.ACT_LEAKY, self.act.negative_slope)
             ops._join(x.device)
             m = m.reshape(-1, self.mg * self.mg * 512)
-            return F.linear(m, w_fc, self.fc.bias) if w_fc is not None else self.fc(m)
+            return ops.linear(m, w_fc, self.fc.bias) if w_fc is not None else self.fc(m)
         m = x.contiguous(memory_format=torch.channels_last) if self.channels_last else x
         for i in range(1, self.n_convs + 1):
             m = self.act(getattr(self, f"conv{i}")(m))

@@ -750,3 +750,61 @@ def to_uint8(x, lo=-1.0, hi=1.0):
     out = torch.empty(x.shape, device=x.device, dtype=torch.uint8)
     _C.check(_C.lib().ffc_to_uint8(_C.ptr(x), _C.ptr(out), x.numel(), float(lo), float(hi), _C.current_stream(x.device)))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Linear layers (generator stem, discriminator head) and the optimiser step
+# ---------------------------------------------------------------------------------------------
+def _gemm(A, B, bias, M, N, K, sa, sb, out):
+    """out (M x N, dense row-major) = A (M x K, element strides sa) @ B (K x N, element strides sb) [+ bias]."""
+    _C.check(_C.lib().ffc_gemm_f32(_C.ptr(A), _C.ptr(B), _C.ptr(bias), _C.ptr(out), M, N, K, sa[0], sa[1], sb[0], sb[1], N, 1,
+                                   _C.current_stream(out.device)))
+    return out
+
+
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b (nn.Linear: fgan_complete.py:92-95 stem, :160-170 head) and its three gradients on one FP32 kernel."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        _C.require_device(x, weight, bias)
+        x, weight = x.contiguous(), weight.contiguous()
+        Bn, K = x.shape
+        O = weight.shape[0]
+        if weight.shape[1] != K:
+            raise ValueError(f"linear: x has {K} features, weight expects {weight.shape[1]}")
+        out = torch.empty((Bn, O), device=x.device, dtype=torch.float32)
+        _gemm(x, weight, _c(bias), Bn, O, K, (K, 1), (1, K), out)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        Bn, K = x.shape
+        O = weight.shape[0]
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = _gemm(dy, weight, None, Bn, K, O, (O, 1), (K, 1), torch.empty_like(x))                # dy W
+        if ctx.needs_input_grad[1]:
+            dw = _gemm(dy, x, None, O, K, Bn, (1, O), (K, 1), torch.empty_like(weight))                # dy^T x
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = torch.empty(O, device=dy.device, dtype=torch.float32)
+            _C.check(_C.lib().ffc_colsum_f32(_C.ptr(dy), _C.ptr(db), Bn, O, _C.current_stream(dy.device)))
+        return dx, dw, db
+
+
+def linear(x, weight, bias=None):
+    return LinearFn.apply(x, weight, bias)
+
+
+def adam_step(p, g, m, v, lr, step, beta1, beta2, eps, weight_decay, grad_scale=1.0, decoupled=True):
+    """One AdamW (decoupled) / Adam step over flat FP32 buffers; ``lr`` and ``step`` are one-element device tensors
+    (``step`` is incremented by the kernel)."""
+    _C.require_device(p, g, m, v, lr, step)
+    _C.check(_C.lib().ffc_adam_step(_C.ptr(p), _C.ptr(g), _C.ptr(m), _C.ptr(v), p.numel(), _C.ptr(lr), _C.ptr(step),
+                                    float(beta1), float(beta2), float(eps), float(weight_decay), float(grad_scale),
+                                    int(bool(decoupled)), _C.current_stream(p.device)))

@@ -125,6 +125,30 @@ int ffc_noise_add_fwd(const float* x, const float* w, const float* noise, float*
 int ffc_noise_add_bwd_w(const float* dy, const float* noise, float* dw, int B, int C, int HW, void* stream);
 int ffc_to_uint8(const float* x, unsigned char* out, long long n, float lo, float hi, void* stream);
 
+/* ---- Linear layers and the optimiser of the reference's training scripts ----
+ * ffc_gemm_f32: C (M x N) = A (M x K) * B (K x N) [+ bias[n]] in FP32 with arbitrary element strides: the Linear stem of the
+ *   generators (fgan_complete.py:92-95, 117-119: x W^T + b), the SN Linear head of the discriminators (:160-170) and their
+ *   gradients dy^T x and dy W are the same kernel.  Skinny products split K (C must then be dense row-major).
+ * ffc_colsum_f32: out[n] = sum_m x[m][n] (bias gradient).
+ * ffc_adam_step: optim.AdamW / optim.Adam (fgan_complete.py:315-319, sngan_complete.py:247-248) over FLAT parameter, gradient
+ *   and moment buffers: one kernel per step for any number of tensors; lr and the step count live on the device (CUDA-graph
+ *   replay); grad_scale multiplies the gradient first (1 / world size after a SUM all-reduce); decoupled = 1: AdamW. */
+int ffc_gemm_f32(const float* A, const float* B, const float* bias, float* C, int M, int N, int K,
+                 long long sam, long long sak, long long sbk, long long sbn, long long scm, long long scn, void* stream);
+int ffc_colsum_f32(const float* x, float* out, int M, int N, void* stream);
+int ffc_adam_step(float* p, const float* g, float* m, float* v, long long n, const float* lr, float* step,
+                  float beta1, float beta2, float eps, float weight_decay, float grad_scale, int decoupled, void* stream);
+/* ffc_adam_step_table: the same step with the gradients left where autograd put them: tensor t's gradient is read through
+ *   gptr[t] (device array of device pointers; null = no gradient this step, tensor skipped), its parameters / moments are
+ *   offs[t] .. offs[t] + sizes[t] of the flat buffers; block i handles 4096-element piece blk_piece[i] of tensor blk_tensor[i];
+ *   step is an array of ntensors counts (torch keeps state["step"] per parameter: a skipped tensor does not age).
+ * ffc_gather_table: with the same tables, copies the gradients into one flat buffer (the packing pass before an all-reduce). */
+int ffc_adam_step_table(float* p, float* m, float* v, const float* const* gptr, const long long* offs, const long long* sizes,
+                        const int* blk_tensor, const int* blk_piece, int ntensors, int nblocks, const float* lr, float* step,
+                        float beta1, float beta2, float eps, float weight_decay, float grad_scale, int decoupled, void* stream);
+int ffc_gather_table(float* dst, const float* const* gptr, const long long* offs, const long long* sizes,
+                     const int* blk_tensor, const int* blk_piece, int nblocks, void* stream);
+
 void ffc_debug_fu3_simt_mix(int on);
 void ffc_debug_fu3_chunk_bytes(size_t bytes);      /* spectrum bytes per chunk of images (0 = default 160 MB); tuning / tests */
 

@@ -151,7 +151,7 @@ def test_fourier_unit_config_shapes(B, C, N, train, fused):
     torch.manual_seed(C * 1000 + N)
     staged = isinstance(fused, str) and fused.startswith("staged")
     if staged and not ops.fu_staged_supported(B, C, C, N, N):
-        pytest.skip("shape not covered by the L2-staged form (4x4 / 8x8 planes, 2*Cout > 128)")
+        pytest.skip("shape not covered by the L2-staged form (4x4 / 8x8 planes)")
     if fused and not staged and not ops.fu_fused_supported(B, C, C, N, N):
         pytest.skip("shape not covered by the fused kernel (general form is tested by fused=False)")
     if fused == "two_pass" and not train:
@@ -168,7 +168,11 @@ def test_fourier_unit_config_shapes(B, C, N, train, fused):
     if fused == "staged_chunked":                                        # two images per chunk: several chunks, the last one ragged
         _C.lib().ffc_debug_fu3_chunk_bytes(2 * C * N * (N + 4) * 4)
     try:
-        _oracle_vs_module(mod, lambda P, xs, tr: R.fourier_unit(xs[0], P, "", tr), [x], train)
+        # the tensor-core mix rounds differently from FP32 FMAs, so on the wide mixes (K = 2C up to 384) a ReLU element can land
+        # on the other side of its kink (seen at C = 96 / 192): those runs compare flip-aware, still at 1e-4 in the max norm
+        errs = _oracle_vs_module(mod, lambda P, xs, tr: R.fourier_unit(xs[0], P, "", tr), [x], train, whole_model=bool(staged))
+        if staged:
+            assert max(v for k, v in errs.items() if k != "_flips") < parity.TOL, errs
     finally:
         _C.lib().ffc_debug_fu_two_pass(0)
         _C.lib().ffc_debug_fu3_chunk_bytes(0)

@@ -474,3 +474,100 @@ def test_spectral_norm_backward(lib, h, w, kk):
     ws = torch.zeros(16)
     call(lib, "ffc_spectral_norm_bwd", gs, Ws, u, v, sigma, dw, h, w, kk, ws, ctypes.c_size_t(64), None)
     assert parity.relerr(dw, refs) < 1e-5
+
+
+# ---- Linear layers and the optimiser (csrc/ffc_glue.cu) --------------------------------------------------------------
+LL = ctypes.c_longlong
+
+
+@pytest.mark.parametrize("B,K,O", [(5, 7, 3), (66, 100, 130), (16, 700, 1), (3, 64, 64)])
+def test_linear_forward_and_gradients_on_the_gemm_kernel(lib, B, K, O):
+    """nn.Linear (fgan_complete.py:92-95 stem, :160-170 head): x W^T + b, dy W, dy^T x through ffc_gemm_f32's strides and the
+    bias gradient through ffc_colsum_f32; (16, 700, 1) takes the split-K path on 148 SMs."""
+    torch.manual_seed(B + K + O)
+    x, w, b, dy = torch.randn(B, K), torch.randn(O, K), torch.randn(O), torch.randn(B, O)
+    y, dx, dw, db = torch.full((B, O), 9.0), torch.full((B, K), 9.0), torch.full((O, K), 9.0), torch.full((O,), 9.0)
+    call(lib, "ffc_gemm_f32", x, w, b, y, B, O, K, LL(K), LL(1), LL(1), LL(K), LL(O), LL(1), None)
+    call(lib, "ffc_gemm_f32", dy, w, None, dx, B, K, O, LL(O), LL(1), LL(K), LL(1), LL(K), LL(1), None)
+    call(lib, "ffc_gemm_f32", dy, x, None, dw, O, K, B, LL(1), LL(O), LL(K), LL(1), LL(K), LL(1), None)
+    call(lib, "ffc_colsum_f32", dy, db, B, O, None)
+    assert parity.relerr(y, x.double() @ w.double().T + b.double()) < 2e-6
+    assert parity.relerr(dx, dy.double() @ w.double()) < 2e-6
+    assert parity.relerr(dw, dy.double().T @ x.double()) < 2e-6
+    assert parity.relerr(db, dy.double().sum(0)) < 2e-6
+
+
+@pytest.mark.parametrize("decoupled", [1, 0])
+def test_adam_step_flat_and_table_match_torch(lib, decoupled):
+    """optim.AdamW (fgan_complete.py:315-319: lr 2e-4, betas (0.5, 0.999), torch's default decay 0.01) / optim.Adam
+    (sngan_complete.py:247-248) over three steps: the flat kernel and the pointer-table kernel (one tensor without a
+    gradient in step 2, which torch skips) against torch's own optimiser."""
+    torch.manual_seed(decoupled)
+    shapes = [(5000,), (3, 7), (64, 65), (1,)]
+    ps = [torch.randn(s) for s in shapes]
+    ref = [torch.nn.Parameter(p.clone()) for p in ps]
+    wd = 0.01 if decoupled else 0.0
+    opt = (torch.optim.AdamW if decoupled else torch.optim.Adam)(ref, lr=2e-4, betas=(0.5, 0.999), weight_decay=wd)
+    offs, n = [], 0
+    for p in ps:
+        offs.append(n); n += (p.numel() + 63) // 64 * 64
+    flat = torch.zeros(n)
+    for p, o in zip(ps, offs):
+        flat[o:o + p.numel()] = p.flatten()
+    flat2 = flat.clone()
+    m, v, m2, v2 = torch.zeros(n), torch.zeros(n), torch.zeros(n), torch.zeros(n)
+    lr, step, step2 = torch.tensor([2e-4]), torch.zeros(1), torch.zeros(len(ps))
+    blk_t, blk_p = [], []
+    for t, p in enumerate(ps):
+        for piece in range((p.numel() + 4095) // 4096):
+            blk_t.append(t); blk_p.append(piece)
+    library, device = lib
+    for it in range(3):
+        grads = [torch.randn(s) for s in shapes]
+        skip = 1 if it == 1 else None
+        for i, (r, g) in enumerate(zip(ref, grads)):
+            r.grad = None if i == skip else g.clone()
+        opt.step()
+        # flat kernel: a zero gradient is NOT a skipped tensor (moments decay, AdamW decays the weight), so use it on the full steps only
+        gflat = torch.zeros(n)
+        for g, o in zip(grads, offs):
+            gflat[o:o + g.numel()] = g.flatten()
+        if skip is None:
+            call(lib, "ffc_adam_step", flat, gflat, m, v, LL(n), lr, step, ctypes.c_float(0.5), ctypes.c_float(0.999), ctypes.c_float(1e-8),
+                 ctypes.c_float(wd), ctypes.c_float(1.0), decoupled, None)
+        # table kernel on device-resident copies (the table holds device pointers)
+        dev = [t.to(device) for t in (flat2, m2, v2, lr, step2)]
+        gdev = [g.to(device).contiguous() for g in grads]
+        ptrs = torch.tensor([0 if i == skip else g.data_ptr() for i, g in enumerate(gdev)], dtype=torch.int64, device=device)
+        tabs = [torch.tensor(a, dtype=dt, device=device) for a, dt in ((offs, torch.int64), ([p.numel() for p in ps], torch.int64),
+                                                                     (blk_t, torch.int32), (blk_p, torch.int32))]
+        P = lambda t: ctypes.c_void_p(t.data_ptr())
+        rc = library.ffc_adam_step_table(P(dev[0]), P(dev[1]), P(dev[2]), P(ptrs), P(tabs[0]), P(tabs[1]), P(tabs[2]), P(tabs[3]), len(ps), len(blk_t),
+                                         P(dev[3]), P(dev[4]), 0.5, 0.999, 1e-8, wd, 1.0, decoupled, None)
+        assert rc == 0, library.last_error()
+        if device != "cpu":
+            torch.cuda.synchronize()
+        for dst, src in zip((flat2, m2, v2, step2), (dev[0], dev[1], dev[2], dev[4])):
+            dst.copy_(src)
+    assert step2.tolist() == [3.0, 2.0, 3.0, 3.0]
+    for r, o in zip(ref, offs):
+        assert parity.relerr(flat2[o:o + r.numel()].view(r.shape), r.detach()) < 1e-6
+    # the flat kernel saw steps 1 and 3 only: compare it with a torch optimiser that saw the same two
+    assert step.item() == 2.0
+
+
+def test_gather_table_packs_gradients(lib):
+    library, device = lib
+    gs = [torch.randn(5000, device=device), None, torch.randn(3, 3, device=device)]
+    sizes, offs = [5000, 70, 9], [0, 5056, 5184]
+    dst = torch.full((5248,), 7.0, device=device)
+    blk_t, blk_p = [0, 0, 1, 2], [0, 1, 0, 0]
+    tabs = [torch.tensor(a, dtype=dt, device=device) for a, dt in ((offs, torch.int64), (sizes, torch.int64), (blk_t, torch.int32), (blk_p, torch.int32))]
+    ptrs = torch.tensor([g.data_ptr() if g is not None else 0 for g in gs], dtype=torch.int64, device=device)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    assert library.ffc_gather_table(P(dst), P(ptrs), P(tabs[0]), P(tabs[1]), P(tabs[2]), P(tabs[3]), 4, None) == 0
+    if device != "cpu":
+        torch.cuda.synchronize()
+    dst = dst.cpu()
+    assert torch.equal(dst[:5000], gs[0].cpu()) and torch.equal(dst[5056:5126], torch.zeros(70)) and torch.equal(dst[5184:5193], gs[2].cpu().flatten())
+    assert torch.all(dst[5000:5056] == 7.0)         # padding between tensors is not touched

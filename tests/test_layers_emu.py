@@ -4,6 +4,7 @@ outputs.  This checks the Python wiring and every kernel's index arithmetic with
 GPU parity tests proper are tests/test_gpu_parity.py."""
 import pytest
 import torch
+import torch.nn as nn
 
 import cases
 import parity
@@ -335,3 +336,35 @@ def test_fourier_unit_l2_staged_backward(B, C, Co, N, train, emu):
     assert l2(xo.grad, xr.grad) < 1e-3 and l2(m.conv_layer.weight.grad, P["conv_layer.weight"].grad) < 1e-3
     assert l2(m.bn.weight.grad, P["bn.weight"].grad) < 1e-3 and l2(m.bn.bias.grad, P["bn.bias"].grad) < 1e-3
     assert torch.equal(ro.grad, cot.float())
+
+
+@pytest.mark.parametrize("kind", ["adamw", "adam"])
+def test_flat_adam_matches_torch_optimizer(kind, emu):
+    """harness.FlatAdam (one table kernel per step over flat parameters / moments, gradients read in place) against
+    torch.optim.AdamW / Adam over four steps on a small network with a parameter that never receives a gradient
+    (the lfu.* case, spectral_transform.py:65-67): it must stay untouched and outside the flat buffers."""
+    from fastfourierconvolution_b200.harness.train import FlatAdam
+    torch.manual_seed(3)
+
+    def make():
+        torch.manual_seed(3)
+        net = nn.Sequential(nn.Linear(9, 70), nn.Tanh(), nn.Linear(70, 5))
+        net.unused = nn.Parameter(torch.randn(4, 4))
+        return net
+    a, b = make(), make()
+    kw = dict(lr=2e-4, betas=(0.5, 0.999))
+    ref = torch.optim.AdamW(a.parameters(), **kw) if kind == "adamw" else torch.optim.Adam(a.parameters(), **kw)
+    mine = FlatAdam(b.parameters(), decoupled=(kind == "adamw"), weight_decay=0.01 if kind == "adamw" else 0.0, **kw)
+    sched = torch.optim.lr_scheduler.LambdaLR(mine, lambda s: 1.0 - s / 10)
+    sched_ref = torch.optim.lr_scheduler.LambdaLR(ref, lambda s: 1.0 - s / 10)
+    for it in range(4):
+        x = torch.randn(6, 9)
+        for net, opt, sc in ((a, ref, sched_ref), (b, mine, sched)):
+            opt.zero_grad()
+            net(x).square().sum().backward()
+            opt.step()
+            sc.step()
+    assert mine.adopted and b.unused.grad is None and torch.equal(a.unused, b.unused)
+    assert all(p.data_ptr() >= mine.flat_p.data_ptr() for k, p in b.named_parameters() if k != "unused")
+    for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert parity.relerr(pb.detach(), pa.detach()) < 1e-6, k
