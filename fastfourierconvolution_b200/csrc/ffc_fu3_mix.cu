@@ -405,12 +405,18 @@ __device__ __forceinline__ void wg_store_rows(float* tile_hi, float* tile_lo, in
 // channels per operand (1: <= 32 channels).  Warps 0-7 build the A operand (g, y -> dY), warps 8-15 the B operand (S), warp 16
 // issues the MMAs: 16 builder warps keep four warps per scheduler busy (with 8, the serial chain wait -> LDS -> split -> STS ->
 // fence -> arrive of a warp was exposed: ncu r02u, issue active 21 %).
-template <int RAW, int NCANON, int U>
+// STACK (2*Cout <= 64): the hi and the lo half of dY are rows 0..63 and 64..127 of ONE 128-row A tile, and the hi and lo halves of
+// S are columns [0, NT) and [NT, 2*NT) of ONE B tile, so a single MMA per 8 bins computes hi*hi, hi*lo, lo*hi (and lo*lo) into
+// four blocks of a 128 x 2*NT accumulator that the reduction kernel adds up: 4 MMAs per chunk instead of 12.  Without STACK
+// (up to 128 rows) the B halves are still concatenated: 2 MMAs per 8 bins.  (Measured: the kernel ran at ~240 cycles per
+// K = 8 MMA whatever the prefetch depth -- the MMA count, not the memory system, set its pace.)
+template <int RAW, int NCANON, int U, bool STACK>
 __global__ void __launch_bounds__(2 * WG_BUILDERS + 32, 1) fu3_wgrad_kernel(const Fu3BwdWgradParams p, const int NT, const int nchunks, const int tmem_cols) {
     extern __shared__ __align__(128) unsigned char wg_smem[];
     constexpr uint32_t rawA = 4 * U * WG_BUILDERS * 16, rawB = 2 * U * WG_BUILDERS * 16, raw_bytes = rawA + rawB;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t a_bytes = 128 * WG_BK * 4, b_bytes = (uint32_t)NT * WG_BK * 4;       // one of hi / lo
+    constexpr uint32_t a_rows = STACK ? 64 : 128;                                        // rows of one of hi / lo
+    const uint32_t a_bytes = a_rows * WG_BK * 4, b_bytes = (uint32_t)NT * WG_BK * 4;     // one of hi / lo
     const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
     unsigned char* raw = wg_smem + (size_t)NCANON * stage_bytes;
     float* consts = reinterpret_cast<float*>(raw + (size_t)RAW * raw_bytes);             // coef | c1 | c2 | mean | invstd, 128 each
@@ -488,8 +494,8 @@ __global__ void __launch_bounds__(2 * WG_BUILDERS + 32, 1) fu3_wgrad_kernel(cons
             const float4* mine = reinterpret_cast<const float4*>(raw + (size_t)(it % RAW) * raw_bytes + (sideB ? rawA : 0)) + bt;
             if (use > 0) umma::mbar_wait(&empty[s], (uint32_t)(use - 1) & 1u);          // the MMAs that read this stage are done
             float* a_hi = reinterpret_cast<float*>(wg_smem + (size_t)s * stage_bytes);
-            float* a_lo = a_hi + 128 * WG_BK;
-            float* b_hi = a_lo + 128 * WG_BK;
+            float* a_lo = a_hi + a_rows * WG_BK;
+            float* b_hi = a_lo + a_rows * WG_BK;
             float* b_lo = b_hi + NT * WG_BK;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -525,16 +531,16 @@ __global__ void __launch_bounds__(2 * WG_BUILDERS + 32, 1) fu3_wgrad_kernel(cons
             const int row = (warp & 3) * 32 + lane;                              // accumulator row = TMEM lane
             const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
             const int col_half = warp >> 2;                                      // warps 0-3: even column groups, 4-7: odd ones
-            const int ncols16 = NT / 16;
+            const int ncols16 = 2 * NT / 16;
             // this CTA's partial tile goes to its own slice of the workspace ([CTA][128][NT], coalesced over the rows' columns is not
             // possible from the TMEM row-per-lane view, so each lane writes 64 contiguous bytes); fu3_wgrad_reduce adds the slices.
             // (One float atomic per element and CTA made 148-way contention on every address: ~40 us for a 128 x 128 tile.)
-            float* part = p.part + (size_t)blockIdx.x * 128 * NT;
+            float* part = p.part + (size_t)blockIdx.x * 128 * 2 * NT;
             for (int cg = col_half; cg < ncols16; cg += 2) {
                 uint32_t rr[16];
                 umma::tmem_ld16(lane_base + tbase + (uint32_t)(16 * cg), rr);
                 umma::wait_ld();
-                float4* dst = reinterpret_cast<float4*>(part + (size_t)row * NT + 16 * cg);
+                float4* dst = reinterpret_cast<float4*>(part + (size_t)row * 2 * NT + 16 * cg);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     dst[j] = make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]), __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3]));
@@ -543,7 +549,7 @@ __global__ void __launch_bounds__(2 * WG_BUILDERS + 32, 1) fu3_wgrad_kernel(cons
         }
     } else {
         // ------------------------------------------------------------------------------------------------ MMA warp
-        const uint32_t idesc = umma::idesc_tf32(128, NT);
+        const uint32_t idesc2 = umma::idesc_tf32(128, 2 * NT), idesc1 = umma::idesc_tf32(128, NT);
         const uint32_t base = umma::smem_u32(wg_smem);
         int it = 0;
         for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, ++it) {
@@ -551,16 +557,17 @@ __global__ void __launch_bounds__(2 * WG_BUILDERS + 32, 1) fu3_wgrad_kernel(cons
             umma::mbar_wait(&full[s], (uint32_t)use & 1u);
             umma::fence_after_sync();
             if (umma::elect_one()) {
-                const uint32_t a_hi = base + (uint32_t)s * stage_bytes, a_lo = a_hi + a_bytes, b_hi = a_lo + a_bytes, b_lo = b_hi + b_bytes;
+                const uint32_t a_hi = base + (uint32_t)s * stage_bytes, a_lo = a_hi + a_bytes, b_hi = a_lo + a_bytes;
 #pragma unroll
                 for (int ks = 0; ks < WG_BK / 8; ++ks) {
+                    // B descriptor over 2*NT rows: the lo tile follows the hi tile in the canonical layout
                     const uint64_t ah = umma::smem_desc_kmajor_noswizzle(a_hi + ks * 256, 128, 1024);
-                    const uint64_t al = umma::smem_desc_kmajor_noswizzle(a_lo + ks * 256, 128, 1024);
-                    const uint64_t bh = umma::smem_desc_kmajor_noswizzle(b_hi + ks * 256, 128, 1024);
-                    const uint64_t bl = umma::smem_desc_kmajor_noswizzle(b_lo + ks * 256, 128, 1024);
-                    umma::mma_tf32_ss(tbase, ah, bh, idesc, (it | ks) ? 1u : 0u);
-                    umma::mma_tf32_ss(tbase, al, bh, idesc, 1u);
-                    umma::mma_tf32_ss(tbase, ah, bl, idesc, 1u);
+                    const uint64_t bb = umma::smem_desc_kmajor_noswizzle(b_hi + ks * 256, 128, 1024);
+                    umma::mma_tf32_ss(tbase, ah, bb, idesc2, (it | ks) ? 1u : 0u);          // STACK: rows (hi | lo) x columns (hi | lo)
+                    if (!STACK) {
+                        const uint64_t al = umma::smem_desc_kmajor_noswizzle(a_lo + ks * 256, 128, 1024);
+                        umma::mma_tf32_ss(tbase, al, bb, idesc1, 1u);                        // lo * hi into the first NT columns
+                    }
                 }
                 umma::commit(&empty[s]);
             }
@@ -573,42 +580,54 @@ __global__ void __launch_bounds__(2 * WG_BUILDERS + 32, 1) fu3_wgrad_kernel(cons
     if (warp == 0) umma::tmem_dealloc(tbase, (uint32_t)tmem_cols);
 }
 
-// dw[n][k] = scale * sum over the CTAs' partial tiles
-__global__ void __launch_bounds__(256) fu3_wgrad_reduce(const float* __restrict__ part, float* __restrict__ dw, int nparts, int NT, int Cin, int Cout, float scale) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= 4 * Cin * Cout) return;
-    const int n = e / (2 * Cin), k = e % (2 * Cin);
-    const float* src = part + (size_t)n * NT + k;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int i = 0;
-    for (; i + 3 < nparts; i += 4) {
-        a0 += __ldg(src + (size_t)i * 128 * NT); a1 += __ldg(src + (size_t)(i + 1) * 128 * NT);
-        a2 += __ldg(src + (size_t)(i + 2) * 128 * NT); a3 += __ldg(src + (size_t)(i + 3) * 128 * NT);
+// dw[n][k] = scale * sum over the CTAs' partial tiles [CTA][128][2*NT] of the blocks that hold hi*hi, hi*lo, lo*hi (lo*lo).
+// One block per 8 consecutive outputs; 32 groups of threads split the CTAs' tiles, shared-memory sum at the end.
+__global__ void __launch_bounds__(256) fu3_wgrad_reduce(const float* __restrict__ part, float* __restrict__ dw, int nparts, int NT, int Cin, int Cout, float scale, int stacked) {
+    __shared__ float red[32][9];
+    const int el = threadIdx.x & 7, pg = threadIdx.x >> 3;       // 8 consecutive outputs (one 32-byte sector per tile) x 32 groups of tiles
+    const int e = blockIdx.x * 8 + el;
+    float acc = 0.f;
+    if (e < 4 * Cin * Cout) {
+        const int n = e / (2 * Cin), k = e % (2 * Cin);
+        const size_t tile = (size_t)128 * 2 * NT;
+        const float* src = part + (size_t)n * 2 * NT + k;
+        for (int i = pg; i < nparts; i += 32) {
+            const float* q = src + (size_t)i * tile;
+            float v = __ldg(q) + __ldg(q + NT);
+            if (stacked) v += __ldg(q + (size_t)64 * 2 * NT) + __ldg(q + (size_t)64 * 2 * NT + NT);
+            acc += v;
+        }
     }
-    for (; i < nparts; ++i) a0 += __ldg(src + (size_t)i * 128 * NT);
-    dw[e] = ((a0 + a1) + (a2 + a3)) * scale;
+    red[pg][el] = acc;
+    __syncthreads();
+    if (pg == 0 && e < 4 * Cin * Cout) {
+        float a = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) a += red[i][el];
+        dw[e] = a * scale;
+    }
 }
-size_t fu3_wgrad_tc_part_floats(int Cin) { return (size_t)148 * 2 * 128 * ((2 * Cin + 15) / 16 * 16); }     // up to 296 CTAs' tiles
+size_t fu3_wgrad_tc_part_floats(int Cin) { return (size_t)296 * 128 * 2 * ((2 * Cin + 15) / 16 * 16); }     // up to 296 CTAs' tiles
 
 bool fu3_wgrad_tc_supported(int Cin, int Cout) { return Cin >= 1 && Cout >= 1 && Cin <= 64 && Cout <= 64; }
 
-template <int RAW, int NCANON, int U>
+template <int RAW, int NCANON, int U, bool STACK>
 static int fu3_wgrad_launch(const Fu3BwdWgradParams& p, int NT, int nchunks, int tmem_cols, size_t smem, ffc_stream_t st) {
     static FfcPerDevice configured_dev = {};
     size_t& configured = *ffc_device_slot(configured_dev);
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(fu3_wgrad_kernel<RAW, NCANON, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(fu3_wgrad_kernel<RAW, NCANON, U, STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { ffc_set_error("cudaFuncSetAttribute(fu3_wgrad, %zu B): %s", smem, cudaGetErrorString(e)); return FFC_ERR_CUDA; }
         configured = smem;
     }
     int grid = nchunks < ffc_sm_count() ? nchunks : ffc_sm_count();
     if (grid < 1) grid = 1;
     if (grid > 296) grid = 296;                                  // the partial-tile workspace holds 296 slices
-    fu3_wgrad_kernel<RAW, NCANON, U><<<grid, 2 * WG_BUILDERS + 32, smem, st>>>(p, NT, nchunks, tmem_cols);
+    fu3_wgrad_kernel<RAW, NCANON, U, STACK><<<grid, 2 * WG_BUILDERS + 32, smem, st>>>(p, NT, nchunks, tmem_cols);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { ffc_set_error("fu3_wgrad launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
     ffc_count_launch();
-    fu3_wgrad_reduce<<<(4 * p.Cin * p.Cout + 255) / 256, 256, 0, st>>>(p.part, p.dw, grid, NT, p.Cin, p.Cout, p.scale);
+    fu3_wgrad_reduce<<<(4 * p.Cin * p.Cout + 7) / 8, 256, 0, st>>>(p.part, p.dw, grid, NT, p.Cin, p.Cout, p.scale, STACK ? 1 : 0);
     e = cudaGetLastError();
     if (e != cudaSuccess) { ffc_set_error("fu3_wgrad_reduce launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
     ffc_count_launch();
@@ -620,13 +639,14 @@ int fu3_wgrad_tc_run(const Fu3BwdWgradParams& p, ffc_stream_t st) {
     const long long Mtot = (long long)p.B * p.NB;
     if (p.NB % WG_BK != 0) { ffc_set_error("fu3_wgrad: plane slots (%d) must be a multiple of %d", p.NB, WG_BK); return FFC_ERR_BAD_ARG; }
     const int nchunks = (int)(Mtot / WG_BK);
-    const size_t stage = (size_t)2 * 128 * WG_BK * 4 + (size_t)2 * NT * WG_BK * 4;
-    const int tmem_cols = NT <= 32 ? 32 : (NT <= 64 ? 64 : 128);
-    const bool wide = p.Cin > 32 || p.Cout > 32;                 // two passes of 32 channels per operand
-    const size_t raw = (size_t)(wide ? 12 : 6) * WG_BUILDERS * 16;
-    // narrow: 2 canonical stages (<= 96 KB) + 4 x 24 KB raw stages (three chunks of loads in flight); wide: 2 x 64 KB + 2 x 48 KB
-    const size_t tail = 5 * 128 * 4 + 10 * 8 + 64;
-    if (wide) return fu3_wgrad_launch<2, 2, 2>(p, NT, nchunks, tmem_cols, 2 * stage + 2 * raw + tail, st);
-    return fu3_wgrad_launch<4, 2, 1>(p, NT, nchunks, tmem_cols, 2 * stage + 4 * raw + tail, st);
+    const int tmem_cols = 2 * NT <= 32 ? 32 : (2 * NT <= 64 ? 64 : (2 * NT <= 128 ? 128 : 256));
+    const size_t tail = 5 * 128 * 4 + 10 * 8 + 64, b_tile = (size_t)2 * NT * WG_BK * 4;
+    if (p.Cin > 32 || p.Cout > 32) {          // two passes of 32 channels per operand: 2 x (32 KB A + <= 32 KB B) + 2 x 48 KB raw
+        const size_t stage = (size_t)2 * 128 * WG_BK * 4 + b_tile, raw = (size_t)12 * WG_BUILDERS * 16;
+        return fu3_wgrad_launch<2, 2, 2, false>(p, NT, nchunks, tmem_cols, 2 * stage + 2 * raw + tail, st);
+    }
+    // <= 32 channels: stacked A tile (16 KB) + <= 16 KB B, three canonical stages, four raw stages of 24 KB
+    const size_t stage = (size_t)2 * 64 * WG_BK * 4 + b_tile, raw = (size_t)6 * WG_BUILDERS * 16;
+    return fu3_wgrad_launch<4, 3, 1, true>(p, NT, nchunks, tmem_cols, 3 * stage + 4 * raw + tail, st);
 }
 #endif  // !FFC_EMU

@@ -198,17 +198,29 @@ __global__ void __launch_bounds__(WG5_THREADS, 1) wgrad_v5_kernel(const WgradV5P
             if (umma::elect_one()) {
                 const uint32_t b_hi = b0 + (uint32_t)sb * stage_bytes, b_lo = b_hi + half_bytes;
                 const uint32_t a_hi = tbase + a_col0 + 64u * (uint32_t)sa, a_lo = a_hi + 32u;
+                if (2 * NT <= 256) {
+                    // the hi and lo halves of the B stage are adjacent rows: one MMA of width 2*NT gives a_hi * b_hi (D_hi) and
+                    // a_hi * b_lo (D_lo), one of width NT adds a_lo * b_hi to D_lo: 8 MMAs per chunk instead of 12
+                    const uint32_t idesc2 = umma::idesc_tf32(128, 2 * NT);
 #pragma unroll
-                for (int ks = 0; ks < WG5_BK / 8; ++ks) {          // cross terms first, then the main products: two
-                    const uint64_t dh = umma::smem_desc_kmajor_noswizzle(b_hi + ks * 256, 128, 1024);   // accumulator switches per chunk
-                    const uint64_t dl = umma::smem_desc_kmajor_noswizzle(b_lo + ks * 256, 128, 1024);
-                    umma::mma_tf32_ts(tbase + (uint32_t)NT, a_lo + ks * 8, dh, idesc, (c | ks) ? 1u : 0u);
-                    umma::mma_tf32_ts(tbase + (uint32_t)NT, a_hi + ks * 8, dl, idesc, 1u);
-                }
+                    for (int ks = 0; ks < WG5_BK / 8; ++ks) {
+                        const uint64_t dh = umma::smem_desc_kmajor_noswizzle(b_hi + ks * 256, 128, 1024);
+                        umma::mma_tf32_ts(tbase, a_hi + ks * 8, dh, idesc2, (c | ks) ? 1u : 0u);
+                        umma::mma_tf32_ts(tbase + (uint32_t)NT, a_lo + ks * 8, dh, idesc, 1u);
+                    }
+                } else {
 #pragma unroll
-                for (int ks = 0; ks < WG5_BK / 8; ++ks) {
-                    const uint64_t dh = umma::smem_desc_kmajor_noswizzle(b_hi + ks * 256, 128, 1024);
-                    umma::mma_tf32_ts(tbase, a_hi + ks * 8, dh, idesc, (c | ks) ? 1u : 0u);
+                    for (int ks = 0; ks < WG5_BK / 8; ++ks) {          // cross terms first, then the main products: two
+                        const uint64_t dh = umma::smem_desc_kmajor_noswizzle(b_hi + ks * 256, 128, 1024);   // accumulator switches per chunk
+                        const uint64_t dl = umma::smem_desc_kmajor_noswizzle(b_lo + ks * 256, 128, 1024);
+                        umma::mma_tf32_ts(tbase + (uint32_t)NT, a_lo + ks * 8, dh, idesc, (c | ks) ? 1u : 0u);
+                        umma::mma_tf32_ts(tbase + (uint32_t)NT, a_hi + ks * 8, dl, idesc, 1u);
+                    }
+#pragma unroll
+                    for (int ks = 0; ks < WG5_BK / 8; ++ks) {
+                        const uint64_t dh = umma::smem_desc_kmajor_noswizzle(b_hi + ks * 256, 128, 1024);
+                        umma::mma_tf32_ts(tbase, a_hi + ks * 8, dh, idesc, (c | ks) ? 1u : 0u);
+                    }
                 }
                 umma::commit(&a_free[sa]);
                 umma::commit(&b_free[sb]);
