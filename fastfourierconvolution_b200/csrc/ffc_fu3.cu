@@ -439,7 +439,7 @@ size_t fu3_mix_tc_packed_floats(int Cin, int Cout);
 int fu3_mix_tc_pack(const float* w, float* wp, int Cin, int Cout, float scale, int transposed, ffc_stream_t st);
 int fu3_mix_tc_run(const Fu3MixParams& p, ffc_stream_t st);
 bool fu3_wgrad_tc_supported(int Cin, int Cout);
-size_t fu3_wgrad_tc_part_floats(int Cin);
+size_t fu3_wgrad_tc_part_floats(int Cin, int Cout);
 int fu3_wgrad_tc_run(const Fu3BwdWgradParams& p, ffc_stream_t st);
 #endif
 static int g_fu3_simt_mix = 0;
@@ -769,7 +769,7 @@ static Fu3BwdPlan fu3_bwd_plan(int B, int Cin, int Cout, int N) {
     off = fu3_align(off + wbytes);
     pl.off_part = off;
 #ifndef FFC_EMU
-    if (fu3_wgrad_tc_supported(Cin, Cout)) off = fu3_align(off + fu3_wgrad_tc_part_floats(Cin) * sizeof(float));
+    if (fu3_wgrad_tc_supported(Cin, Cout)) off = fu3_align(off + fu3_wgrad_tc_part_floats(Cin, Cout) * sizeof(float));
 #endif
     pl.off_g = off; off = fu3_align(off + (size_t)B * Cout * pl.region * 4);
     pl.off_dy = off; off = fu3_align(off + (size_t)B * Cout * pl.region * 4);

@@ -424,7 +424,9 @@ __global__ void __launch_bounds__(2 * WG_BUILDERS + 32, 1) fu3_wgrad_kernel(cons
     uint64_t* empty = full + 4;
     uint64_t* done = empty + 4;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
-    const int Cin = p.Cin, Cout = p.Cout, NB = p.NB;
+    // channel tile of this CTA: 64 complex channels of dY (blockIdx.y) by 64 complex channels of S (blockIdx.z)
+    const int NB = p.NB, o0 = (int)blockIdx.y * 64, c0 = (int)blockIdx.z * 64;
+    const int Cout = (p.Cout - o0) < 64 ? (p.Cout - o0) : 64, Cin = (p.Cin - c0) < 64 ? (p.Cin - c0) : 64;
 
     if (tid == 0) {
         for (int i = 0; i < 4; ++i) { umma::mbar_init(&full[i], 2 * WG_BUILDERS); umma::mbar_init(&empty[i], 1); }
@@ -435,8 +437,9 @@ __global__ void __launch_bounds__(2 * WG_BUILDERS + 32, 1) fu3_wgrad_kernel(cons
     for (uint32_t i = tid; i < (uint32_t)NCANON * stage_bytes / 16; i += blockDim.x) reinterpret_cast<float4*>(wg_smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = tid; i < 128; i += blockDim.x) {
         const bool ok = i < 2 * Cout;
-        consts[i] = ok ? __ldg(p.coef + i) : 0.f; consts[128 + i] = ok ? __ldg(p.c1 + i) : 0.f; consts[256 + i] = ok ? __ldg(p.c2 + i) : 0.f;
-        consts[384 + i] = ok ? __ldg(p.mean + i) : 0.f; consts[512 + i] = ok ? __ldg(p.invstd + i) : 0.f;
+        const int n = 2 * o0 + i;
+        consts[i] = ok ? __ldg(p.coef + n) : 0.f; consts[128 + i] = ok ? __ldg(p.c1 + n) : 0.f; consts[256 + i] = ok ? __ldg(p.c2 + n) : 0.f;
+        consts[384 + i] = ok ? __ldg(p.mean + n) : 0.f; consts[512 + i] = ok ? __ldg(p.invstd + n) : 0.f;
     }
     if (warp == 0) umma::tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
     umma::fence_proxy_async_smem();
@@ -450,7 +453,7 @@ __global__ void __launch_bounds__(2 * WG_BUILDERS + 32, 1) fu3_wgrad_kernel(cons
         const bool sideB = warp >= WG_BUILDERS / 32;
         const int bt = tid & (WG_BUILDERS - 1), bw = warp & 7;
         const int jq = lane >> 2, chl = bw * 4 + (lane & 3);     // bin quad, channel within a pass of 32 channels
-        const int C = sideB ? Cin : Cout;
+        const int C = sideB ? Cin : Cout, Ctot = sideB ? p.Cin : p.Cout, cbase = sideB ? c0 : o0;
         // every thread copies ITS OWN units of chunk i + RAW - 1 into the raw ring with cp.async (16 bytes each) and reads them
         // back after cp.async.wait_group: RAW - 1 chunks of loads per thread stay in flight without holding registers, and no
         // other thread ever touches these bytes, so the ring needs no barrier.
@@ -462,7 +465,7 @@ __global__ void __launch_bounds__(2 * WG_BUILDERS + 32, 1) fu3_wgrad_kernel(cons
             for (int u = 0; u < U; ++u) {
                 const int o = chl + 32 * u;
                 if (o < C) {
-                    const size_t off = (((size_t)b * C + o) * NB + r) * 2 + 8 * jq;
+                    const size_t off = (((size_t)b * Ctot + cbase + o) * NB + r) * 2 + 8 * jq;
                     if (sideB) {
                         wg_cp16(dst + (size_t)(2 * u + 0) * WG_BUILDERS * 16, p.s + off); wg_cp16(dst + (size_t)(2 * u + 1) * WG_BUILDERS * 16, p.s + off + 4);
                     } else {
@@ -515,8 +518,10 @@ __global__ void __launch_bounds__(2 * WG_BUILDERS + 32, 1) fu3_wgrad_kernel(cons
                     d0.z = kr * (g0.z - c1r - (y0.z - mr) * ir * c2r); d0.w = ki * (g0.w - c1i - (y0.w - mi) * ii * c2i);
                     d1.x = kr * (g1.x - c1r - (y1.x - mr) * ir * c2r); d1.y = ki * (g1.y - c1i - (y1.y - mi) * ii * c2i);
                     d1.z = kr * (g1.z - c1r - (y1.z - mr) * ir * c2r); d1.w = ki * (g1.w - c1i - (y1.w - mi) * ii * c2i);
-                    const size_t off = (((size_t)b * Cout + o) * NB + r) * 2 + 8 * jq;
-                    *reinterpret_cast<float4*>(p.dy + off) = d0; *reinterpret_cast<float4*>(p.dy + off + 4) = d1;
+                    if (blockIdx.z == 0) {                      // one column tile writes dY
+                        const size_t off = (((size_t)b * p.Cout + o0 + o) * NB + r) * 2 + 8 * jq;
+                        *reinterpret_cast<float4*>(p.dy + off) = d0; *reinterpret_cast<float4*>(p.dy + off + 4) = d1;
+                    }
                     wg_store_rows(a_hi, a_lo, o, jq, d0, d1);
                 }
             }
@@ -535,7 +540,7 @@ __global__ void __launch_bounds__(2 * WG_BUILDERS + 32, 1) fu3_wgrad_kernel(cons
             // this CTA's partial tile goes to its own slice of the workspace ([CTA][128][NT], coalesced over the rows' columns is not
             // possible from the TMEM row-per-lane view, so each lane writes 64 contiguous bytes); fu3_wgrad_reduce adds the slices.
             // (One float atomic per element and CTA made 148-way contention on every address: ~40 us for a 128 x 128 tile.)
-            float* part = p.part + (size_t)blockIdx.x * 128 * 2 * NT;
+            float* part = p.part + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 128 * 2 * NT;
             for (int cg = col_half; cg < ncols16; cg += 2) {
                 uint32_t rr[16];
                 umma::tmem_ld16(lane_base + tbase + (uint32_t)(16 * cg), rr);
@@ -582,13 +587,14 @@ __global__ void __launch_bounds__(2 * WG_BUILDERS + 32, 1) fu3_wgrad_kernel(cons
 
 // dw[n][k] = scale * sum over the CTAs' partial tiles [CTA][128][2*NT] of the blocks that hold hi*hi, hi*lo, lo*hi (lo*lo).
 // One block per 8 consecutive outputs; 32 groups of threads split the CTAs' tiles, shared-memory sum at the end.
-__global__ void __launch_bounds__(256) fu3_wgrad_reduce(const float* __restrict__ part, float* __restrict__ dw, int nparts, int NT, int Cin, int Cout, float scale, int stacked) {
+__global__ void __launch_bounds__(256) fu3_wgrad_reduce(const float* __restrict__ part, float* __restrict__ dw, int nparts, int NT, int ld, int row0, int col0,
+                                                        int rows, int cols, float scale, int stacked) {
     __shared__ float red[32][9];
     const int el = threadIdx.x & 7, pg = threadIdx.x >> 3;       // 8 consecutive outputs (one 32-byte sector per tile) x 32 groups of tiles
     const int e = blockIdx.x * 8 + el;
     float acc = 0.f;
-    if (e < 4 * Cin * Cout) {
-        const int n = e / (2 * Cin), k = e % (2 * Cin);
+    if (e < rows * cols) {
+        const int n = e / cols, k = e % cols;
         const size_t tile = (size_t)128 * 2 * NT;
         const float* src = part + (size_t)n * 2 * NT + k;
         for (int i = pg; i < nparts; i += 32) {
@@ -600,16 +606,27 @@ __global__ void __launch_bounds__(256) fu3_wgrad_reduce(const float* __restrict_
     }
     red[pg][el] = acc;
     __syncthreads();
-    if (pg == 0 && e < 4 * Cin * Cout) {
+    if (pg == 0 && e < rows * cols) {
         float a = 0.f;
 #pragma unroll
         for (int i = 0; i < 32; ++i) a += red[i][el];
-        dw[e] = a * scale;
+        dw[(size_t)(row0 + e / cols) * ld + col0 + e % cols] = a * scale;
     }
 }
-size_t fu3_wgrad_tc_part_floats(int Cin) { return (size_t)296 * 128 * 2 * ((2 * Cin + 15) / 16 * 16); }     // up to 296 CTAs' tiles
+// channel tiles of 64 x 64 complex channels, persistent CTAs per tile pair
+static void wg_tiling(int Cin, int Cout, int& ty, int& tz, int& NT, int& gx_cap) {
+    ty = (Cout + 63) / 64; tz = (Cin + 63) / 64;
+    const int cw = Cin < 64 ? Cin : 64;
+    NT = (2 * cw + 15) / 16 * 16;
+    gx_cap = 296 / (ty * tz);
+    if (gx_cap < 1) gx_cap = 1;
+}
+size_t fu3_wgrad_tc_part_floats(int Cin, int Cout) {
+    int ty, tz, NT, cap; wg_tiling(Cin, Cout, ty, tz, NT, cap);
+    return (size_t)ty * tz * cap * 128 * 2 * NT;
+}
 
-bool fu3_wgrad_tc_supported(int Cin, int Cout) { return Cin >= 1 && Cout >= 1 && Cin <= 64 && Cout <= 64; }
+bool fu3_wgrad_tc_supported(int Cin, int Cout) { return Cin >= 1 && Cout >= 1 && ((Cin + 63) / 64) * ((Cout + 63) / 64) <= 64; }
 
 template <int RAW, int NCANON, int U, bool STACK>
 static int fu3_wgrad_launch(const Fu3BwdWgradParams& p, int NT, int nchunks, int tmem_cols, size_t smem, ffc_stream_t st) {
@@ -620,22 +637,29 @@ static int fu3_wgrad_launch(const Fu3BwdWgradParams& p, int NT, int nchunks, int
         if (e != cudaSuccess) { ffc_set_error("cudaFuncSetAttribute(fu3_wgrad, %zu B): %s", smem, cudaGetErrorString(e)); return FFC_ERR_CUDA; }
         configured = smem;
     }
-    int grid = nchunks < ffc_sm_count() ? nchunks : ffc_sm_count();
-    if (grid < 1) grid = 1;
-    if (grid > 296) grid = 296;                                  // the partial-tile workspace holds 296 slices
-    fu3_wgrad_kernel<RAW, NCANON, U, STACK><<<grid, 2 * WG_BUILDERS + 32, smem, st>>>(p, NT, nchunks, tmem_cols);
+    int ty, tz, nt_, cap; wg_tiling(p.Cin, p.Cout, ty, tz, nt_, cap);
+    int gx = ffc_sm_count() / (ty * tz);
+    if (gx < 1) gx = 1;
+    if (gx > cap) gx = cap;
+    if (gx > nchunks) gx = nchunks;
+    fu3_wgrad_kernel<RAW, NCANON, U, STACK><<<dim3(gx, ty, tz), 2 * WG_BUILDERS + 32, smem, st>>>(p, NT, nchunks, tmem_cols);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { ffc_set_error("fu3_wgrad launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
     ffc_count_launch();
-    fu3_wgrad_reduce<<<(4 * p.Cin * p.Cout + 7) / 8, 256, 0, st>>>(p.part, p.dw, grid, NT, p.Cin, p.Cout, p.scale, STACK ? 1 : 0);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) { ffc_set_error("fu3_wgrad_reduce launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
-    ffc_count_launch();
+    for (int z = 0; z < tz; ++z)
+        for (int y = 0; y < ty; ++y) {
+            const int rows = 2 * ((p.Cout - 64 * y) < 64 ? (p.Cout - 64 * y) : 64), cols = 2 * ((p.Cin - 64 * z) < 64 ? (p.Cin - 64 * z) : 64);
+            fu3_wgrad_reduce<<<(rows * cols + 7) / 8, 256, 0, st>>>(p.part + (size_t)(z * ty + y) * gx * 128 * 2 * NT, p.dw, gx, NT, 2 * p.Cin,
+                                                                    128 * y, 128 * z, rows, cols, p.scale, STACK ? 1 : 0);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) { ffc_set_error("fu3_wgrad_reduce launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
+            ffc_count_launch();
+        }
     return FFC_OK;
 }
 
 int fu3_wgrad_tc_run(const Fu3BwdWgradParams& p, ffc_stream_t st) {
-    const int NT = (2 * p.Cin + 15) / 16 * 16;
+    int ty, tz, NT, cap; wg_tiling(p.Cin, p.Cout, ty, tz, NT, cap);
     const long long Mtot = (long long)p.B * p.NB;
     if (p.NB % WG_BK != 0) { ffc_set_error("fu3_wgrad: plane slots (%d) must be a multiple of %d", p.NB, WG_BK); return FFC_ERR_BAD_ARG; }
     const int nchunks = (int)(Mtot / WG_BK);

@@ -16,6 +16,16 @@ from .. import ops
 from . import _util
 
 
+def _prefers_staged(c: int, n: int, needs_grad: bool) -> bool:
+    """Where both forms apply, which one is faster (measured, profiles/r03a_fu_paths.jsonl: batch 32..256 on one B200): the
+    single-kernel form wins while an image is small (8 channels, 16 channels at 16x16); from 24 channels -- or 16 at 32x32 --
+    the backward of the L2-staged form (tensor-core mix and weight gradient) is 1.2-1.8x faster, and from 24 channels at
+    32x32 its forward is, too."""
+    if needs_grad:
+        return c >= 24 or (c >= 16 and n >= 32)
+    return c >= 24 and n >= 32
+
+
 class FourierUnitSN(nn.Module):
     def __init__(self, in_channels, out_channels, groups: int = 1, num_classes: int = 1):
         super().__init__()
@@ -28,7 +38,8 @@ class FourierUnitSN(nn.Module):
         self.bn = nn.BatchNorm2d(out_channels * 2)
         self.relu = nn.ReLU(inplace=True)
         # True: the single-kernel fused form where one image's spectrum fits a CTA, else the L2-staged form (csrc/ffc_fu3.cu);
-        # "staged" forces the L2-staged form, False the first-generation general form (tests and benchmarks)
+        # (whichever is faster where both apply); "single" / "staged" force one of them, False the first-generation general form
+        # (tests and benchmarks)
         self.fused = True
 
     def forward(self, x, y=None):
@@ -48,7 +59,10 @@ class FourierUnitSN(nn.Module):
         bn = self.bn
         cin, cout = x.shape[1], weight.shape[0] // 2
         plain_bn = bn.affine and bn.track_running_stats and bn.momentum is not None
-        single = plain_bn and self.fused is True and ops.fu_fused_supported(x.shape[0], cin, cout, h, w)
+        single = plain_bn and self.fused in (True, "single") and ops.fu_fused_supported(x.shape[0], cin, cout, h, w)
+        if single and self.fused is True and _prefers_staged(max(cin, cout), h, torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad)) \
+                and ops.fu_staged_supported(x.shape[0], cin, cout, h, w):
+            single = False
         staged = plain_bn and self.fused and not single and ops.fu_staged_supported(x.shape[0], cin, cout, h, w)
         if single or staged:
             if bn.training:

@@ -157,7 +157,7 @@ def test_fourier_unit_config_shapes(B, C, N, train, fused):
     if fused == "two_pass" and not train:
         pytest.skip("eval mode is always a single pass")
     mod = ffc.FourierUnitSN(C, C)
-    mod.fused = "staged" if staged else bool(fused)      # "staged": csrc/ffc_fu3.cu with the tcgen05 channel mix
+    mod.fused = "staged" if staged else ("single" if fused else False)      # "staged": csrc/ffc_fu3.cu with the tcgen05 channel mix; "single": csrc/ffc_fu2*.cu
     with torch.no_grad():
         mod.bn.running_mean.normal_(0, 0.1)
         mod.bn.running_var.uniform_(0.5, 1.5)
