@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(2 * WG_BUILDERS + 32, 1) fu3_wgrad_kernel(cons
     const int Cout = (p.Cout - o0) < 64 ? (p.Cout - o0) : 64, Cin = (p.Cin - c0) < 64 ? (p.Cin - c0) : 64;
 
     if (tid == 0) {
-        for (int i = 0; i < 4; ++i) { umma::mbar_init(&full[i], 2 * WG_BUILDERS); umma::mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 4; ++i) { umma::mbar_init(&full[i], 2 * WG_BUILDERS / 32); umma::mbar_init(&empty[i], 1); }      // one arrival per builder warp
         umma::mbar_init(done, 1);
         umma::fence_barrier_init();
     }
@@ -526,7 +526,8 @@ __global__ void __launch_bounds__(2 * WG_BUILDERS + 32, 1) fu3_wgrad_kernel(cons
                 }
             }
             umma::fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
-            umma::mbar_arrive(&full[s]);
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive(&full[s]);           // one arrival per warp: 512 arrivals on one mbarrier serialise
         }
         wg_cp_wait<0>();
         // ------------------------------------------------------------------------------------------------ epilogue

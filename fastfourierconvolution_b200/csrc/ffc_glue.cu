@@ -114,7 +114,9 @@ extern "C" int ffc_noise_add_bwd_w(const float* dy, const float* noise, float* d
     ffc_stream_t st = (ffc_stream_t)stream;
     FFC_CHECK(ffc_memset_async(dw, 0, (size_t)C * sizeof(float), st));
     if (B == 0) return FFC_OK;
-    int ns = (2 * ffc_sm_count() + C - 1) / C;
+    // ~8 CTAs per SM: a CTA's loop is a chain of dependent-latency loads (two independent accumulators), so the kernel is
+    // latency bound and wants many short loops rather than few long ones (26 -> ~8 us on the 192-channel 8x8 layers)
+    int ns = (8 * ffc_sm_count() + C - 1) / C;
     const long long total = (long long)B * HW;
     if ((long long)ns * 1024 > total) ns = (int)((total + 1023) / 1024);
     if (ns < 1) ns = 1;
