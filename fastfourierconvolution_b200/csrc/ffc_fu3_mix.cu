@@ -374,31 +374,33 @@ static constexpr int WG_BK = 32;                          // bins per chunk
 static constexpr int WG_BUILDERS = 256;
 
 __device__ __forceinline__ void wg_cp16(void* dst_smem, const void* src_gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(umma::smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(umma::smem_u32(dst_smem)), "l"(src_gmem) : "memory");
 }
 __device__ __forceinline__ void wg_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void wg_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // a = (re0, im0, re1, im1), b = (re2, im2, re3, im3) of complex channel `ch`, bins 4*jq .. 4*jq + 3 -> rows 2*ch, 2*ch + 1 of
-// the canonical tile.  Lanes are (channel % 4, bin quad): lanes of an even bin quad store the re row first, lanes of an odd
-// one the im row, so the eight lanes of a quarter-warp cover all 32 banks with each 16-byte store.
+// the canonical tile (hi and lo).  Lanes are (channel % 4, bin quad): lanes of an even bin quad store the re row first, lanes
+// of an odd one the im row, so the eight lanes of a quarter-warp cover all 32 banks with each 16-byte store.  (Without the
+// ordering every store is a 2-way conflict: 13 M extra wavefronts and the L1 / shared-memory pipe at 89 %, ncu r03h -- the
+// pipe, shared with the cp.async ring and the tensor core's operand reads, is what bounds this kernel.)
 __device__ __forceinline__ void wg_store_rows(float* tile_hi, float* tile_lo, int ch, int jq, const float4 a, const float4 b) {
-    const float re[4] = {a.x, a.z, b.x, b.z}, im[4] = {a.y, a.w, b.y, b.w};
-    float rh[4], rl[4], ih[4], il[4];
+    const bool odd = jq & 1;
+    // first / second row of this lane: (re, im) for even bin quads, (im, re) for odd ones
+    const float f[4] = {odd ? a.y : a.x, odd ? a.w : a.z, odd ? b.y : b.x, odd ? b.w : b.z};
+    const float g[4] = {odd ? a.x : a.y, odd ? a.z : a.w, odd ? b.x : b.y, odd ? b.z : b.w};
+    float fh[4], fl[4], gh[4], gl[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        rh[i] = ffc_tf32_hi(re[i]); rl[i] = re[i] - rh[i];
-        ih[i] = ffc_tf32_hi(im[i]); il[i] = im[i] - ih[i];
+        fh[i] = ffc_tf32_hi(f[i]); fl[i] = f[i] - fh[i];
+        gh[i] = ffc_tf32_hi(g[i]); gl[i] = g[i] - gh[i];
     }
     const int off = ((2 * ch) >> 3) * 256 + jq * 32 + ((2 * ch) & 7) * 4;
-    const bool odd = jq & 1;
     const int o1 = off + (odd ? 4 : 0), o2 = off + (odd ? 0 : 4);
-    const float4 rhv = make_float4(rh[0], rh[1], rh[2], rh[3]), ihv = make_float4(ih[0], ih[1], ih[2], ih[3]);
-    const float4 rlv = make_float4(rl[0], rl[1], rl[2], rl[3]), ilv = make_float4(il[0], il[1], il[2], il[3]);
-    *reinterpret_cast<float4*>(tile_hi + o1) = odd ? ihv : rhv;
-    *reinterpret_cast<float4*>(tile_hi + o2) = odd ? rhv : ihv;
-    *reinterpret_cast<float4*>(tile_lo + o1) = odd ? ilv : rlv;
-    *reinterpret_cast<float4*>(tile_lo + o2) = odd ? rlv : ilv;
+    *reinterpret_cast<float4*>(tile_hi + o1) = make_float4(fh[0], fh[1], fh[2], fh[3]);
+    *reinterpret_cast<float4*>(tile_hi + o2) = make_float4(gh[0], gh[1], gh[2], gh[3]);
+    *reinterpret_cast<float4*>(tile_lo + o1) = make_float4(fl[0], fl[1], fl[2], fl[3]);
+    *reinterpret_cast<float4*>(tile_lo + o2) = make_float4(gl[0], gl[1], gl[2], gl[3]);
 }
 
 // RAW: stages of the cp.async ring (prefetch distance RAW - 1 chunks); NCANON: canonical (tensor-core) stages; U: passes of 32
@@ -419,7 +421,7 @@ __global__ void __launch_bounds__(2 * WG_BUILDERS + 32, 1) fu3_wgrad_kernel(cons
     const uint32_t a_bytes = a_rows * WG_BK * 4, b_bytes = (uint32_t)NT * WG_BK * 4;     // one of hi / lo
     const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
     unsigned char* raw = wg_smem + (size_t)NCANON * stage_bytes;
-    float* consts = reinterpret_cast<float*>(raw + (size_t)RAW * raw_bytes);             // coef | c1 | c2 | mean | invstd, 128 each
+    float* consts = reinterpret_cast<float*>(raw + (size_t)RAW * raw_bytes);             // alpha | beta | gamma, 128 each (+ 256 spare)
     uint64_t* full = reinterpret_cast<uint64_t*>(consts + 5 * 128);
     uint64_t* empty = full + 4;
     uint64_t* done = empty + 4;
@@ -435,11 +437,14 @@ __global__ void __launch_bounds__(2 * WG_BUILDERS + 32, 1) fu3_wgrad_kernel(cons
     }
     // rows beyond 2*Cout / 2*Cin of every canonical stage stay zero for the life of the CTA
     for (uint32_t i = tid; i < (uint32_t)NCANON * stage_bytes / 16; i += blockDim.x) reinterpret_cast<float4*>(wg_smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // dY = coef * (g - c1 - (y - mean) * invstd * c2) = alpha * g + beta * y + gamma: two FMAs per value
     for (int i = tid; i < 128; i += blockDim.x) {
         const bool ok = i < 2 * Cout;
         const int n = 2 * o0 + i;
-        consts[i] = ok ? __ldg(p.coef + n) : 0.f; consts[128 + i] = ok ? __ldg(p.c1 + n) : 0.f; consts[256 + i] = ok ? __ldg(p.c2 + n) : 0.f;
-        consts[384 + i] = ok ? __ldg(p.mean + n) : 0.f; consts[512 + i] = ok ? __ldg(p.invstd + n) : 0.f;
+        const float coef = ok ? __ldg(p.coef + n) : 0.f, c1 = ok ? __ldg(p.c1 + n) : 0.f, c2 = ok ? __ldg(p.c2 + n) : 0.f;
+        const float mean = ok ? __ldg(p.mean + n) : 0.f, invstd = ok ? __ldg(p.invstd + n) : 0.f;
+        const float beta = -coef * invstd * c2;
+        consts[i] = coef; consts[128 + i] = beta; consts[256 + i] = -coef * c1 - beta * mean;
     }
     if (warp == 0) umma::tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
     umma::fence_proxy_async_smem();
@@ -454,12 +459,75 @@ __global__ void __launch_bounds__(2 * WG_BUILDERS + 32, 1) fu3_wgrad_kernel(cons
         const int bt = tid & (WG_BUILDERS - 1), bw = warp & 7;
         const int jq = lane >> 2, chl = bw * 4 + (lane & 3);     // bin quad, channel within a pass of 32 channels
         const int C = sideB ? Cin : Cout, Ctot = sideB ? p.Cin : p.Cout, cbase = sideB ? c0 : o0;
+        const unsigned cpi = (unsigned)(NB / WG_BK);             // chunks per image (NB % 32 == 0)
+        if constexpr (RAW == 0) {
+            // DIRECT form: the units of the next chunk are loaded straight into registers (one chunk ahead) while this chunk is
+            // processed.  The cp.async ring below costs a shared-memory write and a read per loaded byte, and the L1 / shared
+            // memory pipe -- shared with the canonical-tile stores and the tensor core's operand reads -- bounds this kernel.
+            constexpr int NR = 4 * U;
+            float4 cur[NR], nxt[NR];
+            auto load = [&](int chunk, float4 (&dst)[NR]) {
+                const int b = (int)((unsigned)chunk / cpi), r = (int)((unsigned)chunk % cpi) * WG_BK;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int o = chl + 32 * u;
+                    if (o < C) {
+                        const size_t off = (((size_t)b * Ctot + cbase + o) * NB + r) * 2 + 8 * jq;
+                        if (sideB) {
+                            dst[4 * u + 0] = __ldg(reinterpret_cast<const float4*>(p.s + off)); dst[4 * u + 1] = __ldg(reinterpret_cast<const float4*>(p.s + off + 4));
+                        } else {
+                            dst[4 * u + 0] = __ldg(reinterpret_cast<const float4*>(p.g + off)); dst[4 * u + 1] = __ldg(reinterpret_cast<const float4*>(p.g + off + 4));
+                            dst[4 * u + 2] = __ldg(reinterpret_cast<const float4*>(p.y + off)); dst[4 * u + 3] = __ldg(reinterpret_cast<const float4*>(p.y + off + 4));
+                        }
+                    }
+                }
+            };
+            if ((int)blockIdx.x < nchunks) load(blockIdx.x, cur);
+            int it = 0;
+            for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, ++it) {
+                const int s = it % NCANON, use = it / NCANON;
+                const int b = (int)((unsigned)chunk / cpi), r = (int)((unsigned)chunk % cpi) * WG_BK;
+                if (chunk + (int)gridDim.x < nchunks) load(chunk + gridDim.x, nxt);
+                if (use > 0) umma::mbar_wait(&empty[s], (uint32_t)(use - 1) & 1u);          // the MMAs that read this stage are done
+                float* a_hi = reinterpret_cast<float*>(wg_smem + (size_t)s * stage_bytes);
+                float* a_lo = a_hi + a_rows * WG_BK;
+                float* b_hi = a_lo + a_rows * WG_BK;
+                float* b_lo = b_hi + NT * WG_BK;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int o = chl + 32 * u;
+                    if (o >= C) continue;
+                    if (sideB) {
+                        wg_store_rows(b_hi, b_lo, o, jq, cur[4 * u + 0], cur[4 * u + 1]);
+                    } else {
+                        const float4 g0 = cur[4 * u + 0], g1 = cur[4 * u + 1], y0 = cur[4 * u + 2], y1 = cur[4 * u + 3];
+                        const int n = 2 * o;
+                        const float ar = consts[n], ai = consts[n + 1], br = consts[128 + n], bi = consts[128 + n + 1];
+                        const float cr = consts[256 + n], ci = consts[256 + n + 1];
+                        float4 d0, d1;
+                        d0.x = fmaf(ar, g0.x, fmaf(br, y0.x, cr)); d0.y = fmaf(ai, g0.y, fmaf(bi, y0.y, ci));
+                        d0.z = fmaf(ar, g0.z, fmaf(br, y0.z, cr)); d0.w = fmaf(ai, g0.w, fmaf(bi, y0.w, ci));
+                        d1.x = fmaf(ar, g1.x, fmaf(br, y1.x, cr)); d1.y = fmaf(ai, g1.y, fmaf(bi, y1.y, ci));
+                        d1.z = fmaf(ar, g1.z, fmaf(br, y1.z, cr)); d1.w = fmaf(ai, g1.w, fmaf(bi, y1.w, ci));
+                        if (blockIdx.z == 0) {                      // one column tile writes dY
+                            const size_t off = (((size_t)b * p.Cout + o0 + o) * NB + r) * 2 + 8 * jq;
+                            *reinterpret_cast<float4*>(p.dy + off) = d0; *reinterpret_cast<float4*>(p.dy + off + 4) = d1;
+                        }
+                        wg_store_rows(a_hi, a_lo, o, jq, d0, d1);
+                    }
+                }
+                umma::fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(&full[s]);           // one arrival per warp: 512 arrivals on one mbarrier serialise
+#pragma unroll
+                for (int i = 0; i < NR; ++i) cur[i] = nxt[i];
+            }
+        } else {
         // every thread copies ITS OWN units of chunk i + RAW - 1 into the raw ring with cp.async (16 bytes each) and reads them
         // back after cp.async.wait_group: RAW - 1 chunks of loads per thread stay in flight without holding registers, and no
         // other thread ever touches these bytes, so the ring needs no barrier.
         auto issue = [&](int chunk, int rs) {
-            const long long m0 = (long long)chunk * WG_BK;
-            const int b = (int)(m0 / NB), r = (int)(m0 % NB);
+            const int b = (int)((unsigned)chunk / cpi), r = (int)((unsigned)chunk % cpi) * WG_BK;     // 32-bit: a 64-bit division is ~100 instructions
             unsigned char* dst = raw + (size_t)rs * raw_bytes + (sideB ? rawA : 0) + (size_t)bt * 16;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -486,14 +554,13 @@ __global__ void __launch_bounds__(2 * WG_BUILDERS + 32, 1) fu3_wgrad_kernel(cons
         int it = 0;
         for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, ++it) {
             const int s = it % NCANON, use = it / NCANON;
-            const long long m0 = (long long)chunk * WG_BK;
-            const int b = (int)(m0 / NB), r = (int)(m0 % NB);
+            const int b = (int)((unsigned)chunk / cpi), r = (int)((unsigned)chunk % cpi) * WG_BK;     // 32-bit: a 64-bit division is ~100 instructions
             {
                 const long long ahead = (long long)chunk + (long long)(RAW - 1) * gridDim.x;
                 if (ahead < nchunks) issue((int)ahead, (it + RAW - 1) % RAW);
                 wg_cp_commit();
             }
-            wg_cp_wait<RAW - 1>();                               // this thread's copies of chunk `it` have landed
+            wg_cp_wait<(RAW > 0 ? RAW - 1 : 0)>();                               // this thread's copies of chunk `it` have landed
             const float4* mine = reinterpret_cast<const float4*>(raw + (size_t)(it % RAW) * raw_bytes + (sideB ? rawA : 0)) + bt;
             if (use > 0) umma::mbar_wait(&empty[s], (uint32_t)(use - 1) & 1u);          // the MMAs that read this stage are done
             float* a_hi = reinterpret_cast<float*>(wg_smem + (size_t)s * stage_bytes);
@@ -510,14 +577,13 @@ __global__ void __launch_bounds__(2 * WG_BUILDERS + 32, 1) fu3_wgrad_kernel(cons
                     const float4 g0 = mine[(4 * u + 0) * WG_BUILDERS], g1 = mine[(4 * u + 1) * WG_BUILDERS];
                     const float4 y0 = mine[(4 * u + 2) * WG_BUILDERS], y1 = mine[(4 * u + 3) * WG_BUILDERS];
                     const int n = 2 * o;
-                    const float kr = consts[n], ki = consts[n + 1], c1r = consts[128 + n], c1i = consts[128 + n + 1];
-                    const float c2r = consts[256 + n], c2i = consts[256 + n + 1], mr = consts[384 + n], mi = consts[384 + n + 1];
-                    const float ir = consts[512 + n], ii = consts[512 + n + 1];
+                    const float ar = consts[n], ai = consts[n + 1], br = consts[128 + n], bi = consts[128 + n + 1];
+                    const float cr = consts[256 + n], ci = consts[256 + n + 1];
                     float4 d0, d1;
-                    d0.x = kr * (g0.x - c1r - (y0.x - mr) * ir * c2r); d0.y = ki * (g0.y - c1i - (y0.y - mi) * ii * c2i);
-                    d0.z = kr * (g0.z - c1r - (y0.z - mr) * ir * c2r); d0.w = ki * (g0.w - c1i - (y0.w - mi) * ii * c2i);
-                    d1.x = kr * (g1.x - c1r - (y1.x - mr) * ir * c2r); d1.y = ki * (g1.y - c1i - (y1.y - mi) * ii * c2i);
-                    d1.z = kr * (g1.z - c1r - (y1.z - mr) * ir * c2r); d1.w = ki * (g1.w - c1i - (y1.w - mi) * ii * c2i);
+                    d0.x = fmaf(ar, g0.x, fmaf(br, y0.x, cr)); d0.y = fmaf(ai, g0.y, fmaf(bi, y0.y, ci));
+                    d0.z = fmaf(ar, g0.z, fmaf(br, y0.z, cr)); d0.w = fmaf(ai, g0.w, fmaf(bi, y0.w, ci));
+                    d1.x = fmaf(ar, g1.x, fmaf(br, y1.x, cr)); d1.y = fmaf(ai, g1.y, fmaf(bi, y1.y, ci));
+                    d1.z = fmaf(ar, g1.z, fmaf(br, y1.z, cr)); d1.w = fmaf(ai, g1.w, fmaf(bi, y1.w, ci));
                     if (blockIdx.z == 0) {                      // one column tile writes dY
                         const size_t off = (((size_t)b * p.Cout + o0 + o) * NB + r) * 2 + 8 * jq;
                         *reinterpret_cast<float4*>(p.dy + off) = d0; *reinterpret_cast<float4*>(p.dy + off + 4) = d1;
@@ -528,6 +594,7 @@ __global__ void __launch_bounds__(2 * WG_BUILDERS + 32, 1) fu3_wgrad_kernel(cons
             umma::fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) umma::mbar_arrive(&full[s]);           // one arrival per warp: 512 arrivals on one mbarrier serialise
+        }
         }
         wg_cp_wait<0>();
         // ------------------------------------------------------------------------------------------------ epilogue
@@ -668,10 +735,12 @@ int fu3_wgrad_tc_run(const Fu3BwdWgradParams& p, ffc_stream_t st) {
     const size_t tail = 5 * 128 * 4 + 10 * 8 + 64, b_tile = (size_t)2 * NT * WG_BK * 4;
     if (p.Cin > 32 || p.Cout > 32) {          // two passes of 32 channels per operand: 2 x (32 KB A + <= 32 KB B) + 2 x 48 KB raw
         const size_t stage = (size_t)2 * 128 * WG_BK * 4 + b_tile, raw = (size_t)12 * WG_BUILDERS * 16;
-        return fu3_wgrad_launch<2, 2, 2, false>(p, NT, nchunks, tmem_cols, 2 * stage + 2 * raw + tail, st);
+        (void)raw;
+        return fu3_wgrad_launch<0, 3, 2, false>(p, NT, nchunks, tmem_cols, 3 * stage + tail, st);
     }
     // <= 32 channels: stacked A tile (16 KB) + <= 16 KB B, three canonical stages, four raw stages of 24 KB
     const size_t stage = (size_t)2 * 64 * WG_BK * 4 + b_tile, raw = (size_t)6 * WG_BUILDERS * 16;
-    return fu3_wgrad_launch<4, 3, 1, true>(p, NT, nchunks, tmem_cols, 3 * stage + 4 * raw + tail, st);
+    (void)raw;
+    return fu3_wgrad_launch<0, 4, 1, true>(p, NT, nchunks, tmem_cols, 4 * stage + tail, st);
 }
 #endif  // !FFC_EMU
