@@ -79,10 +79,13 @@ __global__ void __launch_bounds__(256) pack_v5_kernel(const PackV5Params p) {
         const int NT = v5_tile_n(p.cout, p.nt_full, t);
         const long long per_chunk = 2LL * NT * V5_BK;
         const long long total = (long long)nchunks * NT * V5_BK;
-        for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-            const int kk = (int)(e % V5_BK);
-            const int n = (int)((e / V5_BK) % NT);
-            int chunk = (int)(e / ((long long)V5_BK * NT));
+        // 32-bit index arithmetic (total < 2^31 for every weight this library sees): the three 64-bit divisions per element
+        // were most of this kernel's instructions
+        for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < (unsigned)total; e += gridDim.x * blockDim.x) {
+            const int kk = (int)(e % (unsigned)V5_BK);
+            const unsigned q = e / (unsigned)V5_BK;
+            const int n = (int)(q % (unsigned)NT);
+            int chunk = (int)(q / (unsigned)NT);
             const int chunk_all = chunk;
             int sg = 0;
             if (chunk >= T * p.cps[0]) { sg = 1; chunk -= T * p.cps[0]; }
@@ -391,6 +394,7 @@ int conv_v5_run_block(const float* x0, const float* w0, const float* w0b, int ci
     pp.k = k; pp.stride = stride; pp.pad = pad; pp.transposed = transposed; pp.w0b = w0b; pp.cout0 = cout0;
     for (int c = 0; c < FFC_V5_MAXCLS; ++c) pp.cls_off[c] = pl.cls_off[c];
     const long long per_cls = (long long)k * k * (pl.cps[0] + pl.cps[1]) * V5_BK * ((cout + 15) / 16 * 16);
+    if (per_cls >= (1LL << 31)) { ffc_set_error("ffc_conv2d_fwd_ws: weight too large for the packing kernel (%lld elements per class)", per_cls); return FFC_ERR_BAD_ARG; }
     int gx = (int)((per_cls + 255) / 256); if (gx > ffc_sm_count() * 4) gx = ffc_sm_count() * 4; if (gx < 1) gx = 1;
     pack_v5_kernel<<<dim3(gx, pl.ncls), 256, 0, st>>>(pp);
     cudaError_t e = cudaGetLastError();
