@@ -330,6 +330,28 @@ __global__ void __launch_bounds__(V5_GW * 128 + 64, V5_GW == 2 ? 2 : 1) conv_v5_
     if (warp == V5_MMAWARP) umma::tmem_dealloc(tbase, tmem_cols);
 }
 
+// v -> v > 0 ? v : slope * v in place over one or two tensors (the activation of a split-K convolution, applied after the sum)
+__global__ void __launch_bounds__(256) leaky_inplace_kernel(float* __restrict__ a, long long na, float* __restrict__ b, long long nb, float slope) {
+    const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int which = 0; which < 2; ++which) {
+        float* p = which ? b : a;
+        const long long n = which ? nb : na;
+        if (!p || n == 0) continue;
+        if ((((uintptr_t)p) & 15) == 0) {
+            const long long n4 = n / 4;
+            for (long long i = t0; i < n4; i += stride) {
+                float4 v = reinterpret_cast<float4*>(p)[i];
+                v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+                v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+                reinterpret_cast<float4*>(p)[i] = v;
+            }
+            for (long long i = 4 * n4 + t0; i < n; i += stride) { const float v = p[i]; p[i] = v > 0.f ? v : v * slope; }
+        } else {
+            for (long long i = t0; i < n; i += stride) { const float v = p[i]; p[i] = v > 0.f ? v : v * slope; }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -439,14 +461,20 @@ int conv_v5_run_block(const float* x0, const float* w0, const float* w0b, int ci
             const int n = g.Ta * g.Tb * (pl.cps[0] + pl.cps[1]);
             if (n < min_chunks) min_chunks = n;
         }
-        if (slope == 1.f && ctas * 2 <= ffc_sm_count()) {
-            ksplit = ffc_sm_count() / ctas;
+        // resident CTA slots: the two-warpgroup kernel on narrow tiles keeps two CTAs per SM.  A fused activation no longer blocks
+        // the split: the kernel then stores plain sums (slope 1) and one in-place pass applies the activation afterwards -- the
+        // deep discriminator layers (4x4 / 8x8 planes, 64-96 CTAs with 72-256 chunks each) ran at 0.3-0.6 of a wave.
+        const int slots = ffc_sm_count() * ((!four_wg && pl.nt_full <= 64) ? 2 : 1);
+        if (ctas * 2 <= slots) {
+            ksplit = slots / ctas;
             if (ksplit > min_chunks / 8) ksplit = min_chunks / 8;
             if (ksplit > 16) ksplit = 16;
             if (ksplit < 1) ksplit = 1;
         }
     }
     p.ksplit = ksplit;
+    const bool act_after = ksplit > 1 && slope != 1.f;
+    if (act_after) p.slope = 1.f;
     if (ksplit > 1) {
         const size_t HWo = (size_t)Ho * Wo;
         e = cudaMemsetAsync(y, 0, (size_t)B * cout0 * HWo * sizeof(float), st);
@@ -459,6 +487,16 @@ int conv_v5_run_block(const float* x0, const float* w0, const float* w0b, int ci
     e = cudaGetLastError();
     if (e != cudaSuccess) { ffc_set_error("conv_v5 launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
     ffc_count_launch();
+    if (act_after) {
+        const size_t HWo = (size_t)Ho * Wo;
+        const long long n0 = (long long)B * cout0 * HWo, n1 = y1 ? (long long)B * (cout - cout0) * HWo : 0;
+        const long long most = n0 > n1 ? n0 : n1;
+        int gx = (int)((most / 4 + 255) / 256); if (gx > ffc_sm_count() * 8) gx = ffc_sm_count() * 8; if (gx < 1) gx = 1;
+        leaky_inplace_kernel<<<gx, 256, 0, st>>>(y, n0, y1, n1, slope);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) { ffc_set_error("conv_v5 activation pass launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
+        ffc_count_launch();
+    }
     return FFC_OK;
 }
 #endif  // !FFC_EMU
