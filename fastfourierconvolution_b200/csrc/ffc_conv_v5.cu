@@ -357,12 +357,11 @@ __global__ void __launch_bounds__(256) leaky_inplace_kernel(float* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 struct ConvV5Plan { int nt_full, ntiles, cps[2], ncls; long long cls_off[FFC_V5_MAXCLS]; long long total_floats; };
 
-static ConvV5Plan conv_v5_plan(int cin0, int cin1, int cout, int k, int stride, int pad, int transposed) {
+static ConvV5Plan conv_v5_plan(int cin0, int cin1, int cout, int k, int stride, int pad, int transposed, int nt_max = 192) {
     ConvV5Plan pl;
     const int c16 = (cout + 15) / 16 * 16;
     // widest tile: 2 accumulators of N columns + 128 columns of A stages in the 512 TMEM columns; an even split
     // (e.g. 384 -> 192 + 192, 512 -> 3 x 176) keeps the tiles alike
-    const int nt_max = 192;
     const int nsplit = (c16 + nt_max - 1) / nt_max;
     pl.nt_full = ((c16 + nsplit - 1) / nsplit + 15) / 16 * 16;
     pl.ntiles = (cout + pl.nt_full - 1) / pl.nt_full;
@@ -383,7 +382,9 @@ static ConvV5Plan conv_v5_plan(int cin0, int cin1, int cout, int k, int stride, 
 }
 
 size_t conv_v5_workspace_bytes(int cin0, int cin1, int cout, int k, int stride, int pad, int transposed) {
-    return (size_t)conv_v5_plan(cin0, cin1, cout, k, stride, pad, transposed).total_floats * sizeof(float) + 256;
+    const long long a = conv_v5_plan(cin0, cin1, cout, k, stride, pad, transposed).total_floats;
+    const long long b = conv_v5_plan(cin0, cin1, cout, k, stride, pad, transposed, 128).total_floats;     // the small-grid tiling (conv_v5_run_block)
+    return (size_t)(a > b ? a : b) * sizeof(float) + 256;
 }
 
 // arguments validated by ffc_conv2d_fwd_ws
@@ -404,7 +405,18 @@ int conv_v5_run(const float* x0, const float* w0, int cin0, const float* x1, con
 int conv_v5_run_block(const float* x0, const float* w0, const float* w0b, int cin0, const float* x1, const float* w1, int cin1,
                       const float* bias, const float* addend, float* y, float* y1, int cout0, int B, int cout, int Hi, int Wi, int Ho, int Wo,
                       int k, int stride, int pad, int transposed, float slope, void* workspace, size_t workspace_bytes, ffc_stream_t st) {
-    const ConvV5Plan pl = conv_v5_plan(cin0, cin1, cout, k, stride, pad, transposed);
+    ConvV5Plan pl = conv_v5_plan(cin0, cin1, cout, k, stride, pad, transposed);
+    {
+        // Wide outputs on a small grid (deep layers on 4x4 / 8x8 planes: 512 output channels as 3 tiles of 176 on 32 pixel tiles =
+        // 96 CTAs): when the 128-wide tiling still fits one wave it wins -- every CTA walks the same K loop with a narrower MMA
+        // (896 instead of 1248 tensor cycles per chunk), and the extra A gathers of a fourth column tile are L2 hits.
+        const int s_ = transposed ? stride : 1;
+        const int mt = ffc_cdiv(B * ffc_cdiv(Ho, s_) * ffc_cdiv(Wo, s_), 128) * s_ * s_;
+        if (cout > 128 && mt * pl.ntiles < ffc_sm_count()) {
+            const ConvV5Plan p128 = conv_v5_plan(cin0, cin1, cout, k, stride, pad, transposed, 128);
+            if (p128.ntiles > pl.ntiles && mt * p128.ntiles <= ffc_sm_count()) pl = p128;
+        }
+    }
     const uintptr_t wsa = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
     if (!workspace || wsa + (size_t)pl.total_floats * sizeof(float) > (uintptr_t)workspace + workspace_bytes) {
         ffc_set_error("ffc_conv2d_fwd_ws: workspace too small (%zu bytes needed)", (size_t)pl.total_floats * sizeof(float) + 256);
