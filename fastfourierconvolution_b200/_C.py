@@ -68,6 +68,8 @@ _SIGNATURES = {
     "ffc_to_uint8": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_float, c_float, c_void_p]),
     "ffc_debug_conv_reference": (None, [c_int]),
     "ffc_debug_fu_two_pass": (None, [c_int]),
+    "ffc_debug_fu4": (None, [c_int]),
+    "ffc_fu_workspace_bytes": (c_size_t, [c_int, c_int]),
 }
 _OPTIONAL = set()
 

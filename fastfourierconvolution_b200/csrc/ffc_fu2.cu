@@ -14,18 +14,6 @@
 // When OG < Cout the mix is written to a second plane region (a bin is then shared by several threads).
 #include "ffc_fu2.cuh"
 
-struct Fu2Params {
-    const float* x;          // (B, Cin, N, N)
-    const float* w;          // [2*Cout][2*Cin]
-    const float* gamma; const float* beta;          // [2*Cout]
-    float* running_mean; float* running_var;        // [2*Cout]
-    float* save_mean; float* save_invstd;           // [2*Cout]
-    const float* residual;   // (B, Cout, N, N) or null
-    float* out;              // (B, Cout, N, N)
-    double* sums;            // [4*Cout]: sum(y) then sum(y^2), channel-major (2*Cout each)
-    int B, Cin, Cout, training;
-    float eps, momentum;
-};
 
 template <int N, int CP, int PASS>
 struct Fu2Fwd {
@@ -307,6 +295,10 @@ static bool fu2_fits(int Cin, int Cout) {
     return fu2_plan<N, 32>(Cin, Cout).ok;
 }
 
+// 32x32 planes with up to 8 channels: third generation (ffc_fu4.cu; device build only)
+bool ffc_fu4_supported(int Cin, int Cout, int H, int W);
+int ffc_fu4_launch(const Fu2Params& p, size_t workspace_bytes, ffc_stream_t st);
+
 // the 4x4 planes stay on the first-generation kernel (ffc_fu_fused.cu)
 extern "C" int ffc_fu1_supported(int B, int Cin, int Cout, int H, int W);
 extern "C" int ffc_fu1_fwd(const float* x, const float* w, const float* gamma, const float* beta,
@@ -325,6 +317,12 @@ extern "C" int ffc_fu_fused_supported(int B, int Cin, int Cout, int H, int W) {
         case 32: return fu2_fits<32>(Cin, Cout);
         default: return 0;
     }
+}
+
+// Workspace ffc_fu_fwd makes the best use of (the minimum stays 4*Cout doubles): room for one float per (sum, image) lets the
+// training kernel of ffc_fu4.cu meet its batch statistics without a zeroing launch and without atomics.
+extern "C" size_t ffc_fu_workspace_bytes(int B, int Cout) {
+    return ((size_t)4 * Cout * sizeof(double) + 255) / 256 * 256 + (size_t)4 * Cout * (B > 0 ? B : 0) * sizeof(float);
 }
 
 // Fused FourierUnitSN forward.  w: conv_layer.weight viewed [2*Cout][2*Cin]; gamma/beta/running_*: bn.* [2*Cout];
@@ -351,6 +349,7 @@ extern "C" int ffc_fu_fwd(const float* x, const float* w, const float* gamma, co
     p.sums = (double*)workspace; p.B = B; p.Cin = Cin; p.Cout = Cout; p.training = training;
     p.eps = eps; p.momentum = momentum;
     ffc_stream_t st = (ffc_stream_t)stream;
+    if (ffc_fu4_supported(Cin, Cout, H, W)) return ffc_fu4_launch(p, workspace_bytes, st);       // warp-private transforms (ffc_fu4.cu)
     switch (H) {
         case 8: return fu2_dispatch<8>(p, st);
         case 16: return fu2_dispatch<16>(p, st);

@@ -15,6 +15,20 @@
 #pragma once
 #include "ffc_fft.cuh"
 
+// parameters of the fused forward kernels (ffc_fu2.cu, ffc_fu4.cu)
+struct Fu2Params {
+    const float* x;          // (B, Cin, N, N)
+    const float* w;          // [2*Cout][2*Cin]
+    const float* gamma; const float* beta;          // [2*Cout]
+    float* running_mean; float* running_var;        // [2*Cout]
+    float* save_mean; float* save_invstd;           // [2*Cout]
+    const float* residual;   // (B, Cout, N, N) or null
+    float* out;              // (B, Cout, N, N)
+    double* sums;            // [4*Cout]: sum(y) then sum(y^2), channel-major (2*Cout each)
+    int B, Cin, Cout, training;
+    float eps, momentum;
+};
+
 template <int N>
 struct Fu2G {
     static constexpr int M = N / 2, Wf = M + 1, RS = N + 4, SPS = RS / 2, BINS = N * Wf;

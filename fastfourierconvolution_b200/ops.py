@@ -586,7 +586,7 @@ class FusedFuFn(torch.autograd.Function):
             ws = _C.workspace(L.ffc_fu3_workspace_bytes(B, Cin, Cout, H, W, int(training)), x.device)
             fwd = L.ffc_fu3_fwd
         else:
-            ws = _C.workspace(4 * Cout * 8, x.device)
+            ws = _C.workspace(L.ffc_fu_workspace_bytes(B, Cout), x.device)
             fwd = L.ffc_fu_fwd
         _C.check(fwd(_C.ptr(x), _C.ptr(weight), _C.ptr(gamma), _C.ptr(beta),
                                      _C.ptr(running_mean), _C.ptr(running_var), _C.ptr(save_mean), _C.ptr(save_invstd),
