@@ -69,6 +69,7 @@ _SIGNATURES = {
     "ffc_debug_conv_reference": (None, [c_int]),
     "ffc_debug_fu_two_pass": (None, [c_int]),
     "ffc_debug_fu4": (None, [c_int]),
+    "ffc_fft2_supported": (c_int, [c_int, c_int]),
     "ffc_fu_workspace_bytes": (c_size_t, [c_int, c_int]),
 }
 _OPTIONAL = set()

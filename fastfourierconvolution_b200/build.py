@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libffc_b200.so")
 # one translation unit per source file, compiled in parallel
-UNITS = [os.path.join(CSRC, f) for f in ("ffc_api.cu", "ffc_fft2.cu", "ffc_conv.cu", "ffc_conv_v4.cu", "ffc_conv_v5.cu", "ffc_wgrad_v5.cu", "ffc_conv_small.cu", "ffc_bnact.cu",
+UNITS = [os.path.join(CSRC, f) for f in ("ffc_api.cu", "ffc_fft2.cu", "ffc_dft2.cu", "ffc_conv.cu", "ffc_conv_v4.cu", "ffc_conv_v5.cu", "ffc_wgrad_v5.cu", "ffc_conv_small.cu", "ffc_bnact.cu",
                                          "ffc_fu_fused.cu", "ffc_fu2.cu", "ffc_fu4.cu", "ffc_fu2_bwd.cu", "ffc_specnorm.cu", "ffc_fu3.cu", "ffc_fu3_mix.cu", "ffc_glue.cu")]
 
 NVCC_FLAGS = [

@@ -198,9 +198,22 @@ static int irfft2_launch(const float* spec, const float* residual, float* out, i
 
 static bool fft2_supported(int H, int W) { return H == W && ffc_is_pow2(H) && H >= 4 && H <= 128; }
 
+// every other plane up to 128x128 (odd, non-square, 48x48 ...): direct DFT kernels (ffc_dft2.cu), natural order along u
+bool ffc_dft2_supported(int H, int W);
+int ffc_dft2_fwd(const float* x, float* spec, int nplanes, int H, int W, int colscale, ffc_stream_t st);
+int ffc_dft2_inv(const float* spec, const float* residual, float* out, int nplanes, int H, int W, int colscale,
+                 const float* mean, const float* invstd, const float* gamma, const float* beta, int cout, ffc_stream_t st);
+
+// 2: tuned power-of-two kernels, 1: direct DFT kernels, 0: unsupported
+extern "C" int ffc_fft2_supported(int H, int W) { return fft2_supported(H, W) ? 2 : (ffc_dft2_supported(H, W) ? 1 : 0); }
+
 extern "C" int ffc_rfft2(const float* x, float* spec, int nplanes, int H, int W, int colscale, void* stream) {
     FFC_REQUIRE(x && spec, "ffc_rfft2: null pointer");
-    FFC_REQUIRE(fft2_supported(H, W), "ffc_rfft2: unsupported plane %dx%d (square powers of two 4..128 only)", H, W);
+    FFC_REQUIRE(nplanes >= 0, "ffc_rfft2: negative plane count");
+    if (!fft2_supported(H, W)) {
+        FFC_REQUIRE(ffc_dft2_supported(H, W), "ffc_rfft2: unsupported plane %dx%d (1..128 in both dimensions)", H, W);
+        return nplanes == 0 ? FFC_OK : ffc_dft2_fwd(x, spec, nplanes, H, W, colscale, (ffc_stream_t)stream);
+    }
     FFC_REQUIRE(((uintptr_t)x & 15) == 0, "ffc_rfft2: x must be 16-byte aligned");
     FFC_REQUIRE(nplanes >= 0, "ffc_rfft2: negative plane count");
     if (nplanes == 0) return FFC_OK;
@@ -218,7 +231,11 @@ extern "C" int ffc_rfft2(const float* x, float* spec, int nplanes, int H, int W,
 extern "C" int ffc_irfft2(const float* spec, const float* residual, float* out, int nplanes, int H, int W,
                           int colscale, void* stream) {
     FFC_REQUIRE(spec && out, "ffc_irfft2: null pointer");
-    FFC_REQUIRE(fft2_supported(H, W), "ffc_irfft2: unsupported plane %dx%d (square powers of two 4..128 only)", H, W);
+    FFC_REQUIRE(nplanes >= 0, "ffc_irfft2: negative plane count");
+    if (!fft2_supported(H, W)) {
+        FFC_REQUIRE(ffc_dft2_supported(H, W), "ffc_irfft2: unsupported plane %dx%d (1..128 in both dimensions)", H, W);
+        return nplanes == 0 ? FFC_OK : ffc_dft2_inv(spec, residual, out, nplanes, H, W, colscale, nullptr, nullptr, nullptr, nullptr, 1, (ffc_stream_t)stream);
+    }
     FFC_REQUIRE(((uintptr_t)out & 15) == 0 && ((uintptr_t)residual & 15) == 0, "ffc_irfft2: out/residual must be 16-byte aligned");
     FFC_REQUIRE(nplanes >= 0, "ffc_irfft2: negative plane count");
     if (nplanes == 0) return FFC_OK;
@@ -240,7 +257,11 @@ extern "C" int ffc_irfft2(const float* spec, const float* residual, float* out, 
 extern "C" int ffc_irfft2_bn_relu(const float* spec, const float* residual, float* out, int nplanes, int cout, int H, int W,
                                   const float* mean, const float* invstd, const float* gamma, const float* beta, void* stream) {
     FFC_REQUIRE(spec && out && mean && invstd && gamma && beta, "ffc_irfft2_bn_relu: null pointer");
-    FFC_REQUIRE(fft2_supported(H, W), "ffc_irfft2_bn_relu: unsupported plane %dx%d (square powers of two 4..128 only)", H, W);
+    if (!fft2_supported(H, W)) {
+        FFC_REQUIRE(ffc_dft2_supported(H, W), "ffc_irfft2_bn_relu: unsupported plane %dx%d (1..128 in both dimensions)", H, W);
+        FFC_REQUIRE(nplanes >= 0 && cout > 0 && nplanes % cout == 0, "ffc_irfft2_bn_relu: plane count must be a multiple of cout");
+        return nplanes == 0 ? FFC_OK : ffc_dft2_inv(spec, residual, out, nplanes, H, W, 0, mean, invstd, gamma, beta, cout, (ffc_stream_t)stream);
+    }
     FFC_REQUIRE(((uintptr_t)out & 15) == 0 && ((uintptr_t)residual & 15) == 0, "ffc_irfft2_bn_relu: out/residual must be 16-byte aligned");
     FFC_REQUIRE(nplanes >= 0 && cout > 0 && nplanes % cout == 0, "ffc_irfft2_bn_relu: plane count must be a multiple of cout");
     if (nplanes == 0) return FFC_OK;

@@ -5,7 +5,9 @@ buffers so ``state_dict`` / ``apply(weights_init)`` / optimizers see the referen
 ``forward(x, y=None)``.  The forward runs hand-written sm_100a kernels: a fused shared-memory
 rfft2 -> channel mix -> BatchNorm + ReLU -> irfft2 kernel where one image's spectrum fits in a
 CTA's shared memory, otherwise the general form rfft2 | 1x1 mix | BN statistics | (BN+ReLU)->irfft2 with the
-spectrum staged through L2 in the reference's (B, 2C, H, W/2+1) channel layout (no layout copies).
+spectrum staged through L2 in the reference's (B, 2C, H, W/2+1) channel layout (no layout copies).  Planes that are
+not a square power of two (odd, non-square, the 48x48 of the mg = 6 scripts) take the general form on direct-DFT
+plane kernels (csrc/ffc_dft2.cu), any H, W up to 128 -- the reference accepts every size, and so does this class.
 """
 from __future__ import annotations
 
@@ -53,17 +55,18 @@ class FourierUnitSN(nn.Module):
         if x.dim() != 4:
             raise ValueError("FourierUnitSN expects (B, C, H, W)")
         h, w = x.shape[-2:]
-        if h != w or h & (h - 1) or not 4 <= h <= 128:
-            raise NotImplementedError(f"FourierUnitSN: only square power-of-two planes 4..128 are supported, got {h}x{w}")
+        kind = ops.fft2_supported(h, w)       # 2: tuned power-of-two planes (every BASELINE config), 1: any plane up to 128x128
+        if not kind:
+            raise NotImplementedError(f"FourierUnitSN: planes up to 128x128 are supported, got {h}x{w}")
         weight = _util.effective_weight(self.conv_layer)
         bn = self.bn
         cin, cout = x.shape[1], weight.shape[0] // 2
         plain_bn = bn.affine and bn.track_running_stats and bn.momentum is not None
-        single = plain_bn and self.fused in (True, "single") and ops.fu_fused_supported(x.shape[0], cin, cout, h, w)
+        single = kind == 2 and plain_bn and self.fused in (True, "single") and ops.fu_fused_supported(x.shape[0], cin, cout, h, w)
         if single and self.fused is True and _prefers_staged(max(cin, cout), h, torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad)) \
                 and ops.fu_staged_supported(x.shape[0], cin, cout, h, w):
             single = False
-        staged = plain_bn and self.fused and not single and ops.fu_staged_supported(x.shape[0], cin, cout, h, w)
+        staged = kind == 2 and plain_bn and self.fused and not single and ops.fu_staged_supported(x.shape[0], cin, cout, h, w)
         if single or staged:
             if bn.training:
                 bn.num_batches_tracked.add_(1)
@@ -75,6 +78,6 @@ class FourierUnitSN(nn.Module):
             if bn.training:
                 bn.num_batches_tracked.add_(1)
             return ops.bn_relu_irfft2(mixed, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual,
-                                      bn.training, bn.eps, bn.momentum)
+                                      bn.training, bn.eps, bn.momentum, width=w)
         act = _util.bn_act(mixed, self.bn, (ops.ACT_RELU, 0.0))        # :49
-        return ops.irfft2(act, residual)                               # :51-56
+        return ops.irfft2(act, residual, width=w)                      # :51-56

@@ -437,9 +437,11 @@ def _rfft2(x, colscale):
     return spec
 
 
-def _irfft2(spec, residual, colscale):
+def _irfft2(spec, residual, colscale, width=None):
     B, C2, H, Wf = spec.shape
-    W = 2 * (Wf - 1)
+    W = 2 * (Wf - 1) if width is None else int(width)          # an odd width cannot be told from the spectrum (irfftn's s=)
+    if W // 2 + 1 != Wf:
+        raise ValueError(f"irfft2: width {W} does not match a spectrum of {Wf} columns")
     out = torch.empty((B, C2 // 2, H, W), device=spec.device, dtype=torch.float32)
     _C.check(_C.lib().ffc_irfft2(_C.ptr(spec), _C.ptr(residual), _C.ptr(out), B * (C2 // 2), H, W, colscale,
                                  _C.current_stream(spec.device)))
@@ -452,29 +454,30 @@ class Rfft2Fn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
         _C.require_device(x)
+        ctx.width = x.shape[-1]
         return _rfft2(x.contiguous(), 0)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dspec):
-        return _irfft2(dspec.contiguous(), None, 1)
+        return _irfft2(dspec.contiguous(), None, 1, ctx.width)
 
 
 class Irfft2Fn(torch.autograd.Function):
     """channels -> complex + irfftn(s=(H,W), norm='ortho') [+ residual] (fourier_unity.py:51-56)."""
 
     @staticmethod
-    def forward(ctx, spec, residual):
+    def forward(ctx, spec, residual, width=None):
         _C.require_device(spec, residual)
         ctx.has_res = residual is not None
-        return _irfft2(spec.contiguous(), _c(residual), 0)
+        return _irfft2(spec.contiguous(), _c(residual), 0, width)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dout):
         dout = dout.contiguous()
         dspec = _rfft2(dout, 1) if ctx.needs_input_grad[0] else None
-        return dspec, (dout if ctx.has_res and ctx.needs_input_grad[1] else None)
+        return dspec, (dout if ctx.has_res and ctx.needs_input_grad[1] else None), None
 
 
 class BnReluIrfft2Fn(torch.autograd.Function):
@@ -483,11 +486,13 @@ class BnReluIrfft2Fn(torch.autograd.Function):
     written.  Backward: adjoint transform of dout, then the ordinary BN + ReLU backward on the saved spectrum."""
 
     @staticmethod
-    def forward(ctx, spec, gamma, beta, running_mean, running_var, residual, training, eps, momentum):
+    def forward(ctx, spec, gamma, beta, running_mean, running_var, residual, training, eps, momentum, width=None):
         _C.require_device(spec, gamma, beta, running_mean, running_var, residual)
         spec, residual = spec.contiguous(), _c(residual)
         B, C2, H, Wf = spec.shape
-        W = 2 * (Wf - 1)
+        W = 2 * (Wf - 1) if width is None else int(width)
+        if W // 2 + 1 != Wf:
+            raise ValueError(f"bn_relu_irfft2: width {W} does not match a spectrum of {Wf} columns")
         if not training and (running_mean is None or running_var is None):
             raise ValueError("BatchNorm in eval mode needs running statistics")
         L = _C.lib()
@@ -519,19 +524,24 @@ class BnReluIrfft2Fn(torch.autograd.Function):
                                          _C.ptr(save_mean), _C.ptr(save_invstd), _C.ptr(dgamma), _C.ptr(dbeta),
                                          B, C2, H * Wf, 1, int(training), ACT_RELU, 0.0,
                                          _C.ptr(ws), ws.numel(), _C.current_stream(spec.device)))
-        return dspec, dgamma, dbeta, None, None, (dout if has_res and ctx.needs_input_grad[5] else None), None, None, None
+        return dspec, dgamma, dbeta, None, None, (dout if has_res and ctx.needs_input_grad[5] else None), None, None, None, None
 
 
-def bn_relu_irfft2(spec, gamma, beta, running_mean, running_var, residual, training, eps, momentum):
-    return BnReluIrfft2Fn.apply(spec, gamma, beta, running_mean, running_var, residual, training, eps, momentum)
+def bn_relu_irfft2(spec, gamma, beta, running_mean, running_var, residual, training, eps, momentum, width=None):
+    return BnReluIrfft2Fn.apply(spec, gamma, beta, running_mean, running_var, residual, training, eps, momentum, width)
 
 
 def rfft2(x):
     return Rfft2Fn.apply(x)
 
 
-def irfft2(spec, residual=None):
-    return Irfft2Fn.apply(spec, residual)
+def irfft2(spec, residual=None, width=None):
+    return Irfft2Fn.apply(spec, residual, width)
+
+
+def fft2_supported(H, W) -> int:
+    """2: tuned power-of-two plane kernels, 1: direct DFT kernels (any H, W up to 128), 0: unsupported."""
+    return int(_C.lib().ffc_fft2_supported(int(H), int(W)))
 
 
 # ---------------------------------------------------------------------------------------------

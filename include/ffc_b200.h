@@ -62,7 +62,11 @@ size_t ffc_workspace_bytes(int batch, int max_channels);
  *            cuFFT/pocketfft C2R do.  out = residual + irfft2(spec) when residual != NULL
  *            (the x + fu(x) of spectral_transform.py:108).
  *   colscale = 1 pre-multiplies columns 0 < v < W/2 by 1/2: the adjoint of ffc_rfft2.
- * Supported planes: H == W in {4,8,16,32,64,128}. */
+ * Supported planes: H == W in {4,8,16,32,64,128} on the tuned kernels (16-byte aligned x / out / residual); every other
+ * H, W in 1..128 (odd, non-square, 48x48 of the mg = 6 scripts, fgan_cond_complete.py:325 -- torch.fft accepts any size)
+ * on direct-DFT plane kernels (csrc/ffc_dft2.cu), natural order along u, "interior" columns = those a C2R counts twice
+ * (0 < v, 2v != W).  ffc_fft2_supported: 2 = tuned, 1 = direct DFT, 0 = unsupported. */
+int ffc_fft2_supported(int H, int W);
 int ffc_rfft2(const float* x, float* spec, int nplanes, int H, int W, int colscale, void* stream);
 int ffc_irfft2(const float* spec, const float* residual, float* out, int nplanes, int H, int W,
                int colscale, void* stream);
@@ -79,6 +83,10 @@ int ffc_irfft2(const float* spec, const float* residual, float* out, int nplanes
  * ffc_fu_fused_supported returns 1 for shapes this entry point handles (H == W in {4,8,16,32},
  * Cin, Cout <= 32 and the tile fits in shared memory); other shapes use the general form above. */
 int ffc_fu_fused_supported(int B, int Cin, int Cout, int H, int W);
+/* Workspace ffc_fu_fwd makes the best use of (the minimum stays 4*Cout doubles): with room for one float per (sum, image)
+ * the training kernel of the 32x32 / <= 8 channel unit (csrc/ffc_fu4.cu) meets its batch statistics through per-CTA partial
+ * sums -- no zeroing launch, no atomics, bitwise reproducible. */
+size_t ffc_fu_workspace_bytes(int B, int Cout);
 int ffc_fu_fwd(const float* x, const float* w, const float* gamma, const float* beta,
                float* running_mean, float* running_var, float* save_mean, float* save_invstd,
                const float* residual, float* out,

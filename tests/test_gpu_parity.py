@@ -421,3 +421,43 @@ def test_spectral_norm_weight_dim1_matches_torch_hook(shape, training):
     from test_layers_emu import spectral_norm_errs
     errs = spectral_norm_errs(DEV, shape, training, transposed=True)
     assert max(errs.values()) < 1e-5, errs
+
+
+def _any_size_cases():
+    from test_layers_emu import ANY_SIZE_CASES
+    return ANY_SIZE_CASES + [(32, 16, 16, 48, 48), (8, 8, 8, 96, 96), (4, 8, 8, 33, 65)]
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W", _any_size_cases())
+@pytest.mark.parametrize("train", [True, False])
+def test_fourier_unit_any_plane_size(B, Cin, Cout, H, W, train):
+    """Planes that are not a square power of two (odd, non-square, 48x48 of the mg = 6 scripts) on the direct-DFT kernels
+    (csrc/ffc_dft2.cu) against the float64 oracle: output 1e-5 in the max norm, gradients in the relative L2 norm."""
+    from test_layers_emu import any_size_fu_errs
+    errs = any_size_fu_errs("cuda:0", B, Cin, Cout, H, W, train)
+    assert errs["out"] < 1e-5 and errs["running_var"] < 1e-5, errs
+    assert max(errs["dx"], errs["dW"], errs["dgamma"], errs["dbeta"]) < 2e-3, errs
+
+
+def test_fu_fwd_partial_statistics_are_deterministic():
+    """The training kernel of the 32x32 / 8-channel unit (csrc/ffc_fu4.cu) with a workspace of ffc_fu_workspace_bytes meets
+    its batch statistics through per-CTA partial sums: two runs are bitwise identical, and equal (to rounding) to the
+    atomic path a minimal workspace selects and to the phase kernel of csrc/ffc_fu2.cu."""
+    torch.manual_seed(5)
+    dev = "cuda:0"
+    B, C = 200, 8
+    m = ffc.FourierUnitSN(C, C).to(dev).train()
+    m.fused = "single"
+    x = torch.randn(B, C, 32, 32, device=dev)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    outs = []
+    with torch.no_grad():
+        for variant in ("fu4", "fu4", "fu2"):
+            m.load_state_dict(sd)
+            _C.lib().ffc_debug_fu4(1 if variant == "fu4" else 0)
+            try:
+                outs.append((m(x).clone(), m.bn.running_var.clone()))
+            finally:
+                _C.lib().ffc_debug_fu4(1)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert parity.relerr(outs[0][0], outs[2][0]) < 2e-6 and parity.relerr(outs[0][1], outs[2][1]) < 1e-6

@@ -280,6 +280,55 @@ def test_fourier_unit_sweep_shapes_general_form(B, C, N, emu):
     assert parity.relerr(m.bn.running_var, P["bn.running_var"]) < 1e-5
 
 
+def any_size_fu_errs(dev, B, Cin, Cout, H, W, train):
+    """FourierUnitSN on a plane that is not a square power of two (direct-DFT plane kernels, csrc/ffc_dft2.cu), forward and
+    backward against the float64 oracle; the reference accepts every size ('works for odd H/W')."""
+    torch.manual_seed(H * 131 + W)
+    m = ffc.FourierUnitSN(Cin, Cout).train(train)
+    with torch.no_grad():
+        m.bn.weight.uniform_(0.5, 1.5); m.bn.bias.normal_(0, 0.2)
+        m.bn.running_mean.uniform_(-0.2, 0.2); m.bn.running_var.uniform_(0.5, 1.5)
+    P = {k: (v.double().clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else
+             (v.double().clone() if v.is_floating_point() else v.clone())) for k, v in m.state_dict().items()}
+    x = torch.randn(B, Cin, H, W)
+    xr = x.double().requires_grad_(True)
+    ref = R.fourier_unit(xr, P, "", train)
+    cot = torch.randn(ref.shape, dtype=torch.float64)
+    (ref * cot).sum().backward()
+    m = m.to(dev)
+    xo = x.to(dev).requires_grad_(True)
+    out = m(xo)
+    (out * cot.float().to(dev)).sum().backward()
+
+    def l2(a, b):
+        return ((a.detach().double().cpu() - b.detach().double()).norm() / b.detach().double().norm()).item()
+    return {"out": parity.relerr(out.cpu(), ref.detach()), "dx": l2(xo.grad, xr.grad),
+            "dW": l2(m.conv_layer.weight.grad, P["conv_layer.weight"].grad),
+            "dgamma": l2(m.bn.weight.grad, P["bn.weight"].grad), "dbeta": l2(m.bn.bias.grad, P["bn.bias"].grad),
+            "running_var": parity.relerr(m.bn.running_var.cpu(), P["bn.running_var"])}
+
+
+ANY_SIZE_CASES = [(2, 4, 6, 8, 8), (2, 4, 4, 7, 9), (2, 3, 3, 12, 12), (1, 2, 2, 48, 48), (2, 2, 2, 5, 16), (1, 2, 3, 24, 6), (2, 2, 2, 1, 3)]
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W", ANY_SIZE_CASES)
+@pytest.mark.parametrize("train", [True, False])
+def test_fourier_unit_any_plane_size(B, Cin, Cout, H, W, train, emu):
+    errs = any_size_fu_errs("cpu", B, Cin, Cout, H, W, train)
+    assert errs["out"] < 1e-5 and errs["running_var"] < 1e-5, errs
+    assert max(errs["dx"], errs["dW"], errs["dgamma"], errs["dbeta"]) < 1e-3, errs      # relative L2 (ReLU kinks, see above)
+
+
+def test_spectral_transform_non_power_of_two_plane(emu):
+    """SpectralTransform at 12x12 (mg = 6 scale of fgan_cond_complete.py:325) against the oracle."""
+    torch.manual_seed(3)
+    m = ffc.SpectralTransform(8, 8, stride=1).train()
+    P = {k: (v.double().clone() if v.is_floating_point() else v.clone()) for k, v in m.state_dict().items()}
+    x = torch.randn(2, 8, 12, 12)
+    ref = R.spectral_transform(x.double(), P, "", 1, False, True)
+    assert parity.relerr(m(x), ref) < 1e-5
+
+
 @pytest.mark.parametrize("B,C,N,chunk", [(3, 6, 64, 0), (5, 4, 32, 3 * 4 * 32 * 36 * 4), (2, 40, 16, 0), (1, 4, 128, 0)])
 @pytest.mark.parametrize("train", [True, False])
 def test_fourier_unit_l2_staged_form(B, C, N, chunk, train, emu):
