@@ -224,10 +224,35 @@ static int ffc_launch_coop(int gx, int nt, size_t smem_bytes, ffc_stream_t strea
     ffc_count_launch();
     return FFC_OK;
 }
+// Zero fill as a KERNEL node.  Inside a captured CUDA graph a cudaMemsetAsync node in front of a kernel cost ~5 us of
+// dependency latency on B200 (measured on the fused Fourier unit: memset + cooperative kernel vs the kernel alone,
+// profiles/r04e_fu4_ab.jsonl), a kernel -> kernel edge ~1 us; the library zeroes ~100 small buffers per training step.
+static __global__ void ffc_zero_kernel(uint4* p16, size_t n16, unsigned char* tail, size_t ntail) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) p16[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ntail; i += stride) tail[i] = 0;
+}
 static inline int ffc_memset_async(void* p, int v, size_t n, ffc_stream_t s) {
     if (n == 0) return FFC_OK;
-    cudaError_t e = cudaMemsetAsync(p, v, n, s);
-    if (e != cudaSuccess) { ffc_set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
+    if (v != 0) {
+        cudaError_t e = cudaMemsetAsync(p, v, n, s);
+        if (e != cudaSuccess) { ffc_set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
+        return FFC_OK;
+    }
+    unsigned char* b = static_cast<unsigned char*>(p);
+    size_t head = (16 - ((uintptr_t)b & 15)) & 15;          // bytes up to the first 16-byte boundary
+    if (head > n) head = n;
+    const size_t n16 = (n - head) / 16, ntail = (n - head) % 16;
+    if (head) {                                             // unaligned start: rare, zero it through the tail path of a first launch
+        ffc_zero_kernel<<<1, 32, 0, s>>>(nullptr, 0, b, head);
+    }
+    size_t blocks = (n16 + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    const size_t cap = (size_t)8 * ffc_sm_count();
+    if (blocks > cap) blocks = cap;
+    ffc_zero_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<uint4*>(b + head), n16, b + head + n16 * 16, ntail);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { ffc_set_error("zero-fill launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
     return FFC_OK;
 }
 #endif

@@ -489,9 +489,8 @@ int conv_v5_run_block(const float* x0, const float* w0, const float* w0b, int ci
     if (act_after) p.slope = 1.f;
     if (ksplit > 1) {
         const size_t HWo = (size_t)Ho * Wo;
-        e = cudaMemsetAsync(y, 0, (size_t)B * cout0 * HWo * sizeof(float), st);
-        if (e == cudaSuccess && y1) e = cudaMemsetAsync(y1, 0, (size_t)B * (cout - cout0) * HWo * sizeof(float), st);
-        if (e != cudaSuccess) { ffc_set_error("conv_v5 memset: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
+        FFC_CHECK(ffc_memset_async(y, 0, (size_t)B * cout0 * HWo * sizeof(float), st));
+        if (y1) FFC_CHECK(ffc_memset_async(y1, 0, (size_t)B * (cout - cout0) * HWo * sizeof(float), st));
     }
     const dim3 grid(ffc_cdiv(Mc, 128), pl.ntiles, s * s * ksplit);
     if (four_wg) conv_v5_kernel<4><<<grid, 4 * 128 + 64, smem, st>>>(p);

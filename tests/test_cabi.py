@@ -43,8 +43,9 @@ def test_bad_arguments_return_error_codes_not_crashes():
     L = _C.Library(_C.LIB_PATH)
     buf = (ctypes.c_float * 64)()
     p = ctypes.cast(buf, ctypes.c_void_p)
-    assert L.ffc_rfft2(p, p, 1, 6, 6, 0, None) == 1           # 6x6 is not a supported plane
+    assert L.ffc_rfft2(p, p, 1, 6, 200, 0, None) == 1         # planes beyond 128 are not supported (6x6 is, on the direct-DFT kernels)
     assert b"unsupported plane" in L.ffc_last_error()
+    assert L.ffc_fft2_supported(6, 6) == 1 and L.ffc_fft2_supported(32, 32) == 2 and L.ffc_fft2_supported(6, 200) == 0
     assert L.ffc_rfft2(None, p, 1, 8, 8, 0, None) == 1
     assert L.ffc_conv2d_fwd(p, p, 4, None, None, 0, None, None, p, 1, 4, 8, 8, 9, 9, 3, 1, 1, 0, None) == 1
     assert L.ffc_bn_act_fwd(p, p, p, p, None, None, p, p, 1, 4, 16, 1, 1, 1e-5, 0.1, 3, 0.1, None, 0, None) == 1
