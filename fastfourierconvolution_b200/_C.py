@@ -71,6 +71,7 @@ _SIGNATURES = {
     "ffc_debug_fu4": (None, [c_int]),
     "ffc_fft2_supported": (c_int, [c_int, c_int]),
     "ffc_fu_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "ffc_fu_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
 }
 _OPTIONAL = set()
 

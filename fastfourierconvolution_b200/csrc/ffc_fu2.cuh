@@ -29,6 +29,20 @@ struct Fu2Params {
     float eps, momentum;
 };
 
+// parameters of the fused backward kernels (ffc_fu2_bwd.cu, ffc_fu4.cu)
+struct Fu2BwdParams {
+    const float* x;          // (B, Cin, N, N)
+    const float* dout;       // (B, Cout, N, N)
+    const float* w;          // [2*Cout][2*Cin]
+    const float* gamma; const float* beta;              // [2*Cout]
+    const float* save_mean; const float* save_invstd;   // [2*Cout]
+    float* dx;               // (B, Cin, N, N)
+    float* dw;               // [2*Cout][2*Cin], accumulated with atomics (zeroed by the host wrapper)
+    float* dgamma; float* dbeta;                         // [2*Cout]
+    double* sums;            // [4*Cout]: sum(dZ) then sum(dZ*y^) (zeroed by the host wrapper)
+    int B, Cin, Cout, training;
+};
+
 template <int N>
 struct Fu2G {
     static constexpr int M = N / 2, Wf = M + 1, RS = N + 4, SPS = RS / 2, BINS = N * Wf;

@@ -13,18 +13,6 @@
 // factors ride in the weights, in the reduction epilogues and in the final row scale.
 #include "ffc_fu2.cuh"
 
-struct Fu2BwdParams {
-    const float* x;          // (B, Cin, N, N)
-    const float* dout;       // (B, Cout, N, N)
-    const float* w;          // [2*Cout][2*Cin]
-    const float* gamma; const float* beta;              // [2*Cout]
-    const float* save_mean; const float* save_invstd;   // [2*Cout]
-    float* dx;               // (B, Cin, N, N)
-    float* dw;               // [2*Cout][2*Cin], accumulated with atomics (zeroed by the host wrapper)
-    float* dgamma; float* dbeta;                         // [2*Cout]
-    double* sums;            // [4*Cout]: sum(dZ) then sum(dZ*y^) (zeroed by the host wrapper)
-    int B, Cin, Cout, training;
-};
 
 template <int N, int CP>
 struct Fu2Bwd {
@@ -301,6 +289,10 @@ static int fu2_bwd_entry(const Fu2BwdParams& p, int H, ffc_stream_t st, bool que
     }
 }
 
+// 32x32 planes with up to 8 channels: the warp-private backward of ffc_fu4.cu (device build, workspace of ffc_fu_bwd_workspace_bytes)
+bool ffc_fu4_bwd_supported(int B, int Cin, int Cout, int H, int W, size_t workspace_bytes);
+int ffc_fu4_bwd_launch(const Fu2BwdParams& p, ffc_stream_t st);
+
 // 1 when ffc_fu_bwd handles the shape on the current device: H == W in {8,16,32}, Cin, Cout <= 32, and all B images
 // co-resident (one CTA each) so that the two BatchNorm sums can cross a grid barrier; otherwise callers use the
 // general form (ffc_rfft2 | ffc_conv2d_* | ffc_bn_act_bwd | ffc_irfft2).
@@ -334,5 +326,6 @@ extern "C" int ffc_fu_bwd(const float* x, const float* dout, const float* w, con
         FFC_CHECK(ffc_memset_async(dgamma, 0, (size_t)2 * Cout * sizeof(float), st));
         return ffc_memset_async(dbeta, 0, (size_t)2 * Cout * sizeof(float), st);
     }
+    if (ffc_fu4_bwd_supported(B, Cin, Cout, H, W, workspace_bytes)) return ffc_fu4_bwd_launch(p, st);
     return fu2_bwd_entry(p, H, st, false);
 }

@@ -59,9 +59,14 @@ __device__ __forceinline__ float2 lane_fft_inv(float2 m, const float2* tws, int 
     return m;
 }
 
-// rfft2 (unnormalised) of one 32x32 plane inside one warp; S[0..15] = bins (u = 16*(lane>>4) + k, v = lane & 15),
-// S[16] = bin (u = bitrev5(lane), v = 16).  pb: the warp's tile.
-__device__ __forceinline__ void fwd_plane(const float* __restrict__ src, float* pb, int lane, const float2* tws, float2* S) {
+// rfft2 (unnormalised, times 2) of one 32x32 plane inside one warp.  A lane ends with 17 bins: S[0..15] = bins
+// (u = 16*(lane>>4) + k, v = lane & 15), S[16] = bin (u = bitrev5(lane), v = 16); they are published straight into the warp's
+// tile pb as the exchange image of the plane -- float4 slots [k/2][lane] for the 16 column bins, float2 slots [16][lane] for
+// the Nyquist bin -- so nothing of the plane stays in registers.
+// ADJ: the adjoint of the c2r transform (interior bins count twice; used on the incoming gradient by the backward kernel):
+// the same pass without the doubling of the DC and Nyquist bins, and without the overall factor 2.
+template <bool ADJ>
+__device__ __forceinline__ void fwd_plane(const float* __restrict__ src, float* pb, int lane, const float2* tws) {
     {
         const float4* s4 = reinterpret_cast<const float4*>(src);
         float4 v[8];
@@ -81,10 +86,9 @@ __device__ __forceinline__ void fwd_plane(const float* __restrict__ src, float* 
             z[2 * q + 1] = make_float2(a.z, a.w);
         }
         ffc_fft_regs<M, -1>(z);
-        float2 out[M];
-        // twice the bins (the 1/2 of the even/odd split is folded into the mix weights)
-        out[0] = make_float2(2.0f * (z[0].x + z[0].y), 0.f);
-        ny = 2.0f * (z[0].x - z[0].y);
+        // twice the bins (the 1/2 of the even/odd split is folded into the mix weights), in place over z
+        ny = (ADJ ? 1.0f : 2.0f) * (z[0].x - z[0].y);
+        z[0] = make_float2((ADJ ? 1.0f : 2.0f) * (z[0].x + z[0].y), 0.f);
 #pragma unroll
         for (int k = 1; k <= M / 2; ++k) {
             const float2 a = z[k], b = make_float2(z[M - k].x, -z[M - k].y);
@@ -93,13 +97,13 @@ __device__ __forceinline__ void fwd_plane(const float* __restrict__ src, float* 
             const float2 o = make_float2(dd.y, -dd.x);
             const float2 w = fu2_twc<N>(k);
             const float2 t = make_float2(o.x * w.x + o.y * w.y, o.y * w.x - o.x * w.y);
-            out[k] = make_float2(e.x + t.x, e.y + t.y);
-            if (k != M - k) out[M - k] = make_float2(e.x - t.x, t.y - e.y);
+            z[k] = make_float2(e.x + t.x, e.y + t.y);
+            if (k != M - k) z[M - k] = make_float2(e.x - t.x, t.y - e.y);
         }
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(pb + lane * RSF + 4 * q) = make_float4(out[2 * q].x, out[2 * q].y, out[2 * q + 1].x, out[2 * q + 1].y);
+            *reinterpret_cast<float4*>(pb + lane * RSF + 4 * q) = make_float4(z[2 * q].x, z[2 * q].y, z[2 * q + 1].x, z[2 * q + 1].y);
     }
     __syncwarp();
     const int v = lane & 15, h = lane >> 4;
@@ -109,18 +113,23 @@ __device__ __forceinline__ void fwd_plane(const float* __restrict__ src, float* 
 #pragma unroll
     for (int j = 0; j < M; ++j) a[j] = pb2[(2 * j + h) * (RSF / 2) + v];
     ffc_fft_regs<M, -1>(a);
+    __syncwarp();            // every lane has its column: the tile is free for the exchange image
+    float4* ex4 = reinterpret_cast<float4*>(pb);
 #pragma unroll
-    for (int k = 0; k < M; ++k) {
-        float2 m = a[k];
-        if (k != 0 && h) m = ffc_cmul_tw<-1>(m, fu2_twc<N>(k));       // the odd half sends w^k * O[k] (predicated)
-        const float2 r = shfl_xor2(m, 16);
-        S[k] = ffc_fma2(m, sg2, r);                                   // h = 0: E + w^k O;  h = 1: E - w^k O
+    for (int k = 0; k < M; k += 2) {
+        float2 m0 = a[k], m1 = a[k + 1];
+        if (k != 0 && h) m0 = ffc_cmul_tw<-1>(m0, fu2_twc<N>(k));     // the odd half sends w^k * O[k] (predicated)
+        if (h) m1 = ffc_cmul_tw<-1>(m1, fu2_twc<N>(k + 1));
+        const float2 r0 = shfl_xor2(m0, 16), r1 = shfl_xor2(m1, 16);
+        const float2 s0 = ffc_fma2(m0, sg2, r0), s1 = ffc_fma2(m1, sg2, r1);      // h = 0: E + w^k O;  h = 1: E - w^k O
+        ex4[(k / 2) * 32 + lane] = make_float4(s0.x, s0.y, s1.x, s1.y);
     }
-    S[M] = lane_fft_fwd(make_float2(ny, 0.f), tws, lane);
-    __syncwarp();            // the tile is free again (the caller overwrites it with the exchange image)
+    reinterpret_cast<float2*>(pb)[M * 32 + lane] = lane_fft_fwd(make_float2(ny, 0.f), tws, lane);
 }
 
-// irfft2 (unnormalised, torch c2r semantics) of the plane whose bins Y[17] sit in the layout of fwd_plane -> dst (+ res)
+// irfft2 (unnormalised, torch c2r semantics) of the plane whose bins Y[17] sit in the layout of fwd_plane -> dst (+ res).
+// ADJ: twice the adjoint of the r2c transform (interior bins count half): the same pass with the DC and Nyquist bins doubled.
+template <bool ADJ>
 __device__ __forceinline__ void inv_plane(const float2* Y, float* pb, int lane, const float2* tws,
                                           const float* __restrict__ res, float* __restrict__ dst) {
     const int v = lane & 15, h = lane >> 4;
@@ -150,7 +159,7 @@ __device__ __forceinline__ void inv_plane(const float2* Y, float* pb, int lane, 
             x[2 * q] = make_float2(a.x, a.y);
             x[2 * q + 1] = make_float2(a.z, a.w);
         }
-        z[0] = make_float2(x[0].x + xM, x[0].x - xM);
+        z[0] = make_float2((ADJ ? 2.0f : 1.0f) * (x[0].x + xM), (ADJ ? 2.0f : 1.0f) * (x[0].x - xM));
 #pragma unroll
         for (int k = 1; k <= M / 2; ++k) {
             const float2 p = x[k], q = make_float2(x[M - k].x, -x[M - k].y);
@@ -182,6 +191,61 @@ __device__ __forceinline__ void inv_plane(const float2* Y, float* pb, int lane, 
         d4[j * 32 + lane] = o;
     }
     __syncwarp();
+}
+
+// Channel mix of the NW exchange images at `tiles` (one per warp, PBF floats apart) for this lane's 17 bins, in two halves so
+// that only 2 x 9 accumulator pairs are live at a time.  wq = (W[2o][2c], W[2o+1][2c+1], W[2o+1][2c], W[2o][2c+1]) * scale.
+// TRANSPOSED = false: Y_o = sum_c W[o][c] S_c with o = warp;  true: dS_c = sum_o W[o][c]^T dY_o with c = warp.
+template <bool TRANSPOSED>
+__device__ __forceinline__ void mix17(const float* tiles, const float4* wq_s, int warp, int lane, float2* Y) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        float2 pa[9], pq[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) pa[i] = pq[i] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < NW; ++c) {
+            const float4* xc4 = reinterpret_cast<const float4*>(tiles + c * PBF) + lane;
+            const float4 q = TRANSPOSED ? wq_s[c * NW + warp] : wq_s[warp * NW + c];
+            const float2 wa = TRANSPOSED ? make_float2(q.x, q.z) : make_float2(q.x, q.y);
+            const float2 wb = TRANSPOSED ? make_float2(q.w, q.y) : make_float2(q.z, q.w);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 s = xc4[(4 * half + i) * 32];
+                pa[2 * i] = ffc_fma2(wa, make_float2(s.x, s.y), pa[2 * i]);
+                pq[2 * i] = ffc_fma2(wb, make_float2(s.x, s.y), pq[2 * i]);
+                pa[2 * i + 1] = ffc_fma2(wa, make_float2(s.z, s.w), pa[2 * i + 1]);
+                pq[2 * i + 1] = ffc_fma2(wb, make_float2(s.z, s.w), pq[2 * i + 1]);
+            }
+            if (half == 1) {
+                const float2 sl = reinterpret_cast<const float2*>(tiles + c * PBF)[M * 32 + lane];
+                pa[8] = ffc_fma2(wa, sl, pa[8]);
+                pq[8] = ffc_fma2(wb, sl, pq[8]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < (half == 0 ? 8 : 9); ++i)
+            Y[8 * half + i] = TRANSPOSED ? make_float2(pa[i].x + pa[i].y, pq[i].x + pq[i].y)
+                                         : make_float2(pa[i].x + pq[i].y, pq[i].x + pa[i].y);
+    }
+}
+
+// a lane's 17 bins <-> the exchange image of its plane (float4 slots [k/2][lane], float2 slots [16][lane])
+__device__ __forceinline__ void publish17(float* pb, int lane, const float2* Y) {
+    float4* ex4 = reinterpret_cast<float4*>(pb);
+#pragma unroll
+    for (int i = 0; i < M / 2; ++i) ex4[i * 32 + lane] = make_float4(Y[2 * i].x, Y[2 * i].y, Y[2 * i + 1].x, Y[2 * i + 1].y);
+    reinterpret_cast<float2*>(pb)[M * 32 + lane] = Y[M];
+}
+__device__ __forceinline__ void fetch17(const float* pb, int lane, float2* Y) {
+    const float4* ex4 = reinterpret_cast<const float4*>(pb);
+#pragma unroll
+    for (int i = 0; i < M / 2; ++i) {
+        const float4 s = ex4[i * 32 + lane];
+        Y[2 * i] = make_float2(s.x, s.y);
+        Y[2 * i + 1] = make_float2(s.z, s.w);
+    }
+    Y[M] = reinterpret_cast<const float2*>(pb)[M * 32 + lane];
 }
 
 // BatchNorm constants of output plane o (spectrum channels 2o, 2o+1): y -> relu(y * a + b), the inverse ortho scale folded in;
@@ -256,10 +320,7 @@ __global__ void __launch_bounds__(NW * 32, 2) fu4_kernel(const Fu2Params p, cons
     for (int img = blockIdx.x; img < p.B; img += gridDim.x) {
         float2 Y[M + 1];
         if (warp < p.Cin) {
-            fwd_plane(p.x + ((size_t)img * p.Cin + warp) * (N * N), pb, lane, tws, Y);
-#pragma unroll
-            for (int i = 0; i < M / 2; ++i) ex4[i * 32 + lane] = make_float4(Y[2 * i].x, Y[2 * i].y, Y[2 * i + 1].x, Y[2 * i + 1].y);
-            ex[M * 32 + lane] = Y[M];
+            fwd_plane<false>(p.x + ((size_t)img * p.Cin + warp) * (N * N), pb, lane, tws);
         } else {
 #pragma unroll
             for (int i = 0; i < M / 2; ++i) ex4[i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -267,28 +328,7 @@ __global__ void __launch_bounds__(NW * 32, 2) fu4_kernel(const Fu2Params p, cons
         }
         __syncthreads();
         if (warp < p.Cout) {
-            float2 pa[M + 1], pq[M + 1];
-#pragma unroll
-            for (int i = 0; i <= M; ++i) pa[i] = pq[i] = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int c = 0; c < NW; ++c) {
-                const float4* xc4 = reinterpret_cast<const float4*>(tiles + c * PBF) + lane;
-                const float4 q = wq_s[warp * NW + c];
-                const float2 wa = make_float2(q.x, q.y), wb = make_float2(q.z, q.w);
-#pragma unroll
-                for (int i = 0; i < M / 2; ++i) {
-                    const float4 s = xc4[i * 32];
-                    pa[2 * i] = ffc_fma2(wa, make_float2(s.x, s.y), pa[2 * i]);
-                    pq[2 * i] = ffc_fma2(wb, make_float2(s.x, s.y), pq[2 * i]);
-                    pa[2 * i + 1] = ffc_fma2(wa, make_float2(s.z, s.w), pa[2 * i + 1]);
-                    pq[2 * i + 1] = ffc_fma2(wb, make_float2(s.z, s.w), pq[2 * i + 1]);
-                }
-                const float2 sl = reinterpret_cast<const float2*>(tiles + c * PBF)[M * 32 + lane];
-                pa[M] = ffc_fma2(wa, sl, pa[M]);
-                pq[M] = ffc_fma2(wb, sl, pq[M]);
-            }
-#pragma unroll
-            for (int i = 0; i <= M; ++i) Y[i] = make_float2(pa[i].x + pq[i].y, pq[i].x + pa[i].y);
+            mix17<false>(tiles, wq_s, warp, lane, Y);
             if (MODE != 1) {
 #pragma unroll
                 for (int i = 0; i <= M; ++i) {
@@ -345,7 +385,7 @@ __global__ void __launch_bounds__(NW * 32, 2) fu4_kernel(const Fu2Params p, cons
 #pragma unroll
             for (int i = 0; i <= M; ++i) Y[i] = fu2_bn_relu(Y[i], bn_a, bn_b);
             const size_t g0 = ((size_t)img * p.Cout + warp) * (N * N);
-            inv_plane(Y, pb, lane, tws, p.residual ? p.residual + g0 : nullptr, p.out + g0);
+            inv_plane<false>(Y, pb, lane, tws, p.residual ? p.residual + g0 : nullptr, p.out + g0);
         }
     }
     if (MODE == 0 && warp < p.Cout) {
@@ -360,6 +400,188 @@ __global__ void __launch_bounds__(NW * 32, 2) fu4_kernel(const Fu2Params p, cons
             atomicAdd(p.sums + ((lane & 1) ? 2 * p.Cout + chn : chn), (double)sv);
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Backward of the same unit (autograd of fourier_unity.py:32-58; the math of ffc_fu2_bwd.cu) in the warp-private layout.
+// Two tiles per warp.  With S' = 2N * ortho spectrum of x (fwd_plane), G' = N * ortho adjoint-c2r transform of dout
+// (fwd_plane<ADJ>) and the weights scaled by 1/(2N):
+//   warp w: G'_w -> tile A (private), S'_w -> tile B (published) | barrier | warp o: Y_o = mix (true values), y^ = (Y - mean) *
+//   invstd, mask from y^ * gamma + beta, dZ' = mask * G', sum dZ', sum dZ' y^ -> per-CTA partial sums | GRID BARRIER |
+//   dY = gamma * invstd / N * (dZ' - mean(dZ') - y^ * mean(dZ' y^)) (true dY), dW partial of this image = dY (x) S' over the
+//   lane's bins, 32 sums per warp met by a halving shuffle reduction, written per image; dY -> tile A (published) | barrier |
+//   warp c: dS'_c = transposed mix, inverse adjoint plane -> dx (all scale factors cancel) | GRID BARRIER | dW = sum of the
+//   per-image partials / (2N) (one warp per weight entry; no atomics, bitwise reproducible).
+__global__ void __launch_bounds__(NW * 32, 2) fu4_bwd_kernel(const Fu2BwdParams p, const double inv_count, float* partial, float* dwp) {
+    extern __shared__ __align__(16) float smem_bwd[];
+    float* tilesA = smem_bwd;
+    float* tilesB = smem_bwd + NW * PBF;
+    __shared__ float2 tw_s[32];
+    __shared__ float4 wq_s[NW * NW];
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0);
+    const int img = blockIdx.x;
+    float* pa_tile = tilesA + warp * PBF;
+    float* pb_tile = tilesB + warp * PBF;
+    if (threadIdx.x < 32) tw_s[threadIdx.x] = c_tw128[threadIdx.x * 4];
+    if (threadIdx.x < NW * NW) {
+        const int o = threadIdx.x / NW, c = threadIdx.x % NW;
+        const float scale = 0.5f / (float)N;
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (o < p.Cout && c < p.Cin) {
+            const float* r0 = p.w + (size_t)(2 * o) * 2 * p.Cin + 2 * c;
+            const float* r1 = r0 + 2 * p.Cin;
+            q = make_float4(__ldg(r0) * scale, __ldg(r1 + 1) * scale, __ldg(r1) * scale, __ldg(r0 + 1) * scale);
+        }
+        wq_s[threadIdx.x] = q;
+    }
+    __syncthreads();
+    const float2 tws[4] = {tw_s[lane & 15], tw_s[(lane & 7) * 2], tw_s[(lane & 3) * 4], tw_s[(lane & 1) * 8]};
+    if (warp < p.Cout) fwd_plane<true>(p.dout + ((size_t)img * p.Cout + warp) * (N * N), pa_tile, lane, tws);
+    if (warp < p.Cin) {
+        fwd_plane<false>(p.x + ((size_t)img * p.Cin + warp) * (N * N), pb_tile, lane, tws);
+    } else {
+        float2 zero[M + 1];
+#pragma unroll
+        for (int i = 0; i <= M; ++i) zero[i] = make_float2(0.f, 0.f);
+        publish17(pb_tile, lane, zero);
+    }
+    __syncthreads();
+    float2 dz[M + 1], yh[M + 1];
+    float2 gam = make_float2(0.f, 0.f), istd = gam;
+    if (warp < p.Cout) {
+        const int ch = 2 * warp;
+        istd = make_float2(__ldg(p.save_invstd + ch), __ldg(p.save_invstd + ch + 1));
+        const float2 k1 = make_float2(-__ldg(p.save_mean + ch) * istd.x, -__ldg(p.save_mean + ch + 1) * istd.y);
+        gam = make_float2(__ldg(p.gamma + ch), __ldg(p.gamma + ch + 1));
+        const float2 bet = make_float2(__ldg(p.beta + ch), __ldg(p.beta + ch + 1));
+        mix17<false>(tilesB, wq_s, warp, lane, yh);                  // Y of this lane's bins (true values)
+        fetch17(pa_tile, lane, dz);                                  // G'
+        float st[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i <= M; ++i) {
+            yh[i] = ffc_fma2(yh[i], istd, k1);
+            const float2 z = ffc_fma2(yh[i], gam, bet);
+            dz[i] = make_float2(z.x > 0.f ? dz[i].x : 0.f, z.y > 0.f ? dz[i].y : 0.f);
+            st[0] += dz[i].x; st[1] = fmaf(dz[i].x, yh[i].x, st[1]);
+            st[2] += dz[i].y; st[3] = fmaf(dz[i].y, yh[i].y, st[3]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) st[j] += __shfl_xor_sync(FULL, st[j], m);
+        }
+        if (lane < 4) {          // layout as in the forward: sum(dZ) of channel chn at [chn], sum(dZ y^) at [2*Cout + chn]
+            const float sv = lane == 0 ? st[0] : (lane == 1 ? st[1] : (lane == 2 ? st[2] : st[3]));
+            const int chn = 2 * warp + (lane >> 1);
+            const int idx = (lane & 1) ? 2 * p.Cout + chn : chn;
+            __stcg(partial + (size_t)idx * p.B + blockIdx.x, sv);
+        }
+    }
+    cooperative_groups::this_grid().sync();
+    if (warp < p.Cout) {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        const float* pr = partial + (size_t)(2 * warp) * p.B;
+        for (int b = lane; b < p.B; b += 32) {
+            acc[0] += (double)__ldcg(pr + b);
+            acc[1] += (double)__ldcg(pr + p.B + b);
+            acc[2] += (double)__ldcg(pr + (size_t)2 * p.Cout * p.B + b);
+            acc[3] += (double)__ldcg(pr + (size_t)(2 * p.Cout + 1) * p.B + b);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) acc[j] += __shfl_xor_sync(FULL, acc[j], m);
+        }
+        const float inv_n = 1.0f / (float)N;
+        if (blockIdx.x == 0 && lane == 0) {          // the sums are N * the true ones
+            p.dbeta[2 * warp] = (float)(acc[0] * inv_n); p.dbeta[2 * warp + 1] = (float)(acc[1] * inv_n);
+            p.dgamma[2 * warp] = (float)(acc[2] * inv_n); p.dgamma[2 * warp + 1] = (float)(acc[3] * inv_n);
+        }
+        const float2 a = make_float2(gam.x * istd.x * inv_n, gam.y * istd.y * inv_n);
+        const float2 c1 = p.training ? make_float2((float)(acc[0] * inv_count), (float)(acc[1] * inv_count)) : make_float2(0.f, 0.f);
+        const float2 c2 = p.training ? make_float2((float)(acc[2] * inv_count), (float)(acc[3] * inv_count)) : make_float2(0.f, 0.f);
+        // dY = a * (dZ - c1 - y^ * c2), in place over dz
+#pragma unroll
+        for (int i = 0; i <= M; ++i) {
+            const float2 t = ffc_sub2(ffc_sub2(dz[i], c1), ffc_mul2(yh[i], c2));
+            dz[i] = ffc_mul2(a, t);
+        }
+        // dW partial of this image: v[4c + t], t = 0: dW[2o][2c], 1: dW[2o+1][2c], 2: dW[2o][2c+1], 3: dW[2o+1][2c+1]
+        float v[4 * NW];
+#pragma unroll
+        for (int c = 0; c < NW; ++c) {
+            float2 a1 = make_float2(0.f, 0.f), a2 = a1;
+            const float4* xc4 = reinterpret_cast<const float4*>(tilesB + c * PBF) + lane;
+#pragma unroll
+            for (int i = 0; i < M / 2; ++i) {
+                const float4 s = xc4[i * 32];
+                a1 = ffc_fma2(dz[2 * i], make_float2(s.x, s.x), a1);
+                a2 = ffc_fma2(dz[2 * i], make_float2(s.y, s.y), a2);
+                a1 = ffc_fma2(dz[2 * i + 1], make_float2(s.z, s.z), a1);
+                a2 = ffc_fma2(dz[2 * i + 1], make_float2(s.w, s.w), a2);
+            }
+            const float2 sl = reinterpret_cast<const float2*>(tilesB + c * PBF)[M * 32 + lane];
+            a1 = ffc_fma2(dz[M], make_float2(sl.x, sl.x), a1);
+            a2 = ffc_fma2(dz[M], make_float2(sl.y, sl.y), a2);
+            v[4 * c] = a1.x; v[4 * c + 1] = a1.y; v[4 * c + 2] = a2.x; v[4 * c + 3] = a2.y;
+        }
+        // 32 sums over the 32 lanes by recursive halving: after the step with mask m a lane keeps the half of the values
+        // its bit m selects, so lane j ends with the total of v[j]
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            const bool up = (lane & m) != 0;
+#pragma unroll
+            for (int i = 0; i < m; ++i) {
+                const float send = up ? v[i] : v[i + m];
+                const float keep = up ? v[i + m] : v[i];
+                v[i] = keep + __shfl_xor_sync(FULL, send, m);
+            }
+        }
+        __stcg(dwp + ((size_t)(warp * 32 + lane)) * p.B + blockIdx.x, v[0]);
+        publish17(pa_tile, lane, dz);            // dY of plane `warp` (G' is no longer needed)
+    } else {
+        float2 zero[M + 1];
+#pragma unroll
+        for (int i = 0; i <= M; ++i) zero[i] = make_float2(0.f, 0.f);
+        publish17(pa_tile, lane, zero);
+    }
+    __syncthreads();
+    if (warp < p.Cin) {
+        float2 ds[M + 1];
+        mix17<true>(tilesA, wq_s, warp, lane, ds);
+        inv_plane<true>(ds, pb_tile, lane, tws, nullptr, p.dx + ((size_t)img * p.Cin + warp) * (N * N));
+    }
+    cooperative_groups::this_grid().sync();
+    // dW[row][col] = sum over the images of the partials / (2N): one warp per entry
+    for (int e = blockIdx.x * NW + warp; e < 4 * NW * NW; e += gridDim.x * NW) {
+        const int o = e >> 5, j = e & 31, c = j >> 2, t = j & 3;
+        if (o >= p.Cout || c >= p.Cin) continue;
+        double acc = 0.0;
+        for (int b = lane; b < p.B; b += 32) acc += (double)__ldcg(dwp + (size_t)e * p.B + b);
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(FULL, acc, m);
+        if (lane == 0) p.dw[(size_t)(2 * o + (t & 1)) * 2 * p.Cin + 2 * c + (t >> 1)] = (float)(acc * (0.5 / (double)N));
+    }
+}
+
+static size_t bwd_workspace_bytes(int B, int Cin, int Cout) {
+    (void)Cin;
+    return ((size_t)4 * Cout * sizeof(double) + 255) / 256 * 256 + ((size_t)4 * Cout * B + (size_t)4 * NW * NW * B) * sizeof(float);
+}
+static int bwd_capacity() {
+    static FfcPerDevice cached = {};
+    size_t& c = *ffc_device_slot(cached);
+    if (c == 0) {
+        const int smem = 2 * NW * PBF * (int)sizeof(float);
+        int per_sm = 0, coop = 0, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        if (!coop || cudaFuncSetAttribute(fu4_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 0;
+        cudaFuncSetAttribute(fu4_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fu4_bwd_kernel, NW * 32, smem) != cudaSuccess || per_sm < 1) return 0;
+        c = (size_t)per_sm * ffc_sm_count();
+    }
+    return (int)c;
 }
 
 // resident CTAs of one kernel on the current device (prefers the largest shared-memory carve-out; cached per device)
@@ -420,8 +642,36 @@ int ffc_fu4_launch(const Fu2Params& p, size_t workspace_bytes, ffc_stream_t st) 
     const int c1 = capacity<1>();
     return launch<1>(p.B < c1 ? p.B : c1, p, inv_count, unbias, st);
 }
+
+extern "C" size_t ffc_fu_bwd_workspace_bytes(int B, int Cin, int Cout) {
+    const size_t small = (size_t)4 * (Cout > 0 ? Cout : 0) * sizeof(double);
+    if (B < 1 || Cin < 1 || Cout < 1) return small;
+    const size_t big = fu4::bwd_workspace_bytes(B, Cin, Cout);
+    return big > small ? big : small;
+}
+// the warp-private backward handles the shape with this workspace on the current device (all images co-resident)
+bool ffc_fu4_bwd_supported(int B, int Cin, int Cout, int H, int W, size_t workspace_bytes) {
+    if (!ffc_fu4_supported(Cin, Cout, H, W) || B < 1) return false;
+    if (workspace_bytes < fu4::bwd_workspace_bytes(B, Cin, Cout)) return false;
+    return B <= fu4::bwd_capacity();
+}
+int ffc_fu4_bwd_launch(const Fu2BwdParams& p, ffc_stream_t st) {
+    using namespace fu4;
+    double inv_count = 1.0 / ((double)p.B * BINS);
+    float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(p.sums) + ((size_t)4 * p.Cout * sizeof(double) + 255) / 256 * 256);
+    float* dwp = partial + (size_t)4 * p.Cout * p.B;
+    void* args[] = {(void*)&p, (void*)&inv_count, (void*)&partial, (void*)&dwp};
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void*)fu4_bwd_kernel, dim3(p.B), dim3(NW * 32), args,
+                                                      2 * NW * PBF * sizeof(float), st);
+    if (e != cudaSuccess) { ffc_set_error("fu4 backward cooperative launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
+    ffc_count_launch();
+    return FFC_OK;
+}
 #else
 bool ffc_fu4_supported(int, int, int, int) { return false; }
+extern "C" size_t ffc_fu_bwd_workspace_bytes(int, int, int Cout) { return (size_t)4 * (Cout > 0 ? Cout : 0) * sizeof(double); }
+bool ffc_fu4_bwd_supported(int, int, int, int, int, size_t) { return false; }
+int ffc_fu4_bwd_launch(const Fu2BwdParams&, ffc_stream_t) { return FFC_ERR_BAD_ARG; }
 int ffc_fu4_launch(const Fu2Params&, size_t, ffc_stream_t) { return FFC_ERR_BAD_ARG; }
 extern "C" void ffc_debug_fu4(int) {}
 #endif

@@ -633,7 +633,7 @@ class FusedFuFn(torch.autograd.Function):
             # one cooperative kernel: both spectra stay in shared memory (csrc/ffc_fu2_bwd.cu)
             dx, dw = torch.empty_like(x), torch.empty_like(weight)
             dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(beta)
-            ws = _C.workspace(2 * C2o * 8, x.device)
+            ws = _C.workspace(L.ffc_fu_bwd_workspace_bytes(B, Cin, C2o // 2), x.device)
             _C.check(L.ffc_fu_bwd(_C.ptr(x), _C.ptr(dout), _C.ptr(weight), _C.ptr(gamma), _C.ptr(beta),
                                   _C.ptr(save_mean), _C.ptr(save_invstd), _C.ptr(dx), _C.ptr(dw), _C.ptr(dgamma), _C.ptr(dbeta),
                                   B, Cin, C2o // 2, H, W, int(training), _C.ptr(ws), ws.numel(), st))

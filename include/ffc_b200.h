@@ -175,6 +175,10 @@ int ffc_fu_bwd(const float* x, const float* dout, const float* w, const float* g
                float* dx, float* dw, float* dgamma, float* dbeta,
                int B, int Cin, int Cout, int H, int W, int training,
                void* workspace, size_t workspace_bytes, void* stream);
+/* Workspace ffc_fu_bwd makes the best use of (the minimum stays 4*Cout doubles): with room for the per-image partial sums
+ * and weight-gradient tiles the 32x32 / <= 8 channel unit runs the warp-private backward of csrc/ffc_fu4.cu (no zeroing
+ * launches, no atomics, bitwise reproducible). */
+size_t ffc_fu_bwd_workspace_bytes(int B, int Cin, int Cout);
 
 /* ---- Convolutions -----------------------------------------------------------------------------
  * ffc_conv2d_fwd, transposed = 0: nn.Conv2d forward (layers/ffc/ffc.py:45-68 convl2l/convl2g/convg2l,

@@ -40,7 +40,25 @@ def main():
                 y = mod(xs[0])
                 err = ((y.double() - ref).abs().max() / ref.abs().max()).item()
                 t = timeit(lambda x: mod(x), xs, iters=20)
-            mod.load_state_dict(sd)
+                mod.load_state_dict(sd)
+            if training:
+                with torch.enable_grad():
+                    xg = [x.clone().requires_grad_(True) for x in xs[:max(2, len(xs) // 3)]]
+                    gy = torch.randn_like(xs[0])
+                    x64 = xs[0].double().requires_grad_(True)
+                    P64g = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in P64.items()}
+                    g64 = torch.autograd.grad(ref_fourier_unit(x64, P64g, True), (x64, P64g["conv_layer.weight"], P64g["bn.weight"], P64g["bn.bias"]), gy.double())
+
+                    def fwd_bwd(x):
+                        return torch.autograd.grad(mod(x), (x, mod.conv_layer.weight, mod.bn.weight, mod.bn.bias), gy)
+                    g = fwd_bwd(xg[0])
+                    # relative L2 (a ReLU element on the other side of its kink moves the max norm)
+                    row[name + "_gerr"] = [float(((a.double().reshape(b.shape) - b).norm() / b.norm()).item()) for a, b in zip(g, g64)]
+                    mod.load_state_dict(sd)
+                    tb = timeit(fwd_bwd, xg, iters=20)
+                    mod.load_state_dict(sd)
+                row[name + "_fwdbwd_us"] = round(tb * 1e3, 2)
+                row[name + "_fwdbwd_frac"] = round(20.0 * B * C * 1024 / (tb * 1e-3) / 1e9 / PEAK, 4)
             row[name + "_err"] = err
             row[name + "_us"] = round(t * 1e3, 2)
             row[name + "_frac"] = round(8.0 * B * C * 1024 / (t * 1e-3) / 1e9 / PEAK, 4)
