@@ -15,8 +15,8 @@ def main(path, top=30):
         m = re.search(r"ffc_kernel(?:_coop)?<(\w+)(<[^>]*>)?", full)
         if m:
             name = "ffc_b200:" + m.group(1) + (m.group(2) or "")
-        elif re.match(r"(void )?(conv_v5|wgrad_v5|pack_v5|conv_small\w*|wgrad_small\w*|conv1x1_narrow|fu3_mix|fu3_wgrad|fu3_pack)_kernel|(void )?fu3_wgrad_reduce", full):
-            name = "ffc_b200:" + re.sub(r"\(.*", "", full).replace("void ", "")
+        elif re.match(r"(void )?(conv_v5|wgrad_v5|pack_v5|conv_small\w*|wgrad_small\w*|conv1x1_narrow|fu3_mix|fu3_wgrad|fu3_pack|fu4|fu4_bwd|ffc_zero)_kernel|(void )?fu3_wgrad_reduce", full):
+            name = "ffc_b200:" + re.sub(r"\(.*", "", full).replace("void ", "").replace("fu4::", "")
         else:
             name = re.sub(r"<.*", "", full)[:70]
         v = float(row["Metric Value"].replace(",", ""))
