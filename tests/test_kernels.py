@@ -346,9 +346,18 @@ FU_CASES = [
 ]
 
 
+# 32x32 planes with <= 8 channels run the warp-private kernels of csrc/ffc_fu4.cu: more of them, with unequal channel counts,
+# a batch beyond the co-resident capacity (two-pass form) and one image
+FU_CASES += [(7, 8, 5, 32, 1, True, 0), (4, 1, 8, 32, 1, False, 0), (2, 5, 1, 32, 0, True, 0), (1, 8, 8, 32, 1, False, 0),
+             (330, 2, 2, 32, 1, False, 0), (9, 4, 4, 32, 1, True, 1), (40, 8, 8, 32, 0, False, 0)]
+
+
 @pytest.mark.parametrize("case", FU_CASES)
-def test_fused_fourier_unit_forward(lib, case):
-    """ffc_fu_fwd (cooperative single pass / two-pass / eval) against FourierUnitSN.forward in float64."""
+@pytest.mark.parametrize("ws_mode", ["min", "full"])
+def test_fused_fourier_unit_forward(lib, case, ws_mode):
+    """ffc_fu_fwd (cooperative single pass / two-pass / eval) against FourierUnitSN.forward in float64; with the minimal
+    workspace (4*Cout doubles: zero fill + atomics) and with ffc_fu_workspace_bytes (per-image partial sums where the kernel
+    has that form)."""
     B, Cin, Cout, N, training, has_res, two_pass = case
     torch.manual_seed(B * 1000 + Cin * 10 + N)
     x = torch.randn(B, Cin, N, N)
@@ -363,7 +372,7 @@ def test_fused_fourier_unit_forward(lib, case):
     out = torch.zeros(B, Cout, N, N)
     sm, si = torch.zeros(2 * Cout), torch.zeros(2 * Cout)
     rm, rv = rmean.clone(), rvar.clone()
-    ws = torch.zeros(4 * Cout * 8 + 64, dtype=torch.uint8)
+    ws = torch.zeros(4 * Cout * 8 if ws_mode == "min" else lib[0].ffc_fu_workspace_bytes(B, Cout), dtype=torch.uint8)
     cf = ctypes.c_float
     lib[0].ffc_debug_fu_two_pass(two_pass)
     try:
@@ -405,12 +414,15 @@ FU_BWD_CASES = [
     # B, Cin, Cout, N, training
     (3, 8, 8, 32, 1), (2, 8, 8, 32, 0), (5, 16, 16, 16, 1), (3, 32, 32, 8, 1), (2, 5, 7, 16, 1), (2, 7, 3, 8, 1),
     (2, 12, 20, 8, 0), (2, 3, 2, 32, 1), (2, 16, 16, 32, 1), (2, 24, 9, 16, 1), (1, 32, 32, 16, 1),
+    (7, 8, 5, 32, 1), (4, 1, 8, 32, 1), (2, 5, 1, 32, 0), (1, 8, 8, 32, 1), (70, 4, 4, 32, 1),
 ]
 
 
 @pytest.mark.parametrize("case", FU_BWD_CASES)
-def test_fused_fourier_unit_backward(lib, case):
-    """ffc_fu_bwd against float64 autograd of FourierUnitSN.forward."""
+@pytest.mark.parametrize("ws_mode", ["min", "full"])
+def test_fused_fourier_unit_backward(lib, case, ws_mode):
+    """ffc_fu_bwd against float64 autograd of FourierUnitSN.forward; with ffc_fu_bwd_workspace_bytes the 32x32 / <= 8 channel
+    shapes take the warp-private kernel (csrc/ffc_fu4.cu: per-image partial sums and weight-gradient tiles)."""
     B, Cin, Cout, N, training = case
     torch.manual_seed(B * 1000 + Cin * 10 + N + 1)
     x = torch.randn(B, Cin, N, N)
@@ -422,7 +434,7 @@ def test_fused_fourier_unit_backward(lib, case):
     assert lib[0].ffc_fu_bwd_supported(B, Cin, Cout, N, N) == 1
     dx, dw = torch.zeros_like(x), torch.full_like(w, 7.0)
     dg, db = torch.zeros(2 * Cout), torch.zeros(2 * Cout)
-    ws = torch.zeros(4 * Cout * 8 + 64, dtype=torch.uint8)
+    ws = torch.zeros(4 * Cout * 8 if ws_mode == "min" else lib[0].ffc_fu_bwd_workspace_bytes(B, Cin, Cout), dtype=torch.uint8)
     call(lib, "ffc_fu_bwd", x, dout, w, gamma, beta, mean.float(), invstd.float(), dx, dw, dg, db,
          B, Cin, Cout, N, N, training, ws, ws.numel(), None)
     assert parity.relerr(dx, dx_r) < 5e-6
