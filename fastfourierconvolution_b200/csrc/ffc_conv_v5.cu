@@ -66,6 +66,7 @@ struct PackV5Params {
     const float* w0b; int cout0;   // block form: segment 0 uses w[0] for co < cout0 and w0b for the rest, segment 1 is zero there
     float* wp; long long cls_off[FFC_V5_MAXCLS];
     int nt_full, ntiles, cout, k, stride, pad, transposed;
+    float* zero[2]; long long nzero[2];    // split-K outputs the convolution adds into: zero-filled here (one graph node less)
 };
 
 __global__ void __launch_bounds__(256) pack_v5_kernel(const PackV5Params p) {
@@ -111,6 +112,21 @@ __global__ void __launch_bounds__(256) pack_v5_kernel(const PackV5Params p) {
             dst[(size_t)NT * V5_BK] = v - hi;
         }
         tile_base += (long long)nchunks * per_chunk;
+    }
+    // zero fill of the split-K outputs (one graph node less than a separate fill in front of the convolution)
+    const long long nthreads = (long long)gridDim.x * gridDim.y * blockDim.x, me = ((long long)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int z = 0; z < 2; ++z) {
+        float* q = p.zero[z];
+        const long long n = p.nzero[z];
+        if (!q || n <= 0) continue;
+        if ((((uintptr_t)q) & 15) == 0) {
+            float4* q4 = reinterpret_cast<float4*>(q);
+            for (long long i = me; i < n / 4; i += nthreads) q4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (long long i = (n / 4) * 4 + me; i < n; i += nthreads) q[i] = 0.f;
+        } else {
+            for (long long i = me; i < n; i += nthreads) q[i] = 0.f;
+        }
     }
 }
 
@@ -422,19 +438,7 @@ int conv_v5_run_block(const float* x0, const float* w0, const float* w0b, int ci
         ffc_set_error("ffc_conv2d_fwd_ws: workspace too small (%zu bytes needed)", (size_t)pl.total_floats * sizeof(float) + 256);
         return FFC_ERR_WORKSPACE;
     }
-    PackV5Params pp;
-    pp.w[0] = w0; pp.w[1] = w1; pp.cin[0] = cin0; pp.cin[1] = cin1; pp.cps[0] = pl.cps[0]; pp.cps[1] = pl.cps[1];
-    pp.nseg = x1 ? 2 : 1; pp.wp = (float*)wsa; pp.nt_full = pl.nt_full; pp.ntiles = pl.ntiles; pp.cout = cout;
-    pp.k = k; pp.stride = stride; pp.pad = pad; pp.transposed = transposed; pp.w0b = w0b; pp.cout0 = cout0;
-    for (int c = 0; c < FFC_V5_MAXCLS; ++c) pp.cls_off[c] = pl.cls_off[c];
-    const long long per_cls = (long long)k * k * (pl.cps[0] + pl.cps[1]) * V5_BK * ((cout + 15) / 16 * 16);
-    if (per_cls >= (1LL << 31)) { ffc_set_error("ffc_conv2d_fwd_ws: weight too large for the packing kernel (%lld elements per class)", per_cls); return FFC_ERR_BAD_ARG; }
-    int gx = (int)((per_cls + 255) / 256); if (gx > ffc_sm_count() * 4) gx = ffc_sm_count() * 4; if (gx < 1) gx = 1;
-    pack_v5_kernel<<<dim3(gx, pl.ncls), 256, 0, st>>>(pp);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { ffc_set_error("pack_v5 launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
-    ffc_count_launch();
-
+    cudaError_t e = cudaSuccess;
     ConvV5Params p;
     p.x[0] = x0; p.x[1] = x1; p.cin[0] = cin0; p.cin[1] = cin1; p.cps[0] = pl.cps[0]; p.cps[1] = pl.cps[1]; p.nseg = x1 ? 2 : 1;
     p.wp = (const float*)wsa; p.nt_full = pl.nt_full;
@@ -487,11 +491,25 @@ int conv_v5_run_block(const float* x0, const float* w0, const float* w0b, int ci
     p.ksplit = ksplit;
     const bool act_after = ksplit > 1 && slope != 1.f;
     if (act_after) p.slope = 1.f;
-    if (ksplit > 1) {
-        const size_t HWo = (size_t)Ho * Wo;
-        FFC_CHECK(ffc_memset_async(y, 0, (size_t)B * cout0 * HWo * sizeof(float), st));
-        if (y1) FFC_CHECK(ffc_memset_async(y1, 0, (size_t)B * (cout - cout0) * HWo * sizeof(float), st));
+    PackV5Params pp;
+    pp.w[0] = w0; pp.w[1] = w1; pp.cin[0] = cin0; pp.cin[1] = cin1; pp.cps[0] = pl.cps[0]; pp.cps[1] = pl.cps[1];
+    pp.nseg = x1 ? 2 : 1; pp.wp = (float*)wsa; pp.nt_full = pl.nt_full; pp.ntiles = pl.ntiles; pp.cout = cout;
+    pp.k = k; pp.stride = stride; pp.pad = pad; pp.transposed = transposed; pp.w0b = w0b; pp.cout0 = cout0;
+    for (int c = 0; c < FFC_V5_MAXCLS; ++c) pp.cls_off[c] = pl.cls_off[c];
+    pp.zero[0] = pp.zero[1] = nullptr; pp.nzero[0] = pp.nzero[1] = 0;
+    if (ksplit > 1) {                 // the partial sums of the K split meet in a zeroed output: the packing launch zero-fills it
+        const long long HWo = (long long)Ho * Wo;
+        pp.zero[0] = y; pp.nzero[0] = (long long)B * cout0 * HWo;
+        if (y1) { pp.zero[1] = y1; pp.nzero[1] = (long long)B * (cout - cout0) * HWo; }
     }
+    const long long per_cls = (long long)k * k * (pl.cps[0] + pl.cps[1]) * V5_BK * ((cout + 15) / 16 * 16);
+    if (per_cls >= (1LL << 31)) { ffc_set_error("ffc_conv2d_fwd_ws: weight too large for the packing kernel (%lld elements per class)", per_cls); return FFC_ERR_BAD_ARG; }
+    int gx = (int)((per_cls + 255) / 256); if (gx > ffc_sm_count() * 4) gx = ffc_sm_count() * 4; if (gx < 1) gx = 1;
+    pack_v5_kernel<<<dim3(gx, pl.ncls), 256, 0, st>>>(pp);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { ffc_set_error("pack_v5 launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
+    ffc_count_launch();
+
     const dim3 grid(ffc_cdiv(Mc, 128), pl.ntiles, s * s * ksplit);
     if (four_wg) conv_v5_kernel<4><<<grid, 4 * 128 + 64, smem, st>>>(p);
     else conv_v5_kernel<2><<<grid, 2 * 128 + 64, smem, st>>>(p);
