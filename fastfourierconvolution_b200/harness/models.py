@@ -133,16 +133,18 @@ class SNDiscriminator(nn.Module):
             m = x
             convs = [getattr(self, f"conv{i}") for i in range(1, self.n_convs + 1)]
             # spectral_norm pre-forward hooks (W / sigma, one power iteration each) depend on the weights only: the first
-            # layer's runs here, the others (3 small kernels per layer) on a side stream while the first convolution runs
-            ws = [_util.effective_weight(convs[0])]
-            with ops._Fork(x.device, 0):
-                ws += [_util.effective_weight(c) for c in convs[1:]]
-                w_fc = _util.effective_weight(self.fc) if x.is_cuda else None
+            # layer's runs here, the others (4 small launches per layer) on side streams, each joined right before its own
+            # convolution -- one serial chain joined before the second convolution cost ~120 us of stall per forward
+            ws = [(_util.effective_weight(convs[0]), (lambda: None))]
+            rest = convs[1:] + ([self.fc] if x.is_cuda else [])
+            ws += ops.fork_map(x.device, [(lambda c=c: _util.effective_weight(c)) for c in rest])
             for i, conv in enumerate(convs):
-                if i == 1:
-                    ops._join(x.device)
-                m = ops.conv2d_act(m, ws[i], conv.bias, conv.stride[0], conv.padding[0], ops.ACT_LEAKY, self.act.negative_slope)
-            ops._join(x.device)
+                ws[i][1]()
+                m = ops.conv2d_act(m, ws[i][0], conv.bias, conv.stride[0], conv.padding[0], ops.ACT_LEAKY, self.act.negative_slope)
+            w_fc = None
+            if x.is_cuda:
+                ws[-1][1]()
+                w_fc = ws[-1][0]
             m = m.reshape(-1, self.mg * self.mg * 512)
             return ops.linear(m, w_fc, self.fc.bias) if w_fc is not None else self.fc(m)
         m = x.contiguous(memory_format=torch.channels_last) if self.channels_last else x

@@ -120,6 +120,33 @@ def _join(device):
             cur.wait_stream(s)
 
 
+def fork_map(device, fns, nstreams: int = 4):
+    """Runs every ``fn()`` of ``fns`` on a side stream (round robin over ``nstreams``), all of them after what the current stream
+    holds now, and returns ``[(result, wait)]``: ``wait()`` makes the current stream wait for THAT fn only.  For work that depends
+    on the parameters alone -- the spectral-norm power iterations of a discriminator's layers -- so that layer i's convolution
+    waits for its own weight and not for the whole chain (the chain of seven layers is ~160 us, a batch-32 convolution ~20 us).
+    Every ``wait`` must be called before a CUDA-graph capture of the caller ends (it is what joins the side streams)."""
+    sides = _C.side_streams(device, nstreams) if device.type == "cuda" else None
+    if not sides:
+        return [(fn(), (lambda: None)) for fn in fns]
+    cur = torch.cuda.current_stream(device)
+    out, started = [], set()
+    for j, fn in enumerate(fns):
+        side = sides[j % nstreams]
+        if side == cur:
+            out.append((fn(), (lambda: None)))
+            continue
+        if id(side) not in started:
+            side.wait_stream(cur)
+            started.add(id(side))
+        with torch.cuda.stream(side):
+            r = fn()
+            ev = torch.cuda.Event()
+            ev.record(side)
+        out.append((r, (lambda ev=ev: cur.wait_event(ev))))
+    return out
+
+
 def _conv_backward(cfg, x0, w0, x1, w1, dy, needs):
     """Gradients of Conv2dFn's ten inputs (None where not needed).  The data gradients stay on the current stream; the weight
     and bias gradients -- independent of them -- are queued on side streams (fork / join)."""
