@@ -209,8 +209,10 @@ class FDiscriminatorSN64(nn.Module):
         self.main, self.fc = build_fd_sn64(layers, torch.nn.utils.spectral_norm if sn else (lambda m: m), mg)
 
     def forward(self, x):
-        m = self.resizer(self.main(x))
-        return _sn_linear(self.fc, m.view(-1, self.mg * self.mg * 512))
+        from ..layers import _util
+        with _util.prefetch_spectral_norm(self, x.device):       # 17 power iterations, off the critical path of the convolutions
+            m = self.resizer(self.main(x))
+            return _sn_linear(self.fc, m.view(-1, self.mg * self.mg * 512))
 
 
 class FFCGenerator(nn.Module):

@@ -9,6 +9,47 @@ from torch.nn.utils.weight_norm import WeightNorm as _WeightNorm
 from .. import ops
 
 
+_prefetched = {}      # id(holder module) -> (normalised weight, wait): filled by prefetch_spectral_norm, consumed by effective_weight
+
+
+def _standard_sn_hook(mod: nn.Module):
+    for hook in mod._forward_pre_hooks.values():
+        if isinstance(hook, _SpectralNorm) and hook.name == "weight" and hook.n_power_iterations == 1 and \
+                (hook.dim == 0 or (hook.dim == 1 and mod.weight_orig.dim() == 4)):
+            return hook
+    return None
+
+
+class prefetch_spectral_norm:
+    """``with prefetch_spectral_norm(model, device): y = model(x)`` -- the spectral-norm power iterations of every holder
+    module of ``model`` (they depend on the parameters alone) are launched up front on side streams (``ops.fork_map``), and
+    ``effective_weight`` hands each layer its weight after waiting for that one computation only.  Each holder's iteration
+    still runs exactly once per forward; leftovers (holders the forward did not reach) are joined on exit."""
+
+    def __init__(self, model: nn.Module, device):
+        self.mods = [m for m in model.modules() if _standard_sn_hook(m) is not None]
+        self.device = device
+
+    def __enter__(self):
+        if self.device.type == "cuda" and self.mods:
+            res = ops.fork_map(self.device, [(lambda m=m: _compute_sn(m)) for m in self.mods])
+            for m, r in zip(self.mods, res):
+                _prefetched[id(m)] = r
+        return self
+
+    def __exit__(self, *exc):
+        for m in self.mods:
+            r = _prefetched.pop(id(m), None)
+            if r is not None:
+                r[1]()
+        return False
+
+
+def _compute_sn(mod: nn.Module) -> torch.Tensor:
+    hook = _standard_sn_hook(mod)
+    return ops.spectral_norm_weight(mod.weight_orig, mod.weight_u, mod.weight_v, mod.training, hook.eps, hook.dim)
+
+
 def effective_weight(mod: nn.Module) -> torch.Tensor:
     """The weight a holder module would use in its own forward.
 
@@ -18,6 +59,11 @@ def effective_weight(mod: nn.Module) -> torch.Tensor:
     ``ops.spectral_norm_weight`` (three kernels) for the standard configurations -- one power iteration, ``dim == 0``
     (nn.Conv2d) or ``dim == 1`` (nn.ConvTranspose2d) -- and by running the hook itself otherwise.
     """
+    pre = _prefetched.pop(id(mod), None)
+    if pre is not None:                               # computed on a side stream by prefetch_spectral_norm
+        pre[1]()
+        setattr(mod, "weight", pre[0])
+        return pre[0]
     for hook in mod._forward_pre_hooks.values():
         if isinstance(hook, _SpectralNorm) and hook.name == "weight" and hook.n_power_iterations == 1 and \
                 (hook.dim == 0 or (hook.dim == 1 and mod.weight_orig.dim() == 4)):
