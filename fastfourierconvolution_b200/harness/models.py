@@ -125,6 +125,7 @@ class SNDiscriminator(nn.Module):
         self.fc = sn_fn(nn.Linear(mg * mg * 512, 1))
         self.act = nn.LeakyReLU(0.1)
         self.channels_last = False      # backend="torch" only: run cuDNN in NHWC (same math, no layout round trips)
+        self.concurrent_forwards_ok = backend == "ffc_b200"      # GanTrainer._two_forwards: D(fake) and D(real) on two streams
 
     def forward(self, x):
         if self.backend == "ffc_b200":
@@ -132,12 +133,13 @@ class SNDiscriminator(nn.Module):
             from ..layers import _util
             m = x
             convs = [getattr(self, f"conv{i}") for i in range(1, self.n_convs + 1)]
-            # spectral_norm pre-forward hooks (W / sigma, one power iteration each) depend on the weights only: the first
-            # layer's runs here, the others (4 small launches per layer) on side streams, each joined right before its own
-            # convolution -- one serial chain joined before the second convolution cost ~120 us of stall per forward
-            ws = [(_util.effective_weight(convs[0]), (lambda: None))]
-            rest = convs[1:] + ([self.fc] if x.is_cuda else [])
-            ws += ops.fork_map(x.device, [(lambda c=c: _util.effective_weight(c)) for c in rest])
+            # spectral_norm pre-forward hooks (W / sigma, one power iteration each) depend on the weights only: they run (4 small
+            # launches per layer) on side streams, each joined right before its own convolution -- one serial chain joined
+            # before the second convolution cost ~120 us of stall per forward
+            # (the first layer's too: two forwards queued on different streams, GanTrainer._two_forwards, then still run the
+            # iterations of a layer in program order, on that layer's side stream)
+            mods = convs + ([self.fc] if x.is_cuda else [])
+            ws = ops.fork_map(x.device, [(lambda c=c: _util.effective_weight(c)) for c in mods])
             for i, conv in enumerate(convs):
                 ws[i][1]()
                 m = ops.conv2d_act(m, ws[i][0], conv.bias, conv.stride[0], conv.padding[0], ops.ACT_LEAKY, self.act.negative_slope)

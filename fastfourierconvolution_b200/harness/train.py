@@ -207,7 +207,8 @@ class GanTrainer:
         self.optim_D.zero_grad()
         self.optim_G.zero_grad()
         fake = G(z_d)
-        loss_D = hinge_loss_dis(D(fake), D(real))
+        d_fake, d_real = self._two_forwards(D, fake, real)
+        loss_D = hinge_loss_dis(d_fake, d_real)
         loss_D.backward()
         self.allreduce_bytes += self.optim_D.adopt().all_reduce()
         self.optim_D.step()
@@ -216,6 +217,27 @@ class GanTrainer:
         self.sched_G.step()
         self.sched_D.step()
         return loss_G.detach(), loss_D.detach()
+
+    @staticmethod
+    def _two_forwards(D, fake, real):
+        """D(fake), then D(real) (the order of fgan_complete.py:384-385: the second forward's power iterations start from the
+        first's u / v).  On a GPU the second forward is queued on a side stream: its convolutions do not depend on the first
+        forward's, so the two chains -- and, through autograd's per-node streams, their backward chains -- overlap (a captured
+        step records them as parallel branches; the spectral-norm launches of both stay in order on the streams of
+        ``ops.fork_map``).  FFC_B200_SINGLE_STREAM=1 keeps everything on one stream."""
+        from .. import _C
+        sides = _C.side_streams(real.device, 6) if (real.is_cuda and getattr(D, "concurrent_forwards_ok", False)) else None
+        if not sides:
+            return D(fake), D(real)
+        cur, side = torch.cuda.current_stream(real.device), sides[5]
+        side.wait_stream(cur)                 # fork BEFORE the first forward is queued
+        d_fake = D(fake)
+        with torch.cuda.stream(side):
+            d_real = D(real)
+        cur.wait_stream(side)
+        if not torch.cuda.is_current_stream_capturing():
+            d_real.record_stream(cur)
+        return d_fake, d_real
 
     # ---- whole-step CUDA graph (launch-bound at these layer sizes: ~500 kernels of a few microseconds each)
     _capturing = False

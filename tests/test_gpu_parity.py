@@ -461,3 +461,36 @@ def test_fu_fwd_partial_statistics_are_deterministic():
                 _C.lib().ffc_debug_fu4(1)
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     assert parity.relerr(outs[0][0], outs[2][0]) < 2e-6 and parity.relerr(outs[0][1], outs[2][1]) < 1e-6
+
+
+def test_concurrent_discriminator_forwards_match_the_sequential_order(monkeypatch):
+    """GanTrainer._two_forwards queues D(real) on a side stream while D(fake) runs; the spectral-norm power iterations of the two
+    forwards still happen in program order (fake, then real, from the first's u / v).  Against the same two forwards on one
+    stream: outputs, all gradients of the discriminator loss, and the u / v buffers after both iterations."""
+    def run(single):
+        if single:
+            monkeypatch.setenv("FFC_B200_SINGLE_STREAM", "1")
+        else:
+            monkeypatch.delenv("FFC_B200_SINGLE_STREAM", raising=False)
+        torch.manual_seed(0)
+        D = H.SNDiscriminator(True, 4, 7).to(DEV).train(); D.apply(H.weights_init)
+        g = torch.Generator(device="cpu").manual_seed(1)
+        fake = (torch.rand(32, 3, 32, 32, generator=g) * 2 - 1).to(DEV)
+        real = (torch.rand(32, 3, 32, 32, generator=g) * 2 - 1).to(DEV)
+        d_fake, d_real = H.GanTrainer._two_forwards(D, fake, real)
+        loss = H.hinge_loss_dis(d_fake, d_real)
+        loss.backward()
+        torch.cuda.synchronize()
+        grads = {k: p.grad.detach().clone() for k, p in D.named_parameters()}
+        bufs = {k: b.detach().clone() for k, b in D.named_buffers()}
+        return d_fake.detach().clone(), d_real.detach().clone(), grads, bufs
+    a, b, c = run(False), run(True), run(True)
+    assert parity.relerr(a[0], b[0]) < 1e-5 and parity.relerr(a[1], b[1]) < 1e-5
+    for k in a[3]:
+        assert parity.relerr(a[3][k], b[3][k]) < 1e-5, k                   # u / v after two power iterations
+    # gradients: two runs of the SAME order already differ (float atomics of the split-K convolutions and weight gradients
+    # move activations in the last bit, a LeakyReLU element near zero then flips); the concurrent order must stay within that
+    noise = max(parity.relerr(b[2][k], c[2][k]) for k in b[2])
+    worst = max(parity.relerr(a[2][k], b[2][k]) for k in a[2])
+    print(f"gradient difference concurrent vs sequential {worst:.2e}, sequential vs sequential {noise:.2e}")
+    assert worst < max(2e-3, 4 * noise), (worst, noise)          # one flipped element is worth ~3e-4 here (seen in either pair)
