@@ -22,9 +22,10 @@ struct ChanReduceParams {
     const float* invstd;   // MODE 1
     const float* gamma;    // MODE 1
     const float* beta;     // MODE 1
-    double* out;           // [2C]
+    double* out;           // [2C] accumulated with atomics (zeroed by the caller), or, with `partial`, [nsplit][2C] written once
     int B, C, HW, act, nsplit;
     float slope;
+    int partial;           // 1: every (channel, split) CTA stores its own sums -- no zero fill in front, no atomics; the consumer adds them
 };
 
 template <int MODE>
@@ -107,8 +108,14 @@ struct ChanReduceKernel {
         }
         FFC_PHASE {
             if (tid == 0) {
-                ffc_atomic_add(p.out + c, red[0]);
-                if (MODE != 2) ffc_atomic_add(p.out + p.C + c, red[kThreads]);
+                if (p.partial) {
+                    double* o = p.out + (size_t)split * 2 * p.C;
+                    o[c] = red[0];
+                    if (MODE != 2) o[p.C + c] = red[kThreads];
+                } else {
+                    ffc_atomic_add(p.out + c, red[0]);
+                    if (MODE != 2) ffc_atomic_add(p.out + p.C + c, red[kThreads]);
+                }
             }
         } FFC_SYNC;
     }
@@ -118,10 +125,11 @@ struct ChanReduceKernel {
 // finalize: per-channel mean / invstd from the sums, running-stat update (momentum, unbiased var)
 // ---------------------------------------------------------------------------------------------
 struct BnFinalizeParams {
-    const double* sums;    // [2C]
+    const double* sums;    // [nparts][2C] (nparts = 1: the atomically accumulated sums)
     float* mean; float* invstd;           // [C] saved for backward / used by apply
     float* running_mean; float* running_var;   // [C] or null
     int C; double count; float eps, momentum;
+    int nparts;
 };
 struct BnFinalizeKernel {
     typedef BnFinalizeParams Params;
@@ -130,8 +138,10 @@ struct BnFinalizeKernel {
         FFC_PHASE {
             const int c = ctx.bx * kThreads + tid;
             if (c < p.C) {
-                const double m = p.sums[c] / p.count;
-                double var = p.sums[p.C + c] / p.count - m * m;
+                double s0 = 0.0, s1 = 0.0;
+                for (int q = 0; q < p.nparts; ++q) { s0 += p.sums[(size_t)q * 2 * p.C + c]; s1 += p.sums[(size_t)q * 2 * p.C + p.C + c]; }
+                const double m = s0 / p.count;
+                double var = s1 / p.count - m * m;
                 if (var < 0.0) var = 0.0;
                 p.mean[c] = (float)m;
                 p.invstd[c] = (float)(1.0 / sqrt(var + (double)p.eps));
@@ -256,12 +266,19 @@ struct BnBwdApplyKernel {
 };
 
 // double -> float copy of the first n sums (bias gradient)
-struct D2FParams { const double* in; float* out; int n; };
+struct D2FParams { const double* in; float* out; int n; int nparts; int stride; };    // out[i] = sum over the parts of in[part * stride + i]
 struct D2FKernel {
     typedef D2FParams Params;
     static constexpr int kThreads = 256;
     static FFC_DEVICE void run(const Params& p, const BlockCtx& ctx, float*) {
-        FFC_PHASE { const int i = ctx.bx * kThreads + tid; if (i < p.n) p.out[i] = (float)p.in[i]; } FFC_SYNC;
+        FFC_PHASE {
+            const int i = ctx.bx * kThreads + tid;
+            if (i < p.n) {
+                double s = 0.0;
+                for (int q = 0; q < p.nparts; ++q) s += p.in[(size_t)q * p.stride + i];
+                p.out[i] = (float)s;
+            }
+        } FFC_SYNC;
     }
 };
 
@@ -486,10 +503,12 @@ extern "C" int ffc_bn_act_fwd(const float* x, float* y, const float* gamma, cons
         if (training) {
             FFC_REQUIRE(workspace && workspace_bytes >= (size_t)2 * C * sizeof(double), "ffc_bn_act_fwd: workspace too small");
             double* sums = (double*)workspace;
-            FFC_CHECK(ffc_memset_async(sums, 0, (size_t)2 * C * sizeof(double), st));
-            ChanReduceParams rp{x, nullptr, nullptr, nullptr, nullptr, nullptr, sums, B, C, HW, 0, reduce_split(C, (long long)B * HW), 0.f};
+            ChanReduceParams rp{x, nullptr, nullptr, nullptr, nullptr, nullptr, sums, B, C, HW, 0, reduce_split(C, (long long)B * HW), 0.f, 0};
+            // room for one pair of sums per (channel, split): no zero-fill launch in front, no atomics, bitwise reproducible
+            rp.partial = workspace_bytes >= (size_t)2 * C * rp.nsplit * sizeof(double) ? 1 : 0;
+            if (!rp.partial) FFC_CHECK(ffc_memset_async(sums, 0, (size_t)2 * C * sizeof(double), st));
             FFC_CHECK((ffc_launch<ChanReduceKernel<0>>(C, rp.nsplit, 1, FFC_RED_THREADS, ChanReduceKernel<0>::smem_bytes(), st, rp)));
-            BnFinalizeParams fp{sums, save_mean, save_invstd, running_mean, running_var, C, (double)B * HW, eps, momentum};
+            BnFinalizeParams fp{sums, save_mean, save_invstd, running_mean, running_var, C, (double)B * HW, eps, momentum, rp.partial ? rp.nsplit : 1};
             FFC_CHECK((ffc_launch<BnFinalizeKernel>(ffc_cdiv(C, 256), 1, 1, 256, 0, st, fp)));
         } else {
             FFC_REQUIRE(running_mean && running_var, "ffc_bn_act_fwd: eval mode needs running statistics");
@@ -515,10 +534,11 @@ extern "C" int ffc_bn_stats(const float* x, float* running_mean, float* running_
     if (training) {
         FFC_REQUIRE(workspace && workspace_bytes >= (size_t)2 * C * sizeof(double), "ffc_bn_stats: workspace too small");
         double* sums = (double*)workspace;
-        FFC_CHECK(ffc_memset_async(sums, 0, (size_t)2 * C * sizeof(double), st));
-        ChanReduceParams rp{x, nullptr, nullptr, nullptr, nullptr, nullptr, sums, B, C, HW, 0, reduce_split(C, (long long)B * HW), 0.f};
+        ChanReduceParams rp{x, nullptr, nullptr, nullptr, nullptr, nullptr, sums, B, C, HW, 0, reduce_split(C, (long long)B * HW), 0.f, 0};
+        rp.partial = workspace_bytes >= (size_t)2 * C * rp.nsplit * sizeof(double) ? 1 : 0;
+        if (!rp.partial) FFC_CHECK(ffc_memset_async(sums, 0, (size_t)2 * C * sizeof(double), st));
         FFC_CHECK((ffc_launch<ChanReduceKernel<0>>(C, rp.nsplit, 1, FFC_RED_THREADS, ChanReduceKernel<0>::smem_bytes(), st, rp)));
-        BnFinalizeParams fp{sums, save_mean, save_invstd, running_mean, running_var, C, (double)B * HW, eps, momentum};
+        BnFinalizeParams fp{sums, save_mean, save_invstd, running_mean, running_var, C, (double)B * HW, eps, momentum, rp.partial ? rp.nsplit : 1};
         return ffc_launch<BnFinalizeKernel>(ffc_cdiv(C, 256), 1, 1, 256, 0, st, fp);
     }
     FFC_REQUIRE(running_mean && running_var, "ffc_bn_stats: eval mode needs running statistics");
@@ -542,7 +562,7 @@ extern "C" int ffc_bn_act_bwd(const float* x, const float* dy, float* dx, const 
         FFC_REQUIRE(workspace && workspace_bytes >= (size_t)2 * C * sizeof(double), "ffc_bn_act_bwd: workspace too small");
         double* sums = (double*)workspace;
         FFC_CHECK(ffc_memset_async(sums, 0, (size_t)2 * C * sizeof(double), st));
-        ChanReduceParams rp{x, dy, save_mean, save_invstd, gamma, beta, sums, B, C, HW, act, reduce_split(C, (long long)B * HW), slope};
+        ChanReduceParams rp{x, dy, save_mean, save_invstd, gamma, beta, sums, B, C, HW, act, reduce_split(C, (long long)B * HW), slope, 0};
         FFC_CHECK((ffc_launch<ChanReduceKernel<1>>(C, rp.nsplit, 1, FFC_RED_THREADS, ChanReduceKernel<1>::smem_bytes(), st, rp)));
         ap.mean = save_mean; ap.invstd = save_invstd; ap.gamma = gamma; ap.beta = beta; ap.sums = sums;
     }
@@ -557,12 +577,17 @@ extern "C" int ffc_bias_grad(const float* dy, float* db, int B, int C, int HW,
     FFC_REQUIRE(workspace && workspace_bytes >= (size_t)2 * C * sizeof(double), "ffc_bias_grad: workspace too small");
     ffc_stream_t st = (ffc_stream_t)stream;
     double* sums = (double*)workspace;
-    FFC_CHECK(ffc_memset_async(sums, 0, (size_t)2 * C * sizeof(double), st));
+    int nparts = 1;
     if (B > 0) {
-        ChanReduceParams rp{dy, nullptr, nullptr, nullptr, nullptr, nullptr, sums, B, C, HW, 0, reduce_split(C, (long long)B * HW), 0.f};
+        ChanReduceParams rp{dy, nullptr, nullptr, nullptr, nullptr, nullptr, sums, B, C, HW, 0, reduce_split(C, (long long)B * HW), 0.f, 0};
+        rp.partial = workspace_bytes >= (size_t)2 * C * rp.nsplit * sizeof(double) ? 1 : 0;
+        if (rp.partial) nparts = rp.nsplit;
+        else FFC_CHECK(ffc_memset_async(sums, 0, (size_t)2 * C * sizeof(double), st));
         FFC_CHECK((ffc_launch<ChanReduceKernel<2>>(C, rp.nsplit, 1, FFC_RED_THREADS, ChanReduceKernel<2>::smem_bytes(), st, rp)));
+    } else {
+        FFC_CHECK(ffc_memset_async(sums, 0, (size_t)2 * C * sizeof(double), st));
     }
-    D2FParams dp{sums, db, C};
+    D2FParams dp{sums, db, C, nparts, 2 * C};
     return ffc_launch<D2FKernel>(ffc_cdiv(C, 256), 1, 1, 256, 0, st, dp);
 }
 
