@@ -349,6 +349,34 @@ struct SeScaleKernel {
         const int Ho = p.mode == 1 ? p.Hi * 2 : (p.mode == 2 ? p.Hi / 2 : p.Hi);
         const int Wo = p.mode == 1 ? p.Wi * 2 : (p.mode == 2 ? p.Wi / 2 : p.Wi);
         const long long total = (long long)p.planes * Ho * Wo;
+        // four outputs of one row per thread, 32-bit index math (the element-per-thread form with 64-bit divisions ran at an
+        // eighth of the memory rate: 51 us for the 42 MB of the 16x16 -> 32x32 stage of the fgan32 generator at batch 256)
+        const bool vec = Wo % 4 == 0 && total < (1LL << 31) && ((((uintptr_t)p.x) | ((uintptr_t)p.y)) & 15) == 0;
+        if (vec) {
+            FFC_PHASE {
+                const unsigned q = (unsigned)(Wo / 4), n4 = (unsigned)(total / 4);
+                for (unsigned i = (unsigned)ctx.bx * kThreads + tid; i < n4; i += (unsigned)ctx.gx * kThreads) {
+                    const unsigned ox4 = i % q, t = i / q, oy = t % (unsigned)Ho, pl = t / (unsigned)Ho;
+                    const float* xp = p.x + (size_t)pl * p.Hi * p.Wi;
+                    const float g = FFC_LDG(p.gate + pl);
+                    float4 v;
+                    if (p.mode == 1) {
+                        const float2 a = FFC_LDG(reinterpret_cast<const float2*>(xp + (oy >> 1) * p.Wi + 2 * ox4));
+                        v = make_float4(a.x, a.x, a.y, a.y);
+                    } else if (p.mode == 2) {
+                        const float* r0 = xp + (2 * oy) * p.Wi + 8 * ox4;
+                        const float4 a0 = FFC_LDG(reinterpret_cast<const float4*>(r0)), a1 = FFC_LDG(reinterpret_cast<const float4*>(r0) + 1);
+                        const float4 b0 = FFC_LDG(reinterpret_cast<const float4*>(r0 + p.Wi)), b1 = FFC_LDG(reinterpret_cast<const float4*>(r0 + p.Wi) + 1);
+                        v = make_float4(0.25f * (a0.x + a0.y + b0.x + b0.y), 0.25f * (a0.z + a0.w + b0.z + b0.w),
+                                        0.25f * (a1.x + a1.y + b1.x + b1.y), 0.25f * (a1.z + a1.w + b1.z + b1.w));
+                    } else {
+                        v = FFC_LDG(reinterpret_cast<const float4*>(xp + oy * p.Wi) + ox4);
+                    }
+                    reinterpret_cast<float4*>(p.y)[i] = make_float4(v.x * g, v.y * g, v.z * g, v.w * g);
+                }
+            } FFC_SYNC;
+            return;
+        }
         FFC_PHASE {
             for (long long i = (long long)ctx.bx * kThreads + tid; i < total; i += (long long)ctx.gx * kThreads) {
                 const int ox = (int)(i % Wo), oy = (int)((i / Wo) % Ho);
