@@ -231,7 +231,7 @@ def time_fourier_unit_shape(C, N, B, dev):
         n0 = L.ffc_launch_count()
         fu(xs[0])
         out["launches_fwd_train"] = L.ffc_launch_count() - n0
-        out["fused"] = out["launches_fwd_train"] <= 2            # single-kernel form (1 launch, 2 in its two-pass variant); else L2-staged
+        out["fused"] = out["launches_fwd_train"] <= 3            # single-kernel form (1 launch; + zero fill, + statistics pass in its two-pass variant); the L2-staged form has >= 4
         out["ms_fwd_train"] = _graph_time(lambda x: fu(x), xs)
         fu.eval()
         out["ms_fwd_eval"] = _graph_time(lambda x: fu(x), xs)

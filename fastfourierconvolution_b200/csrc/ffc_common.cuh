@@ -245,6 +245,7 @@ static inline int ffc_memset_async(void* p, int v, size_t n, ffc_stream_t s) {
     const size_t n16 = (n - head) / 16, ntail = (n - head) % 16;
     if (head) {                                             // unaligned start: rare, zero it through the tail path of a first launch
         ffc_zero_kernel<<<1, 32, 0, s>>>(nullptr, 0, b, head);
+        ffc_count_launch();
     }
     size_t blocks = (n16 + 255) / 256;
     if (blocks < 1) blocks = 1;
@@ -253,6 +254,7 @@ static inline int ffc_memset_async(void* p, int v, size_t n, ffc_stream_t s) {
     ffc_zero_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<uint4*>(b + head), n16, b + head + n16 * 16, ntail);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { ffc_set_error("zero-fill launch failed: %s", cudaGetErrorString(e)); return FFC_ERR_CUDA; }
+    ffc_count_launch();
     return FFC_OK;
 }
 #endif
