@@ -252,10 +252,23 @@ int wgrad_v5_run(const float* S, const float* L, float* dW, int B, int SC, int L
     const int ntiles = (SC + p.nt_full - 1) / p.nt_full;
     const int mtiles = ffc_cdiv(LC * k * k, 128);
     const int Ktot = B * Hs * Ws, kchunks = ffc_cdiv(Ktot, WG5_BK);
-    // split K so that the grid has ~2 CTAs per SM, at least 8 chunks per CTA
-    int ksplit = ffc_cdiv(2 * ffc_sm_count(), mtiles * ntiles);
-    if (ksplit > kchunks / 8) ksplit = kchunks / 8;
-    if (ksplit < 1) ksplit = 1;
+    // Split K over CTAs.  One CTA is resident per SM (800 threads, the whole tensor memory), so the launch runs in whole waves
+    // of sm_count CTAs and costs ~ waves * (chunks per CTA + a fixed prologue / epilogue of ~6 chunks): pick the split that
+    // minimises that, at least 8 chunks per CTA.  (The former rule -- about two CTAs per SM, rounded up -- produced 2.05 to
+    // 2.4 waves on the 128- and 256-channel discriminator layers, i.e. a third wave for a few CTAs: 114 -> 89 us and
+    // 104 -> 87 us per launch when the grid fits whole waves, tools/bench_wgrad.py.)
+    const int base = mtiles * ntiles, sms = ffc_sm_count();
+    int max_split = kchunks / 8;
+    if (max_split < 1) max_split = 1;
+    if (max_split > 4 * sms) max_split = 4 * sms;
+    int ksplit = 1;
+    long long best = -1;
+    for (int ks = 1; ks <= max_split; ++ks) {
+        const int cps = ffc_cdiv(kchunks, ks), ks2 = ffc_cdiv(kchunks, cps);
+        const long long waves = ffc_cdiv(base * ks2, sms);
+        const long long cost = waves * (cps + 6);
+        if (best < 0 || cost < best) { best = cost; ksplit = ks2; }
+    }
     p.chunks_per_split = ffc_cdiv(kchunks, ksplit);
     ksplit = ffc_cdiv(kchunks, p.chunks_per_split);
     const size_t smem = (size_t)WG5_SB * 2 * p.nt_full * WG5_BK * 4 + 256;
