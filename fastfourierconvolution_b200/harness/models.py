@@ -84,6 +84,11 @@ class FGenerator(nn.Module):
                                                       uses_sn=(variant != "fgan32")))
 
     def forward(self, z):
+        from ..layers import _util
+        with _util.batched_bn_counters(self):            # the ten num_batches_tracked += 1 of a forward as one launch
+            return self._forward(z)
+
+    def _forward(self, z):
         from .. import ops
         lin = self.noise_to_feature[0]
         if z.is_cuda:    # the Linear stem (fgan_complete.py:92-95, 117-119) on the library's FP32 matrix kernel

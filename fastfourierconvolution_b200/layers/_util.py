@@ -9,6 +9,37 @@ from torch.nn.utils.weight_norm import WeightNorm as _WeightNorm
 from .. import ops
 
 
+_counted = set()      # id(BatchNorm holder) whose num_batches_tracked was already advanced for the running forward (batched_bn_counters)
+
+
+class batched_bn_counters:
+    """``with batched_bn_counters(model, skip=(".lfu.",)): y = model(x)`` -- torch's ``num_batches_tracked += 1`` of every
+    training-mode BatchNorm the forward will run, as ONE multi-tensor launch up front instead of one tiny launch per layer in the
+    middle of the forward (10 per generator forward of fgan32).  ``skip``: name fragments of holders the forward never runs
+    (the constructed-but-unused ``lfu`` of the reference, spectral_transform.py:65-67 vs :94-105), whose counters must stay."""
+
+    def __init__(self, model: nn.Module, skip=(".lfu.",)):
+        self.bns = [m for n, m in model.named_modules()
+                    if isinstance(m, nn.modules.batchnorm._BatchNorm) and m.training and m.track_running_stats
+                    and m.num_batches_tracked is not None and not any(f in "." + n + "." for f in skip)]
+
+    def __enter__(self):
+        if self.bns:
+            torch._foreach_add_([m.num_batches_tracked for m in self.bns], 1)
+            _counted.update(id(m) for m in self.bns)
+        return self
+
+    def __exit__(self, *exc):
+        _counted.difference_update(id(m) for m in self.bns)
+        return False
+
+
+def count_batch(bn: nn.Module) -> None:
+    """torch _BatchNorm.forward's bookkeeping for one holder (a no-op when batched_bn_counters already did it)."""
+    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None and id(bn) not in _counted:
+        bn.num_batches_tracked.add_(1)
+
+
 _prefetched = {}      # id(holder module) -> (normalised weight, wait): filled by prefetch_spectral_norm, consumed by effective_weight
 
 
@@ -103,8 +134,7 @@ def bn_act(x: torch.Tensor, bn: nn.Module, act_code_slope) -> torch.Tensor:
     if bn.momentum is None:
         raise NotImplementedError("BatchNorm2d(momentum=None) (cumulative average) is not supported")
     use_batch_stats = bn.training or bn.running_mean is None
-    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)          # torch _BatchNorm.forward bookkeeping
+    count_batch(bn)                              # torch _BatchNorm.forward bookkeeping
     gamma, beta = bn.weight, bn.bias
     if gamma is None:                            # affine=False
         gamma = torch.ones(bn.num_features, device=x.device)

@@ -68,15 +68,13 @@ class FourierUnitSN(nn.Module):
             single = False
         staged = kind == 2 and plain_bn and self.fused and not single and ops.fu_staged_supported(x.shape[0], cin, cout, h, w)
         if single or staged:
-            if bn.training:
-                bn.num_batches_tracked.add_(1)
+            _util.count_batch(bn)
             return ops.fourier_unit_fused(x, weight.view(2 * cout, 2 * cin), bn.weight, bn.bias, bn.running_mean,
                                           bn.running_var, residual, bn.training, bn.eps, bn.momentum, staged=bool(staged))
         spec = ops.rfft2(x)                                            # fourier_unity.py:38-42
         mixed = ops.conv2d(spec, weight)                               # :45
         if plain_bn:                                                   # :49 applied inside the load of :51-56
-            if bn.training:
-                bn.num_batches_tracked.add_(1)
+            _util.count_batch(bn)
             return ops.bn_relu_irfft2(mixed, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual,
                                       bn.training, bn.eps, bn.momentum, width=w)
         act = _util.bn_act(mixed, self.bn, (ops.ACT_RELU, 0.0))        # :49
