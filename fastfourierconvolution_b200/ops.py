@@ -143,6 +143,8 @@ def fork_map(device, fns, nstreams: int = 4):
             r = fn()
             ev = torch.cuda.Event()
             ev.record(side)
+        if torch.is_tensor(r) and not torch.cuda.is_current_stream_capturing():
+            r.record_stream(cur)          # eager mode: allocated on the side stream's pool, consumed on the current stream
         out.append((r, (lambda ev=ev: cur.wait_event(ev))))
     return out
 
