@@ -71,4 +71,12 @@ CASES = {
               lambda R: lambda P, xs, tr: R.ffc(_tup(xs), P, "", _cfg(R, 32, 64, 4, .25, .25, 2, 1, spectral_norm=True), tr)),
     "snffc_eval": (lambda L: L.SNFFC(32, 32, 3, .25, .25, 1, 1, bias=True), [(2, 24, 8, 8), (2, 8, 8, 8)], False,
                    lambda R: lambda P, xs, tr: R.ffc(_tup(xs), P, "", _cfg(R, 32, 32, 3, .25, .25, 1, 1, bias=True, spectral_norm=True), tr)),
+    # planes that are not a square power of two (the reference accepts every size; here: direct-DFT kernels)
+    "fu_c4to6_7x9": (lambda L: L.FourierUnitSN(4, 6), [(2, 4, 7, 9)], True,
+                     lambda R: lambda P, xs, tr: R.fourier_unit(xs[0], P, "", tr)),
+    "st_12": (lambda L: L.SpectralTransform(16, 16), [(2, 16, 12, 12)], True,
+              lambda R: lambda P, xs, tr: R.spectral_transform(xs[0], P, "", 1, False, tr)),
+    "ffcbn_up_6to12": (lambda L: L.FFC_BN_ACT(32, 16, 4, .25, .25, 2, 1, upsampling=True, **_BN_GELU),
+                       [(2, 24, 6, 6), (2, 8, 6, 6)], True,
+                       lambda R: _bnact(R, lambda R: _cfg(R, 32, 16, 4, .25, .25, 2, 1, norm="bn", act="gelu", upsampling=True))),
 }

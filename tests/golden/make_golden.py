@@ -106,8 +106,13 @@ def main():
     from cases import CASES
     t = torch.randn
     torch.manual_seed(1234)
+    only = set(sys.argv[sys.argv.index("--only") + 1].split(",")) if "--only" in sys.argv else None
     for name, (ctor, shapes, train, _oracle) in CASES.items():
-        record(name, quiet(lambda: ctor(ref_layers)), [torch.randn(*s) for s in shapes], train=train)
+        inputs = [torch.randn(*s) for s in shapes]          # drawn for every case, so that --only leaves the others' inputs as they are
+        if only is None or name in only:
+            record(name, quiet(lambda: ctor(ref_layers)), inputs, train=train)
+    if only is not None:
+        return
 
     # whole models with closed-form weights (oracle.ffc_ref.deterministic_fill), so no weights are stored
     sys.path.insert(0, os.path.join(HERE, "..", ".."))
