@@ -53,6 +53,10 @@ def build_models():
     ns = load_script_classes(os.path.join(REF, "sngan_complete.py"))
     out["sngan_G"] = (quiet(lambda: ns["FGenerator"](z_size=128, mg=4)), (2, 128))
     out["sngan_FD"] = (quiet(lambda: ns["FDiscriminator"](sn=True, mg=4)), (2, 3, 32, 32))
+    # mg = 6 (fgan_cond_complete.py:325): 48x48 images, Fourier units on 24x24 / 48x48 (generator) and 24x24 / 12x12 planes
+    # (discriminator) -- not powers of two: the direct-DFT plane kernels
+    out["sngan_mg6_G"] = (quiet(lambda: ns["FGenerator"](z_size=128, mg=6)), (2, 128))
+    out["sngan_mg6_FD"] = (quiet(lambda: ns["FDiscriminator"](sn=True, mg=6)), (2, 3, 48, 48))
     out["cfg1_G"] = (quiet(lambda: M.FFCGenerator(100, 1, 32)), (2, 100, 1, 1))
     out["cfg1_D"] = (quiet(lambda: M.FFCDiscriminator(1, 32)), (2, 1, 64, 64))
     return out
