@@ -38,7 +38,23 @@ def quiet(fn):
         return fn()
 
 
+class CondBlock(torch.nn.Module):
+    """FFC_BN_ACT with the reference's ConditionalBatchNorm2d as norm_layer and class labels y (ffc_bn_act.py:55-57, 73-79;
+    layers/cond/cond_bn.py:5-23) on a purely local layer (with a global branch the reference itself crashes on y,
+    fourier_unity.py:46-47): the conditional norm stays the caller's module, convolution and activation are the product's."""
+
+    def __init__(self, L):
+        super().__init__()
+        self.blk = L.FFC_BN_ACT(8, 16, 3, 0.0, 0.0, 1, 1, norm_layer=L.ConditionalBatchNorm2d,
+                                activation_layer=torch.nn.LeakyReLU, num_classes=5)
+
+    def forward(self, x):
+        y = torch.arange(x.shape[0], device=x.device) % 5
+        return self.blk(x, y)[0]
+
+
 def build_models():
+    import layers as L
     import models as M
     import models.ffcmodel as fm
     if not getattr(fm.FFCModel, "_shimmed", False):
@@ -57,6 +73,7 @@ def build_models():
     # (discriminator) -- not powers of two: the direct-DFT plane kernels
     out["sngan_mg6_G"] = (quiet(lambda: ns["FGenerator"](z_size=128, mg=6)), (2, 128))
     out["sngan_mg6_FD"] = (quiet(lambda: ns["FDiscriminator"](sn=True, mg=6)), (2, 3, 48, 48))
+    out["cond_block"] = (quiet(lambda: CondBlock(L)), (6, 8, 8, 8))
     out["cfg1_G"] = (quiet(lambda: M.FFCGenerator(100, 1, 32)), (2, 100, 1, 1))
     out["cfg1_D"] = (quiet(lambda: M.FFCDiscriminator(1, 32)), (2, 1, 64, 64))
     return out

@@ -33,7 +33,7 @@ def test_reference_model_classes_run_on_the_product_layers():
     line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1]
     res = json.loads(line[7:])
     assert set(res) == {"fgan32_G", "fgan32_D", "fgan64_G", "fgan64_D", "fgan128_G", "fgan128_D", "sngan_G", "sngan_FD", "sngan_mg6_G", "sngan_mg6_FD",
-                        "cfg1_G", "cfg1_D"}
+                        "cond_block", "cfg1_G", "cfg1_D"}
     for name, e in res.items():
         assert max(e["out"], e["din"], e["grad"]) < 2e-4, (name, e)
         if name.endswith(("_G", "_FD")) or name == "cfg1_D":
