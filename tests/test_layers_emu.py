@@ -114,6 +114,27 @@ def test_eval_generator_emits_uint8(emu):
     assert out.dtype == torch.uint8 and out.shape == (2, 3, 32, 32)
 
 
+def test_generator_forward_advances_every_batchnorm_counter_once(emu):
+    """torch's BatchNorm bookkeeping (num_batches_tracked += 1 per training forward) through layers/_util.batched_bn_counters:
+    every BatchNorm the forward runs advances by exactly one per forward, the constructed-but-unused lfu holders
+    (spectral_transform.py:65-67 vs :94-105) stay at zero as in the reference, eval forwards leave all of them alone."""
+    torch.manual_seed(0)
+    g = H.FGenerator(128, 4, "fgan32").train()
+    z = torch.randn(2, 128)
+    g(z); g(z)
+    counts = {k: int(v) for k, v in g.state_dict().items() if k.endswith("num_batches_tracked")}
+    assert counts and all(v == (0 if ".lfu." in k else 2) for k, v in counts.items()), counts
+    g.eval()
+    with torch.no_grad():
+        g(z)
+    after = {k: int(v) for k, v in g.state_dict().items() if k.endswith("num_batches_tracked")}
+    assert after == counts
+    # a layer used outside the generator still counts for itself
+    m = ffc.FourierUnitSN(4, 4).train()
+    m(torch.randn(2, 4, 8, 8))
+    assert int(m.bn.num_batches_tracked) == 1
+
+
 def test_requires_grad_toggling_like_the_training_loop(emu):
     """fgan_complete.py:368-381 flips requires_grad on G and D every half step."""
     torch.manual_seed(0)
